@@ -1,0 +1,85 @@
+// K1 -- batched IGRF-12 (geocentric), one point per thread, SoA in / SoA out.
+// Replaces n scalar calls of igrf12() [reference src/igrf.jl:67-274], e.g. the
+// 10^6-point map of igrf_data() [src/magnetic_toolbox.jl:108-121] and
+// BASELINE config "10^8 random LEO points".
+//
+// Roofline: FP64 CUDA-core pipe.  Algorithmic work 2243 FLOP/point,
+// 48 B/point of HBM traffic (3 doubles in, 3 out) -> AI ~ 47 FLOP/B, far right of
+// the ridge; HBM is not binding.  Loads/stores are fully coalesced (consecutive
+// threads -> consecutive doubles of each SoA array).
+#pragma once
+#include "common.cuh"
+#include "igrf_device.cuh"
+
+namespace ts {
+
+constexpr int K1_THREADS = 128;
+
+template <int NMAX>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_igrf12_batch(const double* __restrict__ tabG, const double* __restrict__ tabH, double date, int64_t n,
+                const double* __restrict__ r_m, const double* __restrict__ lat, const double* __restrict__ lon,
+                double* __restrict__ Bn, double* __restrict__ Be, double* __restrict__ Bd, int* __restrict__ bad_flag) {
+  __shared__ double2 s_gh[IGRF_NCOEF];
+  igrf_stage_coeffs(s_gh, tabG, tabH, date);
+  __syncthreads();
+  const double PI = 3.141592653589793;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double la = lat[i], lo = lon[i], rr = r_m[i];
+    double bn, be, bd;
+    // reference validation, igrf.jl:84-88 (NaN inputs fail it too)
+    if (!(la >= -PI / 2 && la <= PI / 2 && lo >= -PI && lo <= PI)) {
+      bn = be = bd = nan("");
+      *bad_flag = 1;
+    } else {
+      igrf12_point<NMAX>(s_gh, rr, la, lo, bn, be, bd);
+    }
+    Bn[i] = bn;
+    Be[i] = be;
+    Bd[i] = bd;
+  }
+}
+
+// Register-resident DFMA micro-benchmark: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
+}
+
+inline void igrf_host_constants(IgrfConsts& h) {
+  memset(&h, 0, sizeof(h));
+  for (int n = 1; n <= 13; ++n) {
+    for (int m = 0; m <= n - 1; ++m) {
+      if (n >= 2) {
+        const long aux = (long)(n - m) * (n + m);
+        h.leg_a[n][m] = sqrt((double)((2 * n - 1) * (2 * n - 1)) / (double)aux);
+        h.leg_b[n][m] = sqrt((double)((n + m - 1) * (n - m - 1)) / (double)aux);
+      }
+    }
+    h.leg_d[n] = sqrt((double)(2 * n - 1) / (double)(2 * n));
+    for (int m = 0; m <= n; ++m) {
+      if (m == 0) {
+        const double aux = sqrt((double)(n * (n + 1)) / 2.0);
+        h.dl_a[n][0] = +0.5 * aux;
+        h.dl_b[n][0] = -0.5 * aux;
+      } else if (m == 1) {
+        h.dl_a[n][1] = +0.5 * sqrt((double)(2 * n * (n + 1)));
+        h.dl_b[n][1] = -0.5 * sqrt((double)((n + 2) * (n - 1)));
+      } else {
+        h.dl_a[n][m] = +0.5 * sqrt((double)((n + m) * (n - m + 1)));
+        h.dl_b[n][m] = -0.5 * sqrt((double)((n + m + 1) * (n - m)));
+      }
+    }
+  }
+}
+
+}  // namespace ts
