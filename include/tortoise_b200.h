@@ -69,6 +69,46 @@ int ts_fp64_peak_probe(ts_ctx* ctx, double* tflops_out);
 int ts_igrf12_batch(ts_ctx* ctx, double date, int64_t n, const double* r_m, const double* lat, const double* lon,
                     double* Bn, double* Be, double* Bd, int pointers_are_device);
 
+/* ---- K2: orbit + ECI field table + gramian cutoff --------------------------- *
+ * One entry of ts_field_opts per trial (the reference keeps these in the `params`
+ * struct / globals: p.GM, p.MJD, the hard-coded igrf date 2019 and the constant
+ * field radius (alt+R_E)*1000 of src/magnetic_toolbox.jl:44,81).                   */
+typedef struct ts_field_opts {
+  double GM;             /* km^3/s^2                        (input_parameters.jl:26) */
+  double mjd;            /* modified Julian day of t = 0    (input_parameters.jl:63) */
+  double igrf_date;      /* year A.D. passed to igrf12      (magnetic_toolbox.jl:81: 2019) */
+  double field_radius_m; /* radius passed to igrf12 [m]     (magnetic_toolbox.jl:81: (alt+R_E)*1000) */
+  double t0, tf;         /* s; the orbit is propagated over [t0, 2 tf] with dt = (tf-t0)/N */
+  int64_t N;             /* knot count; the table has 2N rows, pos/vel 2N+1 rows */
+} ts_field_opts;
+
+/* magnetic_simulation(p,t0,tf,N,mag_field) [src/magnetic_toolbox.jl:33-106] (which calls
+ * kep_ECI [src/kep_ECI.jl:1-49] and Euler-integrates OrbitPlotter [src/OrbitPlotter.jl:1-52])
+ * for n_trials trials.  kep6: n_trials x 6 = [e, a km, i deg, RAAN deg, argp deg, nu deg]
+ * (NOT mutated, unlike kep_ECI.jl:7-8).  Ragged layout: trial t owns rows
+ * [B_offs[t], B_offs[t]+2N_t) of B_eci (rows x 3, Tesla; last row 0 like the reference) and
+ * rows [B_offs[t]+t, B_offs[t]+t+2N_t+1) of pos / vel (km, km/s; nullable).  B_offs has
+ * n_trials+1 entries (host pointer).  rows_limit (host, nullable): if rows_limit[t] > 0 only
+ * the first rows_limit[t] table rows are computed (the rest are 0) -- the solver only ever
+ * reads rows <= floor(x8*N+1) (DerivFunction.jl:28, quirk Q1).                            */
+int ts_magnetic_simulation_batch(ts_ctx* ctx, int64_t n_trials, const double* kep6, const ts_field_opts* opts,
+                                 const int64_t* B_offs, const int64_t* rows_limit, double* B_eci, double* pos, double* vel,
+                                 int pointers_are_device);
+
+/* magnetic_gramian(B_N, dt) [src/magnetic_toolbox.jl:1-12]: G (rows x 9 per trial, row-major 3x3,
+ * same row offsets as B_eci).  rows/dt: host arrays of n_trials.                           */
+int ts_magnetic_gramian_batch(ts_ctx* ctx, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
+                              const double* dt, double* G, int pointers_are_device);
+
+/* condition_based_time(B_gram, cutoff) [src/magnetic_toolbox.jl:14-31]: first 1-based sample
+ * whose gramian has cond_2 < cutoff, else 0.  tf_index: host array of n_trials.             */
+int ts_condition_based_time_batch(ts_ctx* ctx, int64_t n_trials, const double* G, const int64_t* offs, const int64_t* rows,
+                                  const double* cutoff, int64_t* tf_index, int pointers_are_device);
+
+/* Fused magnetic_gramian + condition_based_time (no rows x 9 intermediate).               */
+int ts_condition_cutoff_batch(ts_ctx* ctx, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
+                              const double* dt, const double* cutoff, int64_t* tf_index, int pointers_are_device);
+
 #ifdef __cplusplus
 }
 #endif

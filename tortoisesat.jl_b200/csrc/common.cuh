@@ -99,6 +99,17 @@ inline int dev_back(ts_ctx* ctx, DevBuf& b, void* p, size_t bytes) {
   return TS_OK;
 }
 
+// small host array -> device scratch slot
+template <class T>
+inline int upload(ts_ctx* c, int slot, const T* host, size_t count, T** dev) {
+  void* d = nullptr;
+  int rc = scratch_reserve(c, slot, count * sizeof(T) + 16, &d);
+  if (rc) return rc;
+  TS_CUDA(c, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  *dev = (T*)d;
+  return TS_OK;
+}
+
 struct KernelTimer {
   ts_ctx* c;
   explicit KernelTimer(ts_ctx* ctx) : c(ctx) { cudaEventRecord(c->ev0, c->stream); }

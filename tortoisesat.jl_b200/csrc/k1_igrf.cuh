@@ -24,21 +24,22 @@ k1_igrf12_batch(const double* __restrict__ tabG, const double* __restrict__ tabH
   igrf_stage_coeffs(s_gh, tabG, tabH, date);
   __syncthreads();
   const double PI = 3.141592653589793;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double la = lat[i], lo = lon[i], rr = r_m[i];
-    double bn, be, bd;
-    // reference validation, igrf.jl:84-88 (NaN inputs fail it too)
-    if (!(la >= -PI / 2 && la <= PI / 2 && lo >= -PI && lo <= PI)) {
-      bn = be = bd = nan("");
-      *bad_flag = 1;
-    } else {
-      igrf12_point<NMAX>(s_gh, rr, la, lo, bn, be, bd);
-    }
-    Bn[i] = bn;
-    Be[i] = be;
-    Bd[i] = bd;
+  // one point per thread: a grid-stride loop lets the compiler hoist the c[][] recursion
+  // constants into registers (255 regs + spills); without it the body needs 168, no spills.
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double la = lat[i], lo = lon[i], rr = r_m[i];
+  double bn, be, bd;
+  // reference validation, igrf.jl:84-88 (NaN inputs fail it too)
+  if (!(la >= -PI / 2 && la <= PI / 2 && lo >= -PI && lo <= PI)) {
+    bn = be = bd = nan("");
+    *bad_flag = 1;
+  } else {
+    igrf12_point<NMAX>(s_gh, rr, la, lo, bn, be, bd);
   }
+  Bn[i] = bn;
+  Be[i] = be;
+  Bd[i] = bd;
 }
 
 // Register-resident DFMA micro-benchmark: 8 independent chains per thread.

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "igrf_device.cuh"
 #include "k1_igrf.cuh"
+#include "k2_field.cuh"
 
 namespace ts {
 #include "igrf12_tables.inc"
@@ -123,9 +124,7 @@ int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const 
   if ((rc = dev_out(c, dbe, Be, bytes, pointers_are_device))) return rc;
   if ((rc = dev_out(c, dbd, Bd, bytes, pointers_are_device))) return rc;
   TS_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
-  int64_t want = (n + K1_THREADS - 1) / K1_THREADS;
-  const int64_t cap = (int64_t)c->sm_count * 16;  // persistent-style grid: a multiple of the SM count
-  const int blocks = (int)(want < cap ? want : cap);
+  const unsigned blocks = (unsigned)((n + K1_THREADS - 1) / K1_THREADS);
   KernelTimer t(c);
   if (igrf_nmax_for_date(date) == 13)
     k1_igrf12_batch<13><<<blocks, K1_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, date, n, (const double*)dr.d,
@@ -146,6 +145,151 @@ int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const 
   TS_CUDA(c, cudaStreamSynchronize(c->stream));
   t.read();
   if (bad) return fail(c, TS_ERR_DOMAIN, "The latitude must be between -pi/2 and +pi/2 rad and the longitude between -pi and +pi rad.");
+  return TS_OK;
+}
+
+// ---------------------------------------------------------------------------- K2
+static_assert(sizeof(ts_field_opts) == sizeof(ts_field_opts_dev), "field opts layout");
+
+
+int ts_magnetic_simulation_batch(ts_ctx* c, int64_t n_trials, const double* kep6, const ts_field_opts* opts,
+                                 const int64_t* B_offs, const int64_t* rows_limit, double* B_eci, double* pos, double* vel,
+                                 int pointers_are_device) {
+  if (!c) return TS_ERR_ARG;
+  if (n_trials < 0 || (n_trials > 0 && (!kep6 || !opts || !B_offs || !B_eci)))
+    return fail(c, TS_ERR_ARG, "ts_magnetic_simulation_batch: null argument");
+  if (n_trials == 0) return TS_OK;
+  bool any13 = false, any10 = false;
+  int64_t maxN = 0;
+  for (int64_t t = 0; t < n_trials; ++t) {
+    if (!(opts[t].igrf_date >= 1900.0 && opts[t].igrf_date <= 2025.0))
+      return fail(c, TS_ERR_DATE, "trial %lld: IGRF date outside [1900, 2025]", (long long)t);
+    if (opts[t].N < 1 || B_offs[t + 1] - B_offs[t] < 2 * opts[t].N)
+      return fail(c, TS_ERR_ARG, "trial %lld: N < 1 or B_offs does not leave 2N rows", (long long)t);
+    (igrf_nmax_for_date(opts[t].igrf_date) == 13 ? any13 : any10) = true;
+    if (opts[t].N > maxN) maxN = opts[t].N;
+  }
+  TS_CUDA(c, cudaSetDevice(c->device));
+  const int64_t total_rows = B_offs[n_trials];
+  int rc;
+  DevBuf dkep, dB, dpos, dvel;
+  if ((rc = dev_in(c, dkep, kep6, (size_t)n_trials * 6 * sizeof(double), pointers_are_device))) return rc;
+  if ((rc = dev_out(c, dB, B_eci, (size_t)total_rows * 3 * sizeof(double), pointers_are_device))) return rc;
+  const size_t pos_bytes = (size_t)(total_rows + n_trials) * 3 * sizeof(double);
+  double* d_pos = nullptr;
+  if (pos) {
+    if ((rc = dev_out(c, dpos, pos, pos_bytes, pointers_are_device))) return rc;
+    d_pos = (double*)dpos.d;
+  } else {
+    void* p = nullptr;
+    if ((rc = scratch_reserve(c, 0, pos_bytes, &p))) return rc;
+    d_pos = (double*)p;
+  }
+  if (vel && (rc = dev_out(c, dvel, vel, pos_bytes, pointers_are_device))) return rc;
+  ts_field_opts_dev* d_opts = nullptr;
+  int64_t *d_offs = nullptr, *d_lim = nullptr;
+  if ((rc = upload(c, 1, (const ts_field_opts_dev*)opts, (size_t)n_trials, &d_opts))) return rc;
+  if ((rc = upload(c, 2, B_offs, (size_t)n_trials + 1, &d_offs))) return rc;
+  if (rows_limit && (rc = upload(c, 3, rows_limit, (size_t)n_trials, &d_lim))) return rc;
+  KernelTimer tm(c);
+  k2a_orbit_euler<<<(unsigned)((n_trials + 127) / 128), 128, 0, c->stream>>>(n_trials, (const double*)dkep.d, d_opts, d_offs, d_lim,
+                                                                             d_pos, vel ? (double*)dvel.d : nullptr);
+  c->launches++;
+  dim3 grid((unsigned)n_trials, (unsigned)((2 * maxN + K2B_THREADS - 1) / K2B_THREADS));
+  if (any13) {
+    k2b_field_rows<13><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_opts, d_offs, d_lim, d_pos, (double*)dB.d, 13);
+    c->launches++;
+  }
+  if (any10) {
+    k2b_field_rows<10><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_opts, d_offs, d_lim, d_pos, (double*)dB.d, 10);
+    c->launches++;
+  }
+  tm.stop();
+  TS_CUDA(c, cudaGetLastError());
+  if ((rc = dev_back(c, dB, B_eci, (size_t)total_rows * 3 * sizeof(double)))) return rc;
+  if (pos && (rc = dev_back(c, dpos, pos, pos_bytes))) return rc;
+  if (vel && (rc = dev_back(c, dvel, vel, pos_bytes))) return rc;
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
+  return TS_OK;
+}
+
+static int gramian_common(ts_ctx* c, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
+                          const double* dt, const double* cutoff, double* G, int64_t* tf_index, int pad) {
+  if (!c) return TS_ERR_ARG;
+  if (n_trials < 0 || (n_trials > 0 && (!B_eci || !B_offs || !rows || !dt))) return fail(c, TS_ERR_ARG, "gramian: null argument");
+  if (n_trials == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  int64_t total = 0;
+  for (int64_t t = 0; t < n_trials; ++t) total = (B_offs[t] + rows[t] > total) ? B_offs[t] + rows[t] : total;
+  int rc;
+  DevBuf dB, dG;
+  if ((rc = dev_in(c, dB, B_eci, (size_t)total * 3 * sizeof(double), pad))) return rc;
+  if (G && (rc = dev_out(c, dG, G, (size_t)total * 9 * sizeof(double), pad))) return rc;
+  int64_t *d_offs, *d_rows, *d_idx = nullptr;
+  double *d_dt, *d_cut = nullptr;
+  if ((rc = upload(c, 1, B_offs, (size_t)n_trials, &d_offs))) return rc;
+  if ((rc = upload(c, 2, rows, (size_t)n_trials, &d_rows))) return rc;
+  if ((rc = upload(c, 3, dt, (size_t)n_trials, &d_dt))) return rc;
+  if (cutoff && (rc = upload(c, 4, cutoff, (size_t)n_trials, &d_cut))) return rc;
+  if (tf_index) {
+    void* p;
+    if ((rc = scratch_reserve(c, 5, (size_t)n_trials * sizeof(int64_t), &p))) return rc;
+    d_idx = (int64_t*)p;
+  }
+  KernelTimer tm(c);
+  k2c_gramian_cutoff<<<(unsigned)((n_trials + 127) / 128), 128, 0, c->stream>>>(n_trials, (const double*)dB.d, d_offs, d_rows, d_dt,
+                                                                                d_cut, G ? (double*)dG.d : nullptr, d_idx);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  if (G && (rc = dev_back(c, dG, G, (size_t)total * 9 * sizeof(double)))) return rc;
+  if (tf_index) TS_CUDA(c, cudaMemcpyAsync(tf_index, d_idx, (size_t)n_trials * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
+  return TS_OK;
+}
+
+int ts_magnetic_gramian_batch(ts_ctx* c, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
+                              const double* dt, double* G, int pad) {
+  if (c && !G) return fail(c, TS_ERR_ARG, "ts_magnetic_gramian_batch: G is null");
+  return gramian_common(c, n_trials, B_eci, B_offs, rows, dt, nullptr, G, nullptr, pad);
+}
+
+int ts_condition_cutoff_batch(ts_ctx* c, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
+                              const double* dt, const double* cutoff, int64_t* tf_index, int pad) {
+  if (c && (!cutoff || !tf_index)) return fail(c, TS_ERR_ARG, "ts_condition_cutoff_batch: null argument");
+  return gramian_common(c, n_trials, B_eci, B_offs, rows, dt, cutoff, nullptr, tf_index, pad);
+}
+
+int ts_condition_based_time_batch(ts_ctx* c, int64_t n_trials, const double* G, const int64_t* offs, const int64_t* rows,
+                                  const double* cutoff, int64_t* tf_index, int pad) {
+  if (!c) return TS_ERR_ARG;
+  if (n_trials < 0 || (n_trials > 0 && (!G || !offs || !rows || !cutoff || !tf_index)))
+    return fail(c, TS_ERR_ARG, "ts_condition_based_time_batch: null argument");
+  if (n_trials == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  int64_t total = 0;
+  for (int64_t t = 0; t < n_trials; ++t) total = (offs[t] + rows[t] > total) ? offs[t] + rows[t] : total;
+  int rc;
+  DevBuf dG;
+  if ((rc = dev_in(c, dG, G, (size_t)total * 9 * sizeof(double), pad))) return rc;
+  int64_t *d_offs, *d_rows, *d_idx;
+  double* d_cut;
+  if ((rc = upload(c, 1, offs, (size_t)n_trials, &d_offs))) return rc;
+  if ((rc = upload(c, 2, rows, (size_t)n_trials, &d_rows))) return rc;
+  if ((rc = upload(c, 4, cutoff, (size_t)n_trials, &d_cut))) return rc;
+  void* p;
+  if ((rc = scratch_reserve(c, 5, (size_t)n_trials * sizeof(int64_t), &p))) return rc;
+  d_idx = (int64_t*)p;
+  KernelTimer tm(c);
+  k2d_condition_time<<<(unsigned)((n_trials + 127) / 128), 128, 0, c->stream>>>(n_trials, (const double*)dG.d, d_offs, d_rows, d_cut, d_idx);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  TS_CUDA(c, cudaMemcpyAsync(tf_index, d_idx, (size_t)n_trials * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
   return TS_OK;
 }
 

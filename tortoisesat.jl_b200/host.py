@@ -20,6 +20,11 @@ c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
 
 
+FIELD_OPTS_DTYPE = np.dtype([("GM", "<f8"), ("mjd", "<f8"), ("igrf_date", "<f8"), ("field_radius_m", "<f8"), ("t0", "<f8"),
+                             ("tf", "<f8"), ("N", "<i8")])
+GM_EARTH = 3.986004418E14 * (1 / 1000) ** 3  # km^3/s^2 (input_parameters.jl:26)
+
+
 class TortoiseError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("tortoise_b200 error %d: %s" % (code, msg))
@@ -56,6 +61,10 @@ def load_library():
     L.ts_last_kernel_ms.restype = C.c_double
     L.ts_fp64_peak_probe.argtypes = [C.c_void_p, c_double_p]
     L.ts_igrf12_batch.argtypes = [C.c_void_p, C.c_double, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
+    L.ts_magnetic_simulation_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
+    L.ts_magnetic_gramian_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
+    L.ts_condition_based_time_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
+    L.ts_condition_cutoff_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
     _LIB = L
     return L
 
@@ -142,6 +151,57 @@ class Engine:
         return Bn, Be, Bd
 
 
+    # -- K2 ---------------------------------------------------------------
+    def magnetic_simulation_batch(self, kep6, opts, rows_limit=None, want_pos=False):
+        """Batched magnetic_simulation (magnetic_toolbox.jl:33-106).  kep6: (T,6); opts:
+        structured array FIELD_OPTS_DTYPE of length T.  Returns (B_eci, B_offs[, pos, vel])
+        with B_eci rows concatenated per trial (2N_t rows each)."""
+        kep6 = _f64(np.atleast_2d(kep6))
+        T = kep6.shape[0]
+        opts = np.ascontiguousarray(opts, dtype=FIELD_OPTS_DTYPE)
+        offs = np.zeros(T + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(2 * opts["N"])
+        B = np.empty((int(offs[-1]), 3))
+        pos = np.empty((int(offs[-1]) + T, 3)) if want_pos else None
+        vel = np.empty((int(offs[-1]) + T, 3)) if want_pos else None
+        lim = None if rows_limit is None else np.ascontiguousarray(rows_limit, dtype=np.int64)
+        self._check(self.lib.ts_magnetic_simulation_batch(
+            self.h, T, _ptr(kep6), opts.ctypes.data, _ptr(offs), None if lim is None else _ptr(lim), _ptr(B),
+            None if pos is None else _ptr(pos), None if vel is None else _ptr(vel), 0))
+        if want_pos:
+            return B, offs, pos, vel
+        return B, offs
+
+    def magnetic_gramian_batch(self, B, offs, rows, dt):
+        B = _f64(B)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        dt = _f64(dt)
+        G = np.empty((B.shape[0], 3, 3))
+        self._check(self.lib.ts_magnetic_gramian_batch(self.h, rows.shape[0], _ptr(B), _ptr(offs), _ptr(rows), _ptr(dt), _ptr(G), 0))
+        return G
+
+    def condition_based_time_batch(self, G, offs, rows, cutoff):
+        G = _f64(G)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        cutoff = _f64(cutoff)
+        idx = np.zeros(rows.shape[0], dtype=np.int64)
+        self._check(self.lib.ts_condition_based_time_batch(self.h, rows.shape[0], _ptr(G), _ptr(offs), _ptr(rows), _ptr(cutoff),
+                                                           _ptr(idx), 0))
+        return idx
+
+    def condition_cutoff_batch(self, B, offs, rows, dt, cutoff):
+        B = _f64(B)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        dt, cutoff = _f64(dt), _f64(cutoff)
+        idx = np.zeros(rows.shape[0], dtype=np.int64)
+        self._check(self.lib.ts_condition_cutoff_batch(self.h, rows.shape[0], _ptr(B), _ptr(offs), _ptr(rows), _ptr(dt),
+                                                       _ptr(cutoff), _ptr(idx), 0))
+        return idx
+
+
 # ---------------------------------------------------------------------------
 # Reference-named free functions (scalar calls route to batch-of-1; correctness
 # path, not the performance path).  A module-level default engine is created on
@@ -174,3 +234,59 @@ def igrf_data(altitude, year, n=1000):
     r = np.full(LA.size, (altitude + R_E) * 1000.0)
     Bn, Be, Bd = default_engine().igrf12_batch(year, r, LA.ravel(), LO.ravel())
     return np.stack([Bn, Be, Bd], axis=-1).reshape(n, n, 3) / 1.0e9
+
+
+class params:
+    """struct params (input_parameters.jl:4-16)."""
+
+    def __init__(self, type, mass, J, BC, alt, Kep, MJD, GM, R_E, T, w_0):
+        self.type, self.mass, self.J, self.BC, self.alt = type, mass, J, BC, alt
+        self.Kep, self.MJD, self.GM, self.R_E, self.T, self.w_0 = Kep, MJD, GM, R_E, T, w_0
+
+
+def input_parameters(type, Kep, MJD):
+    """input_parameters(type, Kep, MJD) (input_parameters.jl:24-66), including its
+    quirks: alt forced to 400 (:58) and MJD forced to 58155.0 (:63)."""
+    GM = GM_EARTH
+    R_E = 6371.0
+    if type == "1U":
+        mass = .75
+        J = np.diag([0.00125, 0.00125, 0.00125])
+    elif type == "1P":
+        mass = .25
+        J = np.diag([0.0001041667, 0.0001041667, 0.0001041667])
+    elif type == "3U":
+        mass = 2.5
+        J = np.diag([0.020833, 0.020833, 0.0041666])
+    else:
+        raise ValueError("Type not recognized")
+    BC = mass / 2.2 / (J[0, 0] * J[1, 1])
+    Kep = np.array(Kep, dtype=np.float64).reshape(-1)
+    alt = 400.0
+    T = 2 * np.pi * np.sqrt(Kep[1] ** 3 / GM)
+    w_0 = np.sqrt(GM / Kep[1] ** 3)
+    return params(type, mass, J, BC, alt, Kep, 58155.0, GM, R_E, T, w_0)
+
+
+def magnetic_simulation(p, t0, tf, N, mag_field=None, alt=None, igrf_date=2019.0):
+    """magnetic_simulation(p,t0,tf,N,mag_field) -> (B (2N x 3), pos (3 x 2N+1), vel)
+    (magnetic_toolbox.jl:33-106).  `alt` stands for the reference's *global* alt used in
+    the field radius (alt+R_E)*1000 (:81, quirk Q3); default p.alt."""
+    alt = p.alt if alt is None else alt
+    o = np.zeros(1, dtype=FIELD_OPTS_DTYPE)
+    o[0] = (p.GM, p.MJD, igrf_date, (alt + p.R_E) * 1000.0, t0, tf, int(N))
+    B, offs, pos, vel = default_engine().magnetic_simulation_batch(p.Kep.reshape(1, 6), o, want_pos=True)
+    return B, pos.T.copy(), vel.T.copy()
+
+
+def magnetic_gramian(B_N, dt):
+    """magnetic_gramian(B_N,dt) -> 3 x 3 x rows (magnetic_toolbox.jl:1-12)."""
+    B_N = _f64(B_N)
+    G = default_engine().magnetic_gramian_batch(B_N, [0], [B_N.shape[0]], [dt])
+    return np.transpose(G, (1, 2, 0)).copy()
+
+
+def condition_based_time(B_gram, cutoff):
+    """condition_based_time(B_gram,cutoff) (magnetic_toolbox.jl:14-31); B_gram 3 x 3 x rows."""
+    G = np.ascontiguousarray(np.transpose(_f64(B_gram), (2, 0, 1)))
+    return int(default_engine().condition_based_time_batch(G, [0], [G.shape[0]], [cutoff])[0])
