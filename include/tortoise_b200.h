@@ -109,6 +109,61 @@ int ts_condition_based_time_batch(ts_ctx* ctx, int64_t n_trials, const double* G
 int ts_condition_cutoff_batch(ts_ctx* ctx, int64_t n_trials, const double* B_eci, const int64_t* B_offs, const int64_t* rows,
                               const double* dt, const double* cutoff, int64_t* tf_index, int pointers_are_device);
 
+/* ---- K3: batched Augmented-Lagrangian iLQR ---------------------------------- *
+ * Option block = the AugmentedLagrangianSolverOptions / iLQRSolverOptions fields of
+ * TrajectoryOptimization.jl v0.1.2 that the reference sets or relies on
+ * (src/TortoiseSat.jl:194-196: opts_uncon.iterations = 50, iterations = 20); semantics
+ * frozen in SURVEY.md Appendix C (assumptions A1..A10).                             */
+typedef struct ts_ilqr_opts {
+  int32_t max_outer;        /* 20  opts_al.iterations                                  */
+  int32_t max_inner;        /* 50  opts_al.opts_uncon.iterations                       */
+  int32_t max_linesearch;   /* 20  iterations_linesearch                               */
+  int32_t dJ_counter_limit; /* 10                                                      */
+  int32_t stage_cost_dt;    /* 0   A1: 1 = stage cost and its expansion scaled by dt   */
+  int32_t goal_mask;        /* 0x7F Q2: bit i = terminal equality on state i; 0xFF = literal
+                                   goal_constraint(xf) incl. the infeasible clock state */
+  double cost_tol, cost_tol_intermediate;   /* 1e-4, 1e-3 */
+  double grad_tol, grad_tol_intermediate;   /* 1e-5, 1e-5 */
+  double constraint_tol;                    /* 1e-3       */
+  double penalty_initial, penalty_scaling, penalty_max, dual_max; /* 1, 10, 1e8, 1e8 */
+  double ls_lower, ls_upper;                /* 1e-8, 10   */
+  double bp_reg_increase, bp_reg_max, bp_reg_min, bp_reg_fp; /* 1.6, 1e8, 1e-8, 10 */
+  double max_cost_value, max_state_value, max_control_value; /* 1e8 each */
+  double u_max, u_min;      /* BoundConstraint(n,m,u_max=1,u_min=-1)  (TortoiseSat.jl:178) */
+} ts_ilqr_opts;
+void ts_ilqr_default_opts(ts_ilqr_opts* o);
+
+/* per-trial status codes */
+#define TS_ST_CONVERGED 0   /* c_max < constraint_tol                              */
+#define TS_ST_MAX_OUTER 1   /* all outer iterations used                           */
+#define TS_ST_COST_BLOWUP 2 /* J > max_cost_value (TrajOpt would error())          */
+#define TS_ST_REG_MAX 3     /* backward-pass regularisation exceeded bp_reg_max    */
+#define TS_ST_NAN 4
+#define TS_ST_NO_CUTOFF 5   /* condition_based_time returned 0 (magnetic_toolbox.jl:23) */
+
+/* 64-byte per-trial record (what the multi-GPU driver gathers) */
+typedef struct ts_trial_outcome {
+  int32_t status, outer_iters, inner_iters, ls_rollouts;
+  int64_t N;
+  double J, c_max, t_final, slew_time, flops;
+} ts_trial_outcome;
+
+/* solve!(Problem(rk3(Model(DerivFunction,8,3)), LQRObjective(Q,R,Qf,xf,N), constraints, x0, N, dt),
+ *        AugmentedLagrangianSolver)  [src/TortoiseSat.jl:145-146,169,178-199] for n_trials trials.
+ * HOST arrays, one entry (or row) per trial: N_i knots; offs[t] = first knot of trial t in the
+ * ragged X/U/K arrays; x0, xf (8: omega, q scalar-first, clock); Jmat (3x3 row-major); Qd, Qfd
+ * (8 diagonal weights), Rd (3); B_offs/B_rows = first row / row count of the trial's field
+ * table inside B_eci; index_scale = the N of floor(Int,t*N+1) and clock_rate = 1/(tf-t0)
+ * (DerivFunction.jl:28,44, quirk Q1).  dt is the knot spacing.
+ * Arrays that follow pointers_are_device: B_eci (rows x 3), U0 (nullable -> zeros; ragged
+ * (N-1) x 3 at offs*3), X (ragged N x 8 at offs*8), U (ragged (N-1) x 3 at offs*3), K (nullable;
+ * ragged (N-1) x 3 x 8 at offs*24).  out: HOST array of n_trials records.                       */
+int ts_alilqr_solve_batch(ts_ctx* ctx, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* x0,
+                          const double* xf, const double* Jmat, const double* Qd, const double* Qfd, const double* Rd,
+                          const double* B_eci, const int64_t* B_offs, const int64_t* B_rows, const double* index_scale,
+                          const double* clock_rate, double dt, const double* U0, const ts_ilqr_opts* opts, double* X,
+                          double* U, double* K, ts_trial_outcome* out, int pointers_are_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,7 +93,7 @@ def lib():
         L.orc_bryson_weights.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
         L.orc_ilqr_default_opts.argtypes = [C.POINTER(IlqrOpts)]
-        L.orc_alilqr_solve_batch.argtypes = [C.c_int64] + [C.c_void_p] * 14 + [C.c_double, C.c_void_p, C.POINTER(IlqrOpts),
+        L.orc_alilqr_solve_batch.argtypes = [C.c_int64] + [C.c_void_p] * 13 + [C.c_double, C.c_void_p, C.POINTER(IlqrOpts),
                                                                                C.c_void_p, C.c_void_p, C.c_void_p,
                                                                                C.c_void_p, C.c_int]
         L.orc_attitude_simulation.argtypes = [C.POINTER(Dyn), C.POINTER(TvlqrOpts), C.c_int64, C.c_void_p, C.c_void_p,

@@ -1,0 +1,144 @@
+// HOST LANE-EMULATOR -- TEST INFRASTRUCTURE ONLY.
+// Compiles the *same* team-cooperative AL-iLQR source the CUDA kernel K3 uses
+// (tortoisesat.jl_b200/csrc/ilqr_solver.cuh, ilqr_math.cuh) for the CPU, with the
+// warp intrinsics emulated by 8 OS threads + barriers, so the kernel's logic,
+// indexing and synchronisation points can be checked against the oracle here
+// (no GPU in the build container).  Never linked into the product library.
+#include <barrier>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../tortoisesat.jl_b200/csrc/ilqr_solver.cuh"
+
+using namespace ts;
+
+struct TeamShared {
+  std::barrier<> bar{TEAM};
+  double xch[TEAM];
+  unsigned bits[TEAM];
+  std::vector<double> sm = std::vector<double>(TEAM_SMEM_DOUBLES, 0.0);
+};
+struct CpuTeam {
+  TeamShared* sh;
+  int ln;
+  int lane() const { return ln; }
+  double* smem() const { return sh->sm.data(); }
+  void sync() const { sh->bar.arrive_and_wait(); }
+  double bcast(double v, int src) const {
+    sh->xch[ln] = v;
+    sync();
+    const double r = sh->xch[src];
+    sync();
+    return r;
+  }
+  unsigned ballot(bool p) const {
+    sh->bits[ln] = p ? 1u : 0u;
+    sync();
+    unsigned r = 0;
+    for (int i = 0; i < TEAM; ++i) r |= sh->bits[i] << i;
+    sync();
+    return r;
+  }
+  double sum(double v) const {
+    for (int off = 4; off >= 1; off >>= 1) {
+      sh->xch[ln] = v;
+      sync();
+      v += sh->xch[ln ^ off];
+      sync();
+    }
+    return v;
+  }
+  double max(double v) const {
+    for (int off = 4; off >= 1; off >>= 1) {
+      sh->xch[ln] = v;
+      sync();
+      v = fmax(v, sh->xch[ln ^ off]);
+      sync();
+    }
+    return v;
+  }
+};
+
+extern "C" {
+
+void hs_dyn_f(const double* J9, const double* x7, const double* u3, const double* Bn, double* dx7) {
+  Inertia I;
+  memcpy(I.J, J9, 72);
+  inv3_gj(I.J, I.Jinv);
+  dyn_f<0>(I, x7, u3, Bn, dx7);
+}
+void hs_rk3_jac7(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
+                 double dt, double* xn7, double* AB70) {
+  Inertia I;
+  memcpy(I.J, J9, 72);
+  inv3_gj(I.J, I.Jinv);
+  rk3_jac7<0>(I, x7, u3, B1, B2, B3, dt, xn7, AB70);
+}
+void hs_rk4_jac7(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
+                 const double* B4, double dt, double* xn7, double* AB70) {
+  Inertia I;
+  memcpy(I.J, J9, 72);
+  inv3_gj(I.J, I.Jinv);
+  rk4_jac7<1>(I, x7, u3, B1, B2, B3, B4, dt, xn7, AB70);
+}
+
+// One trial, same argument meaning as the C ABI's ts_alilqr_solve_batch for n_trials = 1.
+void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double* Jmat, const double* Qd, const double* Qfd,
+                     const double* Rd, const double* B_eci, int64_t B_rows, double index_scale, double clock_rate, double dt,
+                     const double* U0, const ts_ilqr_opts_dev* opts, double* X, double* U, double* K, ts_trial_outcome_dev* out) {
+  TrialIn in;
+  in.N = (int)N;
+  in.dt = dt;
+  for (int i = 0; i < 7; ++i) in.x0[i] = x0[i];
+  in.clk0 = x0[7];
+  for (int i = 0; i < 8; ++i) {
+    in.xf[i] = xf[i];
+    in.Qd[i] = Qd[i];
+    in.Qfd[i] = Qfd[i];
+  }
+  for (int i = 0; i < 3; ++i) in.Rd[i] = Rd[i];
+  memcpy(in.I.J, Jmat, 72);
+  inv3_gj(in.I.J, in.I.Jinv);
+  in.Bt = B_eci;
+  in.B_rows = B_rows;
+  in.index_scale = index_scale;
+  in.clock_rate = clock_rate;
+  in.U0 = U0;
+  std::vector<double> xu((size_t)9 * N * 10), kd((size_t)N * 24), lam((size_t)N * 6), clk((size_t)N);
+  std::vector<int> rows((size_t)N * 3);
+  TrialWork w;
+  w.xu = xu.data();
+  w.kd = kd.data();
+  w.lam = lam.data();
+  w.clk = clk.data();
+  w.rows = rows.data();
+  w.Nmax = N;
+  TeamShared sh;
+  ts_trial_outcome_dev oc[TEAM];
+  int cur[TEAM];
+  std::vector<std::thread> th;
+  for (int l = 0; l < TEAM; ++l)
+    th.emplace_back([&, l]() {
+      CpuTeam tm{&sh, l};
+      alilqr_solve_team(tm, in, *opts, w, oc[l], cur[l]);
+    });
+  for (auto& t : th) t.join();
+  *out = oc[0];
+  const double* x = xu.data() + (size_t)cur[0] * N * 10;
+  for (int64_t k = 0; k < N; ++k) {
+    for (int i = 0; i < 7; ++i) X[k * 8 + i] = x[k * 10 + i];
+    X[k * 8 + 7] = clk[k];
+    if (k < N - 1) {
+      for (int i = 0; i < 3; ++i) U[k * 3 + i] = x[k * 10 + 7 + i];
+      if (K)
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 7; ++j) K[k * 24 + i * 8 + j] = kd[k * 24 + j * 3 + i];
+          K[k * 24 + i * 8 + 7] = 0.0;
+        }
+    }
+  }
+}
+
+}  // extern "C"

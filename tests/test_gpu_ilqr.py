@@ -1,0 +1,105 @@
+"""GPU: K3 batched AL-iLQR through the C ABI vs the CPU oracle.
+north_star tolerance: converged cost and constraint violation to 1e-6 with the same outer
+AL iteration count; rollouts (state trajectories) to 1e-10 relative where the iteration
+path is identical."""
+import numpy as np
+import pytest
+
+import slew_setup as S
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(slews):
+    rows = np.array([s.B.shape[0] for s in slews], dtype=np.int64)
+    B_offs = np.concatenate([[0], np.cumsum(rows)])[:-1]
+    return dict(N_i=[s.N for s in slews], x0=np.stack([s.x0 for s in slews]), xf=np.stack([s.xf for s in slews]),
+                Jmat=np.stack([s.J.reshape(-1) for s in slews]), Qd=np.stack([s.Qd for s in slews]),
+                Qfd=np.stack([s.Qfd for s in slews]), Rd=np.stack([s.Rd for s in slews]),
+                B_eci=np.concatenate([s.B for s in slews]), B_offs=B_offs, B_rows=rows,
+                index_scale=[s.index_scale for s in slews], clock_rate=[s.clock_rate for s in slews], dt=slews[0].dt)
+
+
+def _gpu_opts(tb, o):
+    g = tb.host.default_ilqr_opts()
+    for f, _ in g._fields_:
+        setattr(g, f, getattr(o, f))
+    return g
+
+
+def _check(engine, slews, o, tb):
+    Xs, Us, Ks, ref = S.oracle_solve(slews, o, nthreads=8)
+    X, U, K, out, offs = engine.alilqr_solve_batch(**_pack(slews), opts=_gpu_opts(tb, o))
+    same_path = 0
+    for t, s in enumerate(slews):
+        r, g = ref[t], out[t]
+        assert g["status"] == r["status"], (t, g, r)
+        assert g["outer_iters"] == r["outer_iters"], (t, g, r)
+        assert g["N"] == s.N
+        assert abs(g["J"] - r["J"]) <= 1e-6 * abs(r["J"]), (t, g["J"], r["J"])
+        assert abs(g["c_max"] - r["c_max"]) <= 1e-6 * max(1.0, r["c_max"]), (t, g["c_max"], r["c_max"])
+        if g["inner_iters"] == r["inner_iters"] and g["ls_rollouts"] == r["ls_rollouts"]:
+            same_path += 1
+            Xg = X[offs[t]:offs[t + 1]]
+            Ug = U[offs[t]:offs[t + 1] - 1]
+            assert np.max(np.abs(Xg - Xs[t])) <= 1e-9, t
+            assert np.max(np.abs(Ug - Us[t])) <= 1e-8 * max(1.0, np.max(np.abs(Us[t]))), t
+            Kg = K[offs[t]:offs[t + 1] - 1]
+            assert np.max(np.abs(Kg - Ks[t])) <= 1e-7 * np.max(np.abs(Ks[t])), t
+    return same_path
+
+
+def test_small_cases_match_oracle(engine):
+    import tortoisesat.jl_b200 as tb
+    qf = np.array([1.0, 0, 0, 0])
+    slews = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 5.0), qf, t_final=60.0),
+             S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 20.0), qf, t_final=30.0),
+             S.build_slew([0, 6871, 51.6, 30, 0, 10], S.J_3U, S.quat_axis_angle([0, 1, 0], 3.0), qf, t_final=50.0),
+             S.build_slew([0, 6771, 96.6, 100, 0, 200], S.J_1U, S.quat_axis_angle([0, 0, 1], 10.0), qf, t_final=45.0, alpha=0.1),
+             S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 1, 0], 2.0), qf, t_final=21.0)]
+    o = orc.default_ilqr_opts()
+    n_same = _check(engine, slews, o, tb)
+    assert n_same >= len(slews) - 1
+
+
+def test_literal_goal_mask_cost_blowup(engine):
+    import tortoisesat.jl_b200 as tb
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 8.0), np.array([1.0, 0, 0, 0]), t_final=40.0)
+    o = orc.default_ilqr_opts()
+    o.goal_mask = 0xFF
+    _check(engine, [s], o, tb)
+    X, U, K, out, offs = engine.alilqr_solve_batch(**_pack([s]), opts=_gpu_opts(tb, o))
+    assert out[0]["status"] == 2 and out[0]["c_max"] > 0.9      # quirk Q2
+
+
+def test_config1_default_slew(engine):
+    """BASELINE configs[0]: the default single slew of src/TortoiseSat.jl (N = 1555)."""
+    import tortoisesat.jl_b200 as tb
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 90.0), np.array([1.0, 0, 0, 0]))
+    assert s.N == 1555 and abs(s.t_final - 311.04) < 1e-9
+    o = orc.default_ilqr_opts()
+    _check(engine, [s], o, tb)
+    X, U, K, out, offs = engine.alilqr_solve_batch(**_pack([s]), opts=_gpu_opts(tb, o))
+    assert out[0]["status"] == 0 and out[0]["c_max"] < 1e-3
+    q = X[-1, 3:7] / np.linalg.norm(X[-1, 3:7])
+    assert 2 * np.degrees(np.arccos(min(1.0, abs(q[0])))) < 0.5
+    assert np.max(np.abs(U)) < 1.01
+
+
+def test_batch_of_random_attitudes_ragged(engine):
+    """32 trials, ragged horizons, random initial attitudes (configs[2]/[3] in miniature)."""
+    import tortoisesat.jl_b200 as tb
+    rng = np.random.default_rng(5)
+    qf = np.array([np.sqrt(2) / 2, np.sqrt(2) / 2, 0, 0])
+    slews = []
+    for t in range(32):
+        ax = rng.normal(size=3)
+        ang = rng.uniform(1, 6)
+        dq = S.quat_axis_angle(ax, ang)
+        q0 = np.array([qf[0] * dq[0] - qf[1:] @ dq[1:], *(qf[0] * dq[1:] + dq[0] * qf[1:] + np.cross(qf[1:], dq[1:]))])
+        slews.append(S.build_slew([0, 6771, 96.6, rng.uniform(0, 360), 0, rng.uniform(0, 360)], S.J_1U, q0, qf,
+                                  t_final=float(rng.uniform(30, 70)), tf=2400.0, alpha=0.1))
+    o = orc.default_ilqr_opts()
+    n_same = _check(engine, slews, o, tb)
+    assert n_same >= 28   # iteration path identical for (nearly) all trials

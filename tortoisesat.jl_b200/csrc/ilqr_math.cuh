@@ -1,0 +1,335 @@
+// Lane-local math of the AL-iLQR / TVLQR kernels: 7-state attitude dynamics, its
+// analytic Jacobians, and the rk3 / rk4 ZOH steps with their Jacobians.
+//
+// Replaces, per knot,
+//   DerivFunction(dx,x,u)              reference src/DerivFunction.jl:1-48
+//   gain_simulator / simulator         src/gain_simulator.jl:1-53, src/simulator.jl:1-42
+//   rk3 / rk4 discretisers             src/attitude_controller.jl:122-132,178-187
+//   ForwardDiff.jacobian! through them (inside TrajectoryOptimization and
+//                                       attitude_controller.jl:103)
+// The 8th ("clock") state of the reference is dynamically decoupled
+// (d f/d x8 = 0 through floor(), quirk Q1/Q2), so the kernels carry 7 states and
+// take the field row of each Runge-Kutta stage as an input.  Derivatives are
+// analytic (chain rule through the stages) instead of dual numbers; they agree
+// with the oracle's forward-mode duals to round-off (tests/test_hostsim.py).
+//
+// Everything here is plain per-thread code: TS_HD makes it compile for the GPU
+// (nvcc) and for the host-side lane emulator used by the CPU tests.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define TS_HD __host__ __device__ __forceinline__
+#else
+#define TS_HD inline
+#endif
+
+namespace ts {
+
+struct Inertia {
+  double J[9];
+  double Jinv[9];
+};
+
+TS_HD void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// Hamilton product, scalar first (qmult.jl:1-3)
+TS_HD void qmult(const double a[4], const double b[4], double o[4]) {
+  o[0] = a[0] * b[0] - (a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
+  o[1] = a[0] * b[1] + b[0] * a[1] + (a[2] * b[3] - a[3] * b[2]);
+  o[2] = a[0] * b[2] + b[0] * a[2] + (a[3] * b[1] - a[1] * b[3]);
+  o[3] = a[0] * b[3] + b[0] * a[3] + (a[1] * b[2] - a[2] * b[1]);
+}
+// qrot.jl:1-3
+TS_HD void qrot(const double q[4], const double r[3], double o[3]) {
+  double c1[3], w[3], c2[3];
+  cross3(q + 1, r, c1);
+  w[0] = c1[0] + q[0] * r[0];
+  w[1] = c1[1] + q[0] * r[1];
+  w[2] = c1[2] + q[0] * r[2];
+  cross3(q + 1, w, c2);
+  o[0] = r[0] + 2.0 * c2[0];
+  o[1] = r[1] + 2.0 * c2[1];
+  o[2] = r[2] + 2.0 * c2[2];
+}
+
+// xdot = f(x,u) for x = [omega(3); q(4)], field row Bn (ECI, Tesla).
+// u_scale_mode 0: u*1e-2 (DerivFunction.jl:37); 1: u/100 (simulator/gain_simulator) -- quirk Q8.
+template <int UMODE>
+TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7]) {
+  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  const double q[4] = {x[3] / nq, x[4] / nq, x[5] / nq, x[6] / nq};
+  const double w4[4] = {0.0, x[0], x[1], x[2]};
+  double qd[4];
+  qmult(q, w4, qd);
+  double BB[3];
+  qrot(q, Bn, BB);
+  double us[3];
+  if (UMODE == 0) {
+    us[0] = u[0] * 1.e-2; us[1] = u[1] * 1.e-2; us[2] = u[2] * 1.e-2;
+  } else {
+    us[0] = u[0] / 100.0; us[1] = u[1] / 100.0; us[2] = u[2] / 100.0;
+  }
+  double tau[3], Jw[3], wJw[3];
+  cross3(us, BB, tau);
+  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * x[0] + I.J[i * 3 + 1] * x[1] + I.J[i * 3 + 2] * x[2];
+  cross3(x, Jw, wJw);
+  const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
+  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
+  for (int i = 0; i < 4; ++i) dx[3 + i] = 0.5 * qd[i];
+}
+
+// f and its Jacobians fx (7x7, row-major) and fu (only rows 0..2 are non-zero: 3x3 row-major).
+template <int UMODE>
+TS_HD void dyn_f_jac(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7], double fx[49],
+                     double fu[9]) {
+  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  const double inq = 1.0 / nq;
+  const double q[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
+  const double s = q[0];
+  const double v[3] = {q[1], q[2], q[3]};
+  const double w[3] = {x[0], x[1], x[2]};
+  const double us_k = (UMODE == 0) ? 1.e-2 : (1.0 / 100.0);
+  const double us[3] = {u[0] * us_k, u[1] * us_k, u[2] * us_k};
+  // ---- value
+  double vxB[3], t1[3], c2[3], BB[3];
+  cross3(v, Bn, vxB);
+  t1[0] = vxB[0] + s * Bn[0];
+  t1[1] = vxB[1] + s * Bn[1];
+  t1[2] = vxB[2] + s * Bn[2];
+  cross3(v, t1, c2);
+  BB[0] = Bn[0] + 2.0 * c2[0];
+  BB[1] = Bn[1] + 2.0 * c2[1];
+  BB[2] = Bn[2] + 2.0 * c2[2];
+  double tau[3], Jw[3], wJw[3];
+  cross3(us, BB, tau);
+  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * w[0] + I.J[i * 3 + 1] * w[1] + I.J[i * 3 + 2] * w[2];
+  cross3(w, Jw, wJw);
+  const double r[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
+  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r[0] + I.Jinv[i * 3 + 1] * r[1] + I.Jinv[i * 3 + 2] * r[2];
+  dx[3] = 0.5 * (-(v[0] * w[0] + v[1] * w[1] + v[2] * w[2]));
+  dx[4] = 0.5 * (s * w[0] + (v[1] * w[2] - v[2] * w[1]));
+  dx[5] = 0.5 * (s * w[1] + (v[2] * w[0] - v[0] * w[2]));
+  dx[6] = 0.5 * (s * w[2] + (v[0] * w[1] - v[1] * w[0]));
+
+  // ---- d(omega_dot)/d(omega) = -Jinv * ( hat(w) J - hat(J w) )
+  double M[9];
+  {
+    // hat(w) J : row i = w x (column-wise) -> (hat(w) J)[i][j] = sum_k hat(w)[i][k] J[k][j]
+    const double hw[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    const double hJw[9] = {0, -Jw[2], Jw[1], Jw[2], 0, -Jw[0], -Jw[1], Jw[0], 0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        M[i * 3 + j] = hw[i * 3 + 0] * I.J[0 * 3 + j] + hw[i * 3 + 1] * I.J[1 * 3 + j] + hw[i * 3 + 2] * I.J[2 * 3 + j] - hJw[i * 3 + j];
+  }
+  for (int i = 0; i < 49; ++i) fx[i] = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      fx[i * 7 + j] = -(I.Jinv[i * 3 + 0] * M[0 * 3 + j] + I.Jinv[i * 3 + 1] * M[1 * 3 + j] + I.Jinv[i * 3 + 2] * M[2 * 3 + j]);
+  // ---- d(omega_dot)/du = Jinv * (-hat(BB)) * us_k
+  {
+    const double nhB[9] = {0, BB[2], -BB[1], -BB[2], 0, BB[0], BB[1], -BB[0], 0};  // -hat(BB)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        fu[i * 3 + j] = (I.Jinv[i * 3 + 0] * nhB[0 * 3 + j] + I.Jinv[i * 3 + 1] * nhB[1 * 3 + j] + I.Jinv[i * 3 + 2] * nhB[2 * 3 + j]) * us_k;
+  }
+  // ---- dBB/d(qhat) (3x4): column 0 = 2 (v x Bn); columns 1..3 = -2 hat(v x Bn) - 2 hat(v) hat(Bn) - 2 s hat(Bn)
+  double dBq[12];
+  {
+    dBq[0 * 4 + 0] = 2.0 * vxB[0];
+    dBq[1 * 4 + 0] = 2.0 * vxB[1];
+    dBq[2 * 4 + 0] = 2.0 * vxB[2];
+    const double hc[9] = {0, -vxB[2], vxB[1], vxB[2], 0, -vxB[0], -vxB[1], vxB[0], 0};
+    const double hv[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    const double hB[9] = {0, -Bn[2], Bn[1], Bn[2], 0, -Bn[0], -Bn[1], Bn[0], 0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double hvhB = hv[i * 3 + 0] * hB[0 * 3 + j] + hv[i * 3 + 1] * hB[1 * 3 + j] + hv[i * 3 + 2] * hB[2 * 3 + j];
+        dBq[i * 4 + 1 + j] = -2.0 * hc[i * 3 + j] - 2.0 * hvhB - 2.0 * s * hB[i * 3 + j];
+      }
+  }
+  // d(qhat)/dq = (I - qhat qhat') / |q|   (4x4, symmetric)
+  double P[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) P[i * 4 + j] = ((i == j ? 1.0 : 0.0) - q[i] * q[j]) * inq;
+  // d(omega_dot)/dq = Jinv * hat(us) * dBq * P
+  {
+    const double hu[9] = {0, -us[2], us[1], us[2], 0, -us[0], -us[1], us[0], 0};
+    double T1[12], T2[12];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j)
+        T1[i * 4 + j] = hu[i * 3 + 0] * dBq[0 * 4 + j] + hu[i * 3 + 1] * dBq[1 * 4 + j] + hu[i * 3 + 2] * dBq[2 * 4 + j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j)
+        T2[i * 4 + j] = I.Jinv[i * 3 + 0] * T1[0 * 4 + j] + I.Jinv[i * 3 + 1] * T1[1 * 4 + j] + I.Jinv[i * 3 + 2] * T1[2 * 4 + j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j)
+        fx[i * 7 + 3 + j] = T2[i * 4 + 0] * P[0 * 4 + j] + T2[i * 4 + 1] * P[1 * 4 + j] + T2[i * 4 + 2] * P[2 * 4 + j] + T2[i * 4 + 3] * P[3 * 4 + j];
+  }
+  // ---- d(qdot)/d(omega): row0 = -v'/2 ; rows 1..3 = (s I + hat(v))/2
+  fx[3 * 7 + 0] = -0.5 * v[0];
+  fx[3 * 7 + 1] = -0.5 * v[1];
+  fx[3 * 7 + 2] = -0.5 * v[2];
+  fx[4 * 7 + 0] = 0.5 * s;      fx[4 * 7 + 1] = -0.5 * v[2];  fx[4 * 7 + 2] = 0.5 * v[1];
+  fx[5 * 7 + 0] = 0.5 * v[2];   fx[5 * 7 + 1] = 0.5 * s;      fx[5 * 7 + 2] = -0.5 * v[0];
+  fx[6 * 7 + 0] = -0.5 * v[1];  fx[6 * 7 + 1] = 0.5 * v[0];   fx[6 * 7 + 2] = 0.5 * s;
+  // ---- d(qdot)/d(qhat) (4x4): row0 = [0, -w'/2]; rows 1..3 = [w/2, -hat(w)/2]; then * P
+  {
+    const double D[16] = {0,          -0.5 * w[0], -0.5 * w[1], -0.5 * w[2],
+                          0.5 * w[0], 0,            0.5 * w[2], -0.5 * w[1],
+                          0.5 * w[1], -0.5 * w[2],  0,           0.5 * w[0],
+                          0.5 * w[2], 0.5 * w[1],  -0.5 * w[0],  0};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        fx[(3 + i) * 7 + 3 + j] = D[i * 4 + 0] * P[0 * 4 + j] + D[i * 4 + 1] * P[1 * 4 + j] + D[i * 4 + 2] * P[2 * 4 + j] + D[i * 4 + 3] * P[3 * 4 + j];
+  }
+}
+
+// rk3 ZOH step (attitude_controller.jl:178-187 == TrajOpt rk3); Bs = field rows of the 3 stages.
+template <int UMODE>
+TS_HD void rk3_step7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
+                     double dt, double xn[7]) {
+  double k1[7], k2[7], k3[7], xs[7];
+  dyn_f<UMODE>(I, x, u, B1, k1);
+  for (int i = 0; i < 7; ++i) k1[i] = k1[i] * dt;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  dyn_f<UMODE>(I, xs, u, B2, k2);
+  for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] + 2.0 * k2[i];
+  dyn_f<UMODE>(I, xs, u, B3, k3);
+  for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0;
+}
+
+// y (7x10) = fx (7x7) * M (7x10) [+ fu in columns 7..9 of rows 0..2], all scaled by dt.
+TS_HD void stage_chain(const double fx[49], const double fu[9], const double M[70], double dt, double out[70]) {
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) {
+      double a = 0.0;
+      for (int l = 0; l < 7; ++l) a += fx[i * 7 + l] * M[l * 10 + j];
+      if (i < 3 && j >= 7) a += fu[i * 3 + (j - 7)];
+      out[i * 10 + j] = a * dt;
+    }
+}
+
+// Jacobian of the rk3 step: AB (7x10 row-major) = [A | B], A = d xn/d x, B = d xn/d u.  Also returns xn.
+template <int UMODE>
+TS_HD void rk3_jac7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
+                    double dt, double xn[7], double AB[70]) {
+  double k1[7], k2[7], k3[7], xs[7], fx[49], fu[9];
+  double K1[70], K2[70], M[70];
+  // stage 1: d k1 = dt [fx | fu]
+  dyn_f_jac<UMODE>(I, x, u, B1, k1, fx, fu);
+  for (int i = 0; i < 7; ++i) k1[i] = k1[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) {
+      double a = (j < 7) ? fx[i * 7 + j] : ((i < 3) ? fu[i * 3 + (j - 7)] : 0.0);
+      K1[i * 10 + j] = a * dt;
+    }
+  // stage 2 at x2 = x + k1/2 : d x2 = [I|0] + K1/2
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  dyn_f_jac<UMODE>(I, xs, u, B2, k2, fx, fu);
+  for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + 0.5 * K1[i * 10 + j];
+  stage_chain(fx, fu, M, dt, K2);
+  // stage 3 at x3 = x - k1 + 2 k2 : d x3 = [I|0] - K1 + 2 K2
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] + 2.0 * k2[i];
+  dyn_f_jac<UMODE>(I, xs, u, B3, k3, fx, fu);
+  for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) - K1[i * 10 + j] + 2.0 * K2[i * 10 + j];
+  double K3[70];
+  stage_chain(fx, fu, M, dt, K3);
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j)
+      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 4.0 * K2[i * 10 + j] + K3[i * 10 + j]) / 6.0;
+}
+
+// rk4 ZOH step (attitude_controller.jl:122-132) with one field row per stage.
+template <int UMODE>
+TS_HD void rk4_jac7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
+                    const double* B4, double dt, double xn[7], double AB[70]) {
+  double k1[7], k2[7], k3[7], k4[7], xs[7], fx[49], fu[9];
+  double K1[70], K2[70], K3[70], K4[70], M[70];
+  dyn_f_jac<UMODE>(I, x, u, B1, k1, fx, fu);
+  for (int i = 0; i < 7; ++i) k1[i] = k1[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) {
+      double a = (j < 7) ? fx[i * 7 + j] : ((i < 3) ? fu[i * 3 + (j - 7)] : 0.0);
+      K1[i * 10 + j] = a * dt;
+    }
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  dyn_f_jac<UMODE>(I, xs, u, B2, k2, fx, fu);
+  for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + 0.5 * K1[i * 10 + j];
+  stage_chain(fx, fu, M, dt, K2);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k2[i] / 2.0;
+  dyn_f_jac<UMODE>(I, xs, u, B3, k3, fx, fu);
+  for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + 0.5 * K2[i * 10 + j];
+  stage_chain(fx, fu, M, dt, K3);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i];
+  dyn_f_jac<UMODE>(I, xs, u, B4, k4, fx, fu);
+  for (int i = 0; i < 7; ++i) k4[i] = k4[i] * dt;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + K3[i * 10 + j];
+  stage_chain(fx, fu, M, dt, K4);
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0;
+  for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 10; ++j)
+      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 2.0 * K2[i * 10 + j] + 2.0 * K3[i * 10 + j] + K4[i * 10 + j]) / 6.0;
+}
+
+// Sequentially accumulated clock state of the reference (x8), replicated exactly:
+// c = rate*dt ; stages at x8, x8 + c/2, x8 - c + 2c ; x8 += (c + 4c + c)/6.   No FMA.
+struct ClockStep {
+  double t1, t2, t3, next;
+};
+TS_HD ClockStep clock_rk3(double x8, double rate, double dt) {
+#ifdef __CUDA_ARCH__
+  const double c = __dmul_rn(rate, dt);
+  ClockStep s;
+  s.t1 = x8;
+  s.t2 = __dadd_rn(x8, __ddiv_rn(c, 2.0));
+  s.t3 = __dadd_rn(__dsub_rn(x8, c), __dmul_rn(2.0, c));
+  s.next = __dadd_rn(x8, __ddiv_rn(__dadd_rn(__dadd_rn(c, __dmul_rn(4.0, c)), c), 6.0));
+  return s;
+#else
+  const volatile double c = rate * dt;
+  ClockStep s;
+  s.t1 = x8;
+  volatile double h = c / 2.0;
+  s.t2 = x8 + h;
+  volatile double a = x8 - c;
+  volatile double b = 2.0 * c;
+  s.t3 = a + b;
+  volatile double c4 = 4.0 * c;
+  volatile double sum = c + c4;
+  sum = sum + c;
+  volatile double inc = sum / 6.0;
+  s.next = x8 + inc;
+  return s;
+#endif
+}
+// 0-based field row for clock value t: floor(t*index_scale + 1) - 1, clamped to the table.
+TS_HD int field_row(double t, double index_scale, long long rows) {
+#ifdef __CUDA_ARCH__
+  const double v = __dadd_rn(__dmul_rn(t, index_scale), 1.0);
+#else
+  volatile double p = t * index_scale;
+  const double v = p + 1.0;
+#endif
+  long long idx = (long long)floor(v);
+  if (idx < 1) idx = 1;
+  if (idx > rows) idx = rows;
+  return (int)(idx - 1);
+}
+
+}  // namespace ts

@@ -1,0 +1,643 @@
+// Augmented-Lagrangian iLQR for ONE trial, executed cooperatively by a TEAM of 8
+// lanes (four teams per warp).  Replaces the solve the reference gets from
+// TrajectoryOptimization.jl v0.1.2 at src/TortoiseSat.jl:145-146,169,178-199
+// (Model+rk3, LQRObjective, BoundConstraint u in [-1,1], goal_constraint(xf),
+// AugmentedLagrangianSolver, solve!) -- algorithm = SURVEY.md Appendix C, the
+// same frozen specification the CPU oracle implements independently.
+//
+// Lane roles inside one iLQR iteration
+//   Jacobian phase  lane l linearises knot (chunk*8 + l): analytic rk3 Jacobians
+//                   [A|B] (7x10) + stage-cost/AL gradients -> team shared memory
+//   Riccati phase   lane j<7 owns column j of A (state column), lanes 0..2 also a
+//                   column of B: M = S*col, G(:,j) = [A B]'*M.  The 3x3 Quu system
+//                   is factorised redundantly by every lane (no exchange), lane j
+//                   solves its own gain column K(:,j); S is re-replicated into
+//                   registers (28 unique entries) through shared memory.
+//   Line search     lane a rolls out step alpha = 2^-a: 8 candidate trajectories
+//                   are evaluated speculatively in parallel, the first one the
+//                   sequential rule of Appendix C would accept is taken.
+// The `Team` parameter abstracts warp intrinsics so that the identical source
+// runs under the host lane-emulator of the CPU tests (tests/hostsim).
+#pragma once
+#include <stdint.h>
+
+#include "ilqr_math.cuh"
+
+#ifdef __CUDACC__
+#define TS_FN __device__ __forceinline__
+#define TS_FN_NOINLINE __device__ __noinline__
+#else
+#define TS_FN inline
+#define TS_FN_NOINLINE inline
+#endif
+
+// Option block of the AL-iLQR solve (C ABI: ts_ilqr_opts has the same layout).
+struct ts_ilqr_opts_dev {
+  int32_t max_outer, max_inner, max_linesearch, dJ_counter_limit, stage_cost_dt, goal_mask;
+  double cost_tol, cost_tol_intermediate, grad_tol, grad_tol_intermediate, constraint_tol;
+  double penalty_initial, penalty_scaling, penalty_max, dual_max;
+  double ls_lower, ls_upper, bp_reg_increase, bp_reg_max, bp_reg_min, bp_reg_fp;
+  double max_cost_value, max_state_value, max_control_value, u_max, u_min;
+};
+// 64-byte per-trial record (C ABI: ts_trial_outcome).
+struct ts_trial_outcome_dev {
+  int32_t status, outer_iters, inner_iters, ls_rollouts;
+  int64_t N;
+  double J, c_max, t_final, slew_time, flops;
+};
+
+namespace ts {
+
+enum { ST_CONVERGED = 0, ST_MAX_OUTER = 1, ST_COST_BLOWUP = 2, ST_REG_MAX = 3, ST_NAN = 4, ST_NO_CUTOFF = 5 };
+
+constexpr int TEAM = 8;
+constexpr int REC = 84;                       // doubles per knot record in shared memory
+constexpr int SM_REC = 0;                     // [8][REC]   Jacobians + cost gradients of the chunk
+constexpr int SM_SCOL = SM_REC + TEAM * REC;  // [7][8]     new S columns
+constexpr int SM_SVEC = SM_SCOL + 56;         // [8]        new s
+constexpr int SM_KQ = SM_SVEC + 8;            // [7][6]     K(:,j), Qux(:,j)
+constexpr int SM_QUU = SM_KQ + 42;            // [9] Quu, [3] Qu
+constexpr int TEAM_SMEM_DOUBLES = SM_QUU + 12 + 2;  // 792 doubles = 6336 B per team
+
+struct TrialIn {
+  int N;
+  double dt;
+  double x0[7], clk0;
+  double xf[8], Qd[8], Qfd[8], Rd[3];
+  Inertia I;
+  const double* Bt;  // field table rows x 3
+  long long B_rows;
+  double index_scale, clock_rate;
+  const double* U0;  // (N-1) x 3 or null
+};
+struct TrialWork {
+  double* xu;    // [9][Nmax][10]  trajectory buffers (x7,u3): current + 8 line-search candidates
+  double* kd;    // [Nmax][24]     K column-major (21) + d (3)
+  double* lam;   // [Nmax][6]      bound multipliers
+  double* clk;   // [Nmax]         clock state
+  int* rows;     // [Nmax][3]      field row of each rk3 stage
+  long long Nmax;
+};
+
+TS_HD int sym_idx(int i, int j) { return (i <= j) ? (i * 7 - i * (i - 1) / 2 + (j - i)) : (j * 7 - j * (j - 1) / 2 + (i - j)); }
+
+TS_HD bool inv3_gj(const double A[9], double out[9]) {
+  double M[3][6];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      M[i][j] = A[i * 3 + j];
+      M[i][3 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 3; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 3; ++r)
+      if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (M[p][c] == 0.0) return false;
+    if (p != c)
+      for (int j = 0; j < 6; ++j) {
+        const double t = M[c][j];
+        M[c][j] = M[p][j];
+        M[p][j] = t;
+      }
+    const double piv = M[c][c];
+    for (int j = 0; j < 6; ++j) M[c][j] /= piv;
+    for (int r = 0; r < 3; ++r) {
+      if (r == c) continue;
+      const double f = M[r][c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < 6; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] = M[i][3 + j];
+  return true;
+}
+
+// Cholesky of a symmetric 3x3 (lower factor, row-major) -- the PD test of the backward pass.
+TS_HD bool chol3(const double A[9], double L[9]) {
+  for (int i = 0; i < 9; ++i) L[i] = 0.0;
+  double s = A[0];
+  if (!(s > 0.0)) return false;
+  L[0] = sqrt(s);
+  L[3] = A[3] / L[0];
+  L[6] = A[6] / L[0];
+  s = A[4] - L[3] * L[3];
+  if (!(s > 0.0)) return false;
+  L[4] = sqrt(s);
+  L[7] = (A[7] - L[6] * L[3]) / L[4];
+  s = A[8] - L[6] * L[6] - L[7] * L[7];
+  if (!(s > 0.0)) return false;
+  L[8] = sqrt(s);
+  return true;
+}
+TS_HD void chol3_solve(const double L[9], const double b[3], double x[3]) {
+  double y[3];
+  y[0] = b[0] / L[0];
+  y[1] = (b[1] - L[3] * y[0]) / L[4];
+  y[2] = (b[2] - L[6] * y[0] - L[7] * y[1]) / L[8];
+  x[2] = y[2] / L[8];
+  x[1] = (y[1] - L[7] * x[2]) / L[4];
+  x[0] = (y[0] - L[3] * x[1] - L[6] * x[2]) / L[0];
+}
+
+struct StageAL {  // stage cost pieces at (x,u)
+  double l;       // 0.5 e'Qe + 0.5 u'Ru (unscaled)
+  double c[6];
+};
+TS_HD void bound_c(const ts_ilqr_opts_dev& o, const double u[3], double c[6]) {
+  for (int i = 0; i < 3; ++i) {
+    c[i] = u[i] - o.u_max;
+    c[3 + i] = o.u_min - u[i];
+  }
+}
+
+// Adds one knot's AL stage cost to Jc in the oracle's summation order; updates cmax.
+TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double sc, double mu, const double x[7], double e8,
+                          const double u[3], const double lam[6], double& Jc, double& cmax) {
+  double l = 0.0;
+  for (int i = 0; i < 7; ++i) {
+    const double e = x[i] - in.xf[i];
+    l += 0.5 * in.Qd[i] * e * e;
+  }
+  if (in.Qd[7] != 0.0) l += 0.5 * in.Qd[7] * e8 * e8;
+  for (int i = 0; i < 3; ++i) l += 0.5 * in.Rd[i] * u[i] * u[i];
+  Jc += l * sc;
+  double c[6];
+  bound_c(o, u, c);
+  for (int i = 0; i < 6; ++i) {
+    const bool act = (c[i] > 0.0) || (lam[i] > 0.0);
+    Jc += lam[i] * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
+    cmax = fmax(cmax, fmax(0.0, c[i]));
+  }
+}
+TS_HD void add_terminal_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double mu, const double x[7], double e8,
+                             const double lam_g[8], double& Jc, double& cmax) {
+  for (int i = 0; i < 8; ++i) {
+    const double e = (i < 7) ? (x[i] - in.xf[i]) : e8;
+    Jc += 0.5 * in.Qfd[i] * e * e;
+    if (o.goal_mask & (1 << i)) {
+      Jc += lam_g[i] * e + 0.5 * mu * e * e;
+      cmax = fmax(cmax, fabs(e));
+    }
+  }
+}
+
+struct Reg {
+  double rho, drho;
+};
+TS_HD void reg_increase(const ts_ilqr_opts_dev& o, Reg& r) {
+  r.drho = fmax(r.drho * o.bp_reg_increase, o.bp_reg_increase);
+  r.rho = fmax(r.rho * r.drho, o.bp_reg_min);
+}
+TS_HD void reg_decrease(const ts_ilqr_opts_dev& o, Reg& r) {
+  r.drho = fmin(r.drho / o.bp_reg_increase, 1.0 / o.bp_reg_increase);
+  r.rho = r.rho * r.drho * ((r.rho * r.drho > o.bp_reg_min) ? 1.0 : 0.0);
+}
+
+// ----------------------------------------------------------------------------------------
+// Jacobian phase for one knot (executed by ONE lane): fills a shared-memory knot record
+//   rec[c*7 + i] = [A|B](i,c)  (column-major, c = 0..9), rec[70+i] = lx, rec[77+i] = lu, rec[80+i] = luu
+template <class Team>
+TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
+                                   int k, double sc, double mu, double* rec) {
+  const double* p = xu_cur + (long long)k * 10;
+  double x[7], u[3], xn[7], AB[70];
+  for (int i = 0; i < 7; ++i) x[i] = p[i];
+  for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
+  const int* r = w.rows + (long long)k * 3;
+  rk3_jac7<0>(in.I, x, u, in.Bt + (long long)r[0] * 3, in.Bt + (long long)r[1] * 3, in.Bt + (long long)r[2] * 3, in.dt, xn, AB);
+  for (int c = 0; c < 10; ++c)
+    for (int i = 0; i < 7; ++i) rec[c * 7 + i] = AB[i * 10 + c];
+  for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
+  double c6[6];
+  bound_c(o, u, c6);
+  const double* lam = w.lam + (long long)k * 6;
+  for (int i = 0; i < 3; ++i) {
+    double lu = sc * in.Rd[i] * u[i];
+    double luu = sc * in.Rd[i];
+    const double lp = lam[i], ln = lam[3 + i];
+    const bool ap = (c6[i] > 0.0) || (lp > 0.0);
+    const bool an = (c6[3 + i] > 0.0) || (ln > 0.0);
+    lu += (lp + (ap ? mu * c6[i] : 0.0)) - (ln + (an ? mu * c6[3 + i] : 0.0));
+    luu += (ap ? mu : 0.0) + (an ? mu : 0.0);
+    rec[77 + i] = lu;
+    rec[80 + i] = luu;
+  }
+}
+
+// Backward Riccati sweep over the current trajectory.  Returns false if the regularisation ran away.
+template <class Team>
+TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
+                         double sc, double mu, const double lam_g[8], Reg& reg, double& dV1, double& dV2) {
+  double* sm = tm.smem();
+  const int lane = tm.lane();
+  const int N = in.N;
+  int restarts = 0;
+  for (;;) {  // regularisation restart loop
+    dV1 = 0.0;
+    dV2 = 0.0;
+    double S[28], s[7];
+    {
+      const double* xN = xu_cur + (long long)(N - 1) * 10;
+      for (int i = 0; i < 28; ++i) S[i] = 0.0;
+      for (int i = 0; i < 7; ++i) {
+        const double e = xN[i] - in.xf[i];
+        double sxx = in.Qfd[i], sx = in.Qfd[i] * e;
+        if (o.goal_mask & (1 << i)) {
+          sxx += mu;
+          sx += lam_g[i] + mu * e;
+        }
+        S[sym_idx(i, i)] = sxx;
+        s[i] = sx;
+      }
+    }
+    bool not_pd = false;
+    const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
+    for (int ch = n_chunks - 1; ch >= 0 && !not_pd; --ch) {
+      const int base = ch * TEAM;
+      tm.sync();  // previous chunk's records fully consumed
+      if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + SM_REC + lane * REC);
+      tm.sync();
+      int kk_hi = N - 2 - base;
+      if (kk_hi > TEAM - 1) kk_hi = TEAM - 1;
+      for (int kk = kk_hi; kk >= 0; --kk) {
+        const double* rec = sm + SM_REC + kk * REC;
+        const int k = base + kk;
+        // ---- P1: column products
+        double Qxxc[7], Quxc[3], Qx = 0.0;
+        if (lane < 7) {
+          double a[7], m[7];
+          for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
+          for (int i = 0; i < 7; ++i) {
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * a[l];
+            m[i] = t;
+          }
+          for (int i = 0; i < 7; ++i) {
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += rec[i * 7 + l] * m[l];
+            Qxxc[i] = t + ((i == lane) ? sc * in.Qd[i] : 0.0);
+          }
+          for (int c = 0; c < 3; ++c) {
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
+            Quxc[c] = t;
+          }
+          double t = 0.0;
+          for (int l = 0; l < 7; ++l) t += a[l] * s[l];
+          Qx = rec[70 + lane] + t;
+        }
+        if (lane < 3) {
+          double b[7], m[7];
+          for (int i = 0; i < 7; ++i) b[i] = rec[(7 + lane) * 7 + i];
+          for (int i = 0; i < 7; ++i) {
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * b[l];
+            m[i] = t;
+          }
+          for (int c = 0; c < 3; ++c) {
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
+            sm[SM_QUU + c * 3 + lane] = t + ((c == lane) ? rec[80 + c] : 0.0);
+          }
+          double t = 0.0;
+          for (int l = 0; l < 7; ++l) t += b[l] * s[l];
+          sm[SM_QUU + 9 + lane] = rec[77 + lane] + t;
+        }
+        tm.sync();
+        // ---- P2: 3x3 solve (every lane, redundantly)
+        double Quu[9], Qu[3], Qr[9], L[9];
+        for (int i = 0; i < 9; ++i) Quu[i] = sm[SM_QUU + i];
+        for (int i = 0; i < 3; ++i) Qu[i] = sm[SM_QUU + 9 + i];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
+        if (!chol3(Qr, L)) {
+          not_pd = true;  // identical decision in every lane of the team
+          break;
+        }
+        double Kc[3] = {0.0, 0.0, 0.0}, d[3], Quud[3], QuuK[3] = {0.0, 0.0, 0.0};
+        {
+          const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
+          chol3_solve(L, nb, d);
+          for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
+        }
+        double* kdk = w.kd + (long long)k * 24;
+        if (lane < 7) {
+          const double nb[3] = {-Quxc[0], -Quxc[1], -Quxc[2]};
+          chol3_solve(L, nb, Kc);
+          for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kc[0] + Quu[i * 3 + 1] * Kc[1] + Quu[i * 3 + 2] * Kc[2];
+          for (int c = 0; c < 3; ++c) {
+            sm[SM_KQ + lane * 6 + c] = Kc[c];
+            sm[SM_KQ + lane * 6 + 3 + c] = Quxc[c];
+            kdk[lane * 3 + c] = Kc[c];
+          }
+        } else {
+          for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
+        }
+        for (int l = 0; l < 3; ++l) {
+          dV1 += d[l] * Qu[l];
+          dV2 += 0.5 * d[l] * Quud[l];
+        }
+        tm.sync();
+        // ---- P3: new S column / s entry
+        if (lane < 7) {
+          for (int i = 0; i < 7; ++i) {
+            const double* kq = sm + SM_KQ + i * 6;
+            double t = Qxxc[i];
+            for (int l = 0; l < 3; ++l) t += kq[l] * QuuK[l];
+            for (int l = 0; l < 3; ++l) t += kq[l] * Quxc[l];
+            for (int l = 0; l < 3; ++l) t += kq[3 + l] * Kc[l];
+            sm[SM_SCOL + lane * 8 + i] = t;
+          }
+          double t = Qx;
+          for (int l = 0; l < 3; ++l) t += Kc[l] * Quud[l];
+          for (int l = 0; l < 3; ++l) t += Kc[l] * Qu[l];
+          for (int l = 0; l < 3; ++l) t += Quxc[l] * d[l];
+          sm[SM_SVEC + lane] = t;
+        }
+        tm.sync();
+        // ---- P4: symmetrise and re-replicate
+        for (int i = 0; i < 7; ++i)
+          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[SM_SCOL + j * 8 + i] + sm[SM_SCOL + i * 8 + j]);
+        for (int i = 0; i < 7; ++i) s[i] = sm[SM_SVEC + i];
+      }
+    }
+    if (!not_pd) break;
+    reg_increase(o, reg);
+    if (reg.rho > o.bp_reg_max || ++restarts > 200) return false;
+  }
+  reg_decrease(o, reg);
+  return true;
+}
+
+// AL cost + c_max of a stored trajectory, knots spread over the lanes (tree-summed).
+template <class Team>
+TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu,
+                             double sc, double mu, const double lam_g[8], double& cmax_out) {
+  double Jc = 0.0, cmax = 0.0;
+  const int N = in.N;
+  for (int k = tm.lane(); k < N - 1; k += TEAM) {
+    const double* p = xu + (long long)k * 10;
+    const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
+    add_stage_cost(in, o, sc, mu, p, e8, p + 7, w.lam + (long long)k * 6, Jc, cmax);
+  }
+  if (tm.lane() == 0) add_terminal_cost(in, o, mu, xu + (long long)(N - 1) * 10, w.clk[N - 1] - in.xf[7], lam_g, Jc, cmax);
+  cmax_out = tm.max(cmax);
+  return tm.sum(Jc);
+}
+
+// One speculative line-search rollout (one lane = one step size).
+struct RollOut {
+  double J, cmax, grad;
+  bool ok;
+};
+template <class Team>
+TS_FN_NOINLINE RollOut rollout_candidate(const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
+                                         double* xu_cand, double alpha, double sc, double mu, const double lam_g[8]) {
+  RollOut r;
+  r.ok = true;
+  double Jc = 0.0, cmax = 0.0, gsum = 0.0;
+  double xb[7];
+  for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
+  const int N = in.N;
+  for (int k = 0; k < N - 1; ++k) {
+    const double* p = xu_cur + (long long)k * 10;
+    const double* kd = w.kd + (long long)k * 24;
+    double ub[3];
+    double dx[7];
+    for (int i = 0; i < 7; ++i) dx[i] = xb[i] - p[i];
+    for (int i = 0; i < 3; ++i) {
+      double t = p[7 + i];
+      for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j];
+      t += alpha * kd[21 + i];
+      ub[i] = t;
+    }
+    const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
+    add_stage_cost(in, o, sc, mu, xb, e8, ub, w.lam + (long long)k * 6, Jc, cmax);
+    double mxg = 0.0;
+    for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(ub[i]) + 1.0));
+    gsum += mxg;
+    double* q = xu_cand + (long long)k * 10;
+    for (int i = 0; i < 7; ++i) q[i] = xb[i];
+    for (int i = 0; i < 3; ++i) q[7 + i] = ub[i];
+    const int* rw = w.rows + (long long)k * 3;
+    double xn[7];
+    rk3_step7<0>(in.I, xb, ub, in.Bt + (long long)rw[0] * 3, in.Bt + (long long)rw[1] * 3, in.Bt + (long long)rw[2] * 3, in.dt, xn);
+    double mx = fabs(w.clk[k + 1]), mu_abs = 0.0;
+    for (int i = 0; i < 7; ++i) {
+      xb[i] = xn[i];
+      mx = fmax(mx, fabs(xn[i]));
+      if (xn[i] != xn[i]) mx = INFINITY;
+    }
+    for (int i = 0; i < 3; ++i) {
+      mu_abs = fmax(mu_abs, fabs(ub[i]));
+      if (ub[i] != ub[i]) mu_abs = INFINITY;
+    }
+    if (!(mx < o.max_state_value) || !(mu_abs < o.max_control_value)) {
+      r.ok = false;
+      break;
+    }
+  }
+  if (r.ok) {
+    double* q = xu_cand + (long long)(N - 1) * 10;
+    for (int i = 0; i < 7; ++i) q[i] = xb[i];
+    q[7] = q[8] = q[9] = 0.0;
+    add_terminal_cost(in, o, mu, xb, w.clk[N - 1] - in.xf[7], lam_g, Jc, cmax);
+  }
+  r.J = Jc;
+  r.cmax = cmax;
+  r.grad = gsum / (double)(N - 1);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------
+template <class Team>
+TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w,
+                             ts_trial_outcome_dev& out, int& cur_out) {
+  const int lane = tm.lane();
+  const int N = in.N;
+  const long long bstride = w.Nmax * 10;
+  const double sc = o.stage_cost_dt ? in.dt : 1.0;
+  // ---- setup: clock trajectory + stage field rows (sequential, exact replica), multipliers, initial rollout
+  if (lane == 0) {
+    double x8 = in.clk0;
+    for (int k = 0; k < N - 1; ++k) {
+      const ClockStep cs = clock_rk3(x8, in.clock_rate, in.dt);
+      w.clk[k] = x8;
+      w.rows[k * 3 + 0] = field_row(cs.t1, in.index_scale, in.B_rows);
+      w.rows[k * 3 + 1] = field_row(cs.t2, in.index_scale, in.B_rows);
+      w.rows[k * 3 + 2] = field_row(cs.t3, in.index_scale, in.B_rows);
+      x8 = cs.next;
+    }
+    w.clk[N - 1] = x8;
+  }
+  for (int i = lane; i < (N - 1) * 6; i += TEAM) w.lam[i] = 0.0;
+  tm.sync();
+  int cur = 0;
+  if (lane == 0) {
+    double* xu = w.xu;
+    double xb[7];
+    for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
+    for (int k = 0; k < N - 1; ++k) {
+      double u[3];
+      for (int i = 0; i < 3; ++i) u[i] = in.U0 ? in.U0[(long long)k * 3 + i] : 0.0;
+      double* q = xu + (long long)k * 10;
+      for (int i = 0; i < 7; ++i) q[i] = xb[i];
+      for (int i = 0; i < 3; ++i) q[7 + i] = u[i];
+      const int* rw = w.rows + (long long)k * 3;
+      double xn[7];
+      rk3_step7<0>(in.I, xb, u, in.Bt + (long long)rw[0] * 3, in.Bt + (long long)rw[1] * 3, in.Bt + (long long)rw[2] * 3, in.dt, xn);
+      for (int i = 0; i < 7; ++i) xb[i] = xn[i];
+    }
+    double* q = xu + (long long)(N - 1) * 10;
+    for (int i = 0; i < 7; ++i) q[i] = xb[i];
+    q[7] = q[8] = q[9] = 0.0;
+  }
+  tm.sync();
+
+  double mu = o.penalty_initial;
+  double lam_g[8];
+  for (int i = 0; i < 8; ++i) lam_g[i] = 0.0;
+  int status = ST_MAX_OUTER, outer = 1, inner_total = 0, ls_total = 0;
+  double J = 0.0, c_max = 0.0;
+  Reg reg;
+  reg.rho = 0.0;
+  reg.drho = 0.0;
+  int it = 0, dJ_zero = 0;
+  double J_prev = trajectory_cost(tm, in, o, w, w.xu + cur * bstride, sc, mu, lam_g, c_max);
+  J = J_prev;
+  bool done = (o.max_outer < 1);
+  while (!done) {
+    const bool last = (outer == o.max_outer);
+    const double ctol = last ? o.cost_tol : o.cost_tol_intermediate;
+    const double gtol = last ? o.grad_tol : o.grad_tol_intermediate;
+    bool inner_done = false, abort_trial = false;
+    ++it;
+    ++inner_total;
+    const double* xu_cur = w.xu + cur * bstride;
+    double dV1, dV2;
+    if (!backward_pass(tm, in, o, w, xu_cur, sc, mu, lam_g, reg, dV1, dV2)) {
+      status = ST_REG_MAX;
+      abort_trial = true;
+    }
+    double Jn = J_prev;
+    if (!abort_trial) {
+      tm.sync();  // gains visible to every lane
+      // ---- speculative parallel line search: candidate c = batch*8 + lane, alpha = 2^-c
+      bool accepted = false;
+      double grad = 0.0;
+      const int n_cand = o.max_linesearch + 1;
+      for (int b0 = 0; b0 < n_cand && !accepted; b0 += TEAM) {
+        const int c = b0 + lane;
+        const bool live = (c < n_cand);
+        const int bufi = (lane < cur) ? lane : lane + 1;
+        RollOut r;
+        r.ok = false;
+        r.J = 0.0;
+        r.cmax = 0.0;
+        r.grad = 0.0;
+        double alpha = 1.0;
+        for (int i = 0; i < c; ++i) alpha /= 2.0;
+        if (live) r = rollout_candidate<Team>(in, o, w, xu_cur, w.xu + bufi * bstride, alpha, sc, mu, lam_g);
+        bool acc = false;
+        if (live && r.ok) {
+          const double expected = -alpha * (dV1 + alpha * dV2);
+          const double z = (expected > 0.0) ? (J_prev - r.J) / expected : -1.0;
+          acc = !((z <= o.ls_lower || z > o.ls_upper) && (r.J >= J_prev));
+        }
+        const unsigned bits = tm.ballot(acc);
+        if (bits) {
+          int a = 0;
+          while (!((bits >> a) & 1u)) ++a;
+          accepted = true;
+          ls_total += b0 + a + 1;
+          Jn = tm.bcast(r.J, a);
+          c_max = tm.bcast(r.cmax, a);
+          grad = tm.bcast(r.grad, a);
+          cur = (a < cur) ? a : a + 1;
+        }
+        tm.sync();
+      }
+      if (!accepted) {
+        ls_total += n_cand;
+        Jn = J_prev;
+        reg_increase(o, reg);
+        reg.rho += o.bp_reg_fp;
+        // gradient with the unchanged controls
+        double g = 0.0;
+        for (int k = lane; k < N - 1; k += TEAM) {
+          const double* p = xu_cur + (long long)k * 10;
+          const double* kd = w.kd + (long long)k * 24;
+          double mxg = 0.0;
+          for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
+          g += mxg;
+        }
+        grad = tm.sum(g) / (double)(N - 1);
+      }
+      if (!(Jn == Jn)) {
+        status = ST_NAN;
+        abort_trial = true;
+      } else if (Jn > o.max_cost_value) {
+        status = ST_COST_BLOWUP;
+        abort_trial = true;
+      } else {
+        const double dJ = fabs(Jn - J_prev);
+        J_prev = Jn;
+        if (dJ == 0.0) ++dJ_zero; else dJ_zero = 0;
+        if ((0.0 < dJ && dJ < ctol) || grad < gtol || dJ_zero > o.dJ_counter_limit || it >= o.max_inner) inner_done = true;
+      }
+      J = Jn;
+    }
+    if (abort_trial) break;
+    if (inner_done) {
+      // ---- outer update: duals (A5), penalty (A6), convergence
+      const double* xu_c = w.xu + cur * bstride;
+      for (int k = lane; k < N - 1; k += TEAM) {
+        double c6[6];
+        bound_c(o, xu_c + (long long)k * 10 + 7, c6);
+        double* lam = w.lam + (long long)k * 6;
+        for (int i = 0; i < 6; ++i) {
+          double l = lam[i] + mu * c6[i];
+          l = fmin(fmax(l, -o.dual_max), o.dual_max);
+          lam[i] = fmax(0.0, l);
+        }
+      }
+      for (int i = 0; i < 8; ++i) {
+        if (!(o.goal_mask & (1 << i))) continue;
+        const double e = ((i < 7) ? xu_c[(long long)(N - 1) * 10 + i] : w.clk[N - 1]) - in.xf[i];
+        const double l = lam_g[i] + mu * e;
+        lam_g[i] = fmin(fmax(l, -o.dual_max), o.dual_max);
+      }
+      mu = fmin(mu * o.penalty_scaling, o.penalty_max);
+      tm.sync();
+      if (c_max < o.constraint_tol) {
+        status = ST_CONVERGED;
+        done = true;
+      } else if (outer >= o.max_outer) {
+        done = true;
+      } else {
+        ++outer;
+        it = 0;
+        dJ_zero = 0;
+        reg.rho = 0.0;
+        reg.drho = 0.0;
+        double cm;
+        J_prev = trajectory_cost(tm, in, o, w, xu_c, sc, mu, lam_g, cm);
+      }
+    }
+  }
+  out.status = status;
+  out.outer_iters = outer;
+  out.inner_iters = inner_total;
+  out.ls_rollouts = ls_total;
+  out.N = N;
+  out.J = J;
+  out.c_max = c_max;
+  out.t_final = 0.0;
+  out.slew_time = 0.0;
+  out.flops = 0.0;
+  cur_out = cur;
+  tm.sync();
+}
+
+}  // namespace ts

@@ -1,0 +1,155 @@
+// K3 -- batched AL-iLQR.  Persistent warps; each warp runs FOUR trials at a time,
+// one per 8-lane team (ilqr_solver.cuh), pulling groups of four trials from an
+// atomic queue (trials pre-sorted by horizon on the host so that the four teams of
+// a warp have similar trip counts and stay convergent).
+//
+// Why 8-lane teams and not one trial per warp: an FP64 warp instruction occupies
+// the SM sub-partition's 16-lane DFMA pipe for 2 issue cycles whatever the number
+// of active lanes, and the sequential parts of iLQR (Riccati recursion, rollouts)
+// expose at most ~10-way parallelism per knot.  Four trials per warp quadruple the
+// useful lanes per issued instruction while still giving 1024 resident warps for a
+// 4096-trial ensemble ("K3 mapping").
+//
+// Working set per trial (HBM/L2, streamed): 9 trajectory buffers (current + 8
+// line-search candidates) x N x 10, gains N x 24, multipliers N x 6 doubles.
+// Shared memory per team: 6336 B (knot records of the current 8-knot chunk and the
+// Riccati exchange buffers).
+#pragma once
+#include "common.cuh"
+#include "ilqr_solver.cuh"
+
+namespace ts {
+
+struct GpuTeam {
+  unsigned mask;
+  int ln, shift;
+  double* sm;
+  __device__ __forceinline__ int lane() const { return ln; }
+  __device__ __forceinline__ double* smem() const { return sm; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, TEAM); }
+  __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffu; }
+  __device__ __forceinline__ double sum(double v) const {
+    v += __shfl_xor_sync(mask, v, 4, TEAM);
+    v += __shfl_xor_sync(mask, v, 2, TEAM);
+    v += __shfl_xor_sync(mask, v, 1, TEAM);
+    return v;
+  }
+  __device__ __forceinline__ double max(double v) const {
+    v = fmax(v, __shfl_xor_sync(mask, v, 4, TEAM));
+    v = fmax(v, __shfl_xor_sync(mask, v, 2, TEAM));
+    v = fmax(v, __shfl_xor_sync(mask, v, 1, TEAM));
+    return v;
+  }
+};
+
+struct K3Args {
+  int64_t n_trials;
+  const int64_t* order;  // trial permutation (sorted by horizon), n_trials entries
+  const int64_t* N_i;
+  const int64_t* offs;
+  const double* x0;      // 8 per trial
+  const double* xf;      // 8
+  const double* Jmat;    // 9
+  const double* Qd;      // 8
+  const double* Qfd;     // 8
+  const double* Rd;      // 3
+  const double* B_eci;
+  const int64_t* B_offs;
+  const int64_t* B_rows;
+  const double* index_scale;
+  const double* clock_rate;
+  double dt;
+  const double* U0;      // nullable, ragged like U
+  ts_ilqr_opts_dev opts;
+  double* X;             // ragged N x 8
+  double* U;             // ragged (N-1) x 3 at offs*3
+  double* K;             // nullable, ragged (N-1) x 3 x 8 at offs*24
+  ts_trial_outcome_dev* out;
+  // work arena
+  double* w_xu;
+  double* w_kd;
+  double* w_lam;
+  double* w_clk;
+  int* w_rows;
+  int64_t Nmax;
+  unsigned long long* queue;
+};
+
+constexpr int K3_WARPS_PER_BLOCK = 1;
+constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
+
+__global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(const K3Args a) {
+  extern __shared__ double k3_smem[];
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane32 = threadIdx.x & 31;
+  const int team = lane32 >> 3;
+  const int64_t gwarp = (int64_t)blockIdx.x * K3_WARPS_PER_BLOCK + warp_in_block;
+  const int64_t slot = gwarp * 4 + team;
+  GpuTeam tm;
+  tm.ln = lane32 & 7;
+  tm.shift = team * 8;
+  tm.mask = 0xffu << tm.shift;
+  tm.sm = k3_smem + (warp_in_block * 4 + team) * TEAM_SMEM_DOUBLES;
+  TrialWork w;
+  w.Nmax = a.Nmax;
+  w.xu = a.w_xu + slot * 9 * a.Nmax * 10;
+  w.kd = a.w_kd + slot * a.Nmax * 24;
+  w.lam = a.w_lam + slot * a.Nmax * 6;
+  w.clk = a.w_clk + slot * a.Nmax;
+  w.rows = a.w_rows + slot * a.Nmax * 3;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane32 == 0) base = atomicAdd(a.queue, 4ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((int64_t)base >= a.n_trials) break;
+    const int64_t qi = (int64_t)base + team;
+    if (qi < a.n_trials) {
+      const int64_t t = a.order ? a.order[qi] : qi;
+      TrialIn in;
+      in.N = (int)a.N_i[t];
+      in.dt = a.dt;
+      for (int i = 0; i < 7; ++i) in.x0[i] = a.x0[t * 8 + i];
+      in.clk0 = a.x0[t * 8 + 7];
+      for (int i = 0; i < 8; ++i) {
+        in.xf[i] = a.xf[t * 8 + i];
+        in.Qd[i] = a.Qd[t * 8 + i];
+        in.Qfd[i] = a.Qfd[t * 8 + i];
+      }
+      for (int i = 0; i < 3; ++i) in.Rd[i] = a.Rd[t * 3 + i];
+      for (int i = 0; i < 9; ++i) in.I.J[i] = a.Jmat[t * 9 + i];
+      inv3_gj(in.I.J, in.I.Jinv);
+      in.Bt = a.B_eci + a.B_offs[t] * 3;
+      in.B_rows = a.B_rows[t];
+      in.index_scale = a.index_scale[t];
+      in.clock_rate = a.clock_rate[t];
+      in.U0 = a.U0 ? a.U0 + a.offs[t] * 3 : nullptr;
+      ts_trial_outcome_dev oc;
+      int cur = 0;
+      alilqr_solve_team(tm, in, a.opts, w, oc, cur);
+      // ---- results: X (N x 8 incl. the clock state), U, K (3 x 8 per knot, zero clock column)
+      const double* xu = w.xu + (int64_t)cur * a.Nmax * 10;
+      double* Xo = a.X + a.offs[t] * 8;
+      double* Uo = a.U + a.offs[t] * 3;
+      for (int k = tm.ln; k < in.N; k += TEAM) {
+        for (int i = 0; i < 7; ++i) Xo[(int64_t)k * 8 + i] = xu[(int64_t)k * 10 + i];
+        Xo[(int64_t)k * 8 + 7] = w.clk[k];
+        if (k < in.N - 1) {
+          for (int i = 0; i < 3; ++i) Uo[(int64_t)k * 3 + i] = xu[(int64_t)k * 10 + 7 + i];
+          if (a.K) {
+            double* Ko = a.K + (a.offs[t] + k) * 24;
+            const double* kd = w.kd + (int64_t)k * 24;
+            for (int i = 0; i < 3; ++i) {
+              for (int j = 0; j < 7; ++j) Ko[i * 8 + j] = kd[j * 3 + i];
+              Ko[i * 8 + 7] = 0.0;
+            }
+          }
+        }
+      }
+      if (tm.ln == 0) a.out[t] = oc;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace ts

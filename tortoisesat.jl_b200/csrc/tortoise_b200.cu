@@ -5,6 +5,10 @@
 #include "igrf_device.cuh"
 #include "k1_igrf.cuh"
 #include "k2_field.cuh"
+#include "k3_alilqr.cuh"
+
+#include <algorithm>
+#include <numeric>
 
 namespace ts {
 #include "igrf12_tables.inc"
@@ -288,6 +292,124 @@ int ts_condition_based_time_batch(ts_ctx* c, int64_t n_trials, const double* G, 
   c->launches++;
   TS_CUDA(c, cudaGetLastError());
   TS_CUDA(c, cudaMemcpyAsync(tf_index, d_idx, (size_t)n_trials * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
+  return TS_OK;
+}
+
+// ---------------------------------------------------------------------------- K3
+static_assert(sizeof(ts_ilqr_opts) == sizeof(ts_ilqr_opts_dev), "ilqr opts layout");
+static_assert(sizeof(ts_trial_outcome) == sizeof(ts_trial_outcome_dev) && sizeof(ts_trial_outcome) == 64, "outcome layout");
+
+void ts_ilqr_default_opts(ts_ilqr_opts* o) {
+  if (!o) return;
+  o->max_outer = 20; o->max_inner = 50; o->max_linesearch = 20; o->dJ_counter_limit = 10;
+  o->stage_cost_dt = 0; o->goal_mask = 0x7F;
+  o->cost_tol = 1e-4; o->cost_tol_intermediate = 1e-3; o->grad_tol = 1e-5; o->grad_tol_intermediate = 1e-5;
+  o->constraint_tol = 1e-3; o->penalty_initial = 1.0; o->penalty_scaling = 10.0; o->penalty_max = 1e8; o->dual_max = 1e8;
+  o->ls_lower = 1e-8; o->ls_upper = 10.0; o->bp_reg_increase = 1.6; o->bp_reg_max = 1e8; o->bp_reg_min = 1e-8;
+  o->bp_reg_fp = 10.0; o->max_cost_value = 1e8; o->max_state_value = 1e8; o->max_control_value = 1e8;
+  o->u_max = 1.0; o->u_min = -1.0;
+}
+
+int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* x0,
+                          const double* xf, const double* Jmat, const double* Qd, const double* Qfd, const double* Rd,
+                          const double* B_eci, const int64_t* B_offs, const int64_t* B_rows, const double* index_scale,
+                          const double* clock_rate, double dt, const double* U0, const ts_ilqr_opts* opts, double* X,
+                          double* U, double* K, ts_trial_outcome* out, int pad) {
+  if (!c) return TS_ERR_ARG;
+  if (n_trials < 0 || (n_trials > 0 && (!N_i || !offs || !x0 || !xf || !Jmat || !Qd || !Qfd || !Rd || !B_eci || !B_offs || !B_rows ||
+                                        !index_scale || !clock_rate || !X || !U || !out)))
+    return fail(c, TS_ERR_ARG, "ts_alilqr_solve_batch: null argument");
+  if (n_trials == 0) return TS_OK;
+  if (!(dt > 0)) return fail(c, TS_ERR_ARG, "ts_alilqr_solve_batch: dt must be > 0");
+  ts_ilqr_opts o;
+  if (opts) o = *opts; else ts_ilqr_default_opts(&o);
+  if (o.max_linesearch < 0 || o.max_linesearch > 63) return fail(c, TS_ERR_ARG, "max_linesearch must be in [0,63]");
+  int64_t Nmax = 0, total_knots = 0, total_rows = 0;
+  for (int64_t t = 0; t < n_trials; ++t) {
+    if (N_i[t] < 2) return fail(c, TS_ERR_ARG, "trial %lld: N < 2", (long long)t);
+    Nmax = std::max(Nmax, N_i[t]);
+    total_knots = std::max(total_knots, offs[t] + N_i[t]);
+    total_rows = std::max(total_rows, B_offs[t] + B_rows[t]);
+    if (B_rows[t] < 1) return fail(c, TS_ERR_ARG, "trial %lld: empty field table", (long long)t);
+  }
+  TS_CUDA(c, cudaSetDevice(c->device));
+  // launch geometry: persistent warps, 4 trials per warp
+  int occ = 0;
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
+  if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
+  const int64_t groups = (n_trials + 3) / 4;
+  const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
+  const int64_t warps = std::min(groups, max_warps);
+  const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
+  const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
+  // trials sorted by horizon (descending) so the four teams of a warp have similar trip counts
+  std::vector<int64_t> order((size_t)n_trials);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return N_i[a] > N_i[b]; });
+
+  int rc;
+  DevBuf dB, dU0, dX, dU, dK;
+  if ((rc = dev_in(c, dB, B_eci, (size_t)total_rows * 3 * sizeof(double), pad))) return rc;
+  if (U0 && (rc = dev_in(c, dU0, U0, (size_t)total_knots * 3 * sizeof(double), pad))) return rc;
+  if ((rc = dev_out(c, dX, X, (size_t)total_knots * 8 * sizeof(double), pad))) return rc;
+  if ((rc = dev_out(c, dU, U, (size_t)total_knots * 3 * sizeof(double), pad))) return rc;
+  if (K && (rc = dev_out(c, dK, K, (size_t)total_knots * 24 * sizeof(double), pad))) return rc;
+  // per-trial small arrays -> one packed upload
+  const size_t T = (size_t)n_trials;
+  const size_t n_i64 = 5 * T, n_f64 = (8 + 8 + 9 + 8 + 8 + 3 + 1 + 1) * T;
+  std::vector<int64_t> hi(n_i64);
+  std::vector<double> hf(n_f64);
+  memcpy(&hi[0 * T], order.data(), T * 8);
+  memcpy(&hi[1 * T], N_i, T * 8);
+  memcpy(&hi[2 * T], offs, T * 8);
+  memcpy(&hi[3 * T], B_offs, T * 8);
+  memcpy(&hi[4 * T], B_rows, T * 8);
+  size_t fo = 0;
+  auto put = [&](const double* src, size_t per) { memcpy(&hf[fo], src, per * T * 8); fo += per * T; return fo - per * T; };
+  const size_t o_x0 = put(x0, 8), o_xf = put(xf, 8), o_J = put(Jmat, 9), o_Qd = put(Qd, 8), o_Qfd = put(Qfd, 8), o_Rd = put(Rd, 3),
+               o_is = put(index_scale, 1), o_cr = put(clock_rate, 1);
+  int64_t* d_i = nullptr;
+  double* d_f = nullptr;
+  if ((rc = upload(c, 1, hi.data(), n_i64, &d_i))) return rc;
+  if ((rc = upload(c, 2, hf.data(), n_f64, &d_f))) return rc;
+  void *p_out, *p_work, *p_q;
+  if ((rc = scratch_reserve(c, 3, T * sizeof(ts_trial_outcome), &p_out))) return rc;
+  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1) * sizeof(double) + (size_t)Nmax * 3 * sizeof(int) + 64;
+  if ((rc = scratch_reserve(c, 6, per_slot * (size_t)slots + 256, &p_work))) return rc;
+  if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
+  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
+  K3Args a;
+  a.n_trials = n_trials;
+  a.order = d_i + 0 * T; a.N_i = d_i + 1 * T; a.offs = d_i + 2 * T; a.B_offs = d_i + 3 * T; a.B_rows = d_i + 4 * T;
+  a.x0 = d_f + o_x0; a.xf = d_f + o_xf; a.Jmat = d_f + o_J; a.Qd = d_f + o_Qd; a.Qfd = d_f + o_Qfd; a.Rd = d_f + o_Rd;
+  a.index_scale = d_f + o_is; a.clock_rate = d_f + o_cr;
+  a.B_eci = (const double*)dB.d;
+  a.dt = dt;
+  a.U0 = U0 ? (const double*)dU0.d : nullptr;
+  memcpy(&a.opts, &o, sizeof(o));
+  a.X = (double*)dX.d; a.U = (double*)dU.d; a.K = K ? (double*)dK.d : nullptr;
+  a.out = (ts_trial_outcome_dev*)p_out;
+  a.Nmax = Nmax;
+  {
+    char* w = (char*)p_work;
+    a.w_xu = (double*)w;   w += (size_t)slots * Nmax * 90 * sizeof(double);
+    a.w_kd = (double*)w;   w += (size_t)slots * Nmax * 24 * sizeof(double);
+    a.w_lam = (double*)w;  w += (size_t)slots * Nmax * 6 * sizeof(double);
+    a.w_clk = (double*)w;  w += (size_t)slots * Nmax * sizeof(double);
+    a.w_rows = (int*)w;
+  }
+  a.queue = (unsigned long long*)p_q;
+  KernelTimer tm(c);
+  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  if ((rc = dev_back(c, dX, X, (size_t)total_knots * 8 * sizeof(double)))) return rc;
+  if ((rc = dev_back(c, dU, U, (size_t)total_knots * 3 * sizeof(double)))) return rc;
+  if (K && (rc = dev_back(c, dK, K, (size_t)total_knots * 24 * sizeof(double)))) return rc;
+  TS_CUDA(c, cudaMemcpyAsync(out, p_out, T * sizeof(ts_trial_outcome), cudaMemcpyDeviceToHost, c->stream));
   TS_CUDA(c, cudaStreamSynchronize(c->stream));
   tm.read();
   return TS_OK;

@@ -25,6 +25,27 @@ FIELD_OPTS_DTYPE = np.dtype([("GM", "<f8"), ("mjd", "<f8"), ("igrf_date", "<f8")
 GM_EARTH = 3.986004418E14 * (1 / 1000) ** 3  # km^3/s^2 (input_parameters.jl:26)
 
 
+OUTCOME_DTYPE = np.dtype([("status", "<i4"), ("outer_iters", "<i4"), ("inner_iters", "<i4"), ("ls_rollouts", "<i4"),
+                          ("N", "<i8"), ("J", "<f8"), ("c_max", "<f8"), ("t_final", "<f8"), ("slew_time", "<f8"),
+                          ("flops", "<f8")])
+
+
+class IlqrOpts(C.Structure):
+    """ts_ilqr_opts (include/tortoise_b200.h)."""
+    _fields_ = [(k, C.c_int32) for k in ("max_outer", "max_inner", "max_linesearch", "dJ_counter_limit", "stage_cost_dt",
+                                         "goal_mask")] + \
+               [(k, C.c_double) for k in ("cost_tol", "cost_tol_intermediate", "grad_tol", "grad_tol_intermediate",
+                                          "constraint_tol", "penalty_initial", "penalty_scaling", "penalty_max", "dual_max",
+                                          "ls_lower", "ls_upper", "bp_reg_increase", "bp_reg_max", "bp_reg_min", "bp_reg_fp",
+                                          "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")]
+
+
+def default_ilqr_opts():
+    o = IlqrOpts()
+    load_library().ts_ilqr_default_opts(C.byref(o))
+    return o
+
+
 class TortoiseError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("tortoise_b200 error %d: %s" % (code, msg))
@@ -65,6 +86,10 @@ def load_library():
     L.ts_magnetic_gramian_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
     L.ts_condition_based_time_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
     L.ts_condition_cutoff_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
+    L.ts_ilqr_default_opts.argtypes = [C.POINTER(IlqrOpts)]
+    L.ts_ilqr_default_opts.restype = None
+    L.ts_alilqr_solve_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 13 + [C.c_double, C.c_void_p,
+                                                                                      C.POINTER(IlqrOpts)] + [C.c_void_p] * 4 + [C.c_int]
     _LIB = L
     return L
 
@@ -200,6 +225,37 @@ class Engine:
         self._check(self.lib.ts_condition_cutoff_batch(self.h, rows.shape[0], _ptr(B), _ptr(offs), _ptr(rows), _ptr(dt),
                                                        _ptr(cutoff), _ptr(idx), 0))
         return idx
+
+
+    # -- K3 ---------------------------------------------------------------
+    def alilqr_solve_batch(self, N_i, x0, xf, Jmat, Qd, Qfd, Rd, B_eci, B_offs, B_rows, index_scale, clock_rate, dt,
+                           U0=None, opts=None, want_K=True):
+        """Batched AL-iLQR solve (TortoiseSat.jl:145-146,169,178-199).  Per-trial rows in
+        x0/xf (T,8), Jmat (T,9), Qd/Qfd (T,8), Rd (T,3); ragged knots addressed through
+        offs = cumsum(N_i).  Returns (X, U, K, outcomes, offs): X (sum N, 8), U (sum N, 3)
+        [row offs[t]+N_t-1 unused], K (sum N, 3, 8) or None."""
+        N_i = np.ascontiguousarray(N_i, dtype=np.int64)
+        T = N_i.shape[0]
+        offs = np.zeros(T + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(N_i)
+        arr = lambda a, w: _f64(np.asarray(a, dtype=np.float64).reshape(T, w))
+        x0, xf, Jmat, Qd, Qfd, Rd = arr(x0, 8), arr(xf, 8), arr(Jmat, 9), arr(Qd, 8), arr(Qfd, 8), arr(Rd, 3)
+        B_eci = _f64(B_eci)
+        B_offs = np.ascontiguousarray(B_offs, dtype=np.int64)
+        B_rows = np.ascontiguousarray(B_rows, dtype=np.int64)
+        index_scale, clock_rate = _f64(index_scale), _f64(clock_rate)
+        tot = int(offs[-1])
+        X = np.zeros((tot, 8))
+        U = np.zeros((tot, 3))
+        K = np.zeros((tot, 3, 8)) if want_K else None
+        out = np.zeros(T, dtype=OUTCOME_DTYPE)
+        o = opts if opts is not None else default_ilqr_opts()
+        U0a = None if U0 is None else _f64(U0)
+        self._check(self.lib.ts_alilqr_solve_batch(
+            self.h, T, _ptr(N_i), _ptr(offs), _ptr(x0), _ptr(xf), _ptr(Jmat), _ptr(Qd), _ptr(Qfd), _ptr(Rd), _ptr(B_eci),
+            _ptr(B_offs), _ptr(B_rows), _ptr(index_scale), _ptr(clock_rate), float(dt), None if U0a is None else _ptr(U0a),
+            C.byref(o), _ptr(X), _ptr(U), None if K is None else _ptr(K), out.ctypes.data, 0))
+        return X, U, K, out, offs
 
 
 # ---------------------------------------------------------------------------
