@@ -164,6 +164,77 @@ int ts_alilqr_solve_batch(ts_ctx* ctx, int64_t n_trials, const int64_t* N_i, con
                           const double* clock_rate, double dt, const double* U0, const ts_ilqr_opts* opts, double* X,
                           double* U, double* K, ts_trial_outcome* out, int pointers_are_device);
 
+/* ---- slew preparation: eigen-axis guess + Bryson weights ---------------------- *
+ * eigen_axis_slew(x0,xf,t) [src/eigen_axis_slew.jl:1-38] over t = t0:dt:t_final[t], followed by
+ * Bryson's rule [src/TortoiseSat.jl:157-168; alpha = 10 there, 0.1 in src/monte_carlo.jl:169;
+ * beta = 1e3].  HOST arrays: x0, xf (8 per trial), Jmat (9), t_final (1) -> Qd, Qfd (8), Rd (3).
+ * Optional guess outputs (nullable): w_guess (ragged nt x 3) / q_guess (ragged nt x 4) at row
+ * offsets goffs[t] (host, n_trials entries), nt = length(t0:dt:t_final[t]).                   */
+int ts_slew_weights_batch(ts_ctx* ctx, int64_t n_trials, const double* x0, const double* xf, const double* Jmat,
+                          const double* t_final, double t0, double dt, double alpha, double beta, double* Qd, double* Qfd,
+                          double* Rd, const int64_t* goffs, double* w_guess, double* q_guess);
+
+/* ---- K4: batched TVLQR closed-loop replay -------------------------------------- */
+typedef struct ts_tvlqr_opts {
+  double dt;                 /* dt_lqr (0.2)                                                  */
+  double t0, tf;             /* t0; tf is taken per trial from t_final[]                       */
+  double Qd[6], Qfd[6], Rd[3]; /* Q_lqr = diag(10,10,10,10,10,10), Qf = 100 Q, R = 7.5e3 I
+                                 (TortoiseSat.jl:251-260)                                     */
+  int32_t dt_squared;        /* 1: linearise with dt^2 (attitude_controller.jl:111,137, Q6)   */
+  int32_t noise_mode;        /* 0 none, 1 explicit `noise` array, 2 Philox4x32-10(seed,trial,step,stage) */
+  uint64_t seed;
+  double w_limit, ang_limit; /* slew limits .05 rad/s, .08727 rad (monte_carlo.jl:69-71)       */
+  int32_t literal_postproc;  /* 1: keep the `[1:3,i]` column bug of monte_carlo.jl:247 (Q12)   */
+  int32_t pad_;
+} ts_tvlqr_opts;
+void ts_tvlqr_default_opts(ts_tvlqr_opts* o);
+
+/* attitude_simulation(simulator, gain_simulator, :rk4, X, U, dt, x0, t0, tf, Q, R, Qf)
+ * [src/attitude_controller.jl:1-48, with attitude_lqr :50-119, rk4 :122-145, simulator.jl,
+ * gain_simulator.jl] for n_trials optimised slews, plus the slew-time rule of
+ * src/monte_carlo.jl:237-262.  HOST per-trial arrays: N_i, offs, x0_lqr (8), Jmat (9), B_offs,
+ * B_rows, index_scale, clock_rate, t_final, q_final (4), stream_id (nullable; Philox stream of
+ * the trial, default = t).  Arrays following pointers_are_device: X_lqr (ragged N x 8), U_lqr
+ * (ragged (N-1) x 3 at offs*3), B_eci, noise (nullable; ragged N x 4 x 9 at offs*36), outputs
+ * (all nullable) X_sim (ragged N x 8), U_sim (N x 3), dX (N x 6), K (N x 3 x 6).  HOST outputs
+ * (nullable): N_sim, slew_time (== t_final[t] when the trial "fails").                          */
+int ts_tvlqr_sim_batch(ts_ctx* ctx, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* X_lqr,
+                       const double* U_lqr, const double* x0_lqr, const double* Jmat, const double* B_eci,
+                       const int64_t* B_offs, const int64_t* B_rows, const double* index_scale, const double* clock_rate,
+                       const double* t_final, const double* q_final, const uint32_t* stream_id, const ts_tvlqr_opts* opts,
+                       const double* noise, double* X_sim, double* U_sim, double* dX, double* K, int64_t* N_sim,
+                       double* slew_time, int pointers_are_device);
+
+/* ---- fused Monte-Carlo run: the metric path -------------------------------------- *
+ * For each trial: scoping field pass -> gramian cutoff -> fine field table -> eigen-axis /
+ * Bryson weights -> AL-iLQR -> (optional) TVLQR replay + slew-time rule, i.e. the loop body of
+ * src/monte_carlo.jl:118-262 with the solver block of src/TortoiseSat.jl:178-199.  Everything
+ * between the per-trial inputs and the 64-byte outcome records stays in HBM.                  */
+typedef struct ts_mc_config {
+  int64_t n_trials;
+  int32_t shared_orbit;  /* 1: all trials use kep6[0..5] / fopts[0] (fixed-orbit ensemble, configs[2]) */
+  int32_t run_tvlqr;     /* 1: K4 replay + slew-time post-processing                                  */
+  double t0, tf;         /* scoping window (0, 2400 in monte_carlo.jl:74-75; 0, 5400 in TortoiseSat.jl) */
+  int64_t N_scope;       /* 5000                                                                      */
+  double cutoff;         /* condition-number cutoff (30 / 50 / 100)                                   */
+  double dt;             /* 0.2                                                                       */
+  double alpha, beta;    /* Bryson weights                                                            */
+  ts_ilqr_opts ilqr;
+  ts_tvlqr_opts tvlqr;
+} ts_mc_config;
+typedef struct ts_mc_stats {
+  int64_t n_trials, n_converged, n_no_cutoff, n_fail_slew;
+  double sum_slew_time, sum_slew_time_sq, sum_t_final, sum_inner_iters, sum_ls_rollouts, sum_knots, flops;
+  double ms_field, ms_prep, ms_solve, ms_tvlqr; /* device time of each stage (CUDA events) */
+} ts_mc_stats;
+/* HOST inputs: kep6 (n x 6, or 1 x 6 if shared_orbit), fopts (n, or 1; only GM, mjd, igrf_date,
+ * field_radius_m are read), x0, xf (n x 8), Jmat (n x 9), q_noise0 (n x 3, nullable: initial
+ * attitude perturbation of the replay, TortoiseSat.jl:231-234), stream_id (nullable).
+ * HOST outputs: out (n records), stats (nullable).                                            */
+int ts_monte_carlo_run(ts_ctx* ctx, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts, const double* x0,
+                       const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
+                       ts_trial_outcome* out, ts_mc_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../tortoisesat.jl_b200/csrc/ilqr_solver.cuh"
+#include "../../tortoisesat.jl_b200/csrc/tvlqr_solver.cuh"
 
 using namespace ts;
 
@@ -139,6 +140,41 @@ void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double
         }
     }
   }
+}
+
+
+void hs_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+void hs_tvlqr_noise(uint64_t seed, uint32_t trial, uint32_t step, uint32_t stage, double* out9) {
+  tvlqr_noise(seed, trial, step, stage, out9);
+}
+// One trial of the K4 source: gains + replay + slew-time rule.
+int64_t hs_tvlqr(int64_t N, const double* X_lqr, const double* U_lqr, const double* x0, const double* Jmat, const double* B_eci,
+                 int64_t B_rows, double index_scale, double clock_rate, double t_final, const double* q_final, uint32_t trial,
+                 const ts_tvlqr_opts_dev* opts, const double* noise, double* X_sim, double* U_sim, double* dX, double* K,
+                 double* slew_time) {
+  TvlqrIn in;
+  in.N = (int)N;
+  in.X_lqr = X_lqr;
+  in.U_lqr = U_lqr;
+  for (int i = 0; i < 8; ++i) in.x0[i] = x0[i];
+  memcpy(in.I.J, Jmat, 72);
+  inv3_gj(in.I.J, in.I.Jinv);
+  in.Bt = B_eci;
+  in.B_rows = B_rows;
+  in.index_scale = index_scale;
+  in.clock_rate = clock_rate;
+  in.noise = noise;
+  in.trial = trial;
+  for (int i = 0; i < 4; ++i) in.q_final[i] = q_final[i];
+  in.t_final = t_final;
+  in.time_step = opts->dt;
+  in.trial_index_1based = (long long)trial + 1;
+  ts_tvlqr_opts_dev o = *opts;
+  o.tf = t_final;
+  tvlqr_gains(in, o, K);
+  return tvlqr_replay(in, o, K, X_sim, U_sim, dX, slew_time);
 }
 
 }  // extern "C"

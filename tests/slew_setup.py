@@ -41,6 +41,11 @@ def hostsim():
         _HS.hs_rk3_jac7.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_rk4_jac7.argtypes = [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_dyn_f.argtypes = [C.c_void_p] * 5
+        _HS.hs_philox4x32_10.argtypes = [C.c_void_p] * 3
+        _HS.hs_tvlqr_noise.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        _HS.hs_tvlqr.argtypes = [C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                                                   C.c_uint32] + [C.c_void_p] * 7
+        _HS.hs_tvlqr.restype = C.c_int64
     return _HS
 
 
@@ -128,3 +133,48 @@ def hostsim_solve(s, opts=None):
                        orc.P(orc.f64(s.Qfd)), orc.P(orc.f64(s.Rd)), orc.P(B), B.shape[0], s.index_scale, s.clock_rate, s.dt,
                        None, C.addressof(o), orc.P(X), orc.P(U), orc.P(K), out.ctypes.data)
     return X, U[:-1], K[:-1].reshape(-1, 3, 8), out[0]
+
+
+def tvlqr_opts_pair(noise_mode=0, seed=0, dt=0.2, literal=0, dt_squared=1, R=7.5e3):
+    """(oracle TvlqrOpts, product TvlqrOpts) with the constants of TortoiseSat.jl:251-260."""
+    import tortoisesat.jl_b200 as tb
+    g = tb.host.default_tvlqr_opts()
+    g.dt, g.noise_mode, g.seed, g.literal_postproc, g.dt_squared = dt, noise_mode, seed, literal, dt_squared
+    for i in range(3):
+        g.Rd[i] = R
+    o = orc.TvlqrOpts()
+    o.dt, o.t0, o.dt_squared, o.noise_mode, o.seed = dt, 0.0, dt_squared, noise_mode, seed
+    for i in range(6):
+        o.Qd[i], o.Qfd[i] = g.Qd[i], g.Qfd[i]
+    for i in range(3):
+        o.Rd[i] = g.Rd[i]
+    return o, g
+
+
+def oracle_tvlqr(s, X, U, x0_lqr, o, trial=0, noise=None, literal=0):
+    """orc_attitude_simulation + orc_mc_slew_time for one Slew; X (N,8), U (N-1,3)."""
+    L = orc.lib()
+    d = orc.make_dyn(s.B, s.index_scale, s.clock_rate, s.J)
+    o.tf = s.t_final
+    N = s.N
+    Xs, Us, dX, K = np.zeros((N, 8)), np.zeros((N, 3)), np.zeros((N, 6)), np.zeros((N - 1, 3, 6))
+    X = orc.f64(X)
+    U = orc.f64(U)
+    ns = L.orc_attitude_simulation(C.byref(d), C.byref(o), N, orc.P(X), orc.P(U), orc.P(orc.f64(x0_lqr)),
+                                   None if noise is None else orc.P(orc.f64(noise)), trial, orc.P(Xs), orc.P(Us), orc.P(dX), orc.P(K))
+    slew = L.orc_mc_slew_time(orc.P(Xs), ns, orc.P(orc.f64(s.xf[3:7])), s.t_final, o.dt, 0.05, 0.08727, literal, trial + 1)
+    return Xs[:ns], Us[:ns], dX[:ns], K, ns, slew
+
+
+def hostsim_tvlqr(s, X, U, x0_lqr, g, trial=0, noise=None):
+    hs = hostsim()
+    N = s.N
+    Xs, Us, dX, K = np.zeros((N, 8)), np.zeros((N, 3)), np.zeros((N, 6)), np.zeros((N, 3, 6))
+    slew = np.zeros(1)
+    B = np.ascontiguousarray(s.B)
+    Up = np.zeros((N, 3))
+    Up[:N - 1] = U
+    ns = hs.hs_tvlqr(N, orc.P(orc.f64(X)), orc.P(Up), orc.P(orc.f64(x0_lqr)), orc.P(orc.f64(s.J.reshape(-1))), orc.P(B), B.shape[0],
+                     s.index_scale, s.clock_rate, s.t_final, orc.P(orc.f64(s.xf[3:7])), trial, C.addressof(g),
+                     None if noise is None else orc.P(orc.f64(noise)), orc.P(Xs), orc.P(Us), orc.P(dX), orc.P(K), orc.P(slew))
+    return Xs[:ns], Us[:ns], dX[:ns], K[:N - 1], ns, slew[0]

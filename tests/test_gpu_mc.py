@@ -1,0 +1,187 @@
+"""GPU: slew preparation, K4 TVLQR replay and the fused Monte-Carlo path vs the CPU oracle."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import slew_setup as S
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GM = S.GM
+
+
+def _perturb(q0, qn):
+    th = np.linalg.norm(qn)
+    out = np.zeros(4)
+    orc.lib().orc_qmult(orc.P(orc.f64(q0)), orc.P(np.concatenate([[math.cos(th / 2)], qn / th * math.sin(th / 2)])), orc.P(out))
+    return out
+
+
+def test_slew_weights_and_guess(engine):
+    from tortoisesat.jl_b200 import host
+    rng = np.random.default_rng(3)
+    T = 9
+    x0 = np.zeros((T, 8))
+    xf = np.zeros((T, 8))
+    Jm = np.zeros((T, 9))
+    tfin = rng.uniform(40, 480, size=T)
+    for t in range(T):
+        q = rng.normal(size=4)
+        x0[t, 3:7] = q / np.linalg.norm(q)
+        xf[t, 3:7] = [math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0]
+        xf[t, 7] = 1
+        Jm[t] = (S.J_1U if t % 2 else S.J_3U).reshape(-1)
+    Qd, Qfd, Rd, wg, qg, goffs = engine.slew_weights_batch(x0, xf, Jm, tfin, dt=0.2, alpha=0.1, beta=1e3, want_guess=True)
+    L = orc.lib()
+    for t in range(T):
+        nt = int(goffs[t + 1] - goffs[t])
+        tt = 0.2 * np.arange(nt)
+        assert nt == int(math.floor(tfin[t] / 0.2 + 1e-9)) + 1
+        w_o, q_o = np.zeros((nt, 3)), np.zeros((nt, 4))
+        L.orc_eigen_axis_slew(orc.P(orc.f64(x0[t, :7])), orc.P(orc.f64(xf[t, :7])), orc.P(tt), nt, orc.P(w_o), orc.P(q_o))
+        Qo, Qfo, Ro = np.zeros(8), np.zeros(8), np.zeros(3)
+        L.orc_bryson_weights(orc.P(w_o), nt, orc.P(orc.f64(Jm[t])), 0.2, 0.1, 1e3, orc.P(Qo), orc.P(Qfo), orc.P(Ro))
+        assert np.allclose(wg[goffs[t]:goffs[t + 1]], w_o, rtol=1e-9, atol=1e-16)
+        assert np.allclose(qg[goffs[t]:goffs[t + 1]], q_o, rtol=0, atol=1e-12)
+        assert np.allclose(Qd[t], Qo, rtol=1e-9) and np.allclose(Qfd[t], Qfo, rtol=1e-9) and np.allclose(Rd[t], Ro, rtol=1e-8)
+    # config-1 known answers
+    x0c = np.concatenate([[0, 0, 0], S.quat_axis_angle([1, 0, 1], 90.0), [0]])
+    xfc = np.array([0, 0, 0, 1.0, 0, 0, 0, 1])
+    Qd, Qfd, Rd = engine.slew_weights_batch([x0c], [xfc], S.J_1P.reshape(1, 9), [311.04], dt=0.2, alpha=10.0, beta=1e3)
+    assert abs(Qd[0, 0] / 317739.65036560915 - 1) < 1e-9 and Qd[0, 3] == 1e4 and abs(Rd[0, 0] / 286.97003750452905 - 1) < 1e-8
+    w, q = host.eigen_axis_slew(x0c[:7], xfc[:7], 0.2 * np.arange(1556))
+    assert w.shape == (1556, 3) and abs(np.max(np.abs(w)) - 5.610018498990348e-3) < 1e-12
+
+
+@pytest.fixture(scope="module")
+def solved_pair():
+    qf = np.array([1.0, 0, 0, 0])
+    sl = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 5.0), qf, t_final=60.0),
+          S.build_slew([0, 6871, 51.6, 30, 0, 10], S.J_3U, S.quat_axis_angle([0, 1, 0], 3.0), qf, t_final=50.0)]
+    Xs, Us, Ks, out = S.oracle_solve(sl, nthreads=2)
+    return sl, Xs, Us
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_tvlqr_replay_matches_oracle(engine, solved_pair, mode):
+    sl, Xs, Us = solved_pair
+    rng = np.random.default_rng(7)
+    o, g = S.tvlqr_opts_pair(noise_mode=mode, seed=77)
+    T = len(sl)
+    N_i = [s.N for s in sl]
+    Xl = np.concatenate(Xs)
+    Ul = np.concatenate([np.vstack([u, np.zeros((1, 3))]) for u in Us])
+    x0l = []
+    for s in sl:
+        x = s.x0.copy()
+        x[3:7] = _perturb(s.x0[3:7], rng.normal(size=3) * (math.pi / 180) ** 2)
+        x[7] = 0
+        x0l.append(x)
+    rows = np.array([s.B.shape[0] for s in sl])
+    B_offs = np.concatenate([[0], np.cumsum(rows)])[:-1]
+    noise = None
+    if mode == 1:
+        noise = rng.normal(size=(sum(N_i), 4, 9)) * np.array([1e-5] * 3 + [3e-4] * 3 + [1e-10] * 3)
+    Xsim, Usim, dX, K, nsim, slew, offs = engine.tvlqr_sim_batch(
+        N_i, Xl, Ul, np.stack(x0l), np.stack([s.J.reshape(-1) for s in sl]), np.concatenate([s.B for s in sl]), B_offs, rows,
+        [s.index_scale for s in sl], [s.clock_rate for s in sl], [s.t_final for s in sl], np.stack([s.xf[3:7] for s in sl]),
+        opts=g, noise=noise, stream_id=[11, 12])
+    for t, s in enumerate(sl):
+        nz = None if noise is None else noise[offs[t]:offs[t + 1]]
+        a = S.oracle_tvlqr(s, Xs[t], Us[t], x0l[t], o, trial=11 + t, noise=nz)
+        assert nsim[t] == a[4]
+        n = int(nsim[t])
+        assert np.max(np.abs(Xsim[offs[t]:offs[t] + n] - a[0])) < 1e-10          # rollouts to 1e-10
+        assert np.max(np.abs(Usim[offs[t]:offs[t] + n] - a[1])) < 1e-9
+        assert np.max(np.abs(dX[offs[t]:offs[t] + n] - a[2])) < 1e-10
+        assert np.max(np.abs(K[offs[t]:offs[t] + s.N - 1] - a[3])) <= 1e-9 * np.max(np.abs(a[3]))
+        assert slew[t] == a[5]
+
+
+def _oracle_trial(kep, fo, x0, xf, J, cfg, qn, sid):
+    """The per-trial pipeline of monte_carlo.jl:118-262 / TortoiseSat.jl:58-265 with the oracle."""
+    s = S.build_slew(kep, J, x0[3:7], xf[3:7], mjd=fo["mjd"], igrf_date=fo["igrf_date"], field_radius_m=fo["field_radius_m"],
+                     t0=cfg.t0, tf=cfg.tf, N_scope=int(cfg.N_scope), cutoff=cfg.cutoff, dt=cfg.dt, alpha=cfg.alpha, beta=cfg.beta)
+    Xs, Us, Ks, out = S.oracle_solve([s])
+    o, g = S.tvlqr_opts_pair(noise_mode=2, seed=int(cfg.tvlqr.seed))
+    x0l = s.x0.copy()
+    x0l[3:7] = _perturb(s.x0[3:7], qn)
+    x0l[7] = 0
+    a = S.oracle_tvlqr(s, Xs[0], Us[0], x0l, o, trial=sid)
+    return s, out[0], a[5]
+
+
+def test_fused_monte_carlo_shared_orbit(engine):
+    """configs[2] in miniature: fixed LEO orbit (monte_carlo.jl:122-127 with RAAN 0, anomaly 90), random attitudes."""
+    from tortoisesat.jl_b200 import host
+    rng = np.random.default_rng(21)
+    n = 4
+    cfg = host.default_mc_config(n, shared_orbit=True, run_tvlqr=True, tf=2400.0, cutoff=30.0, alpha=0.1)
+    cfg.tvlqr.noise_mode = 2
+    cfg.tvlqr.seed = 4242
+    kep = np.array([[0, 6771.0, 96.6, 0.0, 0.0, 90.0]])
+    fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
+    fo[0] = (GM, 58155.0, 2019.0, 6771000.0, 0, 0, 0)
+    qf = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])
+    x0 = np.zeros((n, 8))
+    xf = np.tile(np.concatenate([[0, 0, 0], qf, [1.0]]), (n, 1))
+    for t in range(n):
+        dq = S.quat_axis_angle(rng.normal(size=3), rng.uniform(5, 40))
+        q = np.zeros(4)
+        orc.lib().orc_qmult(orc.P(orc.f64(qf)), orc.P(dq), orc.P(q))
+        x0[t, 3:7] = q
+    Jm = np.tile(S.J_1U.reshape(-1), (n, 1))
+    qn = rng.normal(size=(n, 3)) * (math.pi / 180) ** 2
+    out, st = engine.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn, stream_id=np.arange(100, 100 + n))
+    assert st.n_trials == n and st.n_no_cutoff == 0
+    for t in range(n):
+        s, ref, slew = _oracle_trial(kep[0], fo[0], x0[t], xf[t], S.J_1U, cfg, qn[t], 100 + t)
+        g = out[t]
+        assert g["N"] == s.N and abs(g["t_final"] - s.t_final) < 1e-9
+        assert g["status"] == ref["status"] and g["outer_iters"] == ref["outer_iters"], (t, g, ref)
+        assert abs(g["J"] - ref["J"]) <= 1e-6 * abs(ref["J"])
+        assert abs(g["c_max"] - ref["c_max"]) <= 1e-6 * max(1.0, ref["c_max"])
+        assert g["slew_time"] == slew, (t, g["slew_time"], slew)
+    assert st.flops > 0 and st.ms_solve > 0
+
+
+def test_fused_monte_carlo_sweep_and_no_cutoff(engine):
+    """configs[3] in miniature: per-trial inclination / altitude / RAAN / anomaly / MJD / IGRF date; one
+    equatorial trial never reaches the cutoff -> per-trial status NO_CUTOFF, batch unaffected."""
+    from tortoisesat.jl_b200 import host
+    rng = np.random.default_rng(8)
+    n = 4
+    cfg = host.default_mc_config(n, shared_orbit=False, run_tvlqr=True, tf=2400.0, cutoff=100.0, alpha=0.1)
+    cfg.tvlqr.noise_mode = 2
+    cfg.tvlqr.seed = 9
+    kep = np.zeros((n, 6))
+    fo = np.zeros(n, dtype=host.FIELD_OPTS_DTYPE)
+    for t in range(n):
+        alt = rng.uniform(350, 800)
+        kep[t] = [0, alt + 6371.0, rng.uniform(40, 98), rng.uniform(0, 360), 0, rng.uniform(0, 360)]
+        fo[t] = (GM, rng.uniform(58155, 58520), 2015 + 5 * rng.random(), (alt + 6371.0) * 1000, 0, 0, 0)
+    cfg.cutoff = 100.0
+    qf = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])
+    x0 = np.zeros((n, 8))
+    xf = np.tile(np.concatenate([[0, 0, 0], qf, [1.0]]), (n, 1))
+    for t in range(n):
+        dq = S.quat_axis_angle(rng.normal(size=3), rng.uniform(5, 30))
+        q = np.zeros(4)
+        orc.lib().orc_qmult(orc.P(orc.f64(qf)), orc.P(dq), orc.P(q))
+        x0[t, 3:7] = q
+    Jm = np.tile(S.J_1U.reshape(-1), (n, 1))
+    qn = rng.normal(size=(n, 3)) * (math.pi / 180) ** 2
+    out, st = engine.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn)
+    for t in range(n):
+        s, ref, slew = _oracle_trial(kep[t], fo[t], x0[t], xf[t], S.J_1U, cfg, qn[t], t)
+        g = out[t]
+        assert g["N"] == s.N and abs(g["t_final"] - s.t_final) < 1e-9, (t, g, s.N)
+        assert g["status"] == ref["status"] and g["outer_iters"] == ref["outer_iters"], (t, g, ref)
+        assert abs(g["J"] - ref["J"]) <= 1e-6 * abs(ref["J"])
+        assert g["slew_time"] == slew
+    # a cutoff nobody can reach -> every trial NO_CUTOFF, call still succeeds
+    cfg2 = host.default_mc_config(n, shared_orbit=False, run_tvlqr=False, tf=2400.0, cutoff=1.0)
+    out2, st2 = engine.monte_carlo_run(cfg2, kep, fo, x0, xf, Jm)
+    assert np.all(out2["status"] == 5) and st2.n_no_cutoff == n

@@ -24,8 +24,8 @@ struct ts_ctx {
   double* d_tabH = nullptr;  // 91 x 25
   int* d_flag = nullptr;     // generic device error/flag word
   // grow-only scratch arenas
-  void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* scratch[16] = {};
+  size_t scratch_bytes[16] = {};
 };
 
 namespace ts {

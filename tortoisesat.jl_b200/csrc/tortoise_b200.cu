@@ -6,6 +6,7 @@
 #include "k1_igrf.cuh"
 #include "k2_field.cuh"
 #include "k3_alilqr.cuh"
+#include "k4_tvlqr.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -60,7 +61,7 @@ int ts_create(ts_ctx** out, int device_id) {
 void ts_destroy(ts_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 16; ++i)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->d_tabG) cudaFree(c->d_tabG);
   if (c->d_tabH) cudaFree(c->d_tabH);
@@ -312,6 +313,49 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
 }
 
+// Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
+// Fills a.order / work arena / queue; does not synchronise.
+static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
+  const int64_t n_trials = a.n_trials;
+  int64_t Nmax = 0;
+  for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
+  int occ = 0;
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
+  if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
+  const int64_t groups = (n_trials + 3) / 4;
+  const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
+  const int64_t warps = std::min(groups, max_warps);
+  const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
+  const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
+  // trials sorted by horizon (descending) so the four teams of a warp have similar trip counts
+  std::vector<int64_t> order((size_t)n_trials);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return N_i_host[x] > N_i_host[y]; });
+  int rc;
+  int64_t* d_order = nullptr;
+  if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
+  void *p_work, *p_q;
+  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1) * sizeof(double) + (size_t)Nmax * 3 * sizeof(int) + 64;
+  if ((rc = scratch_reserve(c, 6, per_slot * (size_t)slots + 256, &p_work))) return rc;
+  if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
+  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
+  a.order = d_order;
+  a.Nmax = Nmax;
+  {
+    char* w = (char*)p_work;
+    a.w_xu = (double*)w;   w += (size_t)slots * Nmax * 90 * sizeof(double);
+    a.w_kd = (double*)w;   w += (size_t)slots * Nmax * 24 * sizeof(double);
+    a.w_lam = (double*)w;  w += (size_t)slots * Nmax * 6 * sizeof(double);
+    a.w_clk = (double*)w;  w += (size_t)slots * Nmax * sizeof(double);
+    a.w_rows = (int*)w;
+  }
+  a.queue = (unsigned long long*)p_q;
+  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  return TS_OK;
+}
+
 int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* x0,
                           const double* xf, const double* Jmat, const double* Qd, const double* Qfd, const double* Rd,
                           const double* B_eci, const int64_t* B_offs, const int64_t* B_rows, const double* index_scale,
@@ -326,29 +370,14 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   ts_ilqr_opts o;
   if (opts) o = *opts; else ts_ilqr_default_opts(&o);
   if (o.max_linesearch < 0 || o.max_linesearch > 63) return fail(c, TS_ERR_ARG, "max_linesearch must be in [0,63]");
-  int64_t Nmax = 0, total_knots = 0, total_rows = 0;
+  int64_t total_knots = 0, total_rows = 0;
   for (int64_t t = 0; t < n_trials; ++t) {
     if (N_i[t] < 2) return fail(c, TS_ERR_ARG, "trial %lld: N < 2", (long long)t);
-    Nmax = std::max(Nmax, N_i[t]);
     total_knots = std::max(total_knots, offs[t] + N_i[t]);
     total_rows = std::max(total_rows, B_offs[t] + B_rows[t]);
     if (B_rows[t] < 1) return fail(c, TS_ERR_ARG, "trial %lld: empty field table", (long long)t);
   }
   TS_CUDA(c, cudaSetDevice(c->device));
-  // launch geometry: persistent warps, 4 trials per warp
-  int occ = 0;
-  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
-  if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
-  const int64_t groups = (n_trials + 3) / 4;
-  const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
-  const int64_t warps = std::min(groups, max_warps);
-  const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
-  const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
-  // trials sorted by horizon (descending) so the four teams of a warp have similar trip counts
-  std::vector<int64_t> order((size_t)n_trials);
-  std::iota(order.begin(), order.end(), (int64_t)0);
-  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return N_i[a] > N_i[b]; });
-
   int rc;
   DevBuf dB, dU0, dX, dU, dK;
   if ((rc = dev_in(c, dB, B_eci, (size_t)total_rows * 3 * sizeof(double), pad))) return rc;
@@ -358,14 +387,13 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   if (K && (rc = dev_out(c, dK, K, (size_t)total_knots * 24 * sizeof(double), pad))) return rc;
   // per-trial small arrays -> one packed upload
   const size_t T = (size_t)n_trials;
-  const size_t n_i64 = 5 * T, n_f64 = (8 + 8 + 9 + 8 + 8 + 3 + 1 + 1) * T;
+  const size_t n_i64 = 4 * T, n_f64 = (8 + 8 + 9 + 8 + 8 + 3 + 1 + 1) * T;
   std::vector<int64_t> hi(n_i64);
   std::vector<double> hf(n_f64);
-  memcpy(&hi[0 * T], order.data(), T * 8);
-  memcpy(&hi[1 * T], N_i, T * 8);
-  memcpy(&hi[2 * T], offs, T * 8);
-  memcpy(&hi[3 * T], B_offs, T * 8);
-  memcpy(&hi[4 * T], B_rows, T * 8);
+  memcpy(&hi[0 * T], N_i, T * 8);
+  memcpy(&hi[1 * T], offs, T * 8);
+  memcpy(&hi[2 * T], B_offs, T * 8);
+  memcpy(&hi[3 * T], B_rows, T * 8);
   size_t fo = 0;
   auto put = [&](const double* src, size_t per) { memcpy(&hf[fo], src, per * T * 8); fo += per * T; return fo - per * T; };
   const size_t o_x0 = put(x0, 8), o_xf = put(xf, 8), o_J = put(Jmat, 9), o_Qd = put(Qd, 8), o_Qfd = put(Qfd, 8), o_Rd = put(Rd, 3),
@@ -374,15 +402,11 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   double* d_f = nullptr;
   if ((rc = upload(c, 1, hi.data(), n_i64, &d_i))) return rc;
   if ((rc = upload(c, 2, hf.data(), n_f64, &d_f))) return rc;
-  void *p_out, *p_work, *p_q;
+  void* p_out;
   if ((rc = scratch_reserve(c, 3, T * sizeof(ts_trial_outcome), &p_out))) return rc;
-  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1) * sizeof(double) + (size_t)Nmax * 3 * sizeof(int) + 64;
-  if ((rc = scratch_reserve(c, 6, per_slot * (size_t)slots + 256, &p_work))) return rc;
-  if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
-  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
   K3Args a;
   a.n_trials = n_trials;
-  a.order = d_i + 0 * T; a.N_i = d_i + 1 * T; a.offs = d_i + 2 * T; a.B_offs = d_i + 3 * T; a.B_rows = d_i + 4 * T;
+  a.N_i = d_i + 0 * T; a.offs = d_i + 1 * T; a.B_offs = d_i + 2 * T; a.B_rows = d_i + 3 * T;
   a.x0 = d_f + o_x0; a.xf = d_f + o_xf; a.Jmat = d_f + o_J; a.Qd = d_f + o_Qd; a.Qfd = d_f + o_Qfd; a.Rd = d_f + o_Rd;
   a.index_scale = d_f + o_is; a.clock_rate = d_f + o_cr;
   a.B_eci = (const double*)dB.d;
@@ -391,27 +415,412 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   memcpy(&a.opts, &o, sizeof(o));
   a.X = (double*)dX.d; a.U = (double*)dU.d; a.K = K ? (double*)dK.d : nullptr;
   a.out = (ts_trial_outcome_dev*)p_out;
-  a.Nmax = Nmax;
-  {
-    char* w = (char*)p_work;
-    a.w_xu = (double*)w;   w += (size_t)slots * Nmax * 90 * sizeof(double);
-    a.w_kd = (double*)w;   w += (size_t)slots * Nmax * 24 * sizeof(double);
-    a.w_lam = (double*)w;  w += (size_t)slots * Nmax * 6 * sizeof(double);
-    a.w_clk = (double*)w;  w += (size_t)slots * Nmax * sizeof(double);
-    a.w_rows = (int*)w;
-  }
-  a.queue = (unsigned long long*)p_q;
   KernelTimer tm(c);
-  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+  if ((rc = k3_launch(c, a, N_i))) return rc;
   tm.stop();
-  c->launches++;
-  TS_CUDA(c, cudaGetLastError());
   if ((rc = dev_back(c, dX, X, (size_t)total_knots * 8 * sizeof(double)))) return rc;
   if ((rc = dev_back(c, dU, U, (size_t)total_knots * 3 * sizeof(double)))) return rc;
   if (K && (rc = dev_back(c, dK, K, (size_t)total_knots * 24 * sizeof(double)))) return rc;
   TS_CUDA(c, cudaMemcpyAsync(out, p_out, T * sizeof(ts_trial_outcome), cudaMemcpyDeviceToHost, c->stream));
   TS_CUDA(c, cudaStreamSynchronize(c->stream));
   tm.read();
+  return TS_OK;
+}
+
+// ---------------------------------------------------------------------------- prep + K4
+static_assert(sizeof(ts_tvlqr_opts) == sizeof(ts_tvlqr_opts_dev), "tvlqr opts layout");
+
+void ts_tvlqr_default_opts(ts_tvlqr_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->dt = 0.2; o->t0 = 0.0; o->tf = 0.0;
+  for (int i = 0; i < 6; ++i) { o->Qd[i] = 10.0; o->Qfd[i] = 1000.0; }
+  for (int i = 0; i < 3; ++i) o->Rd[i] = 7.5e3;
+  o->dt_squared = 1; o->noise_mode = 0; o->seed = 0;
+  o->w_limit = 0.05; o->ang_limit = 0.08727; o->literal_postproc = 0;
+}
+
+int ts_slew_weights_batch(ts_ctx* c, int64_t n, const double* x0, const double* xf, const double* Jmat, const double* t_final,
+                          double t0, double dt, double alpha, double beta, double* Qd, double* Qfd, double* Rd,
+                          const int64_t* goffs, double* w_guess, double* q_guess) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!x0 || !xf || !Jmat || !t_final || !Qd || !Qfd || !Rd))) return fail(c, TS_ERR_ARG, "ts_slew_weights_batch: null argument");
+  if ((w_guess || q_guess) && !goffs) return fail(c, TS_ERR_ARG, "ts_slew_weights_batch: guesses need goffs");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  const size_t T = (size_t)n;
+  int64_t total = 0;
+  if (goffs)
+    for (int64_t t = 0; t < n; ++t) total = std::max(total, goffs[t] + (int64_t)range_len(t0, dt, t_final[t]));
+  std::vector<double> hf((8 + 8 + 9 + 1) * T);
+  memcpy(&hf[0], x0, 8 * T * 8);
+  memcpy(&hf[8 * T], xf, 8 * T * 8);
+  memcpy(&hf[16 * T], Jmat, 9 * T * 8);
+  memcpy(&hf[25 * T], t_final, T * 8);
+  double* d_f;
+  int64_t* d_g = nullptr;
+  int rc;
+  if ((rc = upload(c, 1, hf.data(), hf.size(), &d_f))) return rc;
+  if (goffs && (rc = upload(c, 2, goffs, T, &d_g))) return rc;
+  void *p_o, *p_w = nullptr, *p_q = nullptr;
+  if ((rc = scratch_reserve(c, 3, 19 * T * 8, &p_o))) return rc;
+  if (w_guess && (rc = scratch_reserve(c, 7, (size_t)total * 3 * 8, &p_w))) return rc;
+  if (q_guess && (rc = scratch_reserve(c, 8, (size_t)total * 4 * 8, &p_q))) return rc;
+  PrepArgs a;
+  a.n_trials = n; a.x0 = d_f; a.xf = d_f + 8 * T; a.Jmat = d_f + 16 * T; a.t_final = d_f + 25 * T;
+  a.t0 = t0; a.dt = dt; a.alpha = alpha; a.beta = beta;
+  a.Qd = (double*)p_o; a.Qfd = a.Qd + 8 * T; a.Rd = a.Qd + 16 * T;
+  a.goffs = d_g; a.w_guess = (double*)p_w; a.q_guess = (double*)p_q;
+  KernelTimer tm(c);
+  k_slew_prep<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(a);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  TS_CUDA(c, cudaMemcpyAsync(Qd, a.Qd, 8 * T * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaMemcpyAsync(Qfd, a.Qfd, 8 * T * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaMemcpyAsync(Rd, a.Rd, 3 * T * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (w_guess) TS_CUDA(c, cudaMemcpyAsync(w_guess, p_w, (size_t)total * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (q_guess) TS_CUDA(c, cudaMemcpyAsync(q_guess, p_q, (size_t)total * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
+  return TS_OK;
+}
+
+int ts_tvlqr_sim_batch(ts_ctx* c, int64_t n, const int64_t* N_i, const int64_t* offs, const double* X_lqr, const double* U_lqr,
+                       const double* x0_lqr, const double* Jmat, const double* B_eci, const int64_t* B_offs, const int64_t* B_rows,
+                       const double* index_scale, const double* clock_rate, const double* t_final, const double* q_final,
+                       const uint32_t* stream_id, const ts_tvlqr_opts* opts, const double* noise, double* X_sim, double* U_sim,
+                       double* dX, double* K, int64_t* N_sim, double* slew_time, int pad) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!N_i || !offs || !X_lqr || !U_lqr || !x0_lqr || !Jmat || !B_eci || !B_offs || !B_rows || !index_scale ||
+                          !clock_rate || !t_final || !q_final)))
+    return fail(c, TS_ERR_ARG, "ts_tvlqr_sim_batch: null argument");
+  if (n == 0) return TS_OK;
+  ts_tvlqr_opts o;
+  if (opts) o = *opts; else ts_tvlqr_default_opts(&o);
+  if (o.noise_mode == 1 && !noise) return fail(c, TS_ERR_ARG, "ts_tvlqr_sim_batch: noise_mode 1 needs a noise array");
+  if (o.literal_postproc && !X_sim) return fail(c, TS_ERR_ARG, "ts_tvlqr_sim_batch: literal_postproc needs X_sim");
+  TS_CUDA(c, cudaSetDevice(c->device));
+  const size_t T = (size_t)n;
+  int64_t knots = 0, rows = 0;
+  for (int64_t t = 0; t < n; ++t) {
+    if (N_i[t] < 2) return fail(c, TS_ERR_ARG, "trial %lld: N < 2", (long long)t);
+    knots = std::max(knots, offs[t] + N_i[t]);
+    rows = std::max(rows, B_offs[t] + B_rows[t]);
+  }
+  int rc;
+  DevBuf dX_, dU_, dB, dNz, oX, oU, odX, oK;
+  if ((rc = dev_in(c, dX_, X_lqr, (size_t)knots * 8 * 8, pad))) return rc;
+  if ((rc = dev_in(c, dU_, U_lqr, (size_t)knots * 3 * 8, pad))) return rc;
+  if ((rc = dev_in(c, dB, B_eci, (size_t)rows * 3 * 8, pad))) return rc;
+  if (o.noise_mode == 1 && (rc = dev_in(c, dNz, noise, (size_t)knots * 36 * 8, pad))) return rc;
+  if (X_sim && (rc = dev_out(c, oX, X_sim, (size_t)knots * 8 * 8, pad))) return rc;
+  if (U_sim && (rc = dev_out(c, oU, U_sim, (size_t)knots * 3 * 8, pad))) return rc;
+  if (dX && (rc = dev_out(c, odX, dX, (size_t)knots * 6 * 8, pad))) return rc;
+  double* dK = nullptr;
+  if (K) {
+    if ((rc = dev_out(c, oK, K, (size_t)knots * 18 * 8, pad))) return rc;
+    dK = (double*)oK.d;
+  } else {
+    void* p;
+    if ((rc = scratch_reserve(c, 9, (size_t)knots * 18 * 8, &p))) return rc;
+    dK = (double*)p;
+  }
+  std::vector<int64_t> hi(4 * T);
+  memcpy(&hi[0], N_i, T * 8); memcpy(&hi[T], offs, T * 8); memcpy(&hi[2 * T], B_offs, T * 8); memcpy(&hi[3 * T], B_rows, T * 8);
+  std::vector<double> hf((8 + 9 + 1 + 1 + 1 + 4) * T);
+  memcpy(&hf[0], x0_lqr, 8 * T * 8); memcpy(&hf[8 * T], Jmat, 9 * T * 8); memcpy(&hf[17 * T], index_scale, T * 8);
+  memcpy(&hf[18 * T], clock_rate, T * 8); memcpy(&hf[19 * T], t_final, T * 8); memcpy(&hf[20 * T], q_final, 4 * T * 8);
+  int64_t* d_i; double* d_f; uint32_t* d_s = nullptr;
+  if ((rc = upload(c, 1, hi.data(), hi.size(), &d_i))) return rc;
+  if ((rc = upload(c, 2, hf.data(), hf.size(), &d_f))) return rc;
+  if (stream_id && (rc = upload(c, 3, stream_id, T, &d_s))) return rc;
+  void* p_o;
+  if ((rc = scratch_reserve(c, 5, T * 16, &p_o))) return rc;
+  K4Args a;
+  a.n_trials = n; a.N_i = d_i; a.offs = d_i + T; a.B_offs = d_i + 2 * T; a.B_rows = d_i + 3 * T;
+  a.X_lqr = (const double*)dX_.d; a.U_lqr = (const double*)dU_.d; a.x0_lqr = d_f; a.Jmat = d_f + 8 * T;
+  a.B_eci = (const double*)dB.d; a.index_scale = d_f + 17 * T; a.clock_rate = d_f + 18 * T; a.t_final = d_f + 19 * T;
+  a.q_final = d_f + 20 * T; a.stream_id = d_s;
+  memcpy(&a.opts, &o, sizeof(o));
+  a.noise = (o.noise_mode == 1) ? (const double*)dNz.d : nullptr;
+  a.X_sim = X_sim ? (double*)oX.d : nullptr; a.U_sim = U_sim ? (double*)oU.d : nullptr; a.dX = dX ? (double*)odX.d : nullptr;
+  a.K = dK; a.N_sim = (int64_t*)p_o; a.slew_time = (double*)((int64_t*)p_o + T);
+  KernelTimer tm(c);
+  k4_tvlqr_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(a);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  if (X_sim && (rc = dev_back(c, oX, X_sim, (size_t)knots * 8 * 8))) return rc;
+  if (U_sim && (rc = dev_back(c, oU, U_sim, (size_t)knots * 3 * 8))) return rc;
+  if (dX && (rc = dev_back(c, odX, dX, (size_t)knots * 6 * 8))) return rc;
+  if (K && (rc = dev_back(c, oK, K, (size_t)knots * 18 * 8))) return rc;
+  if (N_sim) TS_CUDA(c, cudaMemcpyAsync(N_sim, a.N_sim, T * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (slew_time) TS_CUDA(c, cudaMemcpyAsync(slew_time, a.slew_time, T * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
+  return TS_OK;
+}
+
+// ---------------------------------------------------------------------------- fused Monte-Carlo
+// Algorithmic FLOP per unit (SURVEY.md section 8d / DESIGN.md): IGRF sample 2393 (2243 + rotations),
+// rk3 Jacobian 2600 + backward step 3500 per knot-iteration, 500 per line-search rollout knot,
+// TVLQR ~7700 per knot.
+static const double FL_FIELD = 2393.0, FL_ITER = 6100.0, FL_ROLL = 500.0, FL_TVLQR = 7700.0;
+
+int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts, const double* x0,
+                       const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
+                       ts_trial_outcome* out, ts_mc_stats* stats) {
+  if (!c) return TS_ERR_ARG;
+  if (!cfg || !kep6 || !fopts || !x0 || !xf || !Jmat || !out) return fail(c, TS_ERR_ARG, "ts_monte_carlo_run: null argument");
+  const int64_t n = cfg->n_trials;
+  if (n < 0) return fail(c, TS_ERR_ARG, "n_trials < 0");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return TS_OK;
+  if (!(cfg->dt > 0) || cfg->N_scope < 1 || !(cfg->tf > cfg->t0)) return fail(c, TS_ERR_ARG, "ts_monte_carlo_run: bad config");
+  TS_CUDA(c, cudaSetDevice(c->device));
+  const int64_t nf = cfg->shared_orbit ? 1 : n;
+  const size_t NF = (size_t)nf;
+  int rc;
+  cudaEvent_t e[6];
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&e[i]);
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]); } } evg{e};
+
+  // ---- stage 1: scoping pass (2*N_scope samples per orbit) + gramian cutoff
+  std::vector<ts_field_opts> fo(NF);
+  std::vector<int64_t> offs_s(NF + 1);
+  bool any13 = false, any10 = false;
+  for (int64_t f = 0; f < nf; ++f) {
+    fo[f] = fopts[f];
+    fo[f].t0 = cfg->t0; fo[f].tf = cfg->tf; fo[f].N = cfg->N_scope;
+    if (!(fo[f].igrf_date >= 1900.0 && fo[f].igrf_date <= 2025.0)) return fail(c, TS_ERR_DATE, "orbit %lld: IGRF date outside [1900, 2025]", (long long)f);
+    (igrf_nmax_for_date(fo[f].igrf_date) == 13 ? any13 : any10) = true;
+    offs_s[f] = 2 * cfg->N_scope * f;
+  }
+  offs_s[nf] = 2 * cfg->N_scope * nf;
+  double* d_kep; ts_field_opts_dev* d_fo; int64_t* d_offs_s;
+  if ((rc = upload(c, 1, kep6, 6 * NF, &d_kep))) return rc;
+  if ((rc = upload(c, 2, (const ts_field_opts_dev*)fo.data(), NF, &d_fo))) return rc;
+  if ((rc = upload(c, 3, offs_s.data(), NF + 1, &d_offs_s))) return rc;
+  void *p_pos, *p_Bs, *p_sm;
+  if ((rc = scratch_reserve(c, 0, (size_t)(offs_s[nf] + nf) * 3 * 8, &p_pos))) return rc;
+  if ((rc = scratch_reserve(c, 7, (size_t)offs_s[nf] * 3 * 8, &p_Bs))) return rc;
+  if ((rc = scratch_reserve(c, 10, NF * 32, &p_sm))) return rc;
+  std::vector<int64_t> rows_s(NF, 2 * cfg->N_scope);
+  std::vector<double> dts(NF, (cfg->tf - cfg->t0) / (double)cfg->N_scope), cuts(NF, cfg->cutoff);
+  int64_t* d_rows_s = (int64_t*)p_sm;
+  double* d_dts = (double*)((char*)p_sm + NF * 8);
+  double* d_cuts = (double*)((char*)p_sm + NF * 16);
+  int64_t* d_idx = (int64_t*)((char*)p_sm + NF * 24);
+  TS_CUDA(c, cudaMemcpyAsync(d_rows_s, rows_s.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
+  TS_CUDA(c, cudaMemcpyAsync(d_dts, dts.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
+  TS_CUDA(c, cudaMemcpyAsync(d_cuts, cuts.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
+  cudaEventRecord(e[0], c->stream);
+  k2a_orbit_euler<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, d_kep, d_fo, d_offs_s, nullptr, (double*)p_pos, nullptr);
+  c->launches++;
+  {
+    dim3 grid((unsigned)nf, (unsigned)((2 * cfg->N_scope + K2B_THREADS - 1) / K2B_THREADS));
+    if (any13) { k2b_field_rows<13><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 13); c->launches++; }
+    if (any10) { k2b_field_rows<10><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 10); c->launches++; }
+  }
+  k2c_gramian_cutoff<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, (double*)p_Bs, d_offs_s, d_rows_s, d_dts, d_cuts, nullptr, d_idx);
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  std::vector<int64_t> idx(NF);
+  TS_CUDA(c, cudaMemcpyAsync(idx.data(), d_idx, NF * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+
+  // ---- host: horizons (TortoiseSat.jl:82-86), fine-pass layout
+  std::vector<double> tfin(NF, 0.0);
+  std::vector<int64_t> Nf(NF, 0), offs_f(NF + 1, 0), lim(NF, 0);
+  std::vector<ts_field_opts> fo2(NF);
+  int64_t maxNf = 1;
+  double field_samples = 0.0;
+  for (int64_t f = 0; f < nf; ++f) {
+    fo2[f] = fo[f];
+    field_samples += 2.0 * (double)cfg->N_scope - 1.0;
+    if (idx[f] > 0) {
+      tfin[f] = (double)idx[f] * (cfg->tf - cfg->t0) / (double)cfg->N_scope;
+      Nf[f] = (int64_t)floor((tfin[f] - cfg->t0) / cfg->dt);
+    }
+    if (Nf[f] < 2) { Nf[f] = 0; fo2[f].N = 1; fo2[f].tf = cfg->t0 + 1.0; lim[f] = 1; offs_f[f + 1] = offs_f[f] + 2; continue; }
+    fo2[f].tf = tfin[f];
+    fo2[f].N = Nf[f];
+    // rows the solver / replay can index: floor(x8*N + 1), x8 <= N*dt/(tf-t0)   (DerivFunction.jl:28,44)
+    const double x8max = (double)(Nf[f] + 1) * cfg->dt / (cfg->tf - cfg->t0);
+    int64_t need = (int64_t)floor(x8max * (double)Nf[f] + 1.0) + 4;
+    if (need > 2 * Nf[f] - 1) need = 2 * Nf[f] - 1;
+    lim[f] = need;
+    field_samples += (double)need;
+    offs_f[f + 1] = offs_f[f] + 2 * Nf[f];
+    maxNf = std::max(maxNf, Nf[f]);
+  }
+  // active trials
+  std::vector<int64_t> act;
+  act.reserve((size_t)n);
+  for (int64_t t = 0; t < n; ++t) {
+    const int64_t f = cfg->shared_orbit ? 0 : t;
+    if (Nf[f] >= 2) act.push_back(t);
+    else {
+      memset(&out[t], 0, sizeof(out[t]));
+      out[t].status = TS_ST_NO_CUTOFF;
+    }
+  }
+  const int64_t na = (int64_t)act.size();
+  const size_t NA = (size_t)na;
+  double ms_field = 0, ms_prep = 0, ms_solve = 0, ms_tvlqr = 0;
+  if (na > 0) {
+    // ---- stage 2: fine field tables
+    ts_field_opts_dev* d_fo2; int64_t *d_offs_f, *d_lim;
+    if ((rc = upload(c, 2, (const ts_field_opts_dev*)fo2.data(), NF, &d_fo2))) return rc;
+    if ((rc = upload(c, 3, offs_f.data(), NF + 1, &d_offs_f))) return rc;
+    if ((rc = upload(c, 11, lim.data(), NF, &d_lim))) return rc;
+    void* p_pos2;
+    if ((rc = scratch_reserve(c, 0, std::max((size_t)(offs_s[nf] + nf) * 3 * 8, (size_t)(offs_f[nf] + nf) * 3 * 8), &p_pos2))) return rc;
+    // per-trial layout
+    std::vector<int64_t> hi(4 * NA + 1);
+    std::vector<double> hf((8 + 8 + 9 + 1 + 1 + 1 + 8 + 4) * NA);
+    int64_t knots = 0;
+    for (int64_t a = 0; a < na; ++a) {
+      const int64_t t = act[a], f = cfg->shared_orbit ? 0 : t;
+      hi[a] = Nf[f];
+      hi[NA + a] = knots;
+      hi[2 * NA + a] = offs_f[f];
+      hi[3 * NA + a] = 2 * Nf[f];
+      knots += Nf[f];
+      memcpy(&hf[8 * a], x0 + 8 * t, 64);
+      memcpy(&hf[8 * NA + 8 * a], xf + 8 * t, 64);
+      memcpy(&hf[16 * NA + 9 * a], Jmat + 9 * t, 72);
+      hf[25 * NA + a] = tfin[f];
+      hf[26 * NA + a] = (double)Nf[f];
+      hf[27 * NA + a] = 1.0 / (cfg->tf - cfg->t0);
+      // x0_lqr (TortoiseSat.jl:227-234): omega from x0, attitude perturbed by q_noise0, clock 0
+      double* xl = &hf[28 * NA + 8 * a];
+      for (int i = 0; i < 3; ++i) xl[i] = x0[8 * t + i];
+      const double* q0 = x0 + 8 * t + 3;
+      if (q_noise0) {
+        const double* qn = q_noise0 + 3 * t;
+        const double th = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2]);
+        const double sh = sin(th / 2);
+        const double qp[4] = {cos(th / 2), qn[0] / th * sh, qn[1] / th * sh, qn[2] / th * sh};
+        ts::qmult(q0, qp, xl + 3);
+      } else {
+        for (int i = 0; i < 4; ++i) xl[3 + i] = q0[i];
+      }
+      xl[7] = 0.0;
+      memcpy(&hf[36 * NA + 4 * a], xf + 8 * t + 3, 32);
+    }
+    hi[4 * NA] = knots;
+    int64_t* d_i; double* d_f;
+    if ((rc = upload(c, 12, hi.data(), hi.size(), &d_i))) return rc;
+    if ((rc = upload(c, 13, hf.data(), hf.size(), &d_f))) return rc;
+    // device block: fine field tables, weights, X, U, outcomes, slew times
+    const size_t b_B = (size_t)offs_f[nf] * 3 * 8, b_w = 19 * NA * 8, b_X = (size_t)knots * 8 * 8, b_U = (size_t)knots * 3 * 8,
+                 b_o = NA * sizeof(ts_trial_outcome), b_s = NA * 16;
+    void* p_blk;
+    if ((rc = scratch_reserve(c, 8, b_B + b_w + b_X + b_U + b_o + b_s + 512, &p_blk))) return rc;
+    char* w = (char*)p_blk;
+    double* d_Bf = (double*)w; w += b_B;
+    double* d_Qd = (double*)w; w += b_w;
+    double* d_X = (double*)w; w += b_X;
+    double* d_U = (double*)w; w += b_U;
+    ts_trial_outcome_dev* d_out = (ts_trial_outcome_dev*)w; w += b_o;
+    int64_t* d_nsim = (int64_t*)w; double* d_slew = (double*)(w + NA * 8);
+    cudaEventRecord(e[1], c->stream);  // (stage-1 time = e0..sync above; fine pass added below)
+    k2a_orbit_euler<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, d_kep, d_fo2, d_offs_f, d_lim, (double*)p_pos2, nullptr);
+    c->launches++;
+    {
+      int64_t maxlim = 1;
+      for (int64_t f = 0; f < nf; ++f) maxlim = std::max(maxlim, 2 * std::max<int64_t>(Nf[f], 1));
+      dim3 grid((unsigned)nf, (unsigned)((maxlim + K2B_THREADS - 1) / K2B_THREADS));
+      if (any13) { k2b_field_rows<13><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo2, d_offs_f, d_lim, (double*)p_pos2, d_Bf, 13); c->launches++; }
+      if (any10) { k2b_field_rows<10><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo2, d_offs_f, d_lim, (double*)p_pos2, d_Bf, 10); c->launches++; }
+    }
+    cudaEventRecord(e[2], c->stream);
+    // ---- stage 3: eigen-axis guess + Bryson weights
+    PrepArgs pa;
+    pa.n_trials = na; pa.x0 = d_f; pa.xf = d_f + 8 * NA; pa.Jmat = d_f + 16 * NA; pa.t_final = d_f + 25 * NA;
+    pa.t0 = cfg->t0; pa.dt = cfg->dt; pa.alpha = cfg->alpha; pa.beta = cfg->beta;
+    pa.Qd = d_Qd; pa.Qfd = d_Qd + 8 * NA; pa.Rd = d_Qd + 16 * NA;
+    pa.goffs = nullptr; pa.w_guess = nullptr; pa.q_guess = nullptr;
+    k_slew_prep<<<(unsigned)((na + 127) / 128), 128, 0, c->stream>>>(pa);
+    c->launches++;
+    cudaEventRecord(e[3], c->stream);
+    // ---- stage 4: AL-iLQR
+    K3Args ka;
+    ka.n_trials = na;
+    ka.N_i = d_i; ka.offs = d_i + NA; ka.B_offs = d_i + 2 * NA; ka.B_rows = d_i + 3 * NA;
+    ka.x0 = d_f; ka.xf = d_f + 8 * NA; ka.Jmat = d_f + 16 * NA; ka.Qd = pa.Qd; ka.Qfd = pa.Qfd; ka.Rd = pa.Rd;
+    ka.index_scale = d_f + 26 * NA; ka.clock_rate = d_f + 27 * NA;
+    ka.B_eci = d_Bf; ka.dt = cfg->dt; ka.U0 = nullptr;
+    memcpy(&ka.opts, &cfg->ilqr, sizeof(ka.opts));
+    ka.X = d_X; ka.U = d_U; ka.K = nullptr; ka.out = d_out;
+    if ((rc = k3_launch(c, ka, hi.data()))) return rc;
+    cudaEventRecord(e[4], c->stream);
+    // ---- stage 5: TVLQR replay + slew-time rule
+    if (cfg->run_tvlqr) {
+      void* p_K;
+      if ((rc = scratch_reserve(c, 9, (size_t)knots * 18 * 8, &p_K))) return rc;
+      uint32_t* d_sid = nullptr;
+      std::vector<uint32_t> sid(NA);
+      for (int64_t a = 0; a < na; ++a) sid[a] = stream_id ? stream_id[act[a]] : (uint32_t)act[a];
+      if ((rc = upload(c, 14, sid.data(), NA, &d_sid))) return rc;
+      K4Args k4;
+      k4.n_trials = na; k4.N_i = d_i; k4.offs = d_i + NA; k4.B_offs = d_i + 2 * NA; k4.B_rows = d_i + 3 * NA;
+      k4.X_lqr = d_X; k4.U_lqr = d_U; k4.x0_lqr = d_f + 28 * NA; k4.Jmat = d_f + 16 * NA; k4.B_eci = d_Bf;
+      k4.index_scale = d_f + 26 * NA; k4.clock_rate = d_f + 27 * NA; k4.t_final = d_f + 25 * NA; k4.q_final = d_f + 36 * NA;
+      k4.stream_id = d_sid;
+      memcpy(&k4.opts, &cfg->tvlqr, sizeof(k4.opts));
+      k4.opts.dt = cfg->dt; k4.opts.t0 = cfg->t0;
+      if (k4.opts.noise_mode == 1) k4.opts.noise_mode = 2;  // no explicit array in the fused path
+      k4.opts.literal_postproc = 0;                          // needs X_sim storage; fused path uses the fixed rule (Q12)
+      k4.noise = nullptr; k4.X_sim = nullptr; k4.U_sim = nullptr; k4.dX = nullptr; k4.K = (double*)p_K;
+      k4.N_sim = d_nsim; k4.slew_time = d_slew;
+      k4_tvlqr_kernel<<<(unsigned)((na + 63) / 64), 64, 0, c->stream>>>(k4);
+      c->launches++;
+    }
+    cudaEventRecord(e[5], c->stream);
+    TS_CUDA(c, cudaGetLastError());
+    std::vector<ts_trial_outcome> oa(NA);
+    std::vector<double> slew(NA, 0.0);
+    TS_CUDA(c, cudaMemcpyAsync(oa.data(), d_out, b_o, cudaMemcpyDeviceToHost, c->stream));
+    if (cfg->run_tvlqr) TS_CUDA(c, cudaMemcpyAsync(slew.data(), d_slew, NA * 8, cudaMemcpyDeviceToHost, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e[0], e[1]); ms_field = ms;
+    cudaEventElapsedTime(&ms, e[1], e[2]); ms_field += ms;
+    cudaEventElapsedTime(&ms, e[2], e[3]); ms_prep = ms;
+    cudaEventElapsedTime(&ms, e[3], e[4]); ms_solve = ms;
+    cudaEventElapsedTime(&ms, e[4], e[5]); ms_tvlqr = ms;
+    for (int64_t a = 0; a < na; ++a) {
+      const int64_t t = act[a], f = cfg->shared_orbit ? 0 : t;
+      out[t] = oa[a];
+      out[t].t_final = tfin[f];
+      out[t].slew_time = cfg->run_tvlqr ? slew[a] : 0.0;
+      const double kn = (double)(Nf[f] - 1);
+      out[t].flops = kn * ((double)oa[a].inner_iters * FL_ITER + (double)oa[a].ls_rollouts * FL_ROLL) + (cfg->run_tvlqr ? kn * FL_TVLQR : 0.0);
+    }
+  }
+  c->last_kernel_ms = ms_field + ms_prep + ms_solve + ms_tvlqr;
+  if (stats) {
+    stats->n_trials = n;
+    stats->flops = field_samples * FL_FIELD;
+    for (int64_t t = 0; t < n; ++t) {
+      const ts_trial_outcome& o = out[t];
+      if (o.status == TS_ST_NO_CUTOFF) { stats->n_no_cutoff++; continue; }
+      if (o.status == TS_ST_CONVERGED) stats->n_converged++;
+      stats->sum_t_final += o.t_final;
+      stats->sum_inner_iters += o.inner_iters;
+      stats->sum_ls_rollouts += o.ls_rollouts;
+      stats->sum_knots += (double)o.N;
+      stats->flops += o.flops;
+      if (cfg->run_tvlqr) {
+        if (o.slew_time == o.t_final) stats->n_fail_slew++;
+        if (o.slew_time > 0.0) { stats->sum_slew_time += o.slew_time; stats->sum_slew_time_sq += o.slew_time * o.slew_time; }
+      }
+    }
+    stats->ms_field = ms_field; stats->ms_prep = ms_prep; stats->ms_solve = ms_solve; stats->ms_tvlqr = ms_tvlqr;
+  }
   return TS_OK;
 }
 

@@ -1,0 +1,345 @@
+// TVLQR closed-loop replay of ONE optimised slew (one thread per trial) and the
+// Monte-Carlo slew-time post-processing.  Replaces
+//   attitude_simulation(f!,f_gains!,:rk4,X,U,dt,x0,t0,tf,Q,R,Qf)   reference src/attitude_controller.jl:1-48
+//   attitude_lqr (ForwardDiff Jacobians of rk4(f_augmented(gain_simulator)))  :95-119
+//   attitude_lqr (G(q) projection to 6x6/6x3 + backward Riccati)            :50-93
+//   rk4 of simulator with fresh noise in every stage                        :122-132, src/simulator.jl:1-42
+//   slew-time / fail detection of the Monte-Carlo script                    src/monte_carlo.jl:237-262
+// Quirks kept: the linearisation step is dt^2 (attitude_controller.jl:111,137, Q6);
+// u/100 in the simulators (Q8); noise redrawn in each RK stage (Q7).
+#pragma once
+#include <stdint.h>
+
+#include "ilqr_math.cuh"
+#include "philox.cuh"
+
+struct ts_tvlqr_opts_dev {
+  double dt, t0, tf;
+  double Qd[6], Qfd[6], Rd[3];
+  int32_t dt_squared;   // 1 = reference behaviour (Q6)
+  int32_t noise_mode;   // 0 none, 1 explicit array, 2 Philox(seed, trial, step, stage)
+  uint64_t seed;
+  // slew-time detection (monte_carlo.jl:69-71,237-262)
+  double w_limit, ang_limit;
+  int32_t literal_postproc;  // 1 = keep the `[1:3,i]` column bug (Q12)
+  int32_t pad_;
+};
+
+namespace ts {
+
+// length(a:s:b) for Float64 ranges (t_sim / t_total)
+TS_HD long long range_len(double a, double s, double b) {
+  if (b < a) return 0;
+  return (long long)floor((b - a) / s + 1e-9) + 1;
+}
+
+TS_HD void inv3_general(const double A[9], double out[9]) {
+  // Gauss-Jordan with partial pivoting (== inv() of a dense 3x3)
+  double M[3][6];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      M[i][j] = A[i * 3 + j];
+      M[i][3 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 3; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 3; ++r)
+      if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (p != c)
+      for (int j = 0; j < 6; ++j) {
+        const double t = M[c][j];
+        M[c][j] = M[p][j];
+        M[p][j] = t;
+      }
+    const double piv = M[c][c];
+    for (int j = 0; j < 6; ++j) M[c][j] /= piv;
+    for (int r = 0; r < 3; ++r) {
+      if (r == c) continue;
+      const double f = M[r][c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < 6; ++j) M[r][j] -= f * M[c][j];
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] = M[i][3 + j];
+}
+
+struct TvlqrIn {
+  int N;                 // knots of the optimised trajectory
+  const double* X_lqr;   // N x 8
+  const double* U_lqr;   // (N-1) x 3
+  double x0[8];
+  Inertia I;
+  const double* Bt;
+  long long B_rows;
+  double index_scale, clock_rate;
+  const double* noise;   // (N_sim-1) x 4 x 9 or null
+  uint32_t trial;        // Philox stream id
+  double q_final[4];
+  double t_final, time_step;
+  long long trial_index_1based;
+};
+
+// stage clocks of rk4 on the decoupled clock state: c = rate*h; x8, x8+c/2, x8+c/2, x8+c; next = x8 + (c+2c+2c+c)/6
+TS_HD void clock_rk4(double x8, double rate, double h, double t[4], double& next) {
+#ifdef __CUDA_ARCH__
+  const double c = __dmul_rn(rate, h);
+  t[0] = x8;
+  t[1] = __dadd_rn(x8, __ddiv_rn(c, 2.0));
+  t[2] = t[1];
+  t[3] = __dadd_rn(x8, c);
+  const double s = __dadd_rn(__dadd_rn(__dadd_rn(c, __dmul_rn(2.0, c)), __dmul_rn(2.0, c)), c);
+  next = __dadd_rn(x8, __ddiv_rn(s, 6.0));
+#else
+  const volatile double c = rate * h;
+  volatile double hc = c / 2.0;
+  t[0] = x8;
+  t[1] = x8 + hc;
+  t[2] = t[1];
+  t[3] = x8 + c;
+  volatile double c2 = 2.0 * c;
+  volatile double s = c + c2;
+  s = s + c2;
+  s = s + c;
+  volatile double inc = s / 6.0;
+  next = x8 + inc;
+#endif
+}
+
+// simulator(dx,x,u) (simulator.jl:1-42) for the 7 dynamic states; nz = 9 scaled perturbations or null
+TS_HD void simulator7(const Inertia& I, const double x[7], const double u[3], const double* Bn, const double* nz, double dx[7]) {
+  double om[3] = {x[0], x[1], x[2]};
+  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  double q[4] = {x[3] / nq, x[4] / nq, x[5] / nq, x[6] / nq};
+  double Bf[3] = {Bn[0], Bn[1], Bn[2]};
+  if (nz) {
+    for (int i = 0; i < 3; ++i) om[i] = x[i] + nz[i];
+    const double th = sqrt(nz[3] * nz[3] + nz[4] * nz[4] + nz[5] * nz[5]);
+    const double sh = sin(th / 2);
+    const double qn[4] = {cos(th / 2), nz[3] / th * sh, nz[4] / th * sh, nz[5] / th * sh};
+    double q2[4];
+    qmult(q, qn, q2);
+    for (int i = 0; i < 4; ++i) q[i] = q2[i];
+    for (int i = 0; i < 3; ++i) Bf[i] = Bn[i] + nz[6 + i];
+  }
+  const double w4[4] = {0.0, om[0], om[1], om[2]};
+  double qd[4], BB[3], tau[3], Jw[3], wJw[3];
+  qmult(q, w4, qd);
+  qrot(q, Bf, BB);
+  const double us[3] = {u[0] / 100.0, u[1] / 100.0, u[2] / 100.0};
+  cross3(us, BB, tau);
+  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * om[0] + I.J[i * 3 + 1] * om[1] + I.J[i * 3 + 2] * om[2];
+  cross3(om, Jw, wJw);
+  const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
+  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
+  for (int i = 0; i < 4; ++i) dx[3 + i] = 0.5 * qd[i];
+}
+
+// Gains K ((N-1) x 18, row-major 3x6 per knot) -- attitude_lqr, both methods.
+TS_HD void tvlqr_gains(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, double* K) {
+  const int N = in.N;
+  const double h = o.dt_squared ? o.dt * o.dt : o.dt;
+  double S[36];
+  for (int i = 0; i < 36; ++i) S[i] = 0.0;
+  for (int i = 0; i < 6; ++i) S[i * 6 + i] = o.Qfd[i];
+  for (int k = N - 2; k >= 0; --k) {
+    const double* xk = in.X_lqr + (long long)k * 8;
+    const double* xn_ = in.X_lqr + (long long)(k + 1) * 8;
+    double tcl[4], nxt;
+    clock_rk4(xk[7], in.clock_rate, h, tcl, nxt);
+    const double* Br[4];
+    for (int s = 0; s < 4; ++s) Br[s] = in.Bt + (long long)field_row(tcl[s], in.index_scale, in.B_rows) * 3;
+    double xo[7], AB[70];
+    rk4_jac7<1>(in.I, xk, in.U_lqr + (long long)k * 3, Br[0], Br[1], Br[2], Br[3], h, xo, AB);
+    // G(q) = [-v'; s I + hat(v)]   (attitude_controller.jl:59-71)
+    double Gk[12], Gn[12];
+    {
+      const double s = xk[3], v0 = xk[4], v1 = xk[5], v2 = xk[6];
+      const double g[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
+      for (int i = 0; i < 12; ++i) Gk[i] = g[i];
+    }
+    {
+      const double s = xn_[3], v0 = xn_[4], v1 = xn_[5], v2 = xn_[6];
+      const double g[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
+      for (int i = 0; i < 12; ++i) Gn[i] = g[i];
+    }
+    // T1 = perm_Gn * [Aq | Bq]  (6 x 10): rows 0..2 = rows 0..2 of AB; rows 3..5 = Gn' * rows 3..6
+    double T1[60];
+    for (int j = 0; j < 10; ++j) {
+      for (int i = 0; i < 3; ++i) T1[i * 10 + j] = AB[i * 10 + j];
+      for (int i = 0; i < 3; ++i) {
+        double s = 0.0;
+        // the reference multiplies the full 6x7 permutation matrix: zeros from the identity block first
+        for (int l = 0; l < 4; ++l) s += Gn[l * 3 + i] * AB[(3 + l) * 10 + j];
+        T1[(3 + i) * 10 + j] = s;
+      }
+    }
+    // A = T1[:, 0:7] * perm_Gk (6x6), B = T1[:, 7:10] (6x3)
+    double A[36], B[18];
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < 3; ++j) A[i * 6 + j] = T1[i * 10 + j];
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 4; ++l) s += T1[i * 10 + 3 + l] * Gk[l * 3 + j];
+        A[i * 6 + 3 + j] = s;
+      }
+      for (int j = 0; j < 3; ++j) B[i * 3 + j] = T1[i * 10 + 7 + j];
+    }
+    // K = inv(R + B'SB) (B'SA) ; S = Q + K'RK + (A-BK)'S(A-BK)
+    double SB[18], SA[36], BSB[9], BSA[18], Minv[9], Kk[18], Acl[36], SAcl[36];
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * B[l * 3 + j];
+        SB[i * 3 + j] = s;
+      }
+      for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * A[l * 6 + j];
+        SA[i * 6 + j] = s;
+      }
+    }
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SB[l * 3 + j];
+        BSB[i * 3 + j] = s + ((i == j) ? o.Rd[i] : 0.0);
+      }
+      for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SA[l * 6 + j];
+        BSA[i * 6 + j] = s;
+      }
+    }
+    inv3_general(BSB, Minv);
+    double* Kout = K + (long long)k * 18;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 3; ++l) s += Minv[i * 3 + l] * BSA[l * 6 + j];
+        Kk[i * 6 + j] = s;
+        Kout[i * 6 + j] = s;
+      }
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 3; ++l) s += B[i * 3 + l] * Kk[l * 6 + j];
+        Acl[i * 6 + j] = A[i * 6 + j] - s;
+      }
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * Acl[l * 6 + j];
+        SAcl[i * 6 + j] = s;
+      }
+    double Sn[36];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = (i == j) ? o.Qd[i] : 0.0;
+        double kr = 0.0;
+        for (int l = 0; l < 3; ++l) kr += Kk[l * 6 + i] * o.Rd[l] * Kk[l * 6 + j];
+        s += kr;
+        double t = 0.0;
+        for (int l = 0; l < 6; ++l) t += Acl[l * 6 + i] * SAcl[l * 6 + j];
+        Sn[i * 6 + j] = s + t;
+      }
+    for (int i = 0; i < 36; ++i) S[i] = Sn[i];
+  }
+}
+
+// Closed-loop replay + slew-time detection.  Outputs nullable.  Returns N_sim; *slew_time_out as
+// monte_carlo.jl:237-262 (== t_final when the trial "fails").
+TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
+                             double* dX, double* slew_time_out) {
+  const int N = in.N;
+  long long N_sim = range_len(o.t0, o.dt, o.tf);
+  if (N_sim > N) N_sim = range_len(o.t0, o.dt, o.tf - o.dt);
+  if (N_sim > N) N_sim = N;
+  double x[8];
+  for (int i = 0; i < 8; ++i) x[i] = in.x0[i];
+  double slew = in.t_final;
+  const double qi[4] = {in.q_final[0], -in.q_final[1], -in.q_final[2], -in.q_final[3]};
+  // literal post-processing reads omega of column = trial index (quirk Q12): that column is only
+  // known once the replay has reached it, so the literal mode evaluates the rule in a second pass.
+  for (long long k = 0; k < N_sim; ++k) {
+    if (X_sim)
+      for (int i = 0; i < 8; ++i) X_sim[k * 8 + i] = x[i];
+    if (!o.literal_postproc) {
+      const long long j = k + 1;
+      const double wn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+      double qe[4];
+      qmult(qi, x + 3, qe);
+      const double ang = 2 * acos(fmin(qe[0], 1.0));
+      if (j > 10 && wn < o.w_limit && ang < o.ang_limit && slew == in.t_final) slew = in.time_step * (double)j;
+    }
+    if (k == N_sim - 1) {
+      if (U_sim) U_sim[k * 3 + 0] = U_sim[k * 3 + 1] = U_sim[k * 3 + 2] = 0.0;
+      if (dX)
+        for (int i = 0; i < 6; ++i) dX[k * 6 + i] = 0.0;
+      break;
+    }
+    const double* xr = in.X_lqr + k * 8;
+    double d6[6], u[3];
+    for (int i = 0; i < 3; ++i) d6[i] = x[i] - xr[i];
+    {
+      const double qri[4] = {xr[3], -xr[4], -xr[5], -xr[6]};
+      double qe[4];
+      qmult(qri, x + 3, qe);
+      d6[3] = qe[1];
+      d6[4] = qe[2];
+      d6[5] = qe[3];
+    }
+    const double* Kk = K + k * 18;
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < 6; ++j) s += Kk[i * 6 + j] * d6[j];
+      u[i] = in.U_lqr[k * 3 + i] - s;
+    }
+    if (U_sim)
+      for (int i = 0; i < 3; ++i) U_sim[k * 3 + i] = u[i];
+    if (dX)
+      for (int i = 0; i < 6; ++i) dX[k * 6 + i] = d6[i];
+    // rk4(simulator) with per-stage noise
+    double tcl[4], nxt;
+    clock_rk4(x[7], in.clock_rate, o.dt, tcl, nxt);
+    double k1[7], k2[7], k3[7], k4[7], xs[7], nzb[9];
+    const double* nz[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int s = 0; s < 4; ++s) {
+      const double* Bn = in.Bt + (long long)field_row(tcl[s], in.index_scale, in.B_rows) * 3;
+      if (o.noise_mode == 1) nz[s] = in.noise + (k * 4 + s) * 9;
+      if (o.noise_mode == 2) {
+        tvlqr_noise(o.seed, in.trial, (uint32_t)k, (uint32_t)s, nzb);
+        nz[s] = nzb;
+      }
+      double* ks = (s == 0) ? k1 : (s == 1) ? k2 : (s == 2) ? k3 : k4;
+      if (s == 0)
+        for (int i = 0; i < 7; ++i) xs[i] = x[i];
+      simulator7(in.I, xs, u, Bn, nz[s], ks);
+      for (int i = 0; i < 7; ++i) ks[i] = ks[i] * o.dt;
+      if (s == 0)
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+      if (s == 1)
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k2[i] / 2.0;
+      if (s == 2)
+        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i];
+    }
+    for (int i = 0; i < 7; ++i) x[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0;
+    x[7] = nxt;
+  }
+  if (o.literal_postproc && X_sim) {
+    for (long long j = 1; j <= N_sim; ++j) {
+      long long col = in.trial_index_1based;
+      if (col > N_sim) col = N_sim;
+      const double* w = X_sim + (col - 1) * 8;
+      const double wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      double qe[4];
+      qmult(qi, X_sim + (j - 1) * 8 + 3, qe);
+      const double ang = 2 * acos(fmin(qe[0], 1.0));
+      if (j > 10 && wn < o.w_limit && ang < o.ang_limit && slew == in.t_final) slew = in.time_step * (double)j;
+    }
+  }
+  if (slew_time_out) *slew_time_out = slew;
+  return N_sim;
+}
+
+}  // namespace ts

@@ -40,6 +40,50 @@ class IlqrOpts(C.Structure):
                                           "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")]
 
 
+class TvlqrOpts(C.Structure):
+    """ts_tvlqr_opts (include/tortoise_b200.h)."""
+    _fields_ = [("dt", C.c_double), ("t0", C.c_double), ("tf", C.c_double), ("Qd", C.c_double * 6), ("Qfd", C.c_double * 6),
+                ("Rd", C.c_double * 3), ("dt_squared", C.c_int32), ("noise_mode", C.c_int32), ("seed", C.c_uint64),
+                ("w_limit", C.c_double), ("ang_limit", C.c_double), ("literal_postproc", C.c_int32), ("pad_", C.c_int32)]
+
+
+class FieldOpts(C.Structure):
+    _fields_ = [("GM", C.c_double), ("mjd", C.c_double), ("igrf_date", C.c_double), ("field_radius_m", C.c_double),
+                ("t0", C.c_double), ("tf", C.c_double), ("N", C.c_int64)]
+
+
+class McConfig(C.Structure):
+    """ts_mc_config"""
+    _fields_ = [("n_trials", C.c_int64), ("shared_orbit", C.c_int32), ("run_tvlqr", C.c_int32), ("t0", C.c_double),
+                ("tf", C.c_double), ("N_scope", C.c_int64), ("cutoff", C.c_double), ("dt", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("ilqr", IlqrOpts), ("tvlqr", TvlqrOpts)]
+
+
+class McStats(C.Structure):
+    """ts_mc_stats"""
+    _fields_ = [(k, C.c_int64) for k in ("n_trials", "n_converged", "n_no_cutoff", "n_fail_slew")] + \
+               [(k, C.c_double) for k in ("sum_slew_time", "sum_slew_time_sq", "sum_t_final", "sum_inner_iters",
+                                          "sum_ls_rollouts", "sum_knots", "flops", "ms_field", "ms_prep", "ms_solve",
+                                          "ms_tvlqr")]
+
+
+def default_tvlqr_opts():
+    o = TvlqrOpts()
+    load_library().ts_tvlqr_default_opts(C.byref(o))
+    return o
+
+
+def default_mc_config(n_trials, shared_orbit=True, run_tvlqr=True, t0=0.0, tf=2400.0, N_scope=5000, cutoff=30.0, dt=0.2,
+                      alpha=0.1, beta=1e3):
+    """Defaults = the constants of src/monte_carlo.jl:37-78,169-171."""
+    cfg = McConfig()
+    cfg.n_trials, cfg.shared_orbit, cfg.run_tvlqr = n_trials, int(shared_orbit), int(run_tvlqr)
+    cfg.t0, cfg.tf, cfg.N_scope, cfg.cutoff, cfg.dt, cfg.alpha, cfg.beta = t0, tf, N_scope, cutoff, dt, alpha, beta
+    cfg.ilqr = default_ilqr_opts()
+    cfg.tvlqr = default_tvlqr_opts()
+    return cfg
+
+
 def default_ilqr_opts():
     o = IlqrOpts()
     load_library().ts_ilqr_default_opts(C.byref(o))
@@ -88,6 +132,11 @@ def load_library():
     L.ts_condition_cutoff_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
     L.ts_ilqr_default_opts.argtypes = [C.POINTER(IlqrOpts)]
     L.ts_ilqr_default_opts.restype = None
+    L.ts_tvlqr_default_opts.argtypes = [C.POINTER(TvlqrOpts)]
+    L.ts_tvlqr_default_opts.restype = None
+    L.ts_slew_weights_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_double] * 4 + [C.c_void_p] * 6
+    L.ts_tvlqr_sim_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 14 + [C.POINTER(TvlqrOpts)] + [C.c_void_p] * 7 + [C.c_int]
+    L.ts_monte_carlo_run.argtypes = [C.c_void_p, C.POINTER(McConfig)] + [C.c_void_p] * 8 + [C.POINTER(McStats)]
     L.ts_alilqr_solve_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 13 + [C.c_double, C.c_void_p,
                                                                                       C.POINTER(IlqrOpts)] + [C.c_void_p] * 4 + [C.c_int]
     _LIB = L
@@ -258,6 +307,74 @@ class Engine:
         return X, U, K, out, offs
 
 
+    # -- prep / K4 / fused MC ----------------------------------------------
+    def slew_weights_batch(self, x0, xf, Jmat, t_final, t0=0.0, dt=0.2, alpha=10.0, beta=1e3, want_guess=False):
+        """eigen_axis_slew + Bryson weights (eigen_axis_slew.jl:1-38, TortoiseSat.jl:157-168)."""
+        x0 = _f64(np.atleast_2d(x0))
+        T = x0.shape[0]
+        xf, Jmat, t_final = _f64(np.asarray(xf).reshape(T, 8)), _f64(np.asarray(Jmat).reshape(T, 9)), _f64(np.asarray(t_final).reshape(T))
+        Qd, Qfd, Rd = np.zeros((T, 8)), np.zeros((T, 8)), np.zeros((T, 3))
+        goffs = wg = qg = None
+        if want_guess:
+            nt = np.array([int(np.floor((tf_ - t0) / dt + 1e-9)) + 1 for tf_ in t_final], dtype=np.int64)
+            goffs = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
+            wg, qg = np.zeros((int(goffs[-1]), 3)), np.zeros((int(goffs[-1]), 4))
+        self._check(self.lib.ts_slew_weights_batch(self.h, T, _ptr(x0), _ptr(xf), _ptr(Jmat), _ptr(t_final), t0, dt, alpha, beta,
+                                                   _ptr(Qd), _ptr(Qfd), _ptr(Rd), None if goffs is None else _ptr(goffs),
+                                                   None if wg is None else _ptr(wg), None if qg is None else _ptr(qg)))
+        if want_guess:
+            return Qd, Qfd, Rd, wg, qg, goffs
+        return Qd, Qfd, Rd
+
+    def tvlqr_sim_batch(self, N_i, X_lqr, U_lqr, x0_lqr, Jmat, B_eci, B_offs, B_rows, index_scale, clock_rate, t_final, q_final,
+                        opts=None, noise=None, stream_id=None, want_traj=True):
+        """Batched attitude_simulation (attitude_controller.jl:1-48) + slew-time rule.  X_lqr (sum N, 8),
+        U_lqr (sum N, 3) ragged by offs = cumsum(N_i)."""
+        N_i = np.ascontiguousarray(N_i, dtype=np.int64)
+        T = N_i.shape[0]
+        offs = np.zeros(T + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(N_i)
+        tot = int(offs[-1])
+        X_lqr, U_lqr = _f64(X_lqr), _f64(U_lqr)
+        arr = lambda a, w: _f64(np.asarray(a, dtype=np.float64).reshape(T, w))
+        x0_lqr, Jmat, q_final = arr(x0_lqr, 8), arr(Jmat, 9), arr(q_final, 4)
+        B_eci = _f64(B_eci)
+        B_offs = np.ascontiguousarray(B_offs, dtype=np.int64)
+        B_rows = np.ascontiguousarray(B_rows, dtype=np.int64)
+        index_scale, clock_rate, t_final = _f64(index_scale), _f64(clock_rate), _f64(t_final)
+        o = opts if opts is not None else default_tvlqr_opts()
+        nz = None if noise is None else _f64(noise)
+        sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.uint32)
+        Xs = np.zeros((tot, 8)) if want_traj else None
+        Us = np.zeros((tot, 3)) if want_traj else None
+        dX = np.zeros((tot, 6)) if want_traj else None
+        K = np.zeros((tot, 3, 6)) if want_traj else None
+        nsim = np.zeros(T, dtype=np.int64)
+        slew = np.zeros(T)
+        pp = lambda a: None if a is None else _ptr(a)
+        self._check(self.lib.ts_tvlqr_sim_batch(self.h, T, _ptr(N_i), _ptr(offs), _ptr(X_lqr), _ptr(U_lqr), _ptr(x0_lqr), _ptr(Jmat),
+                                                _ptr(B_eci), _ptr(B_offs), _ptr(B_rows), _ptr(index_scale), _ptr(clock_rate),
+                                                _ptr(t_final), _ptr(q_final), pp(sid), C.byref(o), pp(nz), pp(Xs), pp(Us), pp(dX),
+                                                pp(K), _ptr(nsim), _ptr(slew), 0))
+        return Xs, Us, dX, K, nsim, slew, offs
+
+    def monte_carlo_run(self, cfg, kep6, fopts, x0, xf, Jmat, q_noise0=None, stream_id=None):
+        """Fused Monte-Carlo (monte_carlo.jl:118-262 with the solver block of TortoiseSat.jl:178-199).
+        fopts: structured array FIELD_OPTS_DTYPE (only GM, mjd, igrf_date, field_radius_m are read)."""
+        n = int(cfg.n_trials)
+        kep6 = _f64(np.atleast_2d(kep6))
+        fopts = np.ascontiguousarray(fopts, dtype=FIELD_OPTS_DTYPE)
+        x0, xf, Jmat = _f64(np.asarray(x0).reshape(n, 8)), _f64(np.asarray(xf).reshape(n, 8)), _f64(np.asarray(Jmat).reshape(n, 9))
+        qn = None if q_noise0 is None else _f64(np.asarray(q_noise0).reshape(n, 3))
+        sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.uint32)
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        st = McStats()
+        self._check(self.lib.ts_monte_carlo_run(self.h, C.byref(cfg), _ptr(kep6), fopts.ctypes.data, _ptr(x0), _ptr(xf), _ptr(Jmat),
+                                                None if qn is None else _ptr(qn), None if sid is None else _ptr(sid),
+                                                out.ctypes.data, C.byref(st)))
+        return out, st
+
+
 # ---------------------------------------------------------------------------
 # Reference-named free functions (scalar calls route to batch-of-1; correctness
 # path, not the performance path).  A module-level default engine is created on
@@ -346,3 +463,15 @@ def condition_based_time(B_gram, cutoff):
     """condition_based_time(B_gram,cutoff) (magnetic_toolbox.jl:14-31); B_gram 3 x 3 x rows."""
     G = np.ascontiguousarray(np.transpose(_f64(B_gram), (2, 0, 1)))
     return int(default_engine().condition_based_time_batch(G, [0], [G.shape[0]], [cutoff])[0])
+
+
+def eigen_axis_slew(x0, xf, t):
+    """eigen_axis_slew(x0,xf,t) -> (w_guess (nt x 3), q_guess (nt x 4))  (eigen_axis_slew.jl:1-38).
+    t must be a uniform range t0:dt:t_end, as in the reference."""
+    t = _f64(t)
+    x0p = np.concatenate([np.asarray(x0, dtype=float)[:7], [0.0]])
+    xfp = np.concatenate([np.asarray(xf, dtype=float)[:7], [0.0]])
+    dt = float(t[1] - t[0])
+    _, _, _, wg, qg, _ = default_engine().slew_weights_batch([x0p], [xfp], np.eye(3).reshape(1, 9), [float(t[-1])], t0=float(t[0]),
+                                                            dt=dt, want_guess=True)
+    return wg[:len(t)], qg[:len(t)]
