@@ -42,6 +42,9 @@ struct CpuTeam {
     sync();
     return r;
   }
+  void stage16(double* dst, const double* src, int n16) const { memcpy(dst, src, (size_t)n16 * 16); }
+  void stage_commit() const {}
+  void stage_wait(int) const {}
   double sum(double v) const {
     for (int off = 4; off >= 1; off >>= 1) {
       sh->xch[ln] = v;
@@ -77,6 +80,13 @@ void hs_rk3_jac7(const double* J9, const double* x7, const double* u3, const dou
   inv3_gj(I.J, I.Jinv);
   rk3_jac7<0>(I, x7, u3, B1, B2, B3, dt, xn7, AB70);
 }
+void hs_rk3_jac7_jvp(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
+                     double dt, double* colmajor70) {
+  Inertia I;
+  memcpy(I.J, J9, 72);
+  inv3_gj(I.J, I.Jinv);
+  rk3_jac7_jvp(I, x7, u3, B1, B2, B3, dt, colmajor70);
+}
 void hs_rk4_jac7(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
                  const double* B4, double dt, double* xn7, double* AB70) {
   Inertia I;
@@ -108,13 +118,13 @@ void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double
   in.clock_rate = clock_rate;
   in.U0 = U0;
   std::vector<double> xu((size_t)9 * N * 10), kd((size_t)N * 24), lam((size_t)N * 6), clk((size_t)N);
-  std::vector<int> rows((size_t)N * 3);
+  std::vector<double> bk((size_t)N * 10);
   TrialWork w;
   w.xu = xu.data();
   w.kd = kd.data();
   w.lam = lam.data();
   w.clk = clk.data();
-  w.rows = rows.data();
+  w.bk = bk.data();
   w.Nmax = N;
   TeamShared sh;
   ts_trial_outcome_dev oc[TEAM];

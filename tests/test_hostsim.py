@@ -33,6 +33,12 @@ def test_analytic_rk3_jacobian_vs_forward_mode_duals(J):
         assert np.max(np.abs(AB[:, :7] - A[:7, :7])) < 1e-14
         assert np.max(np.abs(AB[:, 7:] - B[:7])) < 1e-12 * max(1.0, np.max(np.abs(B)))
         assert np.all(A[:7, 7] == 0) and np.all(A[7, :7] == 0) and A[7, 7] == 1.0   # clock state decoupled (Q2)
+        # the register-resident JVP form the K3 kernel actually uses (column-major output)
+        cm = np.zeros((10, 7))
+        hs.hs_rk3_jac7_jvp(orc.P(np.ascontiguousarray(J)), orc.P(np.ascontiguousarray(x[:7])), orc.P(u), orc.P(r[0]), orc.P(r[1]),
+                           orc.P(r[2]), dt, orc.P(cm))
+        assert np.max(np.abs(cm.T[:, :7] - A[:7, :7])) < 1e-14
+        assert np.max(np.abs(cm.T[:, 7:] - B[:7])) < 1e-12 * max(1.0, np.max(np.abs(B)))
 
 
 CASES = [  # (slew angle deg, horizon s, goal mask, expected status)

@@ -20,5 +20,9 @@ args = dict(N_i=[base.N] * n, x0=x0, xf=np.tile(base.xf, (n, 1)), Jmat=np.tile(b
 X, U, K, out, offs = eng.alilqr_solve_batch(**args)
 ms = eng.last_kernel_ms()
 its = out["inner_iters"]
+i = int(np.argmax(its))
+print("slowest trial cycles: backward %.3g (linearise %.3g) forward %.3g ; per knot-iter: bwd %.0f (lin %.0f) fwd %.0f" % (
+    out["t_final"][i], out["flops"][i], out["slew_time"][i], out["t_final"][i] / (its[i] * base.N), out["flops"][i] / (its[i] * base.N),
+    out["slew_time"][i] / (its[i] * base.N)))
 print("n", n, "N", base.N, "kernel ms", ms, "status", np.bincount(out["status"], minlength=5).tolist(), "inner mean/max", its.mean(), its.max(),
       "ls mean", out["ls_rollouts"].mean(), "cycles/knot-iter (max trial, 1.9GHz)", ms * 1e-3 * 1.9e9 / (its.max() * base.N))

@@ -31,6 +31,16 @@ struct Inertia {
   double Jinv[9];
 };
 
+// 1/sqrt(s): one MUFU + Newton steps on the GPU instead of sqrt followed by four divisions
+TS_HD double rnorm(double s) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(s);
+#else
+  return 1.0 / sqrt(s);
+#endif
+}
+#define TS_SIXTH (1.0 / 6.0)
+
 TS_HD void cross3(const double a[3], const double b[3], double o[3]) {
   o[0] = a[1] * b[2] - a[2] * b[1];
   o[1] = a[2] * b[0] - a[0] * b[2];
@@ -60,8 +70,8 @@ TS_HD void qrot(const double q[4], const double r[3], double o[3]) {
 // u_scale_mode 0: u*1e-2 (DerivFunction.jl:37); 1: u/100 (simulator/gain_simulator) -- quirk Q8.
 template <int UMODE>
 TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7]) {
-  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
-  const double q[4] = {x[3] / nq, x[4] / nq, x[5] / nq, x[6] / nq};
+  const double inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  const double q[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
   const double w4[4] = {0.0, x[0], x[1], x[2]};
   double qd[4];
   qmult(q, w4, qd);
@@ -71,7 +81,7 @@ TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const d
   if (UMODE == 0) {
     us[0] = u[0] * 1.e-2; us[1] = u[1] * 1.e-2; us[2] = u[2] * 1.e-2;
   } else {
-    us[0] = u[0] / 100.0; us[1] = u[1] / 100.0; us[2] = u[2] / 100.0;
+    us[0] = u[0] * 0.01; us[1] = u[1] * 0.01; us[2] = u[2] * 0.01;
   }
   double tau[3], Jw[3], wJw[3];
   cross3(us, BB, tau);
@@ -86,13 +96,12 @@ TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const d
 template <int UMODE>
 TS_HD void dyn_f_jac(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7], double fx[49],
                      double fu[9]) {
-  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
-  const double inq = 1.0 / nq;
+  const double inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
   const double q[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
   const double s = q[0];
   const double v[3] = {q[1], q[2], q[3]};
   const double w[3] = {x[0], x[1], x[2]};
-  const double us_k = (UMODE == 0) ? 1.e-2 : (1.0 / 100.0);
+  const double us_k = 1.e-2;
   const double us[3] = {u[0] * us_k, u[1] * us_k, u[2] * us_k};
   // ---- value
   double vxB[3], t1[3], c2[3], BB[3];
@@ -195,13 +204,13 @@ TS_HD void rk3_step7(const Inertia& I, const double x[7], const double u[3], con
   double k1[7], k2[7], k3[7], xs[7];
   dyn_f<UMODE>(I, x, u, B1, k1);
   for (int i = 0; i < 7; ++i) k1[i] = k1[i] * dt;
-  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * k1[i];
   dyn_f<UMODE>(I, xs, u, B2, k2);
   for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
   for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] + 2.0 * k2[i];
   dyn_f<UMODE>(I, xs, u, B3, k3);
   for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
-  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0;
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) * TS_SIXTH;
 }
 
 // y (7x10) = fx (7x7) * M (7x10) [+ fu in columns 7..9 of rows 0..2], all scaled by dt.
@@ -230,7 +239,7 @@ TS_HD void rk3_jac7(const Inertia& I, const double x[7], const double u[3], cons
       K1[i * 10 + j] = a * dt;
     }
   // stage 2 at x2 = x + k1/2 : d x2 = [I|0] + K1/2
-  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * k1[i];
   dyn_f_jac<UMODE>(I, xs, u, B2, k2, fx, fu);
   for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
   for (int i = 0; i < 7; ++i)
@@ -244,10 +253,101 @@ TS_HD void rk3_jac7(const Inertia& I, const double x[7], const double u[3], cons
     for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) - K1[i * 10 + j] + 2.0 * K2[i * 10 + j];
   double K3[70];
   stage_chain(fx, fu, M, dt, K3);
-  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0;
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) * TS_SIXTH;
   for (int i = 0; i < 7; ++i)
     for (int j = 0; j < 10; ++j)
-      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 4.0 * K2[i * 10 + j] + K3[i * 10 + j]) / 6.0;
+      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 4.0 * K2[i * 10 + j] + K3[i * 10 + j]) * TS_SIXTH;
+}
+
+// ---- register-resident linearisation: Jacobian-vector products ------------------------------
+// The matrix form above keeps K1, K2, K3 and a stage Jacobian alive (~260 doubles) and spills;
+// the kernel instead pushes the 10 unit directions through the three stages one at a time with
+// analytic JVPs.  Live state: three StagePt (3 x 23 doubles) + one direction (~30 doubles).
+struct StagePt {
+  double inq, s, v[3], w[3], us[3], Bn[3], t1[3], BB[3], Jw[3];
+};
+// f(x,u) at a stage point + the intermediates its JVP needs
+TS_HD void stage_eval(const Inertia& I, const double x[7], const double u[3], const double* Bn, StagePt& sp, double dx[7]) {
+  sp.inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  sp.s = x[3] * sp.inq;
+  for (int i = 0; i < 3; ++i) {
+    sp.v[i] = x[4 + i] * sp.inq;
+    sp.w[i] = x[i];
+    sp.us[i] = u[i] * 1.e-2;
+    sp.Bn[i] = Bn[i];
+  }
+  double vxB[3], c2[3], tau[3], wJw[3];
+  cross3(sp.v, sp.Bn, vxB);
+  for (int i = 0; i < 3; ++i) sp.t1[i] = vxB[i] + sp.s * sp.Bn[i];
+  cross3(sp.v, sp.t1, c2);
+  for (int i = 0; i < 3; ++i) sp.BB[i] = sp.Bn[i] + 2.0 * c2[i];
+  cross3(sp.us, sp.BB, tau);
+  for (int i = 0; i < 3; ++i) sp.Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
+  cross3(sp.w, sp.Jw, wJw);
+  const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
+  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
+  dx[3] = 0.5 * (-(sp.v[0] * sp.w[0] + sp.v[1] * sp.w[1] + sp.v[2] * sp.w[2]));
+  dx[4] = 0.5 * (sp.s * sp.w[0] + (sp.v[1] * sp.w[2] - sp.v[2] * sp.w[1]));
+  dx[5] = 0.5 * (sp.s * sp.w[1] + (sp.v[2] * sp.w[0] - sp.v[0] * sp.w[2]));
+  dx[6] = 0.5 * (sp.s * sp.w[2] + (sp.v[0] * sp.w[1] - sp.v[1] * sp.w[0]));
+}
+// out = fx*vx + fu*vu at the stage point
+TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double vx[7], const double vu[3], double out[7]) {
+  const double dot = sp.s * vx[3] + sp.v[0] * vx[4] + sp.v[1] * vx[5] + sp.v[2] * vx[6];
+  const double ds = (vx[3] - sp.s * dot) * sp.inq;
+  const double dv[3] = {(vx[4] - sp.v[0] * dot) * sp.inq, (vx[5] - sp.v[1] * dot) * sp.inq, (vx[6] - sp.v[2] * dot) * sp.inq};
+  const double dw[3] = {vx[0], vx[1], vx[2]};
+  double a[3], b[3];
+  cross3(dv, sp.w, a);
+  cross3(sp.v, dw, b);
+  out[3] = 0.5 * (-((dv[0] * sp.w[0] + dv[1] * sp.w[1] + dv[2] * sp.w[2]) + (sp.v[0] * dw[0] + sp.v[1] * dw[1] + sp.v[2] * dw[2])));
+  for (int i = 0; i < 3; ++i) out[4 + i] = 0.5 * (ds * sp.w[i] + sp.s * dw[i] + a[i] + b[i]);
+  double dt1[3], c1[3], c2[3];
+  cross3(dv, sp.Bn, dt1);
+  for (int i = 0; i < 3; ++i) dt1[i] += ds * sp.Bn[i];
+  cross3(dv, sp.t1, c1);
+  cross3(sp.v, dt1, c2);
+  const double dBB[3] = {2.0 * (c1[0] + c2[0]), 2.0 * (c1[1] + c2[1]), 2.0 * (c1[2] + c2[2])};
+  const double dus[3] = {vu[0] * 1.e-2, vu[1] * 1.e-2, vu[2] * 1.e-2};
+  double t1[3], t2[3], g1[3], g2[3], Jdw[3];
+  cross3(dus, sp.BB, t1);
+  cross3(sp.us, dBB, t2);
+  for (int i = 0; i < 3; ++i) Jdw[i] = I.J[i * 3 + 0] * dw[0] + I.J[i * 3 + 1] * dw[1] + I.J[i * 3 + 2] * dw[2];
+  cross3(dw, sp.Jw, g1);
+  cross3(sp.w, Jdw, g2);
+  const double r[3] = {t1[0] + t2[0] - g1[0] - g2[0], t1[1] + t2[1] - g1[1] - g2[1], t1[2] + t2[2] - g1[2] - g2[2]};
+  for (int i = 0; i < 3; ++i) out[i] = I.Jinv[i * 3 + 0] * r[0] + I.Jinv[i * 3 + 1] * r[1] + I.Jinv[i * 3 + 2] * r[2];
+}
+// Jacobian of the rk3 step by JVPs; column c of [A|B] is written to colmajor[c*7 .. c*7+6].
+TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
+                        double dt, double* colmajor) {
+  StagePt s1, s2, s3;
+  double k1[7], k2[7], k3[7], xs[7];
+  stage_eval(I, x, u, B1, s1, k1);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k1[i] * dt);
+  stage_eval(I, xs, u, B2, s2, k2);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] * dt + 2.0 * (k2[i] * dt);
+  stage_eval(I, xs, u, B3, s3, k3);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int c = 0; c < 10; ++c) {
+    double vx[7], vu[3], t1[7], t2[7], t3[7], y[7];
+    for (int i = 0; i < 7; ++i) vx[i] = (i == c) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; ++i) vu[i] = (7 + i == c) ? 1.0 : 0.0;
+    stage_jvp(I, s1, vx, vu, t1);
+    for (int i = 0; i < 7; ++i) {
+      t1[i] *= dt;
+      y[i] = vx[i] + 0.5 * t1[i];
+    }
+    stage_jvp(I, s2, y, vu, t2);
+    for (int i = 0; i < 7; ++i) {
+      t2[i] *= dt;
+      y[i] = vx[i] - t1[i] + 2.0 * t2[i];
+    }
+    stage_jvp(I, s3, y, vu, t3);
+    for (int i = 0; i < 7; ++i) colmajor[c * 7 + i] = vx[i] + (t1[i] + 4.0 * t2[i] + t3[i] * dt) * TS_SIXTH;
+  }
 }
 
 // rk4 ZOH step (attitude_controller.jl:122-132) with one field row per stage.
@@ -263,13 +363,13 @@ TS_HD void rk4_jac7(const Inertia& I, const double x[7], const double u[3], cons
       double a = (j < 7) ? fx[i * 7 + j] : ((i < 3) ? fu[i * 3 + (j - 7)] : 0.0);
       K1[i * 10 + j] = a * dt;
     }
-  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * k1[i];
   dyn_f_jac<UMODE>(I, xs, u, B2, k2, fx, fu);
   for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
   for (int i = 0; i < 7; ++i)
     for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + 0.5 * K1[i * 10 + j];
   stage_chain(fx, fu, M, dt, K2);
-  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k2[i] / 2.0;
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * k2[i];
   dyn_f_jac<UMODE>(I, xs, u, B3, k3, fx, fu);
   for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
   for (int i = 0; i < 7; ++i)
@@ -281,10 +381,10 @@ TS_HD void rk4_jac7(const Inertia& I, const double x[7], const double u[3], cons
   for (int i = 0; i < 7; ++i)
     for (int j = 0; j < 10; ++j) M[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + K3[i * 10 + j];
   stage_chain(fx, fu, M, dt, K4);
-  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0;
+  for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) * TS_SIXTH;
   for (int i = 0; i < 7; ++i)
     for (int j = 0; j < 10; ++j)
-      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 2.0 * K2[i * 10 + j] + 2.0 * K3[i * 10 + j] + K4[i * 10 + j]) / 6.0;
+      AB[i * 10 + j] = ((i == j) ? 1.0 : 0.0) + (K1[i * 10 + j] + 2.0 * K2[i * 10 + j] + 2.0 * K3[i * 10 + j] + K4[i * 10 + j]) * TS_SIXTH;
 }
 
 // Sequentially accumulated clock state of the reference (x8), replicated exactly:

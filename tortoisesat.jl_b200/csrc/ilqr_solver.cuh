@@ -26,9 +26,11 @@
 #ifdef __CUDACC__
 #define TS_FN __device__ __forceinline__
 #define TS_FN_NOINLINE __device__ __noinline__
+#define TS_NO_UNROLL _Pragma("unroll 1")
 #else
 #define TS_FN inline
 #define TS_FN_NOINLINE inline
+#define TS_NO_UNROLL
 #endif
 
 // Option block of the AL-iLQR solve (C ABI: ts_ilqr_opts has the same layout).
@@ -48,6 +50,15 @@ struct ts_trial_outcome_dev {
 
 namespace ts {
 
+// cycle counter for the per-phase diagnostics returned in the outcome record of the low-level solve
+TS_HD long long ts_clock() {
+#ifdef __CUDA_ARCH__
+  return clock64();
+#else
+  return 0;
+#endif
+}
+
 enum { ST_CONVERGED = 0, ST_MAX_OUTER = 1, ST_COST_BLOWUP = 2, ST_REG_MAX = 3, ST_NAN = 4, ST_NO_CUTOFF = 5 };
 
 constexpr int TEAM = 8;
@@ -57,7 +68,11 @@ constexpr int SM_SCOL = SM_REC + TEAM * REC;  // [7][8]     new S columns
 constexpr int SM_SVEC = SM_SCOL + 56;         // [8]        new s
 constexpr int SM_KQ = SM_SVEC + 8;            // [7][6]     K(:,j), Qux(:,j)
 constexpr int SM_QUU = SM_KQ + 42;            // [9] Quu, [3] Qu
-constexpr int TEAM_SMEM_DOUBLES = SM_QUU + 12 + 2;  // 792 doubles = 6336 B per team
+// forward pass: double-buffered staging of 8-knot chunks, overlaid on the backward-pass regions
+constexpr int FWD_REC = 50;                   // [x7 u3 | K 21 d 3 | lam 6 | B 9 +pad] doubles per knot
+constexpr int SM_FWD = 0;                     // [2][8][FWD_REC]
+constexpr int TEAM_SMEM_DOUBLES = 2 * TEAM * FWD_REC;  // 800 doubles = 6400 B per team (>= SM_QUU + 12)
+static_assert(TEAM_SMEM_DOUBLES >= SM_QUU + 12, "team shared memory layout");
 
 struct TrialIn {
   int N;
@@ -75,7 +90,7 @@ struct TrialWork {
   double* kd;    // [Nmax][24]     K column-major (21) + d (3)
   double* lam;   // [Nmax][6]      bound multipliers
   double* clk;   // [Nmax]         clock state
-  int* rows;     // [Nmax][3]      field row of each rk3 stage
+  double* bk;    // [Nmax][10]     field vectors of the three rk3 stages of each knot (9 used)
   long long Nmax;
 };
 
@@ -113,31 +128,33 @@ TS_HD bool inv3_gj(const double A[9], double out[9]) {
   return true;
 }
 
-// Cholesky of a symmetric 3x3 (lower factor, row-major) -- the PD test of the backward pass.
+// Cholesky of a symmetric 3x3 -- the PD test of the backward pass.  L holds the strictly-lower
+// entries at [3],[6],[7] and the RECIPROCALS of the diagonal at [0],[4],[8] so that the two
+// triangular solves per lane need no division (3 divisions per knot instead of 15).
 TS_HD bool chol3(const double A[9], double L[9]) {
   for (int i = 0; i < 9; ++i) L[i] = 0.0;
   double s = A[0];
   if (!(s > 0.0)) return false;
-  L[0] = sqrt(s);
-  L[3] = A[3] / L[0];
-  L[6] = A[6] / L[0];
+  L[0] = rnorm(s);
+  L[3] = A[3] * L[0];
+  L[6] = A[6] * L[0];
   s = A[4] - L[3] * L[3];
   if (!(s > 0.0)) return false;
-  L[4] = sqrt(s);
-  L[7] = (A[7] - L[6] * L[3]) / L[4];
+  L[4] = rnorm(s);
+  L[7] = (A[7] - L[6] * L[3]) * L[4];
   s = A[8] - L[6] * L[6] - L[7] * L[7];
   if (!(s > 0.0)) return false;
-  L[8] = sqrt(s);
+  L[8] = rnorm(s);
   return true;
 }
 TS_HD void chol3_solve(const double L[9], const double b[3], double x[3]) {
   double y[3];
-  y[0] = b[0] / L[0];
-  y[1] = (b[1] - L[3] * y[0]) / L[4];
-  y[2] = (b[2] - L[6] * y[0] - L[7] * y[1]) / L[8];
-  x[2] = y[2] / L[8];
-  x[1] = (y[1] - L[7] * x[2]) / L[4];
-  x[0] = (y[0] - L[3] * x[1] - L[6] * x[2]) / L[0];
+  y[0] = b[0] * L[0];
+  y[1] = (b[1] - L[3] * y[0]) * L[4];
+  y[2] = (b[2] - L[6] * y[0] - L[7] * y[1]) * L[8];
+  x[2] = y[2] * L[8];
+  x[1] = (y[1] - L[7] * x[2]) * L[4];
+  x[0] = (y[0] - L[3] * x[1] - L[6] * x[2]) * L[0];
 }
 
 struct StageAL {  // stage cost pieces at (x,u)
@@ -201,13 +218,11 @@ template <class Team>
 TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
                                    int k, double sc, double mu, double* rec) {
   const double* p = xu_cur + (long long)k * 10;
-  double x[7], u[3], xn[7], AB[70];
+  double x[7], u[3];
   for (int i = 0; i < 7; ++i) x[i] = p[i];
   for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
-  const int* r = w.rows + (long long)k * 3;
-  rk3_jac7<0>(in.I, x, u, in.Bt + (long long)r[0] * 3, in.Bt + (long long)r[1] * 3, in.Bt + (long long)r[2] * 3, in.dt, xn, AB);
-  for (int c = 0; c < 10; ++c)
-    for (int i = 0; i < 7; ++i) rec[c * 7 + i] = AB[i * 10 + c];
+  const double* b = w.bk + (long long)k * 10;
+  rk3_jac7_jvp(in.I, x, u, b, b + 3, b + 6, in.dt, rec);
   for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
   double c6[6];
   bound_c(o, u, c6);
@@ -228,7 +243,7 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
 // Backward Riccati sweep over the current trajectory.  Returns false if the regularisation ran away.
 template <class Team>
 TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
-                         double sc, double mu, const double lam_g[8], Reg& reg, double& dV1, double& dV2) {
+                         double sc, double mu, const double lam_g[8], Reg& reg, double& dV1, double& dV2, long long& cyc_lin) {
   double* sm = tm.smem();
   const int lane = tm.lane();
   const int N = in.N;
@@ -253,13 +268,17 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
     }
     bool not_pd = false;
     const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
+    TS_NO_UNROLL
     for (int ch = n_chunks - 1; ch >= 0 && !not_pd; --ch) {
       const int base = ch * TEAM;
       tm.sync();  // previous chunk's records fully consumed
+      const long long tl0 = ts_clock();
       if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + SM_REC + lane * REC);
       tm.sync();
+      cyc_lin += ts_clock() - tl0;
       int kk_hi = N - 2 - base;
       if (kk_hi > TEAM - 1) kk_hi = TEAM - 1;
+      TS_NO_UNROLL
       for (int kk = kk_hi; kk >= 0; --kk) {
         const double* rec = sm + SM_REC + kk * REC;
         const int k = base + kk;
@@ -386,57 +405,103 @@ TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   return tm.sum(Jc);
 }
 
-// One speculative line-search rollout (one lane = one step size).
+// One batch of speculative line-search rollouts: lane a rolls out its own step size alpha; the
+// per-knot inputs every lane needs (x_k,u_k | K_k,d_k | lambda_k | stage field vectors) are
+// staged through shared memory in double-buffered 8-knot chunks (asynchronous copies issued one
+// chunk ahead, so the ~1 us HBM/L2 latency is off the sequential critical path).
 struct RollOut {
   double J, cmax, grad;
   bool ok;
 };
 template <class Team>
-TS_FN_NOINLINE RollOut rollout_candidate(const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
-                                         double* xu_cand, double alpha, double sc, double mu, const double lam_g[8]) {
+TS_FN void stage_chunk(Team& tm, const TrialWork& w, const double* xu_cur, int base, int N, double* buf) {
+  const int k = base + tm.lane();
+  if (k < N - 1) {
+    double* dst = buf + tm.lane() * FWD_REC;
+    tm.stage16(dst, xu_cur + (long long)k * 10, 5);
+    tm.stage16(dst + 10, w.kd + (long long)k * 24, 12);
+    tm.stage16(dst + 34, w.lam + (long long)k * 6, 3);
+    tm.stage16(dst + 40, w.bk + (long long)k * 10, 5);
+  }
+  tm.stage_commit();
+}
+template <class Team>
+TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
+                                     double* xu_cand, bool live, double alpha, double sc, double mu, const double lam_g[8],
+                                     double clk_absmax) {
   RollOut r;
-  r.ok = true;
+  r.ok = live;
   double Jc = 0.0, cmax = 0.0, gsum = 0.0;
   double xb[7];
   for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
   const int N = in.N;
-  for (int k = 0; k < N - 1; ++k) {
-    const double* p = xu_cur + (long long)k * 10;
-    const double* kd = w.kd + (long long)k * 24;
-    double ub[3];
-    double dx[7];
-    for (int i = 0; i < 7; ++i) dx[i] = xb[i] - p[i];
-    for (int i = 0; i < 3; ++i) {
-      double t = p[7 + i];
-      for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j];
-      t += alpha * kd[21 + i];
-      ub[i] = t;
+  double* sm = tm.smem() + SM_FWD;
+  const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
+  tm.sync();
+  stage_chunk(tm, w, xu_cur, 0, N, sm);
+  TS_NO_UNROLL
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int base = ch * TEAM;
+    if (ch + 1 < n_chunks) {
+      stage_chunk(tm, w, xu_cur, base + TEAM, N, sm + ((ch + 1) & 1) * TEAM * FWD_REC);
+      tm.stage_wait(1);
+    } else {
+      tm.stage_wait(0);
     }
-    const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
-    add_stage_cost(in, o, sc, mu, xb, e8, ub, w.lam + (long long)k * 6, Jc, cmax);
-    double mxg = 0.0;
-    for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(ub[i]) + 1.0));
-    gsum += mxg;
-    double* q = xu_cand + (long long)k * 10;
-    for (int i = 0; i < 7; ++i) q[i] = xb[i];
-    for (int i = 0; i < 3; ++i) q[7 + i] = ub[i];
-    const int* rw = w.rows + (long long)k * 3;
-    double xn[7];
-    rk3_step7<0>(in.I, xb, ub, in.Bt + (long long)rw[0] * 3, in.Bt + (long long)rw[1] * 3, in.Bt + (long long)rw[2] * 3, in.dt, xn);
-    double mx = fabs(w.clk[k + 1]), mu_abs = 0.0;
-    for (int i = 0; i < 7; ++i) {
-      xb[i] = xn[i];
-      mx = fmax(mx, fabs(xn[i]));
-      if (xn[i] != xn[i]) mx = INFINITY;
+    tm.sync();
+    const double* buf = sm + (ch & 1) * TEAM * FWD_REC;
+    int kk_n = N - 1 - base;
+    if (kk_n > TEAM) kk_n = TEAM;
+    if (r.ok) {
+      TS_NO_UNROLL
+      for (int kk = 0; kk < kk_n; ++kk) {
+        const int k = base + kk;
+        const double* p = buf + kk * FWD_REC;
+        const double* kd = p + 10;
+        double ub[3];
+        double dx[7];
+        for (int i = 0; i < 7; ++i) dx[i] = xb[i] - p[i];
+        for (int i = 0; i < 3; ++i) {
+          double t = p[7 + i];
+          for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j];
+          t += alpha * kd[21 + i];
+          ub[i] = t;
+        }
+        const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
+        add_stage_cost(in, o, sc, mu, xb, e8, ub, p + 34, Jc, cmax);
+        {  // max_i |d_i| / (|u_i| + 1) with one division: pick the maximiser by cross-multiplication
+          double na = fabs(kd[21]), da = fabs(ub[0]) + 1.0;
+          for (int i = 1; i < 3; ++i) {
+            const double nb = fabs(kd[21 + i]), db = fabs(ub[i]) + 1.0;
+            if (nb * da > na * db) {
+              na = nb;
+              da = db;
+            }
+          }
+          gsum += na / da;
+        }
+        double* q = xu_cand + (long long)k * 10;
+        for (int i = 0; i < 7; ++i) q[i] = xb[i];
+        for (int i = 0; i < 3; ++i) q[7 + i] = ub[i];
+        double xn[7];
+        rk3_step7<0>(in.I, xb, ub, p + 40, p + 43, p + 46, in.dt, xn);
+        double mx = clk_absmax, mu_abs = 0.0;
+        for (int i = 0; i < 7; ++i) {
+          xb[i] = xn[i];
+          mx = fmax(mx, fabs(xn[i]));
+          if (xn[i] != xn[i]) mx = INFINITY;
+        }
+        for (int i = 0; i < 3; ++i) {
+          mu_abs = fmax(mu_abs, fabs(ub[i]));
+          if (ub[i] != ub[i]) mu_abs = INFINITY;
+        }
+        if (!(mx < o.max_state_value) || !(mu_abs < o.max_control_value)) {
+          r.ok = false;
+          break;
+        }
+      }
     }
-    for (int i = 0; i < 3; ++i) {
-      mu_abs = fmax(mu_abs, fabs(ub[i]));
-      if (ub[i] != ub[i]) mu_abs = INFINITY;
-    }
-    if (!(mx < o.max_state_value) || !(mu_abs < o.max_control_value)) {
-      r.ok = false;
-      break;
-    }
+    tm.sync();  // chunk buffer free for the copy issued two chunks ahead
   }
   if (r.ok) {
     double* q = xu_cand + (long long)(N - 1) * 10;
@@ -459,18 +524,25 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   const long long bstride = w.Nmax * 10;
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
   // ---- setup: clock trajectory + stage field rows (sequential, exact replica), multipliers, initial rollout
+  double clk_absmax = 0.0;
   if (lane == 0) {
     double x8 = in.clk0;
     for (int k = 0; k < N - 1; ++k) {
       const ClockStep cs = clock_rk3(x8, in.clock_rate, in.dt);
       w.clk[k] = x8;
-      w.rows[k * 3 + 0] = field_row(cs.t1, in.index_scale, in.B_rows);
-      w.rows[k * 3 + 1] = field_row(cs.t2, in.index_scale, in.B_rows);
-      w.rows[k * 3 + 2] = field_row(cs.t3, in.index_scale, in.B_rows);
+      clk_absmax = fmax(clk_absmax, fabs(x8));
+      const double tt[3] = {cs.t1, cs.t2, cs.t3};
+      for (int st = 0; st < 3; ++st) {
+        const double* br = in.Bt + (long long)field_row(tt[st], in.index_scale, in.B_rows) * 3;
+        for (int c = 0; c < 3; ++c) w.bk[(long long)k * 10 + st * 3 + c] = br[c];
+      }
+      w.bk[(long long)k * 10 + 9] = 0.0;
       x8 = cs.next;
     }
     w.clk[N - 1] = x8;
+    clk_absmax = fmax(clk_absmax, fabs(x8));
   }
+  clk_absmax = tm.bcast(clk_absmax, 0);
   for (int i = lane; i < (N - 1) * 6; i += TEAM) w.lam[i] = 0.0;
   tm.sync();
   int cur = 0;
@@ -484,9 +556,9 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
       double* q = xu + (long long)k * 10;
       for (int i = 0; i < 7; ++i) q[i] = xb[i];
       for (int i = 0; i < 3; ++i) q[7 + i] = u[i];
-      const int* rw = w.rows + (long long)k * 3;
+      const double* b = w.bk + (long long)k * 10;
       double xn[7];
-      rk3_step7<0>(in.I, xb, u, in.Bt + (long long)rw[0] * 3, in.Bt + (long long)rw[1] * 3, in.Bt + (long long)rw[2] * 3, in.dt, xn);
+      rk3_step7<0>(in.I, xb, u, b, b + 3, b + 6, in.dt, xn);
       for (int i = 0; i < 7; ++i) xb[i] = xn[i];
     }
     double* q = xu + (long long)(N - 1) * 10;
@@ -504,6 +576,7 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   reg.rho = 0.0;
   reg.drho = 0.0;
   int it = 0, dJ_zero = 0;
+  long long cyc_bwd = 0, cyc_fwd = 0, cyc_lin = 0;
   double J_prev = trajectory_cost(tm, in, o, w, w.xu + cur * bstride, sc, mu, lam_g, c_max);
   J = J_prev;
   bool done = (o.max_outer < 1);
@@ -516,10 +589,13 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
     ++inner_total;
     const double* xu_cur = w.xu + cur * bstride;
     double dV1, dV2;
-    if (!backward_pass(tm, in, o, w, xu_cur, sc, mu, lam_g, reg, dV1, dV2)) {
+    const long long tb0 = ts_clock();
+    if (!backward_pass(tm, in, o, w, xu_cur, sc, mu, lam_g, reg, dV1, dV2, cyc_lin)) {
       status = ST_REG_MAX;
       abort_trial = true;
     }
+    const long long tf0 = ts_clock();
+    cyc_bwd += tf0 - tb0;
     double Jn = J_prev;
     if (!abort_trial) {
       tm.sync();  // gains visible to every lane
@@ -531,14 +607,9 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
         const int c = b0 + lane;
         const bool live = (c < n_cand);
         const int bufi = (lane < cur) ? lane : lane + 1;
-        RollOut r;
-        r.ok = false;
-        r.J = 0.0;
-        r.cmax = 0.0;
-        r.grad = 0.0;
         double alpha = 1.0;
         for (int i = 0; i < c; ++i) alpha /= 2.0;
-        if (live) r = rollout_candidate<Team>(in, o, w, xu_cur, w.xu + bufi * bstride, alpha, sc, mu, lam_g);
+        const RollOut r = forward_batch(tm, in, o, w, xu_cur, w.xu + bufi * bstride, live, alpha, sc, mu, lam_g, clk_absmax);
         bool acc = false;
         if (live && r.ok) {
           const double expected = -alpha * (dV1 + alpha * dV2);
@@ -574,6 +645,7 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
         }
         grad = tm.sum(g) / (double)(N - 1);
       }
+      cyc_fwd += ts_clock() - tf0;
       if (!(Jn == Jn)) {
         status = ST_NAN;
         abort_trial = true;
@@ -633,9 +705,10 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   out.N = N;
   out.J = J;
   out.c_max = c_max;
-  out.t_final = 0.0;
-  out.slew_time = 0.0;
-  out.flops = 0.0;
+  // diagnostics of the low-level solve (SM cycles): backward pass, forward pass, linearisation share
+  out.t_final = (double)cyc_bwd;
+  out.slew_time = (double)cyc_fwd;
+  out.flops = (double)cyc_lin;
   cur_out = cur;
   tm.sync();
 }

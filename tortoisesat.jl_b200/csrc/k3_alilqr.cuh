@@ -25,10 +25,28 @@ struct GpuTeam {
   int ln, shift;
   double* sm;
   __device__ __forceinline__ int lane() const { return ln; }
-  __device__ __forceinline__ double* smem() const { return sm; }
+  __device__ __forceinline__ double* smem() const {
+    double* p = sm;
+    __builtin_assume(__isShared(p));  // lets ptxas emit LDS/STS instead of generic LD/ST
+    return p;
+  }
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
   __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, TEAM); }
   __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffu; }
+  // asynchronous global->shared copies (cp.async / LDGSTS), 16 B per piece
+  __device__ __forceinline__ void stage16(double* dst, const double* src, int n16) const {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+    for (int i = 0; i < n16; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 16u * i), "l"(src + 2 * i) : "memory");
+  }
+  __device__ __forceinline__ void stage_commit() const { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+  __device__ __forceinline__ void stage_wait(int pending) const {
+    if (pending == 0)
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    else
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+  }
   __device__ __forceinline__ double sum(double v) const {
     v += __shfl_xor_sync(mask, v, 4, TEAM);
     v += __shfl_xor_sync(mask, v, 2, TEAM);
@@ -71,7 +89,7 @@ struct K3Args {
   double* w_kd;
   double* w_lam;
   double* w_clk;
-  int* w_rows;
+  double* w_bk;
   int64_t Nmax;
   unsigned long long* queue;
 };
@@ -80,7 +98,7 @@ constexpr int K3_WARPS_PER_BLOCK = 1;
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
 __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(const K3Args a) {
-  extern __shared__ double k3_smem[];
+  extern __shared__ __align__(16) double k3_smem[];
   const int warp_in_block = threadIdx.x >> 5;
   const int lane32 = threadIdx.x & 31;
   const int team = lane32 >> 3;
@@ -97,7 +115,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
   w.kd = a.w_kd + slot * a.Nmax * 24;
   w.lam = a.w_lam + slot * a.Nmax * 6;
   w.clk = a.w_clk + slot * a.Nmax;
-  w.rows = a.w_rows + slot * a.Nmax * 3;
+  w.bk = a.w_bk + slot * a.Nmax * 10;
   for (;;) {
     unsigned long long base = 0;
     if (lane32 == 0) base = atomicAdd(a.queue, 4ull);

@@ -335,7 +335,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   int64_t* d_order = nullptr;
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
   void *p_work, *p_q;
-  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1) * sizeof(double) + (size_t)Nmax * 3 * sizeof(int) + 64;
+  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1 + 10) * sizeof(double) + 64;
   if ((rc = scratch_reserve(c, 6, per_slot * (size_t)slots + 256, &p_work))) return rc;
   if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
   TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
@@ -347,7 +347,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
     a.w_kd = (double*)w;   w += (size_t)slots * Nmax * 24 * sizeof(double);
     a.w_lam = (double*)w;  w += (size_t)slots * Nmax * 6 * sizeof(double);
     a.w_clk = (double*)w;  w += (size_t)slots * Nmax * sizeof(double);
-    a.w_rows = (int*)w;
+    a.w_bk = (double*)w;
   }
   a.queue = (unsigned long long*)p_q;
   k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);

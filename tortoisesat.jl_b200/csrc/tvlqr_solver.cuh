@@ -323,7 +323,7 @@ TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, cons
       if (s == 2)
         for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i];
     }
-    for (int i = 0; i < 7; ++i) x[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) / 6.0;
+    for (int i = 0; i < 7; ++i) x[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) * TS_SIXTH;
     x[7] = nxt;
   }
   if (o.literal_postproc && X_sim) {
