@@ -1,0 +1,286 @@
+# TortoiseB200.jl -- Julia host side of libtortoise_b200.so (B200-native batched Monte-Carlo engine).
+#
+# Drop-in for the data-parallel hot path of RoboticExplorationLab/TortoiseSat.jl: every function
+# below keeps the NAME and ARGUMENT MEANING of the reference function it replaces (file:line cited)
+# and forwards to the C ABI declared in include/tortoise_b200.h through `ccall`.  Scalar calls are
+# batch-of-1 (correctness path); the `*_batch` / `monte_carlo` entry points are the performance path.
+#
+# NOTE: this image has no Julia toolchain, so this file is NOT executed by the test-suite; the
+# identical C ABI is exercised from Python ctypes (tortoisesat.jl_b200/host.py).  Array layout: Julia
+# is column-major, the library is "row-major by sample" => a field table is passed as a 3 x rows
+# Matrix{Float64}, a trajectory as 8 x N, so no transposition or copy is needed.
+module TortoiseB200
+
+using LinearAlgebra
+
+const LIB = get(ENV, "TORTOISE_B200_LIB", joinpath(@__DIR__, "..", "tortoisesat.jl_b200", "libtortoise_b200.so"))
+
+# ----------------------------------------------------------------------------- context
+mutable struct Engine
+    h::Ptr{Cvoid}
+end
+function Engine(device::Integer = 0)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:ts_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+    rc == 0 || error("ts_create failed ($rc): no usable CUDA device (there is no CPU fallback)")
+    e = Engine(r[])
+    finalizer(x -> ccall((:ts_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), e)
+    e
+end
+const _default = Ref{Union{Nothing,Engine}}(nothing)
+engine() = (_default[] === nothing && (_default[] = Engine(0)); _default[])
+lasterr(e::Engine) = unsafe_string(ccall((:ts_last_error, LIB), Cstring, (Ptr{Cvoid},), e.h))
+check(e::Engine, rc) = rc == 0 ? nothing : error("tortoise_b200 error $rc: $(lasterr(e))")
+
+# ----------------------------------------------------------------------------- structs of the C ABI
+struct FieldOpts            # ts_field_opts
+    GM::Float64; mjd::Float64; igrf_date::Float64; field_radius_m::Float64; t0::Float64; tf::Float64; N::Int64
+end
+struct IlqrOpts             # ts_ilqr_opts
+    max_outer::Int32; max_inner::Int32; max_linesearch::Int32; dJ_counter_limit::Int32; stage_cost_dt::Int32; goal_mask::Int32
+    cost_tol::Float64; cost_tol_intermediate::Float64; grad_tol::Float64; grad_tol_intermediate::Float64; constraint_tol::Float64
+    penalty_initial::Float64; penalty_scaling::Float64; penalty_max::Float64; dual_max::Float64
+    ls_lower::Float64; ls_upper::Float64; bp_reg_increase::Float64; bp_reg_max::Float64; bp_reg_min::Float64; bp_reg_fp::Float64
+    max_cost_value::Float64; max_state_value::Float64; max_control_value::Float64; u_max::Float64; u_min::Float64
+end
+struct TrialOutcome         # ts_trial_outcome (64 bytes)
+    status::Int32; outer_iters::Int32; inner_iters::Int32; ls_rollouts::Int32; N::Int64
+    J::Float64; c_max::Float64; t_final::Float64; slew_time::Float64; flops::Float64
+end
+struct TvlqrOpts            # ts_tvlqr_opts
+    dt::Float64; t0::Float64; tf::Float64
+    Qd::NTuple{6,Float64}; Qfd::NTuple{6,Float64}; Rd::NTuple{3,Float64}
+    dt_squared::Int32; noise_mode::Int32; seed::UInt64
+    w_limit::Float64; ang_limit::Float64; literal_postproc::Int32; pad_::Int32
+end
+struct McConfig             # ts_mc_config
+    n_trials::Int64; shared_orbit::Int32; run_tvlqr::Int32; t0::Float64; tf::Float64; N_scope::Int64
+    cutoff::Float64; dt::Float64; alpha::Float64; beta::Float64; ilqr::IlqrOpts; tvlqr::TvlqrOpts
+end
+struct McStats              # ts_mc_stats
+    n_trials::Int64; n_converged::Int64; n_no_cutoff::Int64; n_fail_slew::Int64
+    sum_slew_time::Float64; sum_slew_time_sq::Float64; sum_t_final::Float64; sum_inner_iters::Float64
+    sum_ls_rollouts::Float64; sum_knots::Float64; flops::Float64
+    ms_field::Float64; ms_prep::Float64; ms_solve::Float64; ms_tvlqr::Float64
+end
+function default_ilqr_opts()
+    r = Ref{IlqrOpts}()
+    ccall((:ts_ilqr_default_opts, LIB), Cvoid, (Ref{IlqrOpts},), r); r[]
+end
+function default_tvlqr_opts()
+    r = Ref{TvlqrOpts}()
+    ccall((:ts_tvlqr_default_opts, LIB), Cvoid, (Ref{TvlqrOpts},), r); r[]
+end
+
+# ----------------------------------------------------------------------------- L0 parameters
+# struct params / input_parameters(type,Kep,MJD)            reference src/input_parameters.jl:4-16,24-66
+struct params
+    type::AbstractString; mass::Float64; J::Array{Float64}; BC::Float64; alt::Float64; Kep::Array{Float64}
+    MJD::Float64; GM::Float64; R_E::Float64; T::Float64; ω_0::Float64
+end
+function input_parameters(type, Kep, MJD)
+    GM = 3.986004418E14 * (1 / 1000)^3
+    R_E = 6371.0
+    if type == "1U"
+        mass = .75; J = [0.00125 0 0; 0 0.00125 0; 0 0 0.00125]
+    elseif type == "1P"
+        mass = .25; J = [0.0001041667 0 0; 0 0.0001041667 0; 0 0 0.0001041667]
+    elseif type == "3U"
+        mass = 2.5; J = [0.020833 0 0; 0 0.020833 0; 0 0 0.0041666]
+    else
+        error("Type not recognized")
+    end
+    BC = mass / 2.2 / (J[1, 1] * J[2, 2])
+    alt = 400                      # quirk Q10: forced (input_parameters.jl:58)
+    T = 2 * pi * sqrt(Kep[2] .^ 3 / GM)
+    ω_0 = sqrt(GM / Kep[2]^3)
+    MJD = 58155.0                  # quirk Q10: forced (input_parameters.jl:63)
+    params(type, mass, J, BC, alt, vec(collect(Float64, Kep)), MJD, GM, R_E, T, ω_0)
+end
+
+# ----------------------------------------------------------------------------- K1: IGRF
+# igrf12(date, r, λ, Ω)                                     reference src/igrf.jl:67-274
+function igrf12_batch(date::Real, r::Vector{Float64}, λ::Vector{Float64}, Ω::Vector{Float64}; e::Engine = engine())
+    n = length(r)
+    Bn = Vector{Float64}(undef, n); Be = similar(Bn); Bd = similar(Bn)
+    rc = ccall((:ts_igrf12_batch, LIB), Cint,
+               (Ptr{Cvoid}, Cdouble, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+               e.h, date, n, r, λ, Ω, Bn, Be, Bd, 0)
+    check(e, rc)
+    Bn, Be, Bd
+end
+function igrf12(date::Number, r::Number, λ::Number, Ω::Number; show_warns = true)
+    show_warns && (date > 2020) &&
+        @warn("The magnetic field computed with this IGRF version may be of reduced accuracy for years greater than 2020.")
+    Bn, Be, Bd = igrf12_batch(date, [Float64(r)], [Float64(λ)], [Float64(Ω)])
+    [Bn[1]; Be[1]; Bd[1]]
+end
+# igrf_data(altitude, year): the 1000 x 1000 x 3 map       reference src/magnetic_toolbox.jl:108-121
+function igrf_data(altitude, year::Int64)
+    R_E = 6378; N = 1000
+    lat = collect(range(-π / 2, length = N, π / 2)); long = collect(range(-π, length = N, π))
+    LA = repeat(lat, inner = N); LO = repeat(long, outer = N)
+    Bn, Be, Bd = igrf12_batch(year, fill((altitude + R_E) * 1000.0, N * N), LA, LO)
+    mag_field = zeros(N, N, 3)
+    for i = 1:N, j = 1:N
+        k = (i - 1) * N + j
+        mag_field[i, j, :] = [Bn[k], Be[k], Bd[k]] / 1.e9
+    end
+    mag_field        # (the B-spline wrapper of :124-125 is outside the hot path)
+end
+
+# ----------------------------------------------------------------------------- K2: orbit + field table
+# magnetic_simulation(p,t0,tf,N,mag_field)                  reference src/magnetic_toolbox.jl:33-106
+function magnetic_simulation(p::params, t0, tf, N, mag_field = nothing; alt = p.alt, igrf_date = 2019.0, e::Engine = engine())
+    N = Int(N)
+    fo = [FieldOpts(p.GM, p.MJD, igrf_date, (alt + p.R_E) * 1000.0, t0, tf, N)]
+    offs = Int64[0, 2N]
+    B = zeros(3, 2N); pos = zeros(3, 2N + 1); vel = zeros(3, 2N + 1)
+    rc = ccall((:ts_magnetic_simulation_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{FieldOpts}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+               e.h, 1, p.Kep, fo, offs, C_NULL, B, pos, vel, 0)
+    check(e, rc)
+    Matrix(B'), pos, vel        # B_N_sim is (2N x 3) in the reference
+end
+# legacy 7-argument form used at src/monte_carlo.jl:134,149
+magnetic_simulation(A::AbstractVector, t0, tf, N, mag_field, GM, MJD_0; alt = 400, R_E = 6371.0) =
+    magnetic_simulation(params("", 0.0, zeros(3, 3), 0.0, alt, collect(Float64, A), MJD_0, GM, R_E, 0.0, 0.0), t0, tf, N, mag_field)
+
+# magnetic_gramian(B_N,dt) -> 3 x 3 x rows                 reference src/magnetic_toolbox.jl:1-12
+function magnetic_gramian(B_N, dt; e::Engine = engine())
+    rows = size(B_N, 1)
+    Bt = Matrix{Float64}(B_N'); G = zeros(3, 3, rows)
+    rc = ccall((:ts_magnetic_gramian_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint),
+               e.h, 1, Bt, Int64[0], Int64[rows], Float64[dt], G, 0)
+    check(e, rc)
+    G                               # symmetric 3x3 blocks: row/column-major agree
+end
+# condition_based_time(B_gram,cutoff)                       reference src/magnetic_toolbox.jl:14-31
+function condition_based_time(B_gram, cutoff; e::Engine = engine())
+    rows = size(B_gram, 3); idx = Int64[0]
+    rc = ccall((:ts_condition_based_time_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Cint),
+               e.h, 1, B_gram, Int64[0], Int64[rows], Float64[cutoff], idx, 0)
+    check(e, rc)
+    Int(idx[1])
+end
+
+# ----------------------------------------------------------------------------- slew preparation
+# eigen_axis_slew(x0,xf,t) -> (ω_guess (nt x 3), q_guess (nt x 4))    reference src/eigen_axis_slew.jl:1-38
+function eigen_axis_slew(x0, xf, t; e::Engine = engine())
+    nt = length(t); dt = t[2] - t[1]
+    Qd = zeros(8); Qfd = zeros(8); Rd = zeros(3); wg = zeros(3, nt); qg = zeros(4, nt)
+    rc = ccall((:ts_slew_weights_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble,
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+               e.h, 1, [x0[1:7]; 0.0], [xf[1:7]; 0.0], vec(Matrix(1.0I, 3, 3)), Float64[t[end]], t[1], dt, 1.0, 1.0,
+               Qd, Qfd, Rd, Int64[0], wg, qg)
+    check(e, rc)
+    Matrix(wg'), Matrix(qg')
+end
+# Bryson's-rule weights of src/TortoiseSat.jl:157-168 (α = 10) / src/monte_carlo.jl:165-176 (α = 0.1)
+function bryson_weights(x0, xf, J, t_final; t0 = 0.0, dt = 0.2, α = 1.e1, β = 1.e3, e::Engine = engine())
+    Qd = zeros(8); Qfd = zeros(8); Rd = zeros(3)
+    rc = ccall((:ts_slew_weights_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble,
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+               e.h, 1, collect(Float64, x0), collect(Float64, xf), vec(Matrix{Float64}(J')), Float64[t_final], t0, dt, α, β,
+               Qd, Qfd, Rd, C_NULL, C_NULL, C_NULL)
+    check(e, rc)
+    Matrix(Diagonal(Qd)), Matrix(Diagonal(Rd)), Matrix(Diagonal(Qfd))
+end
+
+# ----------------------------------------------------------------------------- K3: AL-iLQR
+# Replaces the TrajectoryOptimization.jl block of src/TortoiseSat.jl:145-146,169,178-199:
+#   model_d = rk3(Model(DerivFunction,8,3)); obj = LQRObjective(Q,R,Qf,xf,N); bnd = BoundConstraint(8,3,u_max=1,u_min=-1);
+#   goal = goal_constraint(xf); sat = Problem(...); solver = AugmentedLagrangianSolver(sat,opts_al); solve!(sat,solver)
+# B_ECI is the (rows x 3) field table the reference keeps in a global; N_field / tf_scope are the
+# globals N and tf that DerivFunction reads (src/DerivFunction.jl:28,44).
+function solve_slew(x0, xf, J, Q, R, Qf, B_ECI, N::Integer, dt; N_field = N, tf_scope = 5400.0, t0 = 0.0,
+                    U0 = nothing, opts::IlqrOpts = default_ilqr_opts(), e::Engine = engine())
+    Bt = Matrix{Float64}(B_ECI'); X = zeros(8, N); U = zeros(3, N); K = zeros(8, 3, N)
+    out = Vector{TrialOutcome}(undef, 1)
+    rc = ccall((:ts_alilqr_solve_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64},
+                Ref{IlqrOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{TrialOutcome}, Cint),
+               e.h, 1, Int64[N], Int64[0], collect(Float64, x0), collect(Float64, xf), vec(Matrix{Float64}(J')), diag(Q), diag(Qf),
+               diag(R), Bt, Int64[0], Int64[size(Bt, 2)], Float64[N_field], Float64[1 / (tf_scope - t0)], dt,
+               U0 === nothing ? C_NULL : U0, Ref(opts), X, U, K, out, 0)
+    check(e, rc)
+    X, U[:, 1:N-1], permutedims(K, (2, 1, 3))[:, :, 1:N-1], out[1]
+end
+
+# ----------------------------------------------------------------------------- K4: TVLQR replay
+# attitude_simulation(f!,f_gains!,integration,X_lqr,U_lqr,dt_lqr,x0_lqr,t0,tf,Q_lqr,R_lqr,Qf_lqr) -> (X_sim,U_sim,dX,K)
+#                                                           reference src/attitude_controller.jl:1-48
+# f!, f_gains!, integration are accepted for signature compatibility: the library implements
+# simulator / gain_simulator / :rk4 (src/simulator.jl, src/gain_simulator.jl, attitude_controller.jl:122-145).
+function attitude_simulation(f!, f_gains!, integration, X_lqr::Matrix, U_lqr::Matrix, dt_lqr::Float64, x0_lqr::AbstractVector,
+                             t0::Float64, tf::Float64, Q_lqr, R_lqr, Qf_lqr; B_ECI, J, N_field = size(X_lqr, 2), tf_scope = 5400.0,
+                             noise_mode = 2, seed = 0, q_final = [1.0, 0, 0, 0], e::Engine = engine())
+    N = size(X_lqr, 2)
+    o = default_tvlqr_opts()
+    o = TvlqrOpts(dt_lqr, t0, tf, Tuple(diag(Q_lqr)), Tuple(diag(Qf_lqr)), Tuple(diag(R_lqr)), o.dt_squared, noise_mode, seed,
+                  o.w_limit, o.ang_limit, 0, 0)
+    Up = zeros(3, N); Up[:, 1:size(U_lqr, 2)] = U_lqr
+    Bt = Matrix{Float64}(B_ECI')
+    X_sim = zeros(8, N); U_sim = zeros(3, N); dX = zeros(6, N); K = zeros(6, 3, N); nsim = Int64[0]; slew = Float64[0]
+    rc = ccall((:ts_tvlqr_sim_batch, LIB), Cint,
+               (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}, Ref{TvlqrOpts},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Cint),
+               e.h, 1, Int64[N], Int64[0], X_lqr, Up, collect(Float64, x0_lqr), vec(Matrix{Float64}(J')), Bt, Int64[0],
+               Int64[size(Bt, 2)], Float64[N_field], Float64[1 / (tf_scope - t0)], Float64[tf], collect(Float64, q_final), C_NULL,
+               Ref(o), C_NULL, X_sim, U_sim, dX, K, nsim, slew, 0)
+    check(e, rc)
+    n = nsim[1]
+    X_sim[:, 1:n], U_sim[:, 1:n], dX[:, 1:n], permutedims(K, (2, 1, 3))[:, :, 1:N-1]
+end
+
+# ----------------------------------------------------------------------------- fused Monte-Carlo
+# The loop of src/monte_carlo.jl:118-262 (with the solver block of src/TortoiseSat.jl:178-199) for
+# number_sims trials in ONE library call.  Returns the arrays the script leaves in globals
+# (src/monte_carlo.jl:52-66,237-240): A, t_final, slew_time, fails + the per-trial outcome records.
+function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination = 96.6, MJD_0 = 58155.0, igrf_date = 2019.0,
+                     t0 = 0.0, tf = 60 * 40, cutoff = 30, N = 5000, J = [0.00125 0 0; 0 0.00125 0; 0 0 0.00125],
+                     q_0 = nothing, q_final = [sqrt(2) / 2; sqrt(2) / 2; 0; 0], α = 1.e-1, β = 1.e3, seed = 0, run_tvlqr = true,
+                     ilqr::IlqrOpts = default_ilqr_opts(), e::Engine = engine())
+    GM = 3.986004418E14 * (1 / 1000)^3
+    A = zeros(6, number_sims)                       # column i = A[i,:] of the reference
+    fo = Vector{FieldOpts}(undef, number_sims)
+    x0 = zeros(8, number_sims); xf = zeros(8, number_sims); Jm = zeros(9, number_sims); qn = zeros(3, number_sims)
+    for i in 1:number_sims
+        A[:, i] = [0, alt + R_E, inclination, rand() * 360, 0, rand() * 360]      # monte_carlo.jl:122-127
+        fo[i] = FieldOpts(GM, MJD_0, igrf_date, (alt + R_E) * 1000.0, 0.0, 0.0, 0)
+        x0[4:7, i] = q_0 === nothing ? normalize(randn(4)) : q_0
+        xf[4:7, i] = q_final; xf[8, i] = 1
+        Jm[:, i] = vec(Matrix{Float64}(J'))
+        qn[:, i] = randn(3) * (1 * pi / 180)^2                                    # monte_carlo.jl:207
+    end
+    tv = default_tvlqr_opts()
+    tv = TvlqrOpts(0.2, t0, 0.0, ntuple(_ -> 10.0, 6), ntuple(_ -> 1000.0, 6), ntuple(_ -> 0.5e3, 3), tv.dt_squared, 2, seed,
+                   0.05, 0.08727, 0, 0)                                            # monte_carlo.jl:69-71,216-226
+    cfg = McConfig(number_sims, 0, run_tvlqr ? 1 : 0, t0, tf, N, cutoff, 0.2, α, β, ilqr, tv)
+    out = Vector{TrialOutcome}(undef, number_sims); st = Ref{McStats}()
+    rc = ccall((:ts_monte_carlo_run, LIB), Cint,
+               (Ptr{Cvoid}, Ref{McConfig}, Ptr{Float64}, Ptr{FieldOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{UInt32}, Ptr{TrialOutcome}, Ref{McStats}),
+               e.h, Ref(cfg), A, fo, x0, xf, Jm, qn, C_NULL, out, st)
+    check(e, rc)
+    t_final = [o.t_final for o in out]; slew_time = [o.slew_time for o in out]
+    fails = [o.slew_time == o.t_final ? 1.0 : 0.0 for o in out]                  # monte_carlo.jl:257-261
+    (A = Matrix(A'), t_final = t_final, slew_time = slew_time, fails = fails, outcomes = out, stats = st[])
+end
+
+# ----------------------------------------------------------------------------- small host-side helpers kept verbatim in meaning
+qmult(q1, q2) = [q1[1] * q2[1] - q1[2:4]' * q2[2:4]; q1[1] * q2[2:4] + q2[1] * q1[2:4] + cross(q1[2:4], q2[2:4])]  # src/qmult.jl
+qrot(q, r) = r + 2 * cross(q[2:4], cross(q[2:4], r) + q[1] * r)                                                      # src/qrot.jl
+q_inv(q) = [q[1]; -q[2:4]]                                                              # src/attitude_controller.jl:164-166
+hat(x) = [0 -x[3] x[2]; x[3] 0 -x[1]; -x[2] x[1] 0]                                     # src/magnetic_toolbox.jl:142-146
+
+export Engine, params, input_parameters, igrf12, igrf12_batch, igrf_data, magnetic_simulation, magnetic_gramian,
+       condition_based_time, eigen_axis_slew, bryson_weights, solve_slew, attitude_simulation, monte_carlo, qmult, qrot, q_inv, hat
+
+end # module

@@ -25,7 +25,7 @@
 
 #ifdef __CUDACC__
 #define TS_FN __device__ __forceinline__
-#define TS_FN_NOINLINE __device__ __noinline__
+#define TS_FN_NOINLINE __device__ __forceinline__  /* single call sites: inlining keeps TrialIn/opts out of local memory */
 #define TS_NO_UNROLL _Pragma("unroll 1")
 #else
 #define TS_FN inline
@@ -71,8 +71,10 @@ constexpr int SM_QUU = SM_KQ + 42;            // [9] Quu, [3] Qu
 // forward pass: double-buffered staging of 8-knot chunks, overlaid on the backward-pass regions
 constexpr int FWD_REC = 50;                   // [x7 u3 | K 21 d 3 | lam 6 | B 9 +pad] doubles per knot
 constexpr int SM_FWD = 0;                     // [2][8][FWD_REC]
-constexpr int TEAM_SMEM_DOUBLES = 2 * TEAM * FWD_REC;  // 800 doubles = 6400 B per team (>= SM_QUU + 12)
-static_assert(TEAM_SMEM_DOUBLES >= SM_QUU + 12, "team shared memory layout");
+constexpr int SM_WORK = 2 * TEAM * FWD_REC;   // 800 doubles of working buffers
+static_assert(SM_WORK >= SM_QUU + 12, "team shared memory layout");
+constexpr int SM_TRIAL = SM_WORK;             // the trial's TrialIn block (read-only during the solve)
+constexpr int TEAM_SMEM_DOUBLES = SM_WORK + 64;  // 864 doubles = 6912 B per team
 
 struct TrialIn {
   int N;
@@ -85,6 +87,7 @@ struct TrialIn {
   double index_scale, clock_rate;
   const double* U0;  // (N-1) x 3 or null
 };
+static_assert(sizeof(TrialIn) <= 64 * sizeof(double), "TrialIn must fit its shared-memory slot");
 struct TrialWork {
   double* xu;    // [9][Nmax][10]  trajectory buffers (x7,u3): current + 8 line-search candidates
   double* kd;    // [Nmax][24]     K column-major (21) + d (3)

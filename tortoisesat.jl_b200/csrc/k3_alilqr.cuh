@@ -84,13 +84,10 @@ struct K3Args {
   double* U;             // ragged (N-1) x 3 at offs*3
   double* K;             // nullable, ragged (N-1) x 3 x 8 at offs*24
   ts_trial_outcome_dev* out;
-  // work arena
-  double* w_xu;
-  double* w_kd;
-  double* w_lam;
-  double* w_clk;
-  double* w_bk;
-  int64_t Nmax;
+  // work arena: one contiguous block per team slot [xu 9x | kd | lam | bk | clk] (2 MB pages: ~2 per trial)
+  double* w_base;
+  int64_t per_slot;  // doubles per slot (even)
+  int64_t Nmax;      // padded to even
   unsigned long long* queue;
 };
 
@@ -111,11 +108,11 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
   tm.sm = k3_smem + (warp_in_block * 4 + team) * TEAM_SMEM_DOUBLES;
   TrialWork w;
   w.Nmax = a.Nmax;
-  w.xu = a.w_xu + slot * 9 * a.Nmax * 10;
-  w.kd = a.w_kd + slot * a.Nmax * 24;
-  w.lam = a.w_lam + slot * a.Nmax * 6;
-  w.clk = a.w_clk + slot * a.Nmax;
-  w.bk = a.w_bk + slot * a.Nmax * 10;
+  w.xu = a.w_base + slot * a.per_slot;
+  w.kd = w.xu + 90 * a.Nmax;
+  w.lam = w.kd + 24 * a.Nmax;
+  w.bk = w.lam + 6 * a.Nmax;
+  w.clk = w.bk + 10 * a.Nmax;
   for (;;) {
     unsigned long long base = 0;
     if (lane32 == 0) base = atomicAdd(a.queue, 4ull);
@@ -124,24 +121,36 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
     const int64_t qi = (int64_t)base + team;
     if (qi < a.n_trials) {
       const int64_t t = a.order ? a.order[qi] : qi;
-      TrialIn in;
-      in.N = (int)a.N_i[t];
-      in.dt = a.dt;
-      for (int i = 0; i < 7; ++i) in.x0[i] = a.x0[t * 8 + i];
-      in.clk0 = a.x0[t * 8 + 7];
-      for (int i = 0; i < 8; ++i) {
-        in.xf[i] = a.xf[t * 8 + i];
-        in.Qd[i] = a.Qd[t * 8 + i];
-        in.Qfd[i] = a.Qfd[t * 8 + i];
+      // the trial's read-only parameters live in the team's shared memory (not in local memory)
+      TrialIn* inp = reinterpret_cast<TrialIn*>(tm.smem() + SM_TRIAL);
+      __builtin_assume(__isShared(inp));
+      tm.sync();
+      if (tm.ln == 0) {
+        inp->N = (int)a.N_i[t];
+        inp->dt = a.dt;
+        for (int i = 0; i < 7; ++i) inp->x0[i] = a.x0[t * 8 + i];
+        inp->clk0 = a.x0[t * 8 + 7];
+        for (int i = 0; i < 8; ++i) {
+          inp->xf[i] = a.xf[t * 8 + i];
+          inp->Qd[i] = a.Qd[t * 8 + i];
+          inp->Qfd[i] = a.Qfd[t * 8 + i];
+        }
+        for (int i = 0; i < 3; ++i) inp->Rd[i] = a.Rd[t * 3 + i];
+        double Jm[9], Ji[9];
+        for (int i = 0; i < 9; ++i) Jm[i] = a.Jmat[t * 9 + i];
+        inv3_gj(Jm, Ji);
+        for (int i = 0; i < 9; ++i) {
+          inp->I.J[i] = Jm[i];
+          inp->I.Jinv[i] = Ji[i];
+        }
+        inp->Bt = a.B_eci + a.B_offs[t] * 3;
+        inp->B_rows = a.B_rows[t];
+        inp->index_scale = a.index_scale[t];
+        inp->clock_rate = a.clock_rate[t];
+        inp->U0 = a.U0 ? a.U0 + a.offs[t] * 3 : nullptr;
       }
-      for (int i = 0; i < 3; ++i) in.Rd[i] = a.Rd[t * 3 + i];
-      for (int i = 0; i < 9; ++i) in.I.J[i] = a.Jmat[t * 9 + i];
-      inv3_gj(in.I.J, in.I.Jinv);
-      in.Bt = a.B_eci + a.B_offs[t] * 3;
-      in.B_rows = a.B_rows[t];
-      in.index_scale = a.index_scale[t];
-      in.clock_rate = a.clock_rate[t];
-      in.U0 = a.U0 ? a.U0 + a.offs[t] * 3 : nullptr;
+      tm.sync();
+      const TrialIn& in = *inp;
       ts_trial_outcome_dev oc;
       int cur = 0;
       alilqr_solve_team(tm, in, a.opts, w, oc, cur);

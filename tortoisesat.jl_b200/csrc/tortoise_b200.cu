@@ -335,20 +335,15 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   int64_t* d_order = nullptr;
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
   void *p_work, *p_q;
-  const size_t per_slot = (size_t)Nmax * (90 + 24 + 6 + 1 + 10) * sizeof(double) + 64;
-  if ((rc = scratch_reserve(c, 6, per_slot * (size_t)slots + 256, &p_work))) return rc;
+  Nmax += (Nmax & 1);  // even: keeps every per-knot record 16-byte aligned for the asynchronous copies
+  const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1) + (Nmax & 1);
+  if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)slots + 256, &p_work))) return rc;
   if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
   TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
   a.order = d_order;
   a.Nmax = Nmax;
-  {
-    char* w = (char*)p_work;
-    a.w_xu = (double*)w;   w += (size_t)slots * Nmax * 90 * sizeof(double);
-    a.w_kd = (double*)w;   w += (size_t)slots * Nmax * 24 * sizeof(double);
-    a.w_lam = (double*)w;  w += (size_t)slots * Nmax * 6 * sizeof(double);
-    a.w_clk = (double*)w;  w += (size_t)slots * Nmax * sizeof(double);
-    a.w_bk = (double*)w;
-  }
+  a.w_base = (double*)p_work;
+  a.per_slot = per_slot + (per_slot & 1);
   a.queue = (unsigned long long*)p_q;
   k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
   c->launches++;
