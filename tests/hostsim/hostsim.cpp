@@ -43,6 +43,7 @@ struct CpuTeam {
     return r;
   }
   void stage16(double* dst, const double* src, int n16) const { memcpy(dst, src, (size_t)n16 * 16); }
+  void prefetch_l2(const void*) const {}
   void stage_commit() const {}
   void stage_wait(int) const {}
   double sum(double v) const {

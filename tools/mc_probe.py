@@ -40,6 +40,12 @@ for n in ntr:
     st = np.bincount(out["status"], minlength=5)
     print(n, "kernel ms", ms, "wall s", wall, "trials/s", n / (ms * 1e-3), "status", st.tolist(), "outer mean", out["outer_iters"].mean(),
           "inner mean/max", out["inner_iters"].mean(), out["inner_iters"].max(), "ls mean", out["ls_rollouts"].mean(), flush=True)
+    its = out["inner_iters"].astype(float)
+    i = int(np.argmax(its))
+    kn = its * base.N
+    print("   slowest trial per knot-iter: bwd %.0f (lin %.0f) fwd %.0f | median trial: bwd %.0f (lin %.0f) fwd %.0f" % (
+        out["t_final"][i] / kn[i], out["flops"][i] / kn[i], out["slew_time"][i] / kn[i], np.median(out["t_final"] / kn),
+        np.median(out["flops"] / kn), np.median(out["slew_time"] / kn)), flush=True)
     res[n] = dict(ms=ms, trials_per_s=n / (ms * 1e-3), status=st.tolist(), inner_mean=float(out["inner_iters"].mean()),
                   inner_max=int(out["inner_iters"].max()), ls_mean=float(out["ls_rollouts"].mean()))
 os.makedirs("gpurun_out", exist_ok=True)

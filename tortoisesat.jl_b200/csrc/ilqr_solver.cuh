@@ -220,16 +220,19 @@ TS_HD void reg_decrease(const ts_ilqr_opts_dev& o, Reg& r) {
 template <class Team>
 TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
                                    int k, double sc, double mu, double* rec) {
+  // all global inputs of the knot are loaded up front (one memory round trip, not one per use)
   const double* p = xu_cur + (long long)k * 10;
-  double x[7], u[3];
+  const double* bp = w.bk + (long long)k * 10;
+  const double* lp_ = w.lam + (long long)k * 6;
+  double x[7], u[3], b[9], lam[6];
   for (int i = 0; i < 7; ++i) x[i] = p[i];
   for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
-  const double* b = w.bk + (long long)k * 10;
+  for (int i = 0; i < 9; ++i) b[i] = bp[i];
+  for (int i = 0; i < 6; ++i) lam[i] = lp_[i];
   rk3_jac7_jvp(in.I, x, u, b, b + 3, b + 6, in.dt, rec);
   for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
   double c6[6];
   bound_c(o, u, c6);
-  const double* lam = w.lam + (long long)k * 6;
   for (int i = 0; i < 3; ++i) {
     double lu = sc * in.Rd[i] * u[i];
     double luu = sc * in.Rd[i];
@@ -279,6 +282,12 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + SM_REC + lane * REC);
       tm.sync();
       cyc_lin += ts_clock() - tl0;
+      if (base >= TEAM) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
+        const int kn = base - TEAM + lane;
+        tm.prefetch_l2(xu_cur + (long long)kn * 10);
+        tm.prefetch_l2(w.bk + (long long)kn * 10);
+        tm.prefetch_l2(w.lam + (long long)kn * 6);
+      }
       int kk_hi = N - 2 - base;
       if (kk_hi > TEAM - 1) kk_hi = TEAM - 1;
       TS_NO_UNROLL

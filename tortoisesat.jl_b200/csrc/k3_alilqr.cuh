@@ -40,6 +40,7 @@ struct GpuTeam {
     for (int i = 0; i < n16; ++i)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 16u * i), "l"(src + 2 * i) : "memory");
   }
+  __device__ __forceinline__ void prefetch_l2(const void* p) const { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
   __device__ __forceinline__ void stage_commit() const { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
   __device__ __forceinline__ void stage_wait(int pending) const {
     if (pending == 0)
