@@ -358,6 +358,10 @@ def main():
     total_trials = world * n
     solve_s = float(np.mean(solve_ms)) * 1e-3
     ach = float(np.mean(flops_solve)) / solve_s / 1e12
+    # HBM traffic of K3 per knot-iteration, from the ncu --set full capture profiles/k3_prof_r1b_summary.txt
+    # (2368 trials, N = 300: dram read 32.88 GB + write 52.74 GB over 6.19e7 knot-iterations)
+    K3_DRAM_BYTES_PER_KNOT_ITER = 1383.0
+    knot_iters = float(np.sum((out["N"] - 1).astype(np.float64) * out["inner_iters"]))
     h2d = n * (8 + 8 + 9 + 3) * 8 + n * 4 + len(fo) * (6 * 8 + 56)
     d2h = n * 64 + 8 * len(fo)
     conv = int(vec[1])
@@ -371,7 +375,10 @@ def main():
                        "mean_ls_rollouts": float(vec[8] / max(1.0, vec[0] - vec[2])),
                        "mean_slew_time_s": float(vec[4] / max(1.0, vec[0] - vec[2])), "fail_slew": int(vec[3])},
             "roofline": {"bound": "fp64", "kernel": "k3_alilqr_kernel", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
-                         "frac": ach / peak_fp64, "traffic": None,
+                         "frac": ach / peak_fp64, "traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters,
+                         "traffic_source": "1383 B per knot-iteration (ncu --set full, dram__bytes_read+write, capture of "
+                                           "tools/k3_small.py 2368: 85.6 GB / 6.19e7 knot-iterations) x this run's knot-iterations",
+                         "hbm_gbs_from_traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters / solve_s / 1e9, "hbm_peak_gbs": hbm_peak,
                          "peak_source": "measured live: register-resident DFMA micro-benchmark (ts_fp64_peak_probe); "
                                         "MEASURED_PEAKS.json has no FP64 row",
                          "flop_model": "6100 FLOP per knot-iteration (rk3 Jacobian 2600 + Riccati step 3500) + 500 per "
