@@ -69,6 +69,11 @@ __device__ __forceinline__ void igrf_stage_coeffs(double2* s_gh, const double* _
       v.y = __dadd_rn(h0, __dmul_rn(dh, dt));
     }
     s_gh[k] = v;
+    // (-m g, +m h): folds the factor -m of the d/dphi sum into the coefficients (igrf.jl:235)
+    double2 vm;
+    vm.x = -(double)m * v.x;
+    vm.y = (double)m * v.y;
+    s_gh[IGRF_NCOEF + k] = vm;
   }
 }
 
@@ -143,7 +148,7 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
     {
       const double g = s_gh[k0].x;
       const double dP0 = -c_igrf.dl_a[n][0] * Pn[1] + c_igrf.dl_b[n][0] * Pn[1];
-      aux_r = cr * g * Pn[0];
+      aux_r = g * Pn[0];  // -(n+1)/r is factored out of the sum over m (one DMUL per n instead of per (n,m))
       aux_t = g * dP0;
     }
     // ---- m = 1..n
@@ -155,14 +160,15 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
         dPm = c_igrf.dl_a[n][m] * Pn[m - 1];
       else
         dPm = c_igrf.dl_a[n][m] * Pn[m - 1] + c_igrf.dl_b[n][m] * Pn[m + 1];
+      const double2 ghm = s_gh[IGRF_NCOEF + k0 + m];
       const double GcHs = gh.x * cm[m] + gh.y * sm[m];
-      const double GsHc = gh.x * sm[m] - gh.y * cm[m];
-      aux_r += cr * GcHs * Pn[m];
+      const double mGsHc = ghm.x * sm[m] + ghm.y * cm[m];  // = -m (g sin - h cos)
+      aux_r += GcHs * Pn[m];
       aux_t += GcHs * dPm;
-      aux_p += (-(double)m) * GsHc * (pole ? dPm : Pn[m]);
+      aux_p += mGsHc * (pole ? dPm : Pn[m]);
     }
     fact *= ratio;
-    dVr += aux_r * fact;
+    dVr += (cr * aux_r) * fact;
     dVp += aux_p * fact;
     dVt += aux_t * fact;
     // rotate rows

@@ -14,13 +14,14 @@
 namespace ts {
 
 constexpr int K1_THREADS = 128;
+constexpr int K1_MIN_BLOCKS = 4;  // <= 128 registers: 16 warps per SM keep the FP64 pipe busier than 168 regs / 12 warps
 
 template <int NMAX>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k1_igrf12_batch(const double* __restrict__ tabG, const double* __restrict__ tabH, double date, int64_t n,
                 const double* __restrict__ r_m, const double* __restrict__ lat, const double* __restrict__ lon,
                 double* __restrict__ Bn, double* __restrict__ Be, double* __restrict__ Bd, int* __restrict__ bad_flag) {
-  __shared__ double2 s_gh[IGRF_NCOEF];
+  __shared__ double2 s_gh[2 * IGRF_NCOEF];
   igrf_stage_coeffs(s_gh, tabG, tabH, date);
   __syncthreads();
   const double PI = 3.141592653589793;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(K2B_THREADS)
 k2b_field_rows(const double* __restrict__ tabG, const double* __restrict__ tabH, const ts_field_opts_dev* __restrict__ opts,
                const int64_t* __restrict__ B_offs, const int64_t* __restrict__ rows_limit, const double* __restrict__ pos,
                double* __restrict__ B_eci, int nmax_select) {
-  __shared__ double2 s_gh[IGRF_NCOEF];
+  __shared__ double2 s_gh[2 * IGRF_NCOEF];
   const int64_t t = blockIdx.x;
   const ts_field_opts_dev o = opts[t];
   if (igrf_nmax_for_date(o.igrf_date) != nmax_select) return;  // handled by the other instantiation
