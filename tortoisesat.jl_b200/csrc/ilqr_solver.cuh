@@ -528,14 +528,22 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
 }
 
 // ----------------------------------------------------------------------------------------
+// Solver state of one trial between phases.  In the persistent kernel it lives in registers; in the
+// phase-split ("phased") launch mode it is stored to / loaded from global memory between kernels.
+enum { PH_BACKWARD = 0, PH_FORWARD = 1, PH_DONE = 2 };
+struct TrialState {
+  double mu, lam_g[8];
+  double J_prev, J, c_max, rho, drho, dV1, dV2, clk_absmax;
+  long long cyc_bwd, cyc_fwd, cyc_lin;
+  int it, outer, dJ_zero, inner_total, ls_total, status, cur, phase, b0, pad_;
+};
+
+// setup: clock trajectory + stage field vectors (sequential, exact replica), multipliers, initial rollout, J_prev
 template <class Team>
-TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w,
-                             ts_trial_outcome_dev& out, int& cur_out) {
+TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, TrialState& st) {
   const int lane = tm.lane();
   const int N = in.N;
-  const long long bstride = w.Nmax * 10;
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
-  // ---- setup: clock trajectory + stage field rows (sequential, exact replica), multipliers, initial rollout
   double clk_absmax = 0.0;
   if (lane == 0) {
     double x8 = in.clk0;
@@ -544,9 +552,9 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
       w.clk[k] = x8;
       clk_absmax = fmax(clk_absmax, fabs(x8));
       const double tt[3] = {cs.t1, cs.t2, cs.t3};
-      for (int st = 0; st < 3; ++st) {
-        const double* br = in.Bt + (long long)field_row(tt[st], in.index_scale, in.B_rows) * 3;
-        for (int c = 0; c < 3; ++c) w.bk[(long long)k * 10 + st * 3 + c] = br[c];
+      for (int s3 = 0; s3 < 3; ++s3) {
+        const double* br = in.Bt + (long long)field_row(tt[s3], in.index_scale, in.B_rows) * 3;
+        for (int c = 0; c < 3; ++c) w.bk[(long long)k * 10 + s3 * 3 + c] = br[c];
       }
       w.bk[(long long)k * 10 + 9] = 0.0;
       x8 = cs.next;
@@ -557,7 +565,6 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   clk_absmax = tm.bcast(clk_absmax, 0);
   for (int i = lane; i < (N - 1) * 6; i += TEAM) w.lam[i] = 0.0;
   tm.sync();
-  int cur = 0;
   if (lane == 0) {
     double* xu = w.xu;
     double xb[7];
@@ -578,150 +585,213 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
     q[7] = q[8] = q[9] = 0.0;
   }
   tm.sync();
+  st.mu = o.penalty_initial;
+  for (int i = 0; i < 8; ++i) st.lam_g[i] = 0.0;
+  st.status = ST_MAX_OUTER;
+  st.outer = 1;
+  st.inner_total = 0;
+  st.ls_total = 0;
+  st.rho = 0.0;
+  st.drho = 0.0;
+  st.it = 0;
+  st.dJ_zero = 0;
+  st.cur = 0;
+  st.b0 = 0;
+  st.pad_ = 0;
+  st.dV1 = st.dV2 = 0.0;
+  st.cyc_bwd = st.cyc_fwd = st.cyc_lin = 0;
+  st.clk_absmax = clk_absmax;
+  st.c_max = 0.0;
+  st.J_prev = trajectory_cost(tm, in, o, w, w.xu, sc, st.mu, st.lam_g, st.c_max);
+  st.J = st.J_prev;
+  st.phase = (o.max_outer < 1) ? PH_DONE : PH_BACKWARD;
+}
 
-  double mu = o.penalty_initial;
-  double lam_g[8];
-  for (int i = 0; i < 8; ++i) lam_g[i] = 0.0;
-  int status = ST_MAX_OUTER, outer = 1, inner_total = 0, ls_total = 0;
-  double J = 0.0, c_max = 0.0;
-  Reg reg;
-  reg.rho = 0.0;
-  reg.drho = 0.0;
-  int it = 0, dJ_zero = 0;
-  long long cyc_bwd = 0, cyc_fwd = 0, cyc_lin = 0;
-  double J_prev = trajectory_cost(tm, in, o, w, w.xu + cur * bstride, sc, mu, lam_g, c_max);
-  J = J_prev;
-  bool done = (o.max_outer < 1);
-  while (!done) {
-    const bool last = (outer == o.max_outer);
-    const double ctol = last ? o.cost_tol : o.cost_tol_intermediate;
-    const double gtol = last ? o.grad_tol : o.grad_tol_intermediate;
-    bool inner_done = false, abort_trial = false;
-    ++it;
-    ++inner_total;
-    const double* xu_cur = w.xu + cur * bstride;
-    double dV1, dV2;
-    const long long tb0 = ts_clock();
-    if (!backward_pass(tm, in, o, w, xu_cur, sc, mu, lam_g, reg, dV1, dV2, cyc_lin)) {
-      status = ST_REG_MAX;
-      abort_trial = true;
-    }
-    const long long tf0 = ts_clock();
-    cyc_bwd += tf0 - tb0;
-    double Jn = J_prev;
-    if (!abort_trial) {
-      tm.sync();  // gains visible to every lane
-      // ---- speculative parallel line search: candidate c = batch*8 + lane, alpha = 2^-c
-      bool accepted = false;
-      double grad = 0.0;
-      const int n_cand = o.max_linesearch + 1;
-      for (int b0 = 0; b0 < n_cand && !accepted; b0 += TEAM) {
-        const int c = b0 + lane;
-        const bool live = (c < n_cand);
-        const int bufi = (lane < cur) ? lane : lane + 1;
-        double alpha = 1.0;
-        for (int i = 0; i < c; ++i) alpha /= 2.0;
-        const RollOut r = forward_batch(tm, in, o, w, xu_cur, w.xu + bufi * bstride, live, alpha, sc, mu, lam_g, clk_absmax);
-        bool acc = false;
-        if (live && r.ok) {
-          const double expected = -alpha * (dV1 + alpha * dV2);
-          const double z = (expected > 0.0) ? (J_prev - r.J) / expected : -1.0;
-          acc = !((z <= o.ls_lower || z > o.ls_upper) && (r.J >= J_prev));
-        }
-        const unsigned bits = tm.ballot(acc);
-        if (bits) {
-          int a = 0;
-          while (!((bits >> a) & 1u)) ++a;
-          accepted = true;
-          ls_total += b0 + a + 1;
-          Jn = tm.bcast(r.J, a);
-          c_max = tm.bcast(r.cmax, a);
-          grad = tm.bcast(r.grad, a);
-          cur = (a < cur) ? a : a + 1;
-        }
-        tm.sync();
-      }
-      if (!accepted) {
-        ls_total += n_cand;
-        Jn = J_prev;
-        reg_increase(o, reg);
-        reg.rho += o.bp_reg_fp;
-        // gradient with the unchanged controls
-        double g = 0.0;
-        for (int k = lane; k < N - 1; k += TEAM) {
-          const double* p = xu_cur + (long long)k * 10;
-          const double* kd = w.kd + (long long)k * 24;
-          double mxg = 0.0;
-          for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
-          g += mxg;
-        }
-        grad = tm.sum(g) / (double)(N - 1);
-      }
-      cyc_fwd += ts_clock() - tf0;
-      if (!(Jn == Jn)) {
-        status = ST_NAN;
-        abort_trial = true;
-      } else if (Jn > o.max_cost_value) {
-        status = ST_COST_BLOWUP;
-        abort_trial = true;
-      } else {
-        const double dJ = fabs(Jn - J_prev);
-        J_prev = Jn;
-        if (dJ == 0.0) ++dJ_zero; else dJ_zero = 0;
-        if ((0.0 < dJ && dJ < ctol) || grad < gtol || dJ_zero > o.dJ_counter_limit || it >= o.max_inner) inner_done = true;
-      }
-      J = Jn;
-    }
-    if (abort_trial) break;
-    if (inner_done) {
-      // ---- outer update: duals (A5), penalty (A6), convergence
-      const double* xu_c = w.xu + cur * bstride;
-      for (int k = lane; k < N - 1; k += TEAM) {
-        double c6[6];
-        bound_c(o, xu_c + (long long)k * 10 + 7, c6);
-        double* lam = w.lam + (long long)k * 6;
-        for (int i = 0; i < 6; ++i) {
-          double l = lam[i] + mu * c6[i];
-          l = fmin(fmax(l, -o.dual_max), o.dual_max);
-          lam[i] = fmax(0.0, l);
-        }
-      }
-      for (int i = 0; i < 8; ++i) {
-        if (!(o.goal_mask & (1 << i))) continue;
-        const double e = ((i < 7) ? xu_c[(long long)(N - 1) * 10 + i] : w.clk[N - 1]) - in.xf[i];
-        const double l = lam_g[i] + mu * e;
-        lam_g[i] = fmin(fmax(l, -o.dual_max), o.dual_max);
-      }
-      mu = fmin(mu * o.penalty_scaling, o.penalty_max);
-      tm.sync();
-      if (c_max < o.constraint_tol) {
-        status = ST_CONVERGED;
-        done = true;
-      } else if (outer >= o.max_outer) {
-        done = true;
-      } else {
-        ++outer;
-        it = 0;
-        dJ_zero = 0;
-        reg.rho = 0.0;
-        reg.drho = 0.0;
-        double cm;
-        J_prev = trajectory_cost(tm, in, o, w, xu_c, sc, mu, lam_g, cm);
-      }
+// inner-iteration bookkeeping once a forward pass has produced (Jn, grad): convergence tests, outer AL update
+template <class Team>
+TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, TrialState& st,
+                               double Jn, double grad) {
+  const int lane = tm.lane();
+  const int N = in.N;
+  const double sc = o.stage_cost_dt ? in.dt : 1.0;
+  const long long bstride = w.Nmax * 10;
+  const bool last = (st.outer == o.max_outer);
+  const double ctol = last ? o.cost_tol : o.cost_tol_intermediate;
+  const double gtol = last ? o.grad_tol : o.grad_tol_intermediate;
+  st.phase = PH_BACKWARD;
+  st.b0 = 0;
+  bool inner_done = false;
+  if (!(Jn == Jn)) {
+    st.status = ST_NAN;
+    st.J = Jn;
+    st.phase = PH_DONE;
+    return;
+  }
+  if (Jn > o.max_cost_value) {
+    st.status = ST_COST_BLOWUP;
+    st.J = Jn;
+    st.phase = PH_DONE;
+    return;
+  }
+  const double dJ = fabs(Jn - st.J_prev);
+  st.J_prev = Jn;
+  if (dJ == 0.0) ++st.dJ_zero; else st.dJ_zero = 0;
+  if ((0.0 < dJ && dJ < ctol) || grad < gtol || st.dJ_zero > o.dJ_counter_limit || st.it >= o.max_inner) inner_done = true;
+  st.J = Jn;
+  if (!inner_done) return;
+  // ---- outer update: duals (A5), penalty (A6), convergence
+  const double* xu_c = w.xu + st.cur * bstride;
+  for (int k = lane; k < N - 1; k += TEAM) {
+    double c6[6];
+    bound_c(o, xu_c + (long long)k * 10 + 7, c6);
+    double* lam = w.lam + (long long)k * 6;
+    for (int i = 0; i < 6; ++i) {
+      double l = lam[i] + st.mu * c6[i];
+      l = fmin(fmax(l, -o.dual_max), o.dual_max);
+      lam[i] = fmax(0.0, l);
     }
   }
-  out.status = status;
-  out.outer_iters = outer;
-  out.inner_iters = inner_total;
-  out.ls_rollouts = ls_total;
-  out.N = N;
-  out.J = J;
-  out.c_max = c_max;
+  for (int i = 0; i < 8; ++i) {
+    if (!(o.goal_mask & (1 << i))) continue;
+    const double e = ((i < 7) ? xu_c[(long long)(N - 1) * 10 + i] : w.clk[N - 1]) - in.xf[i];
+    const double l = st.lam_g[i] + st.mu * e;
+    st.lam_g[i] = fmin(fmax(l, -o.dual_max), o.dual_max);
+  }
+  st.mu = fmin(st.mu * o.penalty_scaling, o.penalty_max);
+  tm.sync();
+  if (st.c_max < o.constraint_tol) {
+    st.status = ST_CONVERGED;
+    st.phase = PH_DONE;
+  } else if (st.outer >= o.max_outer) {
+    st.phase = PH_DONE;
+  } else {
+    ++st.outer;
+    st.it = 0;
+    st.dJ_zero = 0;
+    st.rho = 0.0;
+    st.drho = 0.0;
+    double cm;
+    st.J_prev = trajectory_cost(tm, in, o, w, xu_c, sc, st.mu, st.lam_g, cm);
+  }
+}
+
+// phase BACKWARD: one Riccati sweep (with regularisation restarts)
+template <class Team>
+TS_FN void solve_backward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, TrialState& st) {
+  const double sc = o.stage_cost_dt ? in.dt : 1.0;
+  const long long bstride = w.Nmax * 10;
+  ++st.it;
+  ++st.inner_total;
+  const long long t0 = ts_clock();
+  Reg reg;
+  reg.rho = st.rho;
+  reg.drho = st.drho;
+  const bool ok = backward_pass(tm, in, o, w, w.xu + st.cur * bstride, sc, st.mu, st.lam_g, reg, st.dV1, st.dV2, st.cyc_lin);
+  st.rho = reg.rho;
+  st.drho = reg.drho;
+  st.cyc_bwd += ts_clock() - t0;
+  if (!ok) {
+    st.status = ST_REG_MAX;
+    st.phase = PH_DONE;
+    return;
+  }
+  tm.sync();  // gains visible to every lane
+  st.phase = PH_FORWARD;
+  st.b0 = 0;
+}
+
+// phase FORWARD: one batch of 8 speculative line-search candidates c = b0 + lane, alpha = 2^-c
+template <class Team>
+TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, TrialState& st) {
+  const int lane = tm.lane();
+  const int N = in.N;
+  const double sc = o.stage_cost_dt ? in.dt : 1.0;
+  const long long bstride = w.Nmax * 10;
+  const long long t0 = ts_clock();
+  const double* xu_cur = w.xu + st.cur * bstride;
+  const int n_cand = o.max_linesearch + 1;
+  const int c = st.b0 + lane;
+  const bool live = (c < n_cand);
+  const int bufi = (lane < st.cur) ? lane : lane + 1;
+  double alpha = 1.0;
+  for (int i = 0; i < c; ++i) alpha /= 2.0;
+  const RollOut r = forward_batch(tm, in, o, w, xu_cur, w.xu + bufi * bstride, live, alpha, sc, st.mu, st.lam_g, st.clk_absmax);
+  bool acc = false;
+  if (live && r.ok) {
+    const double expected = -alpha * (st.dV1 + alpha * st.dV2);
+    const double z = (expected > 0.0) ? (st.J_prev - r.J) / expected : -1.0;
+    acc = !((z <= o.ls_lower || z > o.ls_upper) && (r.J >= st.J_prev));
+  }
+  const unsigned bits = tm.ballot(acc);
+  if (bits) {
+    int a = 0;
+    while (!((bits >> a) & 1u)) ++a;
+    st.ls_total += st.b0 + a + 1;
+    const double Jn = tm.bcast(r.J, a);
+    st.c_max = tm.bcast(r.cmax, a);
+    const double grad = tm.bcast(r.grad, a);
+    st.cur = (a < st.cur) ? a : a + 1;
+    tm.sync();
+    st.cyc_fwd += ts_clock() - t0;
+    solve_after_forward(tm, in, o, w, st, Jn, grad);
+    return;
+  }
+  tm.sync();
+  st.b0 += TEAM;
+  if (st.b0 < n_cand) {  // next batch of candidates
+    st.cyc_fwd += ts_clock() - t0;
+    return;
+  }
+  // line search exhausted: keep the trajectory, raise the regularisation (App. C step 4)
+  st.ls_total += n_cand;
+  Reg reg;
+  reg.rho = st.rho;
+  reg.drho = st.drho;
+  reg_increase(o, reg);
+  reg.rho += o.bp_reg_fp;
+  st.rho = reg.rho;
+  st.drho = reg.drho;
+  double g = 0.0;
+  for (int k = lane; k < N - 1; k += TEAM) {
+    const double* p = xu_cur + (long long)k * 10;
+    const double* kd = w.kd + (long long)k * 24;
+    double mxg = 0.0;
+    for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
+    g += mxg;
+  }
+  const double grad = tm.sum(g) / (double)(N - 1);
+  st.cyc_fwd += ts_clock() - t0;
+  solve_after_forward(tm, in, o, w, st, st.J_prev, grad);
+}
+
+TS_HD void solve_finish(const TrialIn& in, const TrialState& st, ts_trial_outcome_dev& out) {
+  out.status = st.status;
+  out.outer_iters = st.outer;
+  out.inner_iters = st.inner_total;
+  out.ls_rollouts = st.ls_total;
+  out.N = in.N;
+  out.J = st.J;
+  out.c_max = st.c_max;
   // diagnostics of the low-level solve (SM cycles): backward pass, forward pass, linearisation share
-  out.t_final = (double)cyc_bwd;
-  out.slew_time = (double)cyc_fwd;
-  out.flops = (double)cyc_lin;
-  cur_out = cur;
+  out.t_final = (double)st.cyc_bwd;
+  out.slew_time = (double)st.cyc_fwd;
+  out.flops = (double)st.cyc_lin;
+}
+
+// The whole solve as one loop over phases (persistent-kernel mode and the host lane-emulator).
+template <class Team>
+TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w,
+                             ts_trial_outcome_dev& out, int& cur_out) {
+  TrialState st;
+  solve_init(tm, in, o, w, st);
+  while (st.phase != PH_DONE) {
+    if (st.phase == PH_BACKWARD)
+      solve_backward(tm, in, o, w, st);
+    else
+      solve_forward(tm, in, o, w, st);
+  }
+  solve_finish(in, st, out);
+  cur_out = st.cur;
   tm.sync();
 }
 

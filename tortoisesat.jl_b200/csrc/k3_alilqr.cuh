@@ -92,6 +92,64 @@ struct K3Args {
   unsigned long long* queue;
 };
 
+
+// Fills the team's shared-memory TrialIn block for trial t (lane 0 writes, team syncs).
+__device__ __forceinline__ const TrialIn& k3_load_trial(const GpuTeam& tm, const K3Args& a, int64_t t) {
+  TrialIn* inp = reinterpret_cast<TrialIn*>(tm.smem() + SM_TRIAL);
+  __builtin_assume(__isShared(inp));
+  tm.sync();
+  if (tm.ln == 0) {
+    inp->N = (int)a.N_i[t];
+    inp->dt = a.dt;
+    for (int i = 0; i < 7; ++i) inp->x0[i] = a.x0[t * 8 + i];
+    inp->clk0 = a.x0[t * 8 + 7];
+    for (int i = 0; i < 8; ++i) {
+      inp->xf[i] = a.xf[t * 8 + i];
+      inp->Qd[i] = a.Qd[t * 8 + i];
+      inp->Qfd[i] = a.Qfd[t * 8 + i];
+    }
+    for (int i = 0; i < 3; ++i) inp->Rd[i] = a.Rd[t * 3 + i];
+    double Jm[9], Ji[9];
+    for (int i = 0; i < 9; ++i) Jm[i] = a.Jmat[t * 9 + i];
+    inv3_gj(Jm, Ji);
+    for (int i = 0; i < 9; ++i) {
+      inp->I.J[i] = Jm[i];
+      inp->I.Jinv[i] = Ji[i];
+    }
+    inp->Bt = a.B_eci + a.B_offs[t] * 3;
+    inp->B_rows = a.B_rows[t];
+    inp->index_scale = a.index_scale[t];
+    inp->clock_rate = a.clock_rate[t];
+    inp->U0 = a.U0 ? a.U0 + a.offs[t] * 3 : nullptr;
+  }
+  tm.sync();
+  return *inp;
+}
+
+// Writes a finished trial's results in the reference's shapes: X (N x 8 incl. clock), U, K (3 x 8 per knot).
+__device__ __forceinline__ void k3_store_results(const GpuTeam& tm, const K3Args& a, int64_t t, const TrialWork& w, int N, int cur,
+                                                 const ts_trial_outcome_dev& oc) {
+  const double* xu = w.xu + (int64_t)cur * a.Nmax * 10;
+  double* Xo = a.X + a.offs[t] * 8;
+  double* Uo = a.U + a.offs[t] * 3;
+  for (int k = tm.ln; k < N; k += TEAM) {
+    for (int i = 0; i < 7; ++i) Xo[(int64_t)k * 8 + i] = xu[(int64_t)k * 10 + i];
+    Xo[(int64_t)k * 8 + 7] = w.clk[k];
+    if (k < N - 1) {
+      for (int i = 0; i < 3; ++i) Uo[(int64_t)k * 3 + i] = xu[(int64_t)k * 10 + 7 + i];
+      if (a.K) {
+        double* Ko = a.K + (a.offs[t] + k) * 24;
+        const double* kd = w.kd + (int64_t)k * 24;
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 7; ++j) Ko[i * 8 + j] = kd[j * 3 + i];
+          Ko[i * 8 + 7] = 0.0;
+        }
+      }
+    }
+  }
+  if (tm.ln == 0) a.out[t] = oc;
+}
+
 constexpr int K3_WARPS_PER_BLOCK = 1;
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
@@ -122,62 +180,74 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
     const int64_t qi = (int64_t)base + team;
     if (qi < a.n_trials) {
       const int64_t t = a.order ? a.order[qi] : qi;
-      // the trial's read-only parameters live in the team's shared memory (not in local memory)
-      TrialIn* inp = reinterpret_cast<TrialIn*>(tm.smem() + SM_TRIAL);
-      __builtin_assume(__isShared(inp));
-      tm.sync();
-      if (tm.ln == 0) {
-        inp->N = (int)a.N_i[t];
-        inp->dt = a.dt;
-        for (int i = 0; i < 7; ++i) inp->x0[i] = a.x0[t * 8 + i];
-        inp->clk0 = a.x0[t * 8 + 7];
-        for (int i = 0; i < 8; ++i) {
-          inp->xf[i] = a.xf[t * 8 + i];
-          inp->Qd[i] = a.Qd[t * 8 + i];
-          inp->Qfd[i] = a.Qfd[t * 8 + i];
-        }
-        for (int i = 0; i < 3; ++i) inp->Rd[i] = a.Rd[t * 3 + i];
-        double Jm[9], Ji[9];
-        for (int i = 0; i < 9; ++i) Jm[i] = a.Jmat[t * 9 + i];
-        inv3_gj(Jm, Ji);
-        for (int i = 0; i < 9; ++i) {
-          inp->I.J[i] = Jm[i];
-          inp->I.Jinv[i] = Ji[i];
-        }
-        inp->Bt = a.B_eci + a.B_offs[t] * 3;
-        inp->B_rows = a.B_rows[t];
-        inp->index_scale = a.index_scale[t];
-        inp->clock_rate = a.clock_rate[t];
-        inp->U0 = a.U0 ? a.U0 + a.offs[t] * 3 : nullptr;
-      }
-      tm.sync();
-      const TrialIn& in = *inp;
+      const TrialIn& in = k3_load_trial(tm, a, t);
       ts_trial_outcome_dev oc;
       int cur = 0;
       alilqr_solve_team(tm, in, a.opts, w, oc, cur);
-      // ---- results: X (N x 8 incl. the clock state), U, K (3 x 8 per knot, zero clock column)
-      const double* xu = w.xu + (int64_t)cur * a.Nmax * 10;
-      double* Xo = a.X + a.offs[t] * 8;
-      double* Uo = a.U + a.offs[t] * 3;
-      for (int k = tm.ln; k < in.N; k += TEAM) {
-        for (int i = 0; i < 7; ++i) Xo[(int64_t)k * 8 + i] = xu[(int64_t)k * 10 + i];
-        Xo[(int64_t)k * 8 + 7] = w.clk[k];
-        if (k < in.N - 1) {
-          for (int i = 0; i < 3; ++i) Uo[(int64_t)k * 3 + i] = xu[(int64_t)k * 10 + 7 + i];
-          if (a.K) {
-            double* Ko = a.K + (a.offs[t] + k) * 24;
-            const double* kd = w.kd + (int64_t)k * 24;
-            for (int i = 0; i < 3; ++i) {
-              for (int j = 0; j < 7; ++j) Ko[i * 8 + j] = kd[j * 3 + i];
-              Ko[i * 8 + 7] = 0.0;
-            }
-          }
-        }
-      }
-      if (tm.ln == 0) a.out[t] = oc;
+      k3_store_results(tm, a, t, w, in.N, cur, oc);
     }
     __syncwarp();
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Phase-split launch mode: the same solver phases as separate kernels, driven in lockstep by the
+// host (init, then rounds of [backward, forward x3] until every trial is done, then finish).
+// All resident warps of a launch execute the same phase -> one hot loop in the instruction cache
+// and a per-kernel register allocation; finished trials release their SM slots immediately.
+// One work slot per trial (slot = queue index).  Used when the ensemble has (nearly) uniform
+// horizons; ragged ensembles use the persistent kernel above.
+enum { K3P_INIT = 10, K3P_FINISH = 11 };
+
+__device__ __forceinline__ void k3_team_setup(const K3Args& a, GpuTeam& tm, TrialWork& w, int64_t& qi, double* smem) {
+  const int lane32 = threadIdx.x & 31;
+  const int team = lane32 >> 3;
+  qi = (int64_t)blockIdx.x * 4 + team;
+  tm.ln = lane32 & 7;
+  tm.shift = team * 8;
+  tm.mask = 0xffu << tm.shift;
+  tm.sm = smem + team * TEAM_SMEM_DOUBLES;
+  w.Nmax = a.Nmax;
+  w.xu = a.w_base + qi * a.per_slot;
+  w.kd = w.xu + 90 * a.Nmax;
+  w.lam = w.kd + 24 * a.Nmax;
+  w.bk = w.lam + 6 * a.Nmax;
+  w.clk = w.bk + 10 * a.Nmax;
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(32, 1) k3_phase_kernel(const K3Args a, TrialState* __restrict__ states, int* __restrict__ n_active) {
+  extern __shared__ __align__(16) double k3_smem[];
+  GpuTeam tm;
+  TrialWork w;
+  int64_t qi;
+  k3_team_setup(a, tm, w, qi, k3_smem);
+  if (qi >= a.n_trials) return;
+  TrialState st;
+  if (PHASE != K3P_INIT) {
+    st = states[qi];
+    if (PHASE == PH_BACKWARD && st.phase != PH_BACKWARD) return;
+    if (PHASE == PH_FORWARD && st.phase != PH_FORWARD) return;
+  }
+  const int64_t t = a.order ? a.order[qi] : qi;
+  const TrialIn& in = k3_load_trial(tm, a, t);
+  if (PHASE == K3P_INIT) solve_init(tm, in, a.opts, w, st);
+  if (PHASE == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
+  if (PHASE == PH_FORWARD) {
+    solve_forward(tm, in, a.opts, w, st);
+    if (st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
+  }
+  if (PHASE == PH_BACKWARD && st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
+  if (PHASE == K3P_INIT && st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
+  if (PHASE == K3P_FINISH) {
+    ts_trial_outcome_dev oc;
+    solve_finish(in, st, oc);
+    k3_store_results(tm, a, t, w, in.N, st.cur, oc);
+    return;
+  }
+  tm.sync();
+  if (tm.ln == 0) states[qi] = st;
 }
 
 }  // namespace ts

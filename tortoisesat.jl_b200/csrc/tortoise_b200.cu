@@ -314,17 +314,33 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
 }
 
 // Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
-// Fills a.order / work arena / queue; does not synchronise.
+// Two launch modes (same solver code, ilqr_solver.cuh):
+//   persistent  one kernel, warps pull groups of 4 trials from a queue (ragged horizons)
+//   phased      host-driven lockstep of phase kernels (uniform horizons): every resident warp runs the same
+//               phase, so the hot loop fits the instruction cache and finished trials free their SM slots
+// TS_K3_MODE=persistent|phased overrides the automatic choice.  Returns with all work complete on the stream
+// (the phased mode synchronises to poll the active-trial counter).
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   const int64_t n_trials = a.n_trials;
-  int64_t Nmax = 0;
-  for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
+  int64_t Nmax = 0, Nmin = INT64_MAX;
+  for (int64_t t = 0; t < n_trials; ++t) {
+    Nmax = std::max(Nmax, N_i_host[t]);
+    Nmin = std::min(Nmin, N_i_host[t]);
+  }
+  // measured (profiles/README.md): the phased mode is ~10-25% SLOWER than the persistent kernel on the 4096-trial
+  // ensemble (every round waits for the slowest trial's phase), so it is opt-in only.
+  bool phased = false;
+  (void)Nmin;
+  if (const char* m = getenv("TS_K3_MODE")) {
+    if (!strcmp(m, "persistent")) phased = false;
+    if (!strcmp(m, "phased")) phased = true;
+  }
   int occ = 0;
   TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
   if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
   const int64_t groups = (n_trials + 3) / 4;
   const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
-  const int64_t warps = std::min(groups, max_warps);
+  const int64_t warps = phased ? groups : std::min(groups, max_warps);
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
   // trials sorted by horizon (descending) so the four teams of a warp have similar trip counts
@@ -336,7 +352,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
   void *p_work, *p_q;
   Nmax += (Nmax & 1);  // even: keeps every per-knot record 16-byte aligned for the asynchronous copies
-  const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1) + (Nmax & 1);
+  const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1);
   if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)slots + 256, &p_work))) return rc;
   if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
   TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
@@ -345,7 +361,35 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   a.w_base = (double*)p_work;
   a.per_slot = per_slot + (per_slot & 1);
   a.queue = (unsigned long long*)p_q;
-  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+  if (!phased) {
+    k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+    c->launches++;
+    TS_CUDA(c, cudaGetLastError());
+    return TS_OK;
+  }
+  // ---- phased mode
+  void* p_st;
+  if ((rc = scratch_reserve(c, 15, (size_t)slots * sizeof(TrialState) + 64, &p_st))) return rc;
+  TrialState* d_states = (TrialState*)p_st;
+  int* d_active = (int*)p_q + 4;
+  int h_active = (int)n_trials;
+  TS_CUDA(c, cudaMemcpyAsync(d_active, &h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const int smem = 4 * TEAM_SMEM_DOUBLES * 8;
+  k3_phase_kernel<K3P_INIT><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
+  c->launches++;
+  const int n_batches = (a.opts.max_linesearch + 1 + TEAM - 1) / TEAM;
+  const long long max_rounds = (long long)a.opts.max_outer * a.opts.max_inner + 8;
+  for (long long round = 0; round < max_rounds; ++round) {
+    k3_phase_kernel<PH_BACKWARD><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
+    for (int b = 0; b < n_batches; ++b) k3_phase_kernel<PH_FORWARD><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
+    c->launches += 1 + n_batches;
+    if ((round & 7) == 7 || round < 2) {
+      TS_CUDA(c, cudaMemcpyAsync(&h_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      TS_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (h_active <= 0) break;
+    }
+  }
+  k3_phase_kernel<K3P_FINISH><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
   c->launches++;
   TS_CUDA(c, cudaGetLastError());
   return TS_OK;
