@@ -263,27 +263,26 @@ TS_HD void rk3_jac7(const Inertia& I, const double x[7], const double u[3], cons
 // The matrix form above keeps K1, K2, K3 and a stage Jacobian alive (~260 doubles) and spills;
 // the kernel instead pushes the 10 unit directions through the three stages one at a time with
 // analytic JVPs.  Live state: three StagePt (3 x 23 doubles) + one direction (~30 doubles).
-struct StagePt {
-  double inq, s, v[3], w[3], us[3], Bn[3], t1[3], BB[3], Jw[3];
+struct StagePt {           // 11 doubles per stage: small enough for three of them to stay in registers
+  double inq, s, v[3], w[3], Bn[3];
 };
 // f(x,u) at a stage point + the intermediates its JVP needs
-TS_HD void stage_eval(const Inertia& I, const double x[7], const double u[3], const double* Bn, StagePt& sp, double dx[7]) {
+TS_HD void stage_eval(const Inertia& I, const double x[7], const double us[3], const double* Bn, StagePt& sp, double dx[7]) {
   sp.inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
   sp.s = x[3] * sp.inq;
   for (int i = 0; i < 3; ++i) {
     sp.v[i] = x[4 + i] * sp.inq;
     sp.w[i] = x[i];
-    sp.us[i] = u[i] * 1.e-2;
     sp.Bn[i] = Bn[i];
   }
-  double vxB[3], c2[3], tau[3], wJw[3];
+  double vxB[3], t1[3], c2[3], BB[3], tau[3], Jw[3], wJw[3];
   cross3(sp.v, sp.Bn, vxB);
-  for (int i = 0; i < 3; ++i) sp.t1[i] = vxB[i] + sp.s * sp.Bn[i];
-  cross3(sp.v, sp.t1, c2);
-  for (int i = 0; i < 3; ++i) sp.BB[i] = sp.Bn[i] + 2.0 * c2[i];
-  cross3(sp.us, sp.BB, tau);
-  for (int i = 0; i < 3; ++i) sp.Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
-  cross3(sp.w, sp.Jw, wJw);
+  for (int i = 0; i < 3; ++i) t1[i] = vxB[i] + sp.s * sp.Bn[i];
+  cross3(sp.v, t1, c2);
+  for (int i = 0; i < 3; ++i) BB[i] = sp.Bn[i] + 2.0 * c2[i];
+  cross3(us, BB, tau);
+  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
+  cross3(sp.w, Jw, wJw);
   const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
   for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
   dx[3] = 0.5 * (-(sp.v[0] * sp.w[0] + sp.v[1] * sp.w[1] + sp.v[2] * sp.w[2]));
@@ -291,8 +290,8 @@ TS_HD void stage_eval(const Inertia& I, const double x[7], const double u[3], co
   dx[5] = 0.5 * (sp.s * sp.w[1] + (sp.v[2] * sp.w[0] - sp.v[0] * sp.w[2]));
   dx[6] = 0.5 * (sp.s * sp.w[2] + (sp.v[0] * sp.w[1] - sp.v[1] * sp.w[0]));
 }
-// out = fx*vx + fu*vu at the stage point
-TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double vx[7], const double vu[3], double out[7]) {
+// out = fx*vx + fu*vu at the stage point (t1, BB and J*w are recomputed: 36 FLOP instead of 12 live doubles)
+TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double us[3], const double vx[7], const double vu[3], double out[7]) {
   const double dot = sp.s * vx[3] + sp.v[0] * vx[4] + sp.v[1] * vx[5] + sp.v[2] * vx[6];
   const double ds = (vx[3] - sp.s * dot) * sp.inq;
   const double dv[3] = {(vx[4] - sp.v[0] * dot) * sp.inq, (vx[5] - sp.v[1] * dot) * sp.inq, (vx[6] - sp.v[2] * dot) * sp.inq};
@@ -302,20 +301,28 @@ TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double vx[7], co
   cross3(sp.v, dw, b);
   out[3] = 0.5 * (-((dv[0] * sp.w[0] + dv[1] * sp.w[1] + dv[2] * sp.w[2]) + (sp.v[0] * dw[0] + sp.v[1] * dw[1] + sp.v[2] * dw[2])));
   for (int i = 0; i < 3; ++i) out[4 + i] = 0.5 * (ds * sp.w[i] + sp.s * dw[i] + a[i] + b[i]);
+  double vxB[3], t1[3], cc[3], BB[3];
+  cross3(sp.v, sp.Bn, vxB);
+  for (int i = 0; i < 3; ++i) t1[i] = vxB[i] + sp.s * sp.Bn[i];
+  cross3(sp.v, t1, cc);
+  for (int i = 0; i < 3; ++i) BB[i] = sp.Bn[i] + 2.0 * cc[i];
   double dt1[3], c1[3], c2[3];
   cross3(dv, sp.Bn, dt1);
   for (int i = 0; i < 3; ++i) dt1[i] += ds * sp.Bn[i];
-  cross3(dv, sp.t1, c1);
+  cross3(dv, t1, c1);
   cross3(sp.v, dt1, c2);
   const double dBB[3] = {2.0 * (c1[0] + c2[0]), 2.0 * (c1[1] + c2[1]), 2.0 * (c1[2] + c2[2])};
   const double dus[3] = {vu[0] * 1.e-2, vu[1] * 1.e-2, vu[2] * 1.e-2};
-  double t1[3], t2[3], g1[3], g2[3], Jdw[3];
-  cross3(dus, sp.BB, t1);
-  cross3(sp.us, dBB, t2);
-  for (int i = 0; i < 3; ++i) Jdw[i] = I.J[i * 3 + 0] * dw[0] + I.J[i * 3 + 1] * dw[1] + I.J[i * 3 + 2] * dw[2];
-  cross3(dw, sp.Jw, g1);
+  double ta[3], tb[3], g1[3], g2[3], Jw[3], Jdw[3];
+  cross3(dus, BB, ta);
+  cross3(us, dBB, tb);
+  for (int i = 0; i < 3; ++i) {
+    Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
+    Jdw[i] = I.J[i * 3 + 0] * dw[0] + I.J[i * 3 + 1] * dw[1] + I.J[i * 3 + 2] * dw[2];
+  }
+  cross3(dw, Jw, g1);
   cross3(sp.w, Jdw, g2);
-  const double r[3] = {t1[0] + t2[0] - g1[0] - g2[0], t1[1] + t2[1] - g1[1] - g2[1], t1[2] + t2[2] - g1[2] - g2[2]};
+  const double r[3] = {ta[0] + tb[0] - g1[0] - g2[0], ta[1] + tb[1] - g1[1] - g2[1], ta[2] + tb[2] - g1[2] - g2[2]};
   for (int i = 0; i < 3; ++i) out[i] = I.Jinv[i * 3 + 0] * r[0] + I.Jinv[i * 3 + 1] * r[1] + I.Jinv[i * 3 + 2] * r[2];
 }
 // Jacobian of the rk3 step by JVPs; column c of [A|B] is written to colmajor[c*7 .. c*7+6].
@@ -323,11 +330,12 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
                         double dt, double* colmajor) {
   StagePt s1, s2, s3;
   double k1[7], k2[7], k3[7], xs[7];
-  stage_eval(I, x, u, B1, s1, k1);
+  const double us[3] = {u[0] * 1.e-2, u[1] * 1.e-2, u[2] * 1.e-2};
+  stage_eval(I, x, us, B1, s1, k1);
   for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k1[i] * dt);
-  stage_eval(I, xs, u, B2, s2, k2);
+  stage_eval(I, xs, us, B2, s2, k2);
   for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] * dt + 2.0 * (k2[i] * dt);
-  stage_eval(I, xs, u, B3, s3, k3);
+  stage_eval(I, xs, us, B3, s3, k3);
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
@@ -335,17 +343,17 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
     double vx[7], vu[3], t1[7], t2[7], t3[7], y[7];
     for (int i = 0; i < 7; ++i) vx[i] = (i == c) ? 1.0 : 0.0;
     for (int i = 0; i < 3; ++i) vu[i] = (7 + i == c) ? 1.0 : 0.0;
-    stage_jvp(I, s1, vx, vu, t1);
+    stage_jvp(I, s1, us, vx, vu, t1);
     for (int i = 0; i < 7; ++i) {
       t1[i] *= dt;
       y[i] = vx[i] + 0.5 * t1[i];
     }
-    stage_jvp(I, s2, y, vu, t2);
+    stage_jvp(I, s2, us, y, vu, t2);
     for (int i = 0; i < 7; ++i) {
       t2[i] *= dt;
       y[i] = vx[i] - t1[i] + 2.0 * t2[i];
     }
-    stage_jvp(I, s3, y, vu, t3);
+    stage_jvp(I, s3, us, y, vu, t3);
     for (int i = 0; i < 7; ++i) colmajor[c * 7 + i] = vx[i] + (t1[i] + 4.0 * t2[i] + t3[i] * dt) * TS_SIXTH;
   }
 }

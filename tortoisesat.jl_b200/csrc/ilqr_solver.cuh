@@ -257,20 +257,19 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   for (;;) {  // regularisation restart loop
     dV1 = 0.0;
     dV2 = 0.0;
-    double S[28], s[7];
-    {
+    // terminal value function -> shared memory (the per-knot loop loads S at its top, so the 35 doubles of
+    // S/s are NOT live in registers across the register-hungry linearisation phase)
+    tm.sync();
+    if (lane < 7) {
       const double* xN = xu_cur + (long long)(N - 1) * 10;
-      for (int i = 0; i < 28; ++i) S[i] = 0.0;
-      for (int i = 0; i < 7; ++i) {
-        const double e = xN[i] - in.xf[i];
-        double sxx = in.Qfd[i], sx = in.Qfd[i] * e;
-        if (o.goal_mask & (1 << i)) {
-          sxx += mu;
-          sx += lam_g[i] + mu * e;
-        }
-        S[sym_idx(i, i)] = sxx;
-        s[i] = sx;
+      const double e = xN[lane] - in.xf[lane];
+      double sxx = in.Qfd[lane], sx = in.Qfd[lane] * e;
+      if (o.goal_mask & (1 << lane)) {
+        sxx += mu;
+        sx += lam_g[lane] + mu * e;
       }
+      for (int i = 0; i < 7; ++i) sm[SM_SCOL + lane * 8 + i] = (i == lane) ? sxx : 0.0;
+      sm[SM_SVEC + lane] = sx;
     }
     bool not_pd = false;
     const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
@@ -294,6 +293,11 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       for (int kk = kk_hi; kk >= 0; --kk) {
         const double* rec = sm + SM_REC + kk * REC;
         const int k = base + kk;
+        // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
+        double S[28], s[7];
+        for (int i = 0; i < 7; ++i)
+          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[SM_SCOL + j * 8 + i] + sm[SM_SCOL + i * 8 + j]);
+        for (int i = 0; i < 7; ++i) s[i] = sm[SM_SVEC + i];
         // ---- P1: column products
         double Qxxc[7], Quxc[3], Qx = 0.0;
         if (lane < 7) {
@@ -387,10 +391,6 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           sm[SM_SVEC + lane] = t;
         }
         tm.sync();
-        // ---- P4: symmetrise and re-replicate
-        for (int i = 0; i < 7; ++i)
-          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[SM_SCOL + j * 8 + i] + sm[SM_SCOL + i * 8 + j]);
-        for (int i = 0; i < 7; ++i) s[i] = sm[SM_SVEC + i];
       }
     }
     if (!not_pd) break;
