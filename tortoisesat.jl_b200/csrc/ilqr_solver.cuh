@@ -784,11 +784,13 @@ TS_FN void alilqr_solve_team(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
                              ts_trial_outcome_dev& out, int& cur_out) {
   TrialState st;
   solve_init(tm, in, o, w, st);
+  // One loop iteration = one iLQR iteration: a backward sweep, then forward batches until a step is
+  // taken.  Keeping this shape (rather than "run whatever phase I am in") keeps the four teams of a warp
+  // in the same phase: a team that needs an extra line-search batch makes its siblings wait at the
+  // reconvergence point instead of drifting into the other phase (which would serialise both code paths).
   while (st.phase != PH_DONE) {
-    if (st.phase == PH_BACKWARD)
-      solve_backward(tm, in, o, w, st);
-    else
-      solve_forward(tm, in, o, w, st);
+    if (st.phase == PH_BACKWARD) solve_backward(tm, in, o, w, st);
+    while (st.phase == PH_FORWARD) solve_forward(tm, in, o, w, st);
   }
   solve_finish(in, st, out);
   cur_out = st.cur;
