@@ -213,7 +213,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints a "NCCL version ..." banner on STDOUT when the first communicator is created; keep stdout
+        # clean for the single JSON line by pointing fd 1 at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = tb.Engine(local_rank)
     peak_fp64 = eng.fp64_peak_tflops()
 
