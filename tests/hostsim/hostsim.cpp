@@ -15,14 +15,17 @@
 
 using namespace ts;
 
-struct TeamShared {
-  std::barrier<> bar{TEAM};
-  double xch[TEAM];
-  unsigned bits[TEAM];
-  std::vector<double> sm = std::vector<double>(TEAM_SMEM_DOUBLES, 0.0);
+template <int W_>
+struct TeamSharedT {
+  std::barrier<> bar{W_};
+  double xch[W_];
+  unsigned bits[W_];
+  std::vector<double> sm = std::vector<double>(SmL<W_>::TOTAL, 0.0);
 };
-struct CpuTeam {
-  TeamShared* sh;
+template <int W_>
+struct CpuTeamT {
+  static constexpr int W = W_;
+  TeamSharedT<W_>* sh;
   int ln;
   int lane() const { return ln; }
   double* smem() const { return sh->sm.data(); }
@@ -38,7 +41,7 @@ struct CpuTeam {
     sh->bits[ln] = p ? 1u : 0u;
     sync();
     unsigned r = 0;
-    for (int i = 0; i < TEAM; ++i) r |= sh->bits[i] << i;
+    for (int i = 0; i < W_; ++i) r |= sh->bits[i] << i;
     sync();
     return r;
   }
@@ -47,7 +50,7 @@ struct CpuTeam {
   void stage_commit() const {}
   void stage_wait(int) const {}
   double sum(double v) const {
-    for (int off = 4; off >= 1; off >>= 1) {
+    for (int off = W_ / 2; off >= 1; off >>= 1) {
       sh->xch[ln] = v;
       sync();
       v += sh->xch[ln ^ off];
@@ -56,7 +59,7 @@ struct CpuTeam {
     return v;
   }
   double max(double v) const {
-    for (int off = 4; off >= 1; off >>= 1) {
+    for (int off = W_ / 2; off >= 1; off >>= 1) {
       sh->xch[ln] = v;
       sync();
       v = fmax(v, sh->xch[ln ^ off]);
@@ -65,6 +68,47 @@ struct CpuTeam {
     return v;
   }
 };
+
+template <int W_>
+static void solve_with_width(const TrialIn& in, const ts_ilqr_opts_dev* opts, int64_t N, double* X, double* U, double* K,
+                             ts_trial_outcome_dev* out) {
+  const size_t per_slot = (size_t)9 * N * 10;
+  std::vector<double> xu(4 * per_slot), kd((size_t)N * 24), lam((size_t)N * 6), clk((size_t)N), bk((size_t)N * 10);
+  TrialWork w;
+  w.xu = xu.data();
+  w.xu_warp = xu.data();
+  w.slot_stride = (long long)per_slot;
+  w.kd = kd.data();
+  w.lam = lam.data();
+  w.clk = clk.data();
+  w.bk = bk.data();
+  w.Nmax = N;
+  TeamSharedT<W_> sh;
+  ts_trial_outcome_dev oc[W_];
+  int cur[W_];
+  std::vector<std::thread> th;
+  for (int l = 0; l < W_; ++l)
+    th.emplace_back([&, l]() {
+      CpuTeamT<W_> tm{&sh, l};
+      alilqr_solve_team(tm, in, *opts, w, oc[l], cur[l]);
+    });
+  for (auto& t : th) t.join();
+  *out = oc[0];
+  const double* x = xu_buf<W_>(w, cur[0]);
+  for (int64_t k = 0; k < N; ++k) {
+    for (int i = 0; i < 7; ++i) X[k * 8 + i] = x[k * 10 + i];
+    X[k * 8 + 7] = clk[k];
+    if (k < N - 1) {
+      for (int i = 0; i < 3; ++i) U[k * 3 + i] = x[k * 10 + 7 + i];
+      if (K)
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 7; ++j) K[k * 24 + i * 8 + j] = kd[k * 24 + j * 3 + i];
+          K[k * 24 + i * 8 + 7] = 0.0;
+        }
+    }
+  }
+}
+
 
 extern "C" {
 
@@ -97,9 +141,11 @@ void hs_rk4_jac7(const double* J9, const double* x7, const double* u3, const dou
 }
 
 // One trial, same argument meaning as the C ABI's ts_alilqr_solve_batch for n_trials = 1.
-void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double* Jmat, const double* Qd, const double* Qfd,
-                     const double* Rd, const double* B_eci, int64_t B_rows, double index_scale, double clock_rate, double dt,
-                     const double* U0, const ts_ilqr_opts_dev* opts, double* X, double* U, double* K, ts_trial_outcome_dev* out) {
+// width = 8: a narrow team (one of the four of a warp); width = 32: the wide (whole-warp) team.
+void hs_alilqr_solve_w(int width, int64_t N, const double* x0, const double* xf, const double* Jmat, const double* Qd,
+                       const double* Qfd, const double* Rd, const double* B_eci, int64_t B_rows, double index_scale,
+                       double clock_rate, double dt, const double* U0, const ts_ilqr_opts_dev* opts, double* X, double* U, double* K,
+                       ts_trial_outcome_dev* out) {
   TrialIn in;
   in.N = (int)N;
   in.dt = dt;
@@ -118,41 +164,16 @@ void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double
   in.index_scale = index_scale;
   in.clock_rate = clock_rate;
   in.U0 = U0;
-  std::vector<double> xu((size_t)9 * N * 10), kd((size_t)N * 24), lam((size_t)N * 6), clk((size_t)N);
-  std::vector<double> bk((size_t)N * 10);
-  TrialWork w;
-  w.xu = xu.data();
-  w.kd = kd.data();
-  w.lam = lam.data();
-  w.clk = clk.data();
-  w.bk = bk.data();
-  w.Nmax = N;
-  TeamShared sh;
-  ts_trial_outcome_dev oc[TEAM];
-  int cur[TEAM];
-  std::vector<std::thread> th;
-  for (int l = 0; l < TEAM; ++l)
-    th.emplace_back([&, l]() {
-      CpuTeam tm{&sh, l};
-      alilqr_solve_team(tm, in, *opts, w, oc[l], cur[l]);
-    });
-  for (auto& t : th) t.join();
-  *out = oc[0];
-  const double* x = xu.data() + (size_t)cur[0] * N * 10;
-  for (int64_t k = 0; k < N; ++k) {
-    for (int i = 0; i < 7; ++i) X[k * 8 + i] = x[k * 10 + i];
-    X[k * 8 + 7] = clk[k];
-    if (k < N - 1) {
-      for (int i = 0; i < 3; ++i) U[k * 3 + i] = x[k * 10 + 7 + i];
-      if (K)
-        for (int i = 0; i < 3; ++i) {
-          for (int j = 0; j < 7; ++j) K[k * 24 + i * 8 + j] = kd[k * 24 + j * 3 + i];
-          K[k * 24 + i * 8 + 7] = 0.0;
-        }
-    }
-  }
+  if (width == 32)
+    solve_with_width<32>(in, opts, N, X, U, K, out);
+  else
+    solve_with_width<8>(in, opts, N, X, U, K, out);
 }
-
+void hs_alilqr_solve(int64_t N, const double* x0, const double* xf, const double* Jmat, const double* Qd, const double* Qfd,
+                     const double* Rd, const double* B_eci, int64_t B_rows, double index_scale, double clock_rate, double dt,
+                     const double* U0, const ts_ilqr_opts_dev* opts, double* X, double* U, double* K, ts_trial_outcome_dev* out) {
+  hs_alilqr_solve_w(8, N, x0, xf, Jmat, Qd, Qfd, Rd, B_eci, B_rows, index_scale, clock_rate, dt, U0, opts, X, U, K, out);
+}
 
 void hs_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);

@@ -38,6 +38,9 @@ def hostsim():
         _HS.hs_alilqr_solve.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int64, C.c_double, C.c_double, C.c_double,
                                                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                                           C.c_void_p, C.c_void_p]
+        _HS.hs_alilqr_solve_w.argtypes = [C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                                     C.c_void_p, C.c_void_p]
         _HS.hs_rk3_jac7.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_rk3_jac7_jvp.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p]
         _HS.hs_rk4_jac7.argtypes = [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_void_p]
@@ -122,7 +125,7 @@ def oracle_solve(slews, opts=None, nthreads=1, want_K=True):
     return Xs, Us, Ks, out
 
 
-def hostsim_solve(s, opts=None):
+def hostsim_solve(s, opts=None, width=8):
     hs = hostsim()
     o = opts if opts is not None else orc.default_ilqr_opts()
     X = np.zeros((s.N, 8))
@@ -130,7 +133,7 @@ def hostsim_solve(s, opts=None):
     K = np.zeros((s.N, 24))
     out = np.zeros(1, dtype=orc.OUTCOME_DTYPE)
     B = np.ascontiguousarray(s.B)
-    hs.hs_alilqr_solve(s.N, orc.P(orc.f64(s.x0)), orc.P(orc.f64(s.xf)), orc.P(orc.f64(s.J.reshape(-1))), orc.P(orc.f64(s.Qd)),
+    hs.hs_alilqr_solve_w(width, s.N, orc.P(orc.f64(s.x0)), orc.P(orc.f64(s.xf)), orc.P(orc.f64(s.J.reshape(-1))), orc.P(orc.f64(s.Qd)),
                        orc.P(orc.f64(s.Qfd)), orc.P(orc.f64(s.Rd)), orc.P(B), B.shape[0], s.index_scale, s.clock_rate, s.dt,
                        None, C.addressof(o), orc.P(X), orc.P(U), orc.P(K), out.ctypes.data)
     return X, U[:-1], K[:-1].reshape(-1, 3, 8), out[0]

@@ -65,6 +65,21 @@ def test_team_solver_matches_oracle(angle, tfin, mask, status):
     assert np.max(np.abs(U - Us[0])) < 1e-9
 
 
+@pytest.mark.parametrize("angle,tfin,mask", [(5.0, 60.0, 0x7F), (20.0, 30.0, 0x7F)])
+def test_wide_team_matches_oracle(angle, tfin, mask):
+    """The whole-warp (32-lane) team used for a warp's straggler: 32 knots linearised per chunk, all 21 line-search
+    candidates in one batch.  Must take the same iteration path as the sequential oracle."""
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], angle), np.array([1.0, 0, 0, 0]), t_final=tfin)
+    o = orc.default_ilqr_opts()
+    o.goal_mask = mask
+    Xs, Us, Ks, out = S.oracle_solve([s], o)
+    X, U, K, oc = S.hostsim_solve(s, o, width=32)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "N"):
+        assert oc[f] == out[0][f], f
+    assert abs(oc["J"] - out[0]["J"]) <= 1e-6 * abs(out[0]["J"])
+    assert np.max(np.abs(X - Xs[0])) < 1e-9 and np.max(np.abs(U - Us[0])) < 1e-9
+
+
 def test_stage_cost_dt_and_3u_inertia():
     s = S.build_slew([0, 6871, 51.6, 30, 0, 10], S.J_3U, S.quat_axis_angle([0, 1, 0], 3.0), np.array([1.0, 0, 0, 0]), t_final=50.0)
     o = orc.default_ilqr_opts()

@@ -61,20 +61,28 @@ TS_HD long long ts_clock() {
 
 enum { ST_CONVERGED = 0, ST_MAX_OUTER = 1, ST_COST_BLOWUP = 2, ST_REG_MAX = 3, ST_NAN = 4, ST_NO_CUTOFF = 5 };
 
-constexpr int TEAM = 8;
+constexpr int TEAM = 8;                       // lanes of a (narrow) team
 constexpr int REC = 84;                       // doubles per knot record in shared memory
-constexpr int SM_REC = 0;                     // [8][REC]   Jacobians + cost gradients of the chunk
-constexpr int SM_SCOL = SM_REC + TEAM * REC;  // [7][8]     new S columns
-constexpr int SM_SVEC = SM_SCOL + 56;         // [8]        new s
-constexpr int SM_KQ = SM_SVEC + 8;            // [7][6]     K(:,j), Qux(:,j)
-constexpr int SM_QUU = SM_KQ + 42;            // [9] Quu, [3] Qu
-// forward pass: double-buffered staging of 8-knot chunks, overlaid on the backward-pass regions
-constexpr int FWD_REC = 50;                   // [x7 u3 | K 21 d 3 | lam 6 | B 9 +pad] doubles per knot
-constexpr int SM_FWD = 0;                     // [2][8][FWD_REC]
-constexpr int SM_WORK = 2 * TEAM * FWD_REC;   // 800 doubles of working buffers
-static_assert(SM_WORK >= SM_QUU + 12, "team shared memory layout");
-constexpr int SM_TRIAL = SM_WORK;             // the trial's TrialIn block (read-only during the solve)
-constexpr int TEAM_SMEM_DOUBLES = SM_WORK + 64;  // 864 doubles = 6912 B per team
+constexpr int FWD_REC = 50;                   // [x7 u3 | K 21 d 3 | lam 6 | B 9 +pad] doubles per staged knot
+// Shared-memory layout of a team of W lanes (W = 8: one of four teams of a warp; W = 32: the whole warp
+// working on ONE trial -- "wide" mode, used for the straggler of a warp once its three siblings are done).
+template <int W>
+struct SmL {
+  static constexpr int REC0 = 0;                   // [W][REC]   Jacobians + cost gradients of the chunk
+  static constexpr int SCOL = REC0 + W * REC;      // [7][8]     new S columns
+  static constexpr int SVEC = SCOL + 56;           // [8]        new s
+  static constexpr int KQ = SVEC + 8;              // [7][6]     K(:,j), Qux(:,j)
+  static constexpr int QUU = KQ + 42;              // [9] Quu, [3] Qu
+  static constexpr int BWD_END = QUU + 12;
+  static constexpr int FWD = 0;                    // [2][W][FWD_REC] staged chunks of the forward pass (overlay)
+  static constexpr int FWD_END = 2 * W * FWD_REC;
+  static constexpr int WORK = (BWD_END > FWD_END ? BWD_END : FWD_END) + ((BWD_END > FWD_END ? BWD_END : FWD_END) & 1);
+  static constexpr int TRIAL = WORK;               // the trial's TrialIn block (read-only during the solve)
+  static constexpr int TOTAL = WORK + 64;
+};
+constexpr int TEAM_SMEM_DOUBLES = SmL<TEAM>::TOTAL;   // 864 doubles = 6912 B per narrow team
+static_assert(SmL<32>::TOTAL <= 4 * SmL<TEAM>::TOTAL, "the wide layout must fit the four narrow regions of a warp");
+constexpr int SM_TRIAL = SmL<TEAM>::TRIAL;
 
 struct TrialIn {
   int N;
@@ -89,13 +97,22 @@ struct TrialIn {
 };
 static_assert(sizeof(TrialIn) <= 64 * sizeof(double), "TrialIn must fit its shared-memory slot");
 struct TrialWork {
-  double* xu;    // [9][Nmax][10]  trajectory buffers (x7,u3): current + 8 line-search candidates
+  double* xu;    // [9][Nmax][10]  trajectory buffers (x7,u3) of this slot: current + 8 line-search candidates
+  double* xu_warp;        // xu of the warp's first slot; buffer i of the warp = xu_warp + (i/9)*slot_stride + (i%9)*Nmax*10
+  long long slot_stride;  // doubles between consecutive slots
   double* kd;    // [Nmax][24]     K column-major (21) + d (3)
   double* lam;   // [Nmax][6]      bound multipliers
   double* clk;   // [Nmax]         clock state
   double* bk;    // [Nmax][10]     field vectors of the three rk3 stages of each knot (9 used)
   long long Nmax;
 };
+
+// trajectory buffer i: narrow teams address the 9 buffers of their own slot, the wide team the 36 of the warp
+template <int W>
+TS_HD double* xu_buf(const TrialWork& w, int i) {
+  if (W == TEAM) return w.xu + (long long)i * (w.Nmax * 10);
+  return w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10);
+}
 
 TS_HD int sym_idx(int i, int j) { return (i <= j) ? (i * 7 - i * (i - 1) / 2 + (j - i)) : (j * 7 - j * (j - 1) / 2 + (i - j)); }
 
@@ -250,6 +267,8 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
 template <class Team>
 TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu_cur,
                          double sc, double mu, const double lam_g[8], Reg& reg, double& dV1, double& dV2, long long& cyc_lin) {
+  typedef SmL<Team::W> L;
+  constexpr int W = Team::W;
   double* sm = tm.smem();
   const int lane = tm.lane();
   const int N = in.N;
@@ -268,36 +287,36 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
         sxx += mu;
         sx += lam_g[lane] + mu * e;
       }
-      for (int i = 0; i < 7; ++i) sm[SM_SCOL + lane * 8 + i] = (i == lane) ? sxx : 0.0;
-      sm[SM_SVEC + lane] = sx;
+      for (int i = 0; i < 7; ++i) sm[L::SCOL + lane * 8 + i] = (i == lane) ? sxx : 0.0;
+      sm[L::SVEC + lane] = sx;
     }
     bool not_pd = false;
-    const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
+    const int n_chunks = (N - 1 + W - 1) / W;
     TS_NO_UNROLL
     for (int ch = n_chunks - 1; ch >= 0 && !not_pd; --ch) {
-      const int base = ch * TEAM;
+      const int base = ch * W;
       tm.sync();  // previous chunk's records fully consumed
       const long long tl0 = ts_clock();
-      if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + SM_REC + lane * REC);
+      if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + L::REC0 + lane * REC);
       tm.sync();
       cyc_lin += ts_clock() - tl0;
-      if (base >= TEAM) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
-        const int kn = base - TEAM + lane;
+      if (base >= W) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
+        const int kn = base - W + lane;
         tm.prefetch_l2(xu_cur + (long long)kn * 10);
         tm.prefetch_l2(w.bk + (long long)kn * 10);
         tm.prefetch_l2(w.lam + (long long)kn * 6);
       }
       int kk_hi = N - 2 - base;
-      if (kk_hi > TEAM - 1) kk_hi = TEAM - 1;
+      if (kk_hi > W - 1) kk_hi = W - 1;
       TS_NO_UNROLL
       for (int kk = kk_hi; kk >= 0; --kk) {
-        const double* rec = sm + SM_REC + kk * REC;
+        const double* rec = sm + L::REC0 + kk * REC;
         const int k = base + kk;
         // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
         double S[28], s[7];
         for (int i = 0; i < 7; ++i)
-          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[SM_SCOL + j * 8 + i] + sm[SM_SCOL + i * 8 + j]);
-        for (int i = 0; i < 7; ++i) s[i] = sm[SM_SVEC + i];
+          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[L::SCOL + j * 8 + i] + sm[L::SCOL + i * 8 + j]);
+        for (int i = 0; i < 7; ++i) s[i] = sm[L::SVEC + i];
         // ---- P1: column products
         double Qxxc[7], Quxc[3], Qx = 0.0;
         if (lane < 7) {
@@ -333,17 +352,17 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           for (int c = 0; c < 3; ++c) {
             double t = 0.0;
             for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
-            sm[SM_QUU + c * 3 + lane] = t + ((c == lane) ? rec[80 + c] : 0.0);
+            sm[L::QUU + c * 3 + lane] = t + ((c == lane) ? rec[80 + c] : 0.0);
           }
           double t = 0.0;
           for (int l = 0; l < 7; ++l) t += b[l] * s[l];
-          sm[SM_QUU + 9 + lane] = rec[77 + lane] + t;
+          sm[L::QUU + 9 + lane] = rec[77 + lane] + t;
         }
         tm.sync();
         // ---- P2: 3x3 solve (every lane, redundantly)
         double Quu[9], Qu[3], Qr[9], L[9];
-        for (int i = 0; i < 9; ++i) Quu[i] = sm[SM_QUU + i];
-        for (int i = 0; i < 3; ++i) Qu[i] = sm[SM_QUU + 9 + i];
+        for (int i = 0; i < 9; ++i) Quu[i] = sm[L::QUU + i];
+        for (int i = 0; i < 3; ++i) Qu[i] = sm[L::QUU + 9 + i];
         for (int i = 0; i < 3; ++i)
           for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
         if (!chol3(Qr, L)) {
@@ -362,8 +381,8 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           chol3_solve(L, nb, Kc);
           for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kc[0] + Quu[i * 3 + 1] * Kc[1] + Quu[i * 3 + 2] * Kc[2];
           for (int c = 0; c < 3; ++c) {
-            sm[SM_KQ + lane * 6 + c] = Kc[c];
-            sm[SM_KQ + lane * 6 + 3 + c] = Quxc[c];
+            sm[L::KQ + lane * 6 + c] = Kc[c];
+            sm[L::KQ + lane * 6 + 3 + c] = Quxc[c];
             kdk[lane * 3 + c] = Kc[c];
           }
         } else {
@@ -377,18 +396,18 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
         // ---- P3: new S column / s entry
         if (lane < 7) {
           for (int i = 0; i < 7; ++i) {
-            const double* kq = sm + SM_KQ + i * 6;
+            const double* kq = sm + L::KQ + i * 6;
             double t = Qxxc[i];
             for (int l = 0; l < 3; ++l) t += kq[l] * QuuK[l];
             for (int l = 0; l < 3; ++l) t += kq[l] * Quxc[l];
             for (int l = 0; l < 3; ++l) t += kq[3 + l] * Kc[l];
-            sm[SM_SCOL + lane * 8 + i] = t;
+            sm[L::SCOL + lane * 8 + i] = t;
           }
           double t = Qx;
           for (int l = 0; l < 3; ++l) t += Kc[l] * Quud[l];
           for (int l = 0; l < 3; ++l) t += Kc[l] * Qu[l];
           for (int l = 0; l < 3; ++l) t += Quxc[l] * d[l];
-          sm[SM_SVEC + lane] = t;
+          sm[L::SVEC + lane] = t;
         }
         tm.sync();
       }
@@ -407,7 +426,7 @@ TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
                              double sc, double mu, const double lam_g[8], double& cmax_out) {
   double Jc = 0.0, cmax = 0.0;
   const int N = in.N;
-  for (int k = tm.lane(); k < N - 1; k += TEAM) {
+  for (int k = tm.lane(); k < N - 1; k += Team::W) {
     const double* p = xu + (long long)k * 10;
     const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
     add_stage_cost(in, o, sc, mu, p, e8, p + 7, w.lam + (long long)k * 6, Jc, cmax);
@@ -447,23 +466,25 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
   double xb[7];
   for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
   const int N = in.N;
-  double* sm = tm.smem() + SM_FWD;
-  const int n_chunks = (N - 1 + TEAM - 1) / TEAM;
+  typedef SmL<Team::W> L;
+  constexpr int W = Team::W;
+  double* sm = tm.smem() + L::FWD;
+  const int n_chunks = (N - 1 + W - 1) / W;
   tm.sync();
   stage_chunk(tm, w, xu_cur, 0, N, sm);
   TS_NO_UNROLL
   for (int ch = 0; ch < n_chunks; ++ch) {
-    const int base = ch * TEAM;
+    const int base = ch * W;
     if (ch + 1 < n_chunks) {
-      stage_chunk(tm, w, xu_cur, base + TEAM, N, sm + ((ch + 1) & 1) * TEAM * FWD_REC);
+      stage_chunk(tm, w, xu_cur, base + W, N, sm + ((ch + 1) & 1) * W * FWD_REC);
       tm.stage_wait(1);
     } else {
       tm.stage_wait(0);
     }
     tm.sync();
-    const double* buf = sm + (ch & 1) * TEAM * FWD_REC;
+    const double* buf = sm + (ch & 1) * W * FWD_REC;
     int kk_n = N - 1 - base;
-    if (kk_n > TEAM) kk_n = TEAM;
+    if (kk_n > W) kk_n = W;
     if (r.ok) {
       TS_NO_UNROLL
       for (int kk = 0; kk < kk_n; ++kk) {
@@ -563,7 +584,7 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
     clk_absmax = fmax(clk_absmax, fabs(x8));
   }
   clk_absmax = tm.bcast(clk_absmax, 0);
-  for (int i = lane; i < (N - 1) * 6; i += TEAM) w.lam[i] = 0.0;
+  for (int i = lane; i < (N - 1) * 6; i += Team::W) w.lam[i] = 0.0;
   tm.sync();
   if (lane == 0) {
     double* xu = w.xu;
@@ -640,8 +661,8 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
   st.J = Jn;
   if (!inner_done) return;
   // ---- outer update: duals (A5), penalty (A6), convergence
-  const double* xu_c = w.xu + st.cur * bstride;
-  for (int k = lane; k < N - 1; k += TEAM) {
+  const double* xu_c = xu_buf<Team::W>(w, st.cur);
+  for (int k = lane; k < N - 1; k += Team::W) {
     double c6[6];
     bound_c(o, xu_c + (long long)k * 10 + 7, c6);
     double* lam = w.lam + (long long)k * 6;
@@ -686,7 +707,7 @@ TS_FN void solve_backward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o
   Reg reg;
   reg.rho = st.rho;
   reg.drho = st.drho;
-  const bool ok = backward_pass(tm, in, o, w, w.xu + st.cur * bstride, sc, st.mu, st.lam_g, reg, st.dV1, st.dV2, st.cyc_lin);
+  const bool ok = backward_pass(tm, in, o, w, xu_buf<Team::W>(w, st.cur), sc, st.mu, st.lam_g, reg, st.dV1, st.dV2, st.cyc_lin);
   st.rho = reg.rho;
   st.drho = reg.drho;
   st.cyc_bwd += ts_clock() - t0;
@@ -708,14 +729,14 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
   const long long bstride = w.Nmax * 10;
   const long long t0 = ts_clock();
-  const double* xu_cur = w.xu + st.cur * bstride;
+  const double* xu_cur = xu_buf<Team::W>(w, st.cur);
   const int n_cand = o.max_linesearch + 1;
   const int c = st.b0 + lane;
   const bool live = (c < n_cand);
   const int bufi = (lane < st.cur) ? lane : lane + 1;
   double alpha = 1.0;
   for (int i = 0; i < c; ++i) alpha /= 2.0;
-  const RollOut r = forward_batch(tm, in, o, w, xu_cur, w.xu + bufi * bstride, live, alpha, sc, st.mu, st.lam_g, st.clk_absmax);
+  const RollOut r = forward_batch(tm, in, o, w, xu_cur, xu_buf<Team::W>(w, bufi), live, alpha, sc, st.mu, st.lam_g, st.clk_absmax);
   bool acc = false;
   if (live && r.ok) {
     const double expected = -alpha * (st.dV1 + alpha * st.dV2);
@@ -737,7 +758,7 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
     return;
   }
   tm.sync();
-  st.b0 += TEAM;
+  st.b0 += Team::W;
   if (st.b0 < n_cand) {  // next batch of candidates
     st.cyc_fwd += ts_clock() - t0;
     return;
@@ -752,7 +773,7 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   st.rho = reg.rho;
   st.drho = reg.drho;
   double g = 0.0;
-  for (int k = lane; k < N - 1; k += TEAM) {
+  for (int k = lane; k < N - 1; k += Team::W) {
     const double* p = xu_cur + (long long)k * 10;
     const double* kd = w.kd + (long long)k * 24;
     double mxg = 0.0;

@@ -21,6 +21,7 @@
 namespace ts {
 
 struct GpuTeam {
+  static constexpr int W = TEAM;
   unsigned mask;
   int ln, shift;
   double* sm;
@@ -62,6 +63,51 @@ struct GpuTeam {
   }
 };
 
+// Compiled in only with -DTS_K3_COMPILE_WIDE (measured in round 1: finishing a warp's straggler with all 32 lanes cut the
+// straggler's own per-knot cost by ~15% but the doubled kernel (registers, spills, code size) slowed every other warp,
+// 14.6 s -> 19.4 s on the 4096-trial ensemble; the solver itself is width-generic and tested at W = 32 in tests/hostsim).
+// The whole warp as ONE team of 32 lanes ("wide" mode): used for the last unfinished trial of a warp, whose
+// three siblings' lanes and trajectory buffers would otherwise idle.  32 knots are linearised per chunk and all
+// 21 line-search candidates are rolled out in a single batch.
+struct GpuWideTeam {
+  static constexpr int W = 32;
+  int ln;
+  double* sm;
+  __device__ __forceinline__ int lane() const { return ln; }
+  __device__ __forceinline__ double* smem() const {
+    double* p = sm;
+    __builtin_assume(__isShared(p));
+    return p;
+  }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ __forceinline__ void stage16(double* dst, const double* src, int n16) const {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+    for (int i = 0; i < n16; ++i)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 16u * i), "l"(src + 2 * i) : "memory");
+  }
+  __device__ __forceinline__ void prefetch_l2(const void* p) const { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+  __device__ __forceinline__ void stage_commit() const { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+  __device__ __forceinline__ void stage_wait(int pending) const {
+    if (pending == 0)
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    else
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+  }
+  __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+};
+
 struct K3Args {
   int64_t n_trials;
   const int64_t* order;  // trial permutation (sorted by horizon), n_trials entries
@@ -90,6 +136,7 @@ struct K3Args {
   int64_t per_slot;  // doubles per slot (even)
   int64_t Nmax;      // padded to even
   unsigned long long* queue;
+  int wide_mode;  // 1: the last unfinished trial of a warp's group is finished by all 32 lanes
 };
 
 
@@ -127,12 +174,13 @@ __device__ __forceinline__ const TrialIn& k3_load_trial(const GpuTeam& tm, const
 }
 
 // Writes a finished trial's results in the reference's shapes: X (N x 8 incl. clock), U, K (3 x 8 per knot).
-__device__ __forceinline__ void k3_store_results(const GpuTeam& tm, const K3Args& a, int64_t t, const TrialWork& w, int N, int cur,
+template <class Team>
+__device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a, int64_t t, const TrialWork& w, int N, int cur,
                                                  const ts_trial_outcome_dev& oc) {
-  const double* xu = w.xu + (int64_t)cur * a.Nmax * 10;
+  const double* xu = xu_buf<Team::W>(w, cur);
   double* Xo = a.X + a.offs[t] * 8;
   double* Uo = a.U + a.offs[t] * 3;
-  for (int k = tm.ln; k < N; k += TEAM) {
+  for (int k = tm.ln; k < N; k += Team::W) {
     for (int i = 0; i < 7; ++i) Xo[(int64_t)k * 8 + i] = xu[(int64_t)k * 10 + i];
     Xo[(int64_t)k * 8 + 7] = w.clk[k];
     if (k < N - 1) {
@@ -153,6 +201,10 @@ __device__ __forceinline__ void k3_store_results(const GpuTeam& tm, const K3Args
 constexpr int K3_WARPS_PER_BLOCK = 1;
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
+__device__ __forceinline__ double k3_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ int k3_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ long long k3_shfl_ll(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(const K3Args a) {
   extern __shared__ __align__(16) double k3_smem[];
   const int warp_in_block = threadIdx.x >> 5;
@@ -160,14 +212,17 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
   const int team = lane32 >> 3;
   const int64_t gwarp = (int64_t)blockIdx.x * K3_WARPS_PER_BLOCK + warp_in_block;
   const int64_t slot = gwarp * 4 + team;
+  double* warp_smem = k3_smem + (warp_in_block * 4) * TEAM_SMEM_DOUBLES;
   GpuTeam tm;
   tm.ln = lane32 & 7;
   tm.shift = team * 8;
   tm.mask = 0xffu << tm.shift;
-  tm.sm = k3_smem + (warp_in_block * 4 + team) * TEAM_SMEM_DOUBLES;
+  tm.sm = warp_smem + team * TEAM_SMEM_DOUBLES;
   TrialWork w;
   w.Nmax = a.Nmax;
   w.xu = a.w_base + slot * a.per_slot;
+  w.xu_warp = a.w_base + (gwarp * 4) * a.per_slot;
+  w.slot_stride = a.per_slot;
   w.kd = w.xu + 90 * a.Nmax;
   w.lam = w.kd + 24 * a.Nmax;
   w.bk = w.lam + 6 * a.Nmax;
@@ -178,18 +233,85 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
     base = __shfl_sync(0xffffffffu, base, 0);
     if ((int64_t)base >= a.n_trials) break;
     const int64_t qi = (int64_t)base + team;
-    if (qi < a.n_trials) {
-      const int64_t t = a.order ? a.order[qi] : qi;
-      const TrialIn& in = k3_load_trial(tm, a, t);
-      ts_trial_outcome_dev oc;
-      int cur = 0;
-      alilqr_solve_team(tm, in, a.opts, w, oc, cur);
-      k3_store_results(tm, a, t, w, in.N, cur, oc);
+    const bool have = qi < a.n_trials;
+    const int64_t t = have ? (a.order ? a.order[qi] : qi) : 0;
+    TrialState st;
+    st.phase = PH_DONE;
+    const TrialIn* inp = reinterpret_cast<const TrialIn*>(tm.smem() + SM_TRIAL);
+    if (have) {
+      k3_load_trial(tm, a, t);
+      solve_init(tm, *inp, a.opts, w, st);
+    }
+    bool stored = !have;
+    // ---- iterate: one iLQR iteration per pass for every unfinished team; the warp re-converges here
+    for (;;) {
+      if (!stored && st.phase == PH_DONE) {  // finished: write results now, so the slot's buffers can be lent out
+        ts_trial_outcome_dev oc;
+        solve_finish(*inp, st, oc);
+        k3_store_results(tm, a, t, w, inp->N, st.cur, oc);
+        stored = true;
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, st.phase != PH_DONE);
+      if (!act) break;
+      const unsigned teams_act = ((act & 0x000000ffu) ? 1u : 0u) | ((act & 0x0000ff00u) ? 2u : 0u) | ((act & 0x00ff0000u) ? 4u : 0u) |
+                                 ((act & 0xff000000u) ? 8u : 0u);
+#ifdef TS_K3_COMPILE_WIDE
+      if (a.wide_mode && __popc(teams_act) == 1) {
+        // ---- wide mode: the whole warp finishes the last trial of this group
+        const int lt = __ffs(teams_act) - 1;   // the unfinished team
+        const int src = lt * 8;
+        TrialState ws;
+        ws.mu = k3_shfl_d(st.mu, src);
+        for (int i = 0; i < 8; ++i) ws.lam_g[i] = k3_shfl_d(st.lam_g[i], src);
+        ws.J_prev = k3_shfl_d(st.J_prev, src); ws.J = k3_shfl_d(st.J, src); ws.c_max = k3_shfl_d(st.c_max, src);
+        ws.rho = k3_shfl_d(st.rho, src); ws.drho = k3_shfl_d(st.drho, src); ws.dV1 = k3_shfl_d(st.dV1, src);
+        ws.dV2 = k3_shfl_d(st.dV2, src); ws.clk_absmax = k3_shfl_d(st.clk_absmax, src);
+        ws.cyc_bwd = k3_shfl_ll(st.cyc_bwd, src); ws.cyc_fwd = k3_shfl_ll(st.cyc_fwd, src); ws.cyc_lin = k3_shfl_ll(st.cyc_lin, src);
+        ws.it = k3_shfl_i(st.it, src); ws.outer = k3_shfl_i(st.outer, src); ws.dJ_zero = k3_shfl_i(st.dJ_zero, src);
+        ws.inner_total = k3_shfl_i(st.inner_total, src); ws.ls_total = k3_shfl_i(st.ls_total, src);
+        ws.status = k3_shfl_i(st.status, src); ws.phase = k3_shfl_i(st.phase, src); ws.b0 = 0; ws.pad_ = 0;
+        ws.cur = lt * 9 + k3_shfl_i(st.cur, src);   // buffer index in the warp's 36-buffer space
+        const long long t_l = k3_shfl_ll((long long)t, src);
+        // the trial's TrialIn block moves from the narrow team's region to the wide layout's slot (regions overlap)
+        const double* tin_src = warp_smem + lt * TEAM_SMEM_DOUBLES + SM_TRIAL;
+        const double v0 = tin_src[lane32], v1 = tin_src[32 + lane32];
+        __syncwarp();
+        double* tin_dst = warp_smem + SmL<32>::TRIAL;
+        tin_dst[lane32] = v0;
+        tin_dst[32 + lane32] = v1;
+        __syncwarp();
+        GpuWideTeam wt;
+        wt.ln = lane32;
+        wt.sm = warp_smem;
+        const TrialIn* winp = reinterpret_cast<const TrialIn*>(wt.smem() + SmL<32>::TRIAL);
+        TrialWork ww = w;   // kd / lam / bk / clk of the unfinished trial's own slot
+        ww.xu = a.w_base + (gwarp * 4 + lt) * a.per_slot;
+        ww.kd = ww.xu + 90 * a.Nmax;
+        ww.lam = ww.kd + 24 * a.Nmax;
+        ww.bk = ww.lam + 6 * a.Nmax;
+        ww.clk = ww.bk + 10 * a.Nmax;
+        if (ws.phase == PH_FORWARD) ws.phase = PH_BACKWARD;  // (never the case: teams reach this point between iterations)
+        while (ws.phase != PH_DONE) {
+          if (ws.phase == PH_BACKWARD) solve_backward(wt, *winp, a.opts, ww, ws);
+          while (ws.phase == PH_FORWARD) solve_forward(wt, *winp, a.opts, ww, ws);
+        }
+        ts_trial_outcome_dev oc;
+        solve_finish(*winp, ws, oc);
+        k3_store_results(wt, a, (int64_t)t_l, ww, winp->N, ws.cur, oc);
+        __syncwarp();
+        break;
+      }
+#else
+      (void)teams_act;
+#endif
+      if (st.phase != PH_DONE) {
+        if (st.phase == PH_BACKWARD) solve_backward(tm, *inp, a.opts, w, st);
+        while (st.phase == PH_FORWARD) solve_forward(tm, *inp, a.opts, w, st);
+      }
     }
     __syncwarp();
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Phase-split launch mode: the same solver phases as separate kernels, driven in lockstep by the
@@ -210,6 +332,8 @@ __device__ __forceinline__ void k3_team_setup(const K3Args& a, GpuTeam& tm, Tria
   tm.sm = smem + team * TEAM_SMEM_DOUBLES;
   w.Nmax = a.Nmax;
   w.xu = a.w_base + qi * a.per_slot;
+  w.xu_warp = w.xu;
+  w.slot_stride = a.per_slot;
   w.kd = w.xu + 90 * a.Nmax;
   w.lam = w.kd + 24 * a.Nmax;
   w.bk = w.lam + 6 * a.Nmax;

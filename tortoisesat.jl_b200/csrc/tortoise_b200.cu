@@ -361,6 +361,8 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   a.w_base = (double*)p_work;
   a.per_slot = per_slot + (per_slot & 1);
   a.queue = (unsigned long long*)p_q;
+  a.wide_mode = 1;
+  if (const char* m = getenv("TS_K3_WIDE")) a.wide_mode = atoi(m) ? 1 : 0;
   if (!phased) {
     k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
     c->launches++;
