@@ -107,10 +107,9 @@ struct TrialWork {
   long long Nmax;
 };
 
-// trajectory buffer i: narrow teams address the 9 buffers of their own slot, the wide team the 36 of the warp
+// trajectory buffer i in the warp's buffer space: slot i/9, buffer i%9 (a team that owns a single slot uses 0..8)
 template <int W>
 TS_HD double* xu_buf(const TrialWork& w, int i) {
-  if (W == TEAM) return w.xu + (long long)i * (w.Nmax * 10);
   return w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10);
 }
 

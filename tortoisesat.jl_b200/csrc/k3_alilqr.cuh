@@ -136,7 +136,8 @@ struct K3Args {
   int64_t per_slot;  // doubles per slot (even)
   int64_t Nmax;      // padded to even
   unsigned long long* queue;
-  int wide_mode;  // 1: the last unfinished trial of a warp's group is finished by all 32 lanes
+  int wide_mode;  // 1: the last unfinished trial of a warp's group is finished by all 32 lanes (needs TS_K3_COMPILE_WIDE)
+  int tail_share; // 1: finished siblings lend lanes + buffers to the line search of the group's last trial
 };
 
 
@@ -201,6 +202,18 @@ __device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a
 constexpr int K3_WARPS_PER_BLOCK = 1;
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
+// index of the n-th set bit (n = 0, 1, ...) of a 4-bit mask
+__device__ __forceinline__ int k3_nth_bit(unsigned m, int n) {
+  int idx = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (m & (1u << b)) {
+      if (n == 0) idx = b;
+      --n;
+    }
+  }
+  return idx;
+}
 __device__ __forceinline__ double k3_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ int k3_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ long long k3_shfl_ll(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -241,6 +254,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
     if (have) {
       k3_load_trial(tm, a, t);
       solve_init(tm, *inp, a.opts, w, st);
+      st.cur = team * 9;   // trajectory buffers are addressed in the warp's 36-buffer space from here on
     }
     bool stored = !have;
     // ---- iterate: one iLQR iteration per pass for every unfinished team; the warp re-converges here
@@ -304,9 +318,137 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
 #else
       (void)teams_act;
 #endif
-      if (st.phase != PH_DONE) {
-        if (st.phase == PH_BACKWARD) solve_backward(tm, *inp, a.opts, w, st);
-        while (st.phase == PH_FORWARD) solve_forward(tm, *inp, a.opts, w, st);
+      // "tail sharing": when a single trial of the group is left, its three finished siblings lend their lanes
+      // and trajectory buffers to its line search (candidates 8..31 in the same batch) -- with ONE call site of
+      // forward_batch for both modes, so the kernel does not grow.
+      // assignment of the finished teams to the unfinished ones: idle team j helps active team j mod k as
+      // "part" 1 + j/k; a trial's candidates are c = b0 + 8*part + lane, so one batch covers 8 * (#parts) steps
+      int wt = team, part = 0, nparts = 1;
+      int sp1 = team, sp2 = team, sp3 = team;   // owner's view: the teams that compute parts 1..3 of MY trial
+      if (a.tail_share && teams_act != 0xfu) {
+        const unsigned A = teams_act, I = ~teams_act & 0xfu;
+        const int k = __popc(A), ni = __popc(I);
+        if (A & (1u << team)) {
+          const int r = __popc(A & ((1u << team) - 1u));           // my rank among the active teams
+          nparts = 1 + ((ni > r) ? (ni - r + k - 1) / k : 0);
+          if (nparts > 1) sp1 = k3_nth_bit(I, r);
+          if (nparts > 2) sp2 = k3_nth_bit(I, r + k);
+          if (nparts > 3) sp3 = k3_nth_bit(I, r + 2 * k);
+        } else {
+          const int j = __popc(I & ((1u << team) - 1u));           // my rank among the idle teams
+          const int r = j % k;
+          wt = k3_nth_bit(A, r);
+          part = 1 + j / k;
+          nparts = 1 + (ni - r + k - 1) / k;
+        }
+      }
+      if (st.phase == PH_BACKWARD) solve_backward(tm, *inp, a.opts, w, st);
+      for (;;) {  // forward batches until every trial of the group has taken (or given up on) its step
+        const unsigned fw = __ballot_sync(0xffffffffu, st.phase == PH_FORWARD);
+        if (!fw) break;
+        const int src = wt * 8;
+        const int cur_w = k3_shfl_i(st.cur, src);
+        const int b0_w = k3_shfl_i(st.b0, src);
+        const double mu_w = k3_shfl_d(st.mu, src), Jp_w = k3_shfl_d(st.J_prev, src), dV1_w = k3_shfl_d(st.dV1, src),
+                     dV2_w = k3_shfl_d(st.dV2, src), cam_w = k3_shfl_d(st.clk_absmax, src);
+        const bool fwd_w = k3_shfl_i(st.phase, src) == PH_FORWARD;
+        double lg_w[8];
+        for (int i = 0; i < 8; ++i) lg_w[i] = k3_shfl_d(st.lam_g[i], src);
+        const TrialIn* in_w = reinterpret_cast<const TrialIn*>(warp_smem + wt * TEAM_SMEM_DOUBLES + SM_TRIAL);
+        __builtin_assume(__isShared(in_w));
+        TrialWork ww = w;   // gains / multipliers / field vectors of the trial being rolled out
+        ww.xu = a.w_base + (gwarp * 4 + wt) * a.per_slot;
+        ww.kd = ww.xu + 90 * a.Nmax;
+        ww.lam = ww.kd + 24 * a.Nmax;
+        ww.bk = ww.lam + 6 * a.Nmax;
+        ww.clk = ww.bk + 10 * a.Nmax;
+        const int n_cand = a.opts.max_linesearch + 1;
+        const int c = b0_w + 8 * part + tm.ln;
+        const bool live = fwd_w && (c < n_cand);
+        // candidate buffer: one of this team's own 9 buffers, never the one holding the current trajectory
+        const int lc = cur_w - team * 9;
+        const int bufi = team * 9 + ((lc >= 0 && lc < 9 && tm.ln >= lc) ? tm.ln + 1 : tm.ln);
+        double alpha = 1.0;
+        for (int i = 0; i < c; ++i) alpha /= 2.0;
+        const double sc = a.opts.stage_cost_dt ? a.dt : 1.0;
+        const long long tf0 = ts_clock();
+        RollOut r;
+        r.ok = false;
+        r.J = r.cmax = r.grad = 0.0;
+        if (fwd_w)  // team-uniform: teams whose trial is not in its forward phase just wait at the ballot below
+          r = forward_batch(tm, *in_w, a.opts, ww, xu_buf<TEAM>(w, cur_w), xu_buf<TEAM>(w, bufi), live, alpha, sc, mu_w, lg_w, cam_w);
+        bool acc = false;
+        if (live && r.ok) {
+          const double expected = -alpha * (dV1_w + alpha * dV2_w);
+          const double z = (expected > 0.0) ? (Jp_w - r.J) / expected : -1.0;
+          acc = !((z <= a.opts.ls_lower || z > a.opts.ls_upper) && (r.J >= Jp_w));
+        }
+        const unsigned bits32 = __ballot_sync(0xffffffffu, acc);
+        // the owner assembles its trial's acceptance bits in candidate order from the teams that computed each part
+        unsigned bits = 0;
+        if (wt == team) {
+          bits = (bits32 >> (8 * team)) & 0xffu;
+          if (nparts > 1) bits |= ((bits32 >> (8 * sp1)) & 0xffu) << 8;
+          if (nparts > 2) bits |= ((bits32 >> (8 * sp2)) & 0xffu) << 16;
+          if (nparts > 3) bits |= ((bits32 >> (8 * sp3)) & 0xffu) << 24;
+        }
+        const int step = 8 * nparts;
+        double Jn = 0.0, grad = 0.0, cmx = 0.0;
+        int cur_new = cur_w, a_idx = -1;
+        if (bits) a_idx = __ffs(bits) - 1;
+        {  // the accepted candidate's results travel to the owner's lanes
+          const int pa = a_idx >> 3;
+          const int st_team = (pa == 0) ? team : ((pa == 1) ? sp1 : ((pa == 2) ? sp2 : sp3));
+          const int sl = (a_idx < 0) ? lane32 : (8 * st_team + (a_idx & 7));
+          Jn = k3_shfl_d(r.J, sl);
+          cmx = k3_shfl_d(r.cmax, sl);
+          grad = k3_shfl_d(r.grad, sl);
+          cur_new = k3_shfl_i(bufi, sl);
+        }
+        __syncwarp();
+        if (st.phase == PH_FORWARD) {  // bookkeeping by the team that owns the trial
+          st.cyc_fwd += ts_clock() - tf0;
+          if (a_idx >= 0) {
+            st.ls_total += st.b0 + a_idx + 1;
+            st.c_max = cmx;
+            if (cur_new / 9 != team) {
+              // the winning candidate was rolled out by a helper into ITS slot: bring it home, so that a trial's
+              // current trajectory always lives in its own slot (a helper may serve another trial next time)
+              const int home = team * 9 + ((st.cur - team * 9) + 1) % 9;
+              const double* srcb = xu_buf<TEAM>(w, cur_new);
+              double* dstb = xu_buf<TEAM>(w, home);
+              const long long nd = (long long)inp->N * 10;
+              for (long long i = tm.ln; i < nd; i += TEAM) dstb[i] = srcb[i];
+              tm.sync();
+              cur_new = home;
+            }
+            st.cur = cur_new;
+            solve_after_forward(tm, *inp, a.opts, w, st, Jn, grad);
+          } else {
+            st.b0 += step;
+            if (st.b0 >= n_cand) {  // line search exhausted (App. C step 4)
+              st.ls_total += n_cand;
+              Reg reg;
+              reg.rho = st.rho;
+              reg.drho = st.drho;
+              reg_increase(a.opts, reg);
+              reg.rho += a.opts.bp_reg_fp;
+              st.rho = reg.rho;
+              st.drho = reg.drho;
+              const double* xc = xu_buf<TEAM>(w, st.cur);
+              double g = 0.0;
+              for (int k = tm.ln; k < inp->N - 1; k += TEAM) {
+                const double* p = xc + (long long)k * 10;
+                const double* kd = w.kd + (long long)k * 24;
+                double mxg = 0.0;
+                for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
+                g += mxg;
+              }
+              const double gr = tm.sum(g) / (double)(inp->N - 1);
+              solve_after_forward(tm, *inp, a.opts, w, st, st.J_prev, gr);
+            }
+          }
+        }
       }
     }
     __syncwarp();

@@ -363,6 +363,8 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   a.queue = (unsigned long long*)p_q;
   a.wide_mode = 1;
   if (const char* m = getenv("TS_K3_WIDE")) a.wide_mode = atoi(m) ? 1 : 0;
+  a.tail_share = 1;
+  if (const char* m = getenv("TS_K3_TAIL")) a.tail_share = atoi(m) ? 1 : 0;
   if (!phased) {
     k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
     c->launches++;
