@@ -313,6 +313,14 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
 }
 
+// slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
+static double slew_angle(const double* x0, const double* xf) {
+  double n0 = 0, nf = 0, d = 0;
+  for (int i = 3; i < 7; ++i) { n0 += x0[i] * x0[i]; nf += xf[i] * xf[i]; d += x0[i] * xf[i]; }
+  const double c = fabs(d) / sqrt(n0 * nf + 1e-300);
+  return 2.0 * acos(c > 1.0 ? 1.0 : c);
+}
+
 // Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
 // Two launch modes (same solver code, ilqr_solver.cuh):
 //   persistent  one kernel, warps pull groups of 4 trials from a queue (ragged horizons)
@@ -320,7 +328,7 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
 //               phase, so the hot loop fits the instruction cache and finished trials free their SM slots
 // TS_K3_MODE=persistent|phased overrides the automatic choice.  Returns with all work complete on the stream
 // (the phased mode synchronises to poll the active-trial counter).
-static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
+static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
   const int64_t n_trials = a.n_trials;
   int64_t Nmax = 0, Nmin = INT64_MAX;
   for (int64_t t = 0; t < n_trials; ++t) {
@@ -343,10 +351,32 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
   const int64_t warps = phased ? groups : std::min(groups, max_warps);
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
-  // trials sorted by horizon (descending) so the four teams of a warp have similar trip counts
+  // Queue order.  (1) sort by horizon (descending): the four teams of a warp get similar trip counts.
+  // (2) within a run of (nearly) equal horizons, sort by slew angle and DEAL the trials round-robin over the
+  // groups of four, so each warp gets one trial of every difficulty quartile: the makespan of a single-wave
+  // ensemble is set by the warp with the most stragglers (non-converging large-angle slews), and dealing
+  // them out makes triple clusters (which cannot lend each other lanes) vanishingly rare.
   std::vector<int64_t> order((size_t)n_trials);
   std::iota(order.begin(), order.end(), (int64_t)0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return N_i_host[x] > N_i_host[y]; });
+  if (difficulty_host && n_trials >= 8) {
+    size_t lo = 0;
+    while (lo < (size_t)n_trials) {
+      size_t hi = lo;
+      while (hi < (size_t)n_trials && (double)N_i_host[order[hi]] >= 0.97 * (double)N_i_host[order[lo]]) ++hi;
+      const size_t len = hi - lo;
+      if (len >= 8) {
+        std::vector<int64_t> run(order.begin() + lo, order.begin() + hi);
+        std::stable_sort(run.begin(), run.end(), [&](int64_t x, int64_t y) { return difficulty_host[x] > difficulty_host[y]; });
+        const size_t G = (len + 3) / 4;
+        size_t pos = lo;
+        for (size_t g = 0; g < G; ++g)
+          for (size_t j = 0; j < 4; ++j)
+            if (g + j * G < len) order[pos++] = run[g + j * G];
+      }
+      lo = hi;
+    }
+  }
   int rc;
   int64_t* d_order = nullptr;
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
@@ -458,8 +488,10 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   memcpy(&a.opts, &o, sizeof(o));
   a.X = (double*)dX.d; a.U = (double*)dU.d; a.K = K ? (double*)dK.d : nullptr;
   a.out = (ts_trial_outcome_dev*)p_out;
+  std::vector<double> diff(T);
+  for (size_t t = 0; t < T; ++t) diff[t] = slew_angle(x0 + 8 * t, xf + 8 * t);
   KernelTimer tm(c);
-  if ((rc = k3_launch(c, a, N_i))) return rc;
+  if ((rc = k3_launch(c, a, N_i, diff.data()))) return rc;
   tm.stop();
   if ((rc = dev_back(c, dX, X, (size_t)total_knots * 8 * sizeof(double)))) return rc;
   if ((rc = dev_back(c, dU, U, (size_t)total_knots * 3 * sizeof(double)))) return rc;
@@ -798,7 +830,9 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     ka.B_eci = d_Bf; ka.dt = cfg->dt; ka.U0 = nullptr;
     memcpy(&ka.opts, &cfg->ilqr, sizeof(ka.opts));
     ka.X = d_X; ka.U = d_U; ka.K = nullptr; ka.out = d_out;
-    if ((rc = k3_launch(c, ka, hi.data()))) return rc;
+    std::vector<double> diff(NA);
+    for (int64_t aa = 0; aa < na; ++aa) diff[aa] = slew_angle(x0 + 8 * act[aa], xf + 8 * act[aa]);
+    if ((rc = k3_launch(c, ka, hi.data(), diff.data()))) return rc;
     cudaEventRecord(e[4], c->stream);
     // ---- stage 5: TVLQR replay + slew-time rule
     if (cfg->run_tvlqr) {
