@@ -235,6 +235,27 @@ int ts_monte_carlo_run(ts_ctx* ctx, const ts_mc_config* cfg, const double* kep6,
                        const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
                        ts_trial_outcome* out, ts_mc_stats* stats);
 
+/* ---- element-wise batch versions of the reference's building blocks (all HOST pointers) --- *
+ * Correctness / drop-in paths for callers that use the small functions on their own; the fused
+ * kernels above inline the same device code.                                                    */
+/* kep_ECI(kep,t0,GM) [src/kep_ECI.jl:1-49]: kep6 n x 6, t0 n (nullable -> 0) -> rv6 n x 6 = [r km; v km/s]
+ * (the input is NOT mutated, unlike kep_ECI.jl:7-8).                                            */
+int ts_kep_eci_batch(ts_ctx* ctx, int64_t n, const double* kep6, const double* t0, double GM, double* rv6);
+/* OrbitPlotter(x,p,t) [src/OrbitPlotter.jl:1-52]: x6 n x 6 -> dx6 n x 6.                       */
+int ts_orbit_rhs_batch(ts_ctx* ctx, int64_t n, const double* x6, double* dx6);
+/* legendre(Val{:schmidt},phi,n_max,false) [src/legendre.jl:254-292] and dlegendre(Val{:schmidt},phi,P,false)
+ * [src/dlegendre.jl:221-309]: theta n -> P, dP (nullable) n x (n_max+1)^2 row-major, 1 <= n_max <= 13. */
+int ts_legendre_schmidt_batch(ts_ctx* ctx, int64_t n, const double* theta, int n_max, double* P, double* dP);
+/* mode 0 DerivFunction(dx,x,u) [src/DerivFunction.jl:1-48], 1 gain_simulator [src/gain_simulator.jl:1-53]:
+ *   x n x 8, u n x 3, B = field table (B_rows x 3, the global B_ECI), index_scale = global N, clock_rate = 1/(tf-t0);
+ * mode 2 attitude_dynamics(x,u,B_B,J) [src/attitude_dynamics.jl:2-24]: x n x 7, B = n x 3 body-frame field
+ *   (B_rows, index_scale, clock_rate ignored).  Jmat: one 3x3 row-major inertia.  dx: n x 8 (modes 0,1) / n x 7. */
+int ts_dynamics_batch(ts_ctx* ctx, int mode, int64_t n, const double* x, const double* u, const double* B, int64_t B_rows,
+                      double index_scale, double clock_rate, const double* Jmat, double* dx);
+/* rk3 ZOH step of Model(DerivFunction,8,3) [TrajOpt rk3 = src/attitude_controller.jl:178-187]: x n x 8 -> xn n x 8. */
+int ts_rk3_step_batch(ts_ctx* ctx, int64_t n, const double* x, const double* u, const double* B, int64_t B_rows,
+                      double index_scale, double clock_rate, const double* Jmat, double dt, double* xn);
+
 #ifdef __cplusplus
 }
 #endif

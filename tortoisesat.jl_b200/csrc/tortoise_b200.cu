@@ -7,15 +7,52 @@
 #include "k2_field.cuh"
 #include "k3_alilqr.cuh"
 #include "k4_tvlqr.cuh"
+#include "k5_unitops.cuh"
 
 #include <algorithm>
 #include <numeric>
+#include <utility>
 
 namespace ts {
 #include "igrf12_tables.inc"
 }
 
 using namespace ts;
+
+// generic helper: host inputs -> device scratch, one kernel, outputs back
+struct HostIO {
+  ts_ctx* c;
+  std::vector<std::pair<void*, std::pair<void*, size_t>>> outs;
+  std::vector<void*> bufs;
+  int rc = TS_OK;
+  explicit HostIO(ts_ctx* ctx) : c(ctx) {}
+  ~HostIO() { for (void* p : bufs) cudaFree(p); }
+  template <class T> T* in(const T* h, size_t count) {
+    if (rc || !h || count == 0) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, count * sizeof(T)) != cudaSuccess) { rc = fail(c, TS_ERR_NOMEM, "cudaMalloc failed"); return nullptr; }
+    bufs.push_back(d);
+    cudaMemcpyAsync(d, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    return (T*)d;
+  }
+  template <class T> T* out(T* h, size_t count) {
+    if (rc || !h || count == 0) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, count * sizeof(T)) != cudaSuccess) { rc = fail(c, TS_ERR_NOMEM, "cudaMalloc failed"); return nullptr; }
+    bufs.push_back(d);
+    outs.push_back({d, {h, count * sizeof(T)}});
+    return (T*)d;
+  }
+  int finish() {
+    if (rc) return rc;
+    c->launches++;
+    TS_CUDA(c, cudaGetLastError());
+    for (auto& o : outs) TS_CUDA(c, cudaMemcpyAsync(o.second.first, o.first, o.second.second, cudaMemcpyDeviceToHost, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TS_OK;
+  }
+};
+
 
 extern "C" {
 
@@ -899,6 +936,86 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     stats->ms_field = ms_field; stats->ms_prep = ms_prep; stats->ms_solve = ms_solve; stats->ms_tvlqr = ms_tvlqr;
   }
   return TS_OK;
+}
+
+// ---------------------------------------------------------------------------- K5 element-wise ops
+int ts_kep_eci_batch(ts_ctx* c, int64_t n, const double* kep6, const double* t0, double GM, double* rv6) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!kep6 || !rv6))) return fail(c, TS_ERR_ARG, "ts_kep_eci_batch: null argument");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const double* dk = io.in(kep6, (size_t)n * 6);
+  const double* dt0 = io.in(t0, (size_t)n);
+  double* dr = io.out(rv6, (size_t)n * 6);
+  if (io.rc) return io.rc;
+  k5_kep_eci<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dk, dt0, GM, dr);
+  return io.finish();
+}
+
+int ts_orbit_rhs_batch(ts_ctx* c, int64_t n, const double* x6, double* dx6) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!x6 || !dx6))) return fail(c, TS_ERR_ARG, "ts_orbit_rhs_batch: null argument");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const double* dx = io.in(x6, (size_t)n * 6);
+  double* dd = io.out(dx6, (size_t)n * 6);
+  if (io.rc) return io.rc;
+  k5_orbit_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dx, dd);
+  return io.finish();
+}
+
+int ts_legendre_schmidt_batch(ts_ctx* c, int64_t n, const double* theta, int n_max, double* P, double* dP) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!theta || !P))) return fail(c, TS_ERR_ARG, "ts_legendre_schmidt_batch: null argument");
+  if (n_max < 1 || n_max > 13) return fail(c, TS_ERR_ARG, "n_max must be in [1, 13]");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const size_t d2 = (size_t)(n_max + 1) * (n_max + 1);
+  const double* dth = io.in(theta, (size_t)n);
+  double* dPd = io.out(P, (size_t)n * d2);
+  double* ddP = io.out(dP, (size_t)n * d2);
+  if (io.rc) return io.rc;
+  k5_legendre<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(n, dth, n_max, dPd, ddP);
+  return io.finish();
+}
+
+int ts_dynamics_batch(ts_ctx* c, int mode, int64_t n, const double* x, const double* u, const double* B, int64_t B_rows,
+                      double index_scale, double clock_rate, const double* Jmat, double* dx) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || mode < 0 || mode > 2 || (n > 0 && (!x || !u || !B || !Jmat || !dx))) return fail(c, TS_ERR_ARG, "ts_dynamics_batch: bad argument");
+  if (mode != 2 && B_rows < 1) return fail(c, TS_ERR_ARG, "ts_dynamics_batch: empty field table");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const int nx = (mode == 2) ? 7 : 8;
+  const double* dxs = io.in(x, (size_t)n * nx);
+  const double* du = io.in(u, (size_t)n * 3);
+  const double* dB = io.in(B, (mode == 2) ? (size_t)n * 3 : (size_t)B_rows * 3);
+  const double* dJ = io.in(Jmat, 9);
+  double* dd = io.out(dx, (size_t)n * nx);
+  if (io.rc) return io.rc;
+  k5_dynamics<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(mode, n, dxs, du, dB, B_rows, index_scale, clock_rate, dJ, dd);
+  return io.finish();
+}
+
+int ts_rk3_step_batch(ts_ctx* c, int64_t n, const double* x, const double* u, const double* B, int64_t B_rows, double index_scale,
+                      double clock_rate, const double* Jmat, double dt, double* xn) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || B_rows < 1 || (n > 0 && (!x || !u || !B || !Jmat || !xn))) return fail(c, TS_ERR_ARG, "ts_rk3_step_batch: bad argument");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const double* dxs = io.in(x, (size_t)n * 8);
+  const double* du = io.in(u, (size_t)n * 3);
+  const double* dB = io.in(B, (size_t)B_rows * 3);
+  const double* dJ = io.in(Jmat, 9);
+  double* dd = io.out(xn, (size_t)n * 8);
+  if (io.rc) return io.rc;
+  k5_rk3_step<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dxs, du, dB, B_rows, index_scale, clock_rate, dJ, dt, dd);
+  return io.finish();
 }
 
 }  // extern "C"

@@ -132,6 +132,13 @@ def load_library():
     L.ts_condition_cutoff_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
     L.ts_ilqr_default_opts.argtypes = [C.POINTER(IlqrOpts)]
     L.ts_ilqr_default_opts.restype = None
+    L.ts_kep_eci_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.ts_orbit_rhs_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ts_legendre_schmidt_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ts_dynamics_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                    C.c_double, C.c_void_p, C.c_void_p]
+    L.ts_rk3_step_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                    C.c_void_p, C.c_double, C.c_void_p]
     L.ts_tvlqr_default_opts.argtypes = [C.POINTER(TvlqrOpts)]
     L.ts_tvlqr_default_opts.restype = None
     L.ts_slew_weights_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_double] * 4 + [C.c_void_p] * 6
@@ -307,6 +314,44 @@ class Engine:
         return X, U, K, out, offs
 
 
+    # -- element-wise building blocks --------------------------------------
+    def kep_eci_batch(self, kep6, t0=None, GM=GM_EARTH):
+        kep6 = _f64(np.atleast_2d(kep6))
+        n = kep6.shape[0]
+        t0a = None if t0 is None else _f64(np.broadcast_to(np.asarray(t0, dtype=float), (n,)))
+        rv = np.zeros((n, 6))
+        self._check(self.lib.ts_kep_eci_batch(self.h, n, _ptr(kep6), None if t0a is None else _ptr(t0a), GM, _ptr(rv)))
+        return rv
+
+    def orbit_rhs_batch(self, x6):
+        x6 = _f64(np.atleast_2d(x6))
+        dx = np.zeros_like(x6)
+        self._check(self.lib.ts_orbit_rhs_batch(self.h, x6.shape[0], _ptr(x6), _ptr(dx)))
+        return dx
+
+    def legendre_schmidt_batch(self, theta, n_max=13, want_dP=True):
+        theta = _f64(np.atleast_1d(theta))
+        n = theta.shape[0]
+        P = np.zeros((n, n_max + 1, n_max + 1))
+        dP = np.zeros_like(P) if want_dP else None
+        self._check(self.lib.ts_legendre_schmidt_batch(self.h, n, _ptr(theta), n_max, _ptr(P), None if dP is None else _ptr(dP)))
+        return (P, dP) if want_dP else P
+
+    def dynamics_batch(self, mode, x, u, B, Jmat, index_scale=1.0, clock_rate=0.0):
+        """mode 0 DerivFunction, 1 gain_simulator (x n x 8, B = field table), 2 attitude_dynamics (x n x 7, B = n x 3 body field)."""
+        x, u, B, Jmat = _f64(np.atleast_2d(x)), _f64(np.atleast_2d(u)), _f64(np.atleast_2d(B)), _f64(np.asarray(Jmat).reshape(9))
+        dx = np.zeros_like(x)
+        self._check(self.lib.ts_dynamics_batch(self.h, mode, x.shape[0], _ptr(x), _ptr(u), _ptr(B), B.shape[0], float(index_scale),
+                                               float(clock_rate), _ptr(Jmat), _ptr(dx)))
+        return dx
+
+    def rk3_step_batch(self, x, u, B, Jmat, index_scale, clock_rate, dt):
+        x, u, B, Jmat = _f64(np.atleast_2d(x)), _f64(np.atleast_2d(u)), _f64(np.atleast_2d(B)), _f64(np.asarray(Jmat).reshape(9))
+        xn = np.zeros_like(x)
+        self._check(self.lib.ts_rk3_step_batch(self.h, x.shape[0], _ptr(x), _ptr(u), _ptr(B), B.shape[0], float(index_scale),
+                                               float(clock_rate), _ptr(Jmat), float(dt), _ptr(xn)))
+        return xn
+
     # -- prep / K4 / fused MC ----------------------------------------------
     def slew_weights_batch(self, x0, xf, Jmat, t_final, t0=0.0, dt=0.2, alpha=10.0, beta=1e3, want_guess=False):
         """eigen_axis_slew + Bryson weights (eigen_axis_slew.jl:1-38, TortoiseSat.jl:157-168)."""
@@ -475,3 +520,52 @@ def eigen_axis_slew(x0, xf, t):
     _, _, _, wg, qg, _ = default_engine().slew_weights_batch([x0p], [xfp], np.eye(3).reshape(1, 9), [float(t[-1])], t0=float(t[0]),
                                                             dt=dt, want_guess=True)
     return wg[:len(t)], qg[:len(t)]
+
+
+def kep_ECI(kep_elements, t0, GM):
+    """kep_ECI(kep,t0,GM) -> [r'; v'] (2 x 3)  (kep_ECI.jl:1-35); like the reference it also mutates
+    kep_elements[5] (kep_ECI.jl:7-8)."""
+    k = np.asarray(kep_elements, dtype=np.float64).reshape(-1)
+    rv = default_engine().kep_eci_batch(k.reshape(1, 6), [t0], GM)[0]
+    try:
+        kep_elements[5] = np.fmod(k[5] + t0 * np.sqrt(GM / k[1] ** 3), 360.0)
+    except Exception:
+        pass
+    return rv.reshape(2, 3)
+
+
+def OrbitPlotter(x, p=None, t=None):
+    """OrbitPlotter(x,p,t) -> [v; a]  (OrbitPlotter.jl:1-52)."""
+    return default_engine().orbit_rhs_batch(np.asarray(x, dtype=float).reshape(1, 6))[0]
+
+
+def legendre(phi, n_max, ph_term=False):
+    """legendre(Val{:schmidt}, phi, n_max, false)  (legendre.jl:254-292)."""
+    if ph_term:
+        raise NotImplementedError("only ph_term = false is on the IGRF path (igrf.jl:124)")
+    return default_engine().legendre_schmidt_batch([phi], n_max, want_dP=False)[0]
+
+
+def dlegendre(phi, n_max, ph_term=False):
+    """dlegendre(Val{:schmidt}, phi, n_max, false)  (dlegendre.jl:221-309, via :411-419)."""
+    if ph_term:
+        raise NotImplementedError("only ph_term = false is on the IGRF path (igrf.jl:125)")
+    return default_engine().legendre_schmidt_batch([phi], n_max, want_dP=True)[1][0]
+
+
+def attitude_dynamics(x, u, B_B, J):
+    """attitude_dynamics(x,u,B_B,J) -> xdot (7)  (attitude_dynamics.jl:2-24)."""
+    return default_engine().dynamics_batch(2, np.asarray(x, dtype=float).reshape(1, 7), np.asarray(u, dtype=float).reshape(1, 3),
+                                           np.asarray(B_B, dtype=float).reshape(1, 3), J)[0]
+
+
+def qmult(q1, q2):
+    """qmult.jl:1-3 (host helper)."""
+    q1, q2 = np.asarray(q1, dtype=float), np.asarray(q2, dtype=float)
+    return np.concatenate([[q1[0] * q2[0] - q1[1:] @ q2[1:]], q1[0] * q2[1:] + q2[0] * q1[1:] + np.cross(q1[1:], q2[1:])])
+
+
+def qrot(q, r):
+    """qrot.jl:1-3 (host helper)."""
+    q, r = np.asarray(q, dtype=float), np.asarray(r, dtype=float)
+    return r + 2 * np.cross(q[1:], np.cross(q[1:], r) + q[0] * r)
