@@ -274,13 +274,65 @@ function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination =
     (A = Matrix(A'), t_final = t_final, slew_time = slew_time, fails = fails, outcomes = out, stats = st[])
 end
 
+# ----------------------------------------------------------------------------- element-wise building blocks
+# kep_ECI(kep_elements,t0,GM) -> [r'; v'] (2 x 3)            reference src/kep_ECI.jl:1-35 (mutates kep_elements[6], :7-8)
+function kep_ECI(kep_elements, t0, GM; e::Engine = engine())
+    k = collect(Float64, vec(kep_elements)); rv = zeros(6)
+    check(e, ccall((:ts_kep_eci_batch, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}),
+                   e.h, 1, k, Float64[t0], GM, rv))
+    kep_elements[6] = rem(kep_elements[6] + t0 * sqrt(GM ./ kep_elements[2] .^ 3), 360)
+    [rv[1:3]'; rv[4:6]']
+end
+# OrbitPlotter(x,p,t) -> [v; a]                               reference src/OrbitPlotter.jl:1-52
+function OrbitPlotter(x, p, t; e::Engine = engine())
+    dx = zeros(6)
+    check(e, ccall((:ts_orbit_rhs_batch, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), e.h, 1, collect(Float64, x), dx))
+    dx
+end
+# legendre(Val{:schmidt}, phi, n_max, false) / dlegendre(Val{:schmidt}, phi, P, false)   src/legendre.jl:254-292, src/dlegendre.jl:221-309
+function legendre(::Type{Val{:schmidt}}, phi::Number, n_max::Number, ph_term::Bool = false; e::Engine = engine())
+    ph_term && error("only ph_term = false is on the IGRF path (igrf.jl:124)")
+    d = Int(n_max) + 1; P = zeros(d, d)
+    check(e, ccall((:ts_legendre_schmidt_batch, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}),
+                   e.h, 1, Float64[phi], n_max, P, C_NULL))
+    Matrix(P')                      # the library is row-major
+end
+function dlegendre(::Type{Val{:schmidt}}, phi::Number, P::Matrix, ph_term::Bool = false; e::Engine = engine())
+    ph_term && error("only ph_term = false is on the IGRF path (igrf.jl:125)")
+    d = size(P, 1); Pb = zeros(d, d); dP = zeros(d, d)
+    check(e, ccall((:ts_legendre_schmidt_batch, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}),
+                   e.h, 1, Float64[phi], d - 1, Pb, dP))
+    Matrix(dP')
+end
+# DerivFunction(dx,x,u) / gain_simulator(dx,x,u): in-place 8-state dynamics reading the reference's globals
+# B_ECI (rows x 3), N, p.J, tf, t0                            reference src/DerivFunction.jl:1-48, src/gain_simulator.jl:1-53
+function _dynamics!(mode, dx, x, u, B_ECI, N, J, tf, t0; e::Engine = engine())
+    Bt = Matrix{Float64}(B_ECI'); o = zeros(8)
+    check(e, ccall((:ts_dynamics_batch, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cdouble, Cdouble, Ptr{Float64}, Ptr{Float64}),
+                   e.h, mode, 1, collect(Float64, x), collect(Float64, u), Bt, size(Bt, 2), Float64(N), 1 / (tf - t0),
+                   vec(Matrix{Float64}(J')), o))
+    dx[1:8] = o
+end
+DerivFunction(dx, x, u) = _dynamics!(0, dx, x, u, Main.B_ECI, Main.N, Main.p.J, Main.tf, Main.t0)
+gain_simulator(dx, x, u) = _dynamics!(1, dx, x, u, Main.B_ECI, Main.N, Main.p.J, Main.tf, Main.t0)
+# attitude_dynamics(x,u,B_B,J) -> xdot (7)                      reference src/attitude_dynamics.jl:2-24
+function attitude_dynamics(x, u, B_B, J; e::Engine = engine())
+    o = zeros(7)
+    check(e, ccall((:ts_dynamics_batch, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cdouble, Cdouble, Ptr{Float64}, Ptr{Float64}),
+                   e.h, 2, 1, collect(Float64, x), collect(Float64, u), collect(Float64, B_B), 1, 1.0, 0.0, vec(Matrix{Float64}(J')), o))
+    o
+end
+
 # ----------------------------------------------------------------------------- small host-side helpers kept verbatim in meaning
 qmult(q1, q2) = [q1[1] * q2[1] - q1[2:4]' * q2[2:4]; q1[1] * q2[2:4] + q2[1] * q1[2:4] + cross(q1[2:4], q2[2:4])]  # src/qmult.jl
 qrot(q, r) = r + 2 * cross(q[2:4], cross(q[2:4], r) + q[1] * r)                                                      # src/qrot.jl
 q_inv(q) = [q[1]; -q[2:4]]                                                              # src/attitude_controller.jl:164-166
 hat(x) = [0 -x[3] x[2]; x[3] 0 -x[1]; -x[2] x[1] 0]                                     # src/magnetic_toolbox.jl:142-146
 
-export Engine, params, input_parameters, igrf12, igrf12_batch, igrf_data, magnetic_simulation, magnetic_gramian,
+export Engine, params, input_parameters, igrf12, igrf12_batch, igrf_data, magnetic_simulation, magnetic_gramian, kep_ECI, OrbitPlotter,
+       legendre, dlegendre, DerivFunction, gain_simulator, attitude_dynamics,
        condition_based_time, eigen_axis_slew, bryson_weights, solve_slew, attitude_simulation, monte_carlo, qmult, qrot, q_inv, hat
 
 end # module
