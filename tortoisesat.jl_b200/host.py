@@ -218,7 +218,10 @@ class Engine:
             n = r_m.shape[0]
             if not (lat.shape[0] == n and lon.shape[0] == n):
                 raise ValueError("r, lat, lon must have the same length")
-            Bn, Be, Bd = np.empty(n), np.empty(n), np.empty(n)
+            if out is not None:   # caller-provided host outputs (e.g. views of pinned memory)
+                Bn, Be, Bd = out
+            else:
+                Bn, Be, Bd = np.empty(n), np.empty(n), np.empty(n)
             rc = self.lib.ts_igrf12_batch(self.h, float(date), n, _ptr(r_m), _ptr(lat), _ptr(lon), _ptr(Bn), _ptr(Be),
                                           _ptr(Bd), 0)
             if rc == TS_ERR_DOMAIN:
