@@ -391,7 +391,8 @@ def main():
                        "converged": conv, "no_cutoff": int(vec[2]), "mean_inner_iters": float(vec[7] / max(1.0, vec[0] - vec[2])),
                        "mean_ls_rollouts": float(vec[8] / max(1.0, vec[0] - vec[2])),
                        "mean_slew_time_s": float(vec[4] / max(1.0, vec[0] - vec[2])), "fail_slew": int(vec[3])},
-            "roofline": {"bound": "fp64", "kernel": "k3_alilqr_kernel", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "k3_alilqr_kernel + k3_wide_kernel (one AL-iLQR solve: 4-trials-per-warp launch, "
+                                                      "then one warp per straggler)", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": ach / peak_fp64, "traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters,
                          "traffic_source": "1383 B per knot-iteration (ncu --set full, dram__bytes_read+write, capture of "
                                            "tools/k3_small.py 2368: 85.6 GB / 6.19e7 knot-iterations) x this run's knot-iterations",
@@ -404,6 +405,7 @@ def main():
             "e2e": {"value": total_trials / e2e_s, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "note": "ts_monte_carlo_run with host per-trial inputs + outcome D2H + NCCL gather; trajectories stay in HBM"},
             "stage_ms": {"field": st.ms_field, "prep": st.ms_prep, "solve": st.ms_solve, "tvlqr": st.ms_tvlqr},
+            "k3_split": dict(zip(("persistent_ms", "straggler_ms", "handed_over"), eng.k3_last_split())),
             "gpu_launches": launches, "clocks": clocks}
     # secondary metric: IGRF-12 evals/s (K1), 1e8 points
     try:

@@ -56,6 +56,9 @@ int ts_synchronize(ts_ctx* ctx);
 /* device time (ms, CUDA events on the context's stream) of the kernels launched by the
  * most recent call on ctx, excluding host<->device copies */
 double ts_last_kernel_ms(const ts_ctx* ctx);
+/* diagnostics of the most recent AL-iLQR solve on ctx (K3): device time of the persistent 4-trials-per-warp
+ * kernel, of the straggler kernel (one warp per trial), and how many trials were handed from one to the other */
+int ts_k3_last_split(ts_ctx* ctx, double* persistent_ms, double* straggler_ms, int64_t* n_parked);
 
 /* Measures the FP64 FMA peak of the bound GPU with a register-resident DFMA
  * micro-benchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64 row). */

@@ -80,6 +80,18 @@ def test_wide_team_matches_oracle(angle, tfin, mask):
     assert np.max(np.abs(X - Xs[0])) < 1e-9 and np.max(np.abs(U - Us[0])) < 1e-9
 
 
+def test_team_width_does_not_change_results():
+    """A trial may start in an 8-lane team and be finished by a whole warp (straggler hand-over): the solver must be
+    bit-identical at both widths -- same trajectories, gains, cost and counters."""
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 20.0), np.array([1.0, 0, 0, 0]), t_final=30.0)
+    o = orc.default_ilqr_opts()
+    X8, U8, K8, o8 = S.hostsim_solve(s, o, width=8)
+    X32, U32, K32, o32 = S.hostsim_solve(s, o, width=32)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "N", "J", "c_max"):
+        assert o8[f] == o32[f], f
+    assert np.array_equal(X8, X32) and np.array_equal(U8, U32) and np.array_equal(K8, K32)
+
+
 def test_stage_cost_dt_and_3u_inertia():
     s = S.build_slew([0, 6871, 51.6, 30, 0, 10], S.J_3U, S.quat_axis_angle([0, 1, 0], 3.0), np.array([1.0, 0, 0, 0]), t_final=50.0)
     o = orc.default_ilqr_opts()

@@ -40,6 +40,8 @@ for n in ntr:
     st = np.bincount(out["status"], minlength=5)
     print(n, "kernel ms", ms, "wall s", wall, "trials/s", n / (ms * 1e-3), "status", st.tolist(), "outer mean", out["outer_iters"].mean(),
           "inner mean/max", out["inner_iters"].mean(), out["inner_iters"].max(), "ls mean", out["ls_rollouts"].mean(), flush=True)
+    print("   K3 split: persistent %.0f ms, straggler kernel %.0f ms, %d trials handed over" % eng.k3_last_split(),
+          "| inner-iteration quantiles 50/75/90/95/99:", np.percentile(out["inner_iters"], [50, 75, 90, 95, 99]).tolist(), flush=True)
     its = out["inner_iters"].astype(float)
     i = int(np.argmax(its))
     kn = its * base.N

@@ -16,6 +16,9 @@ struct ts_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_k3[3] = {nullptr, nullptr, nullptr};  // K3: start | persistent kernel done | straggler kernel done
+  unsigned* d_k3_parked = nullptr;                     // device word holding the number of parked trials of the last K3 run
+  bool k3_timed = false;
   char err[512] = {0};
   char name[128] = {0};
   int64_t launches = 0;
@@ -24,8 +27,8 @@ struct ts_ctx {
   double* d_tabH = nullptr;  // 91 x 25
   int* d_flag = nullptr;     // generic device error/flag word
   // grow-only scratch arenas
-  void* scratch[16] = {};
-  size_t scratch_bytes[16] = {};
+  void* scratch[20] = {};
+  size_t scratch_bytes[20] = {};
 };
 
 namespace ts {

@@ -425,11 +425,15 @@ TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
                              double sc, double mu, const double lam_g[8], double& cmax_out) {
   double Jc = 0.0, cmax = 0.0;
   const int N = in.N;
-  for (int k = tm.lane(); k < N - 1; k += Team::W) {
-    const double* p = xu + (long long)k * 10;
-    const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
-    add_stage_cost(in, o, sc, mu, p, e8, p + 7, w.lam + (long long)k * 6, Jc, cmax);
-  }
+  // knots are dealt to the first TEAM lanes whatever the team width: the 8 partial sums and the tree below are
+  // then bit-identical for an 8-lane team and a whole warp (lanes >= 8 contribute exact zeros), so a trial's
+  // iteration path does not depend on where it runs (straggler hand-over, k3_wide_kernel)
+  if (tm.lane() < TEAM)
+    for (int k = tm.lane(); k < N - 1; k += TEAM) {
+      const double* p = xu + (long long)k * 10;
+      const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
+      add_stage_cost(in, o, sc, mu, p, e8, p + 7, w.lam + (long long)k * 6, Jc, cmax);
+    }
   if (tm.lane() == 0) add_terminal_cost(in, o, mu, xu + (long long)(N - 1) * 10, w.clk[N - 1] - in.xf[7], lam_g, Jc, cmax);
   cmax_out = tm.max(cmax);
   return tm.sum(Jc);
@@ -772,13 +776,14 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   st.rho = reg.rho;
   st.drho = reg.drho;
   double g = 0.0;
-  for (int k = lane; k < N - 1; k += Team::W) {
-    const double* p = xu_cur + (long long)k * 10;
-    const double* kd = w.kd + (long long)k * 24;
-    double mxg = 0.0;
-    for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
-    g += mxg;
-  }
+  if (lane < TEAM)  // width-independent summation order, see trajectory_cost
+    for (int k = lane; k < N - 1; k += TEAM) {
+      const double* p = xu_cur + (long long)k * 10;
+      const double* kd = w.kd + (long long)k * 24;
+      double mxg = 0.0;
+      for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
+      g += mxg;
+    }
   const double grad = tm.sum(g) / (double)(N - 1);
   st.cyc_fwd += ts_clock() - t0;
   solve_after_forward(tm, in, o, w, st, st.J_prev, grad);

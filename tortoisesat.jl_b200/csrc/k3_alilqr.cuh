@@ -63,12 +63,11 @@ struct GpuTeam {
   }
 };
 
-// Compiled in only with -DTS_K3_COMPILE_WIDE (measured in round 1: finishing a warp's straggler with all 32 lanes cut the
-// straggler's own per-knot cost by ~15% but the doubled kernel (registers, spills, code size) slowed every other warp,
-// 14.6 s -> 19.4 s on the 4096-trial ensemble; the solver itself is width-generic and tested at W = 32 in tests/hostsim).
-// The whole warp as ONE team of 32 lanes ("wide" mode): used for the last unfinished trial of a warp, whose
-// three siblings' lanes and trajectory buffers would otherwise idle.  32 knots are linearised per chunk and all
-// 21 line-search candidates are rolled out in a single batch.
+// The whole warp as ONE team of 32 lanes: used by k3_wide_kernel for the stragglers the persistent kernel parks.
+// 32 knots are linearised per chunk and all 21 line-search candidates are rolled out in a single batch.
+// (Round-1 measurement: switching to this team INSIDE the persistent kernel doubled its code and registers and
+// slowed every other warp, 14.6 s -> 19.4 s on the 4096-trial ensemble; as a separate launch it costs nothing
+// there.  The solver is width-generic and tested at W = 32 in tests/hostsim.)
 struct GpuWideTeam {
   static constexpr int W = 32;
   int ln;
@@ -136,14 +135,24 @@ struct K3Args {
   int64_t per_slot;  // doubles per slot (even)
   int64_t Nmax;      // padded to even
   unsigned long long* queue;
-  int wide_mode;  // 1: the last unfinished trial of a warp's group is finished by all 32 lanes (needs TS_K3_COMPILE_WIDE)
   int tail_share; // 1: finished siblings lend lanes + buffers to the line search of the group's last trial
+  // straggler hand-over (k3_wide_kernel): once the queue is empty, a trial that has used `suspend_after` inner
+  // iterations is parked (solver state + live arrays copied out) and finished by a whole warp in the second launch
+  int suspend_after;          // 0: never park
+  int park_cap;               // parking places
+  unsigned* park_count;       // places handed out (may overshoot park_cap)
+  TrialState* park_state;     // [park_cap]
+  int64_t* park_trial;        // [park_cap] trial index
+  double* park_data;          // [park_cap][27 * Nmax]: current trajectory 10 | multipliers 6 | stage fields 10 | clock 1
+  unsigned long long* queue2; // work queue of the second launch
+  int* park_order;            // [park_cap] parking places, longest remaining iteration budget first
 };
 
 
 // Fills the team's shared-memory TrialIn block for trial t (lane 0 writes, team syncs).
-__device__ __forceinline__ const TrialIn& k3_load_trial(const GpuTeam& tm, const K3Args& a, int64_t t) {
-  TrialIn* inp = reinterpret_cast<TrialIn*>(tm.smem() + SM_TRIAL);
+template <class Team>
+__device__ __forceinline__ const TrialIn& k3_load_trial(const Team& tm, const K3Args& a, int64_t t) {
+  TrialIn* inp = reinterpret_cast<TrialIn*>(tm.smem() + SmL<Team::W>::TRIAL);
   __builtin_assume(__isShared(inp));
   tm.sync();
   if (tm.ln == 0) {
@@ -194,6 +203,10 @@ __device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a
           Ko[i * 8 + 7] = 0.0;
         }
       }
+    } else {  // the ragged layout keeps N rows per trial: the unused last row of U and K is defined (zero)
+      for (int i = 0; i < 3; ++i) Uo[(int64_t)k * 3 + i] = 0.0;
+      if (a.K)
+        for (int i = 0; i < 24; ++i) a.K[(a.offs[t] + k) * 24 + i] = 0.0;
     }
   }
   if (tm.ln == 0) a.out[t] = oc;
@@ -257,6 +270,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
       st.cur = team * 9;   // trajectory buffers are addressed in the warp's 36-buffer space from here on
     }
     bool stored = !have;
+    bool may_park = a.suspend_after > 0;
     // ---- iterate: one iLQR iteration per pass for every unfinished team; the warp re-converges here
     for (;;) {
       if (!stored && st.phase == PH_DONE) {  // finished: write results now, so the slot's buffers can be lent out
@@ -265,59 +279,39 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
         k3_store_results(tm, a, t, w, inp->N, st.cur, oc);
         stored = true;
       }
+      // straggler hand-over: nothing left in the queue and this trial is past its iteration allowance -> park it
+      // (between two iterations, so its whole state is TrialState + the four live arrays) for k3_wide_kernel
+      if (may_park && !stored && st.phase == PH_BACKWARD && st.inner_total >= a.suspend_after) {  // team-uniform
+        unsigned place = 0xffffffffu;   // lane 0 decides for the team (the queue may move between two lanes' reads)
+        if (tm.ln == 0 && *(volatile unsigned long long*)a.queue >= (unsigned long long)a.n_trials) {
+          place = atomicAdd(a.park_count, 1u);
+          if (place >= (unsigned)a.park_cap) place = 0xfffffffeu;
+        }
+        place = __shfl_sync(tm.mask, place, 0, TEAM);
+        if (place == 0xffffffffu) {
+          // queue not drained yet: fresh trials keep every lane busy, stay
+        } else if (place < (unsigned)a.park_cap) {
+          const int N = inp->N;
+          double* pd = a.park_data + (int64_t)place * (27 * a.Nmax);
+          const double* xc = xu_buf<TEAM>(w, st.cur);
+          for (int i = tm.ln; i < N * 10; i += TEAM) pd[i] = xc[i];
+          for (int i = tm.ln; i < N * 6; i += TEAM) pd[10 * a.Nmax + i] = w.lam[i];
+          for (int i = tm.ln; i < N * 10; i += TEAM) pd[16 * a.Nmax + i] = w.bk[i];
+          for (int i = tm.ln; i < N; i += TEAM) pd[26 * a.Nmax + i] = w.clk[i];
+          if (tm.ln == 0) {
+            a.park_state[place] = st;
+            a.park_trial[place] = t;
+          }
+          st.phase = PH_DONE;
+          stored = true;
+        } else {
+          may_park = false;  // no place left: finish here
+        }
+      }
       const unsigned act = __ballot_sync(0xffffffffu, st.phase != PH_DONE);
       if (!act) break;
       const unsigned teams_act = ((act & 0x000000ffu) ? 1u : 0u) | ((act & 0x0000ff00u) ? 2u : 0u) | ((act & 0x00ff0000u) ? 4u : 0u) |
                                  ((act & 0xff000000u) ? 8u : 0u);
-#ifdef TS_K3_COMPILE_WIDE
-      if (a.wide_mode && __popc(teams_act) == 1) {
-        // ---- wide mode: the whole warp finishes the last trial of this group
-        const int lt = __ffs(teams_act) - 1;   // the unfinished team
-        const int src = lt * 8;
-        TrialState ws;
-        ws.mu = k3_shfl_d(st.mu, src);
-        for (int i = 0; i < 8; ++i) ws.lam_g[i] = k3_shfl_d(st.lam_g[i], src);
-        ws.J_prev = k3_shfl_d(st.J_prev, src); ws.J = k3_shfl_d(st.J, src); ws.c_max = k3_shfl_d(st.c_max, src);
-        ws.rho = k3_shfl_d(st.rho, src); ws.drho = k3_shfl_d(st.drho, src); ws.dV1 = k3_shfl_d(st.dV1, src);
-        ws.dV2 = k3_shfl_d(st.dV2, src); ws.clk_absmax = k3_shfl_d(st.clk_absmax, src);
-        ws.cyc_bwd = k3_shfl_ll(st.cyc_bwd, src); ws.cyc_fwd = k3_shfl_ll(st.cyc_fwd, src); ws.cyc_lin = k3_shfl_ll(st.cyc_lin, src);
-        ws.it = k3_shfl_i(st.it, src); ws.outer = k3_shfl_i(st.outer, src); ws.dJ_zero = k3_shfl_i(st.dJ_zero, src);
-        ws.inner_total = k3_shfl_i(st.inner_total, src); ws.ls_total = k3_shfl_i(st.ls_total, src);
-        ws.status = k3_shfl_i(st.status, src); ws.phase = k3_shfl_i(st.phase, src); ws.b0 = 0; ws.pad_ = 0;
-        ws.cur = lt * 9 + k3_shfl_i(st.cur, src);   // buffer index in the warp's 36-buffer space
-        const long long t_l = k3_shfl_ll((long long)t, src);
-        // the trial's TrialIn block moves from the narrow team's region to the wide layout's slot (regions overlap)
-        const double* tin_src = warp_smem + lt * TEAM_SMEM_DOUBLES + SM_TRIAL;
-        const double v0 = tin_src[lane32], v1 = tin_src[32 + lane32];
-        __syncwarp();
-        double* tin_dst = warp_smem + SmL<32>::TRIAL;
-        tin_dst[lane32] = v0;
-        tin_dst[32 + lane32] = v1;
-        __syncwarp();
-        GpuWideTeam wt;
-        wt.ln = lane32;
-        wt.sm = warp_smem;
-        const TrialIn* winp = reinterpret_cast<const TrialIn*>(wt.smem() + SmL<32>::TRIAL);
-        TrialWork ww = w;   // kd / lam / bk / clk of the unfinished trial's own slot
-        ww.xu = a.w_base + (gwarp * 4 + lt) * a.per_slot;
-        ww.kd = ww.xu + 90 * a.Nmax;
-        ww.lam = ww.kd + 24 * a.Nmax;
-        ww.bk = ww.lam + 6 * a.Nmax;
-        ww.clk = ww.bk + 10 * a.Nmax;
-        if (ws.phase == PH_FORWARD) ws.phase = PH_BACKWARD;  // (never the case: teams reach this point between iterations)
-        while (ws.phase != PH_DONE) {
-          if (ws.phase == PH_BACKWARD) solve_backward(wt, *winp, a.opts, ww, ws);
-          while (ws.phase == PH_FORWARD) solve_forward(wt, *winp, a.opts, ww, ws);
-        }
-        ts_trial_outcome_dev oc;
-        solve_finish(*winp, ws, oc);
-        k3_store_results(wt, a, (int64_t)t_l, ww, winp->N, ws.cur, oc);
-        __syncwarp();
-        break;
-      }
-#else
-      (void)teams_act;
-#endif
       // "tail sharing": when a single trial of the group is left, its three finished siblings lend their lanes
       // and trajectory buffers to its line search (candidates 8..31 in the same batch) -- with ONE call site of
       // forward_batch for both modes, so the kernel does not grow.
@@ -454,6 +448,93 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
     __syncwarp();
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Second launch: every parked straggler is finished by ONE WHOLE WARP (32-lane team): 32 knots linearised per
+// chunk, all 21 line-search candidates in one batch, one warp per SM sub-partition when few trials are left.
+// The makespan of a single-wave ensemble is the latency of its slowest trial (the ~7% of slews that use all
+// max_outer x max_inner iterations), and a lone 8-lane team leaves 3/4 of its warp's issue slots empty.
+// The per-trial arithmetic is that of the width-generic solver: outcomes do not depend on where a trial ran
+// (tests/test_hostsim_*.py run the same source at W = 8 and W = 32).
+// Between the two launches: order the parked trials by their remaining iteration BUDGET, largest first (counting
+// sort, one block).  The trials that will use every remaining iteration (the non-converging ones sit at a low
+// outer count) then start in the first wave, and the short ones fill the warps that free up: longest-
+// processing-time-first on the only estimate available.
+__global__ void __launch_bounds__(1024, 1) k3_park_order_kernel(const K3Args a) {
+  __shared__ int hist[1024];
+  __shared__ int start[1024];
+  unsigned n = *a.park_count;
+  if (n > (unsigned)a.park_cap) n = (unsigned)a.park_cap;
+  const int tid = threadIdx.x;
+  hist[tid] = 0;
+  __syncthreads();
+  const long long full = (long long)a.opts.max_outer * a.opts.max_inner;
+  auto bin_of = [&](unsigned i) {
+    const TrialState& st = a.park_state[i];
+    long long rem = (long long)(a.opts.max_outer - st.outer) * a.opts.max_inner + (a.opts.max_inner - st.it);
+    if (rem < 0) rem = 0;
+    if (rem > full) rem = full;
+    return 1023 - (int)((rem * 1023) / (full > 0 ? full : 1));   // bin 0 = largest budget
+  };
+  for (unsigned i = tid; i < n; i += 1024) atomicAdd(&hist[bin_of(i)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b < 1024; ++b) {
+      start[b] = acc;
+      acc += hist[b];
+    }
+  }
+  __syncthreads();
+  for (unsigned i = tid; i < n; i += 1024) a.park_order[atomicAdd(&start[bin_of(i)], 1)] = (int)i;
+}
+
+__global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
+  extern __shared__ __align__(16) double k3_smem[];
+  const int lane32 = threadIdx.x & 31;
+  const int64_t gwarp = blockIdx.x;
+  GpuWideTeam tm;
+  tm.ln = lane32;
+  tm.sm = k3_smem;
+  TrialWork w;
+  w.Nmax = a.Nmax;
+  w.xu = a.w_base + (gwarp * 4) * a.per_slot;   // the warp's four slots = 36 trajectory buffers, 33 used
+  w.xu_warp = w.xu;
+  w.slot_stride = a.per_slot;
+  w.kd = w.xu + 90 * a.Nmax;
+  w.lam = w.kd + 24 * a.Nmax;
+  w.bk = w.lam + 6 * a.Nmax;
+  w.clk = w.bk + 10 * a.Nmax;
+  unsigned n_parked = *a.park_count;
+  if (n_parked > (unsigned)a.park_cap) n_parked = (unsigned)a.park_cap;
+  for (;;) {
+    unsigned long long qpos = 0;
+    if (lane32 == 0) qpos = atomicAdd(a.queue2, 1ull);
+    qpos = __shfl_sync(0xffffffffu, qpos, 0);
+    if (qpos >= n_parked) break;
+    const int64_t idx = a.park_order[qpos];
+    const int64_t t = a.park_trial[idx];
+    const TrialIn& in = k3_load_trial(tm, a, t);
+    const int N = in.N;
+    const double* pd = a.park_data + (int64_t)idx * (27 * a.Nmax);
+    for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];
+    for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * a.Nmax + i];
+    for (int i = lane32; i < N * 10; i += 32) w.bk[i] = pd[16 * a.Nmax + i];
+    for (int i = lane32; i < N; i += 32) w.clk[i] = pd[26 * a.Nmax + i];
+    TrialState st = a.park_state[idx];
+    st.cur = 0;
+    __syncwarp();
+    while (st.phase != PH_DONE) {
+      if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
+      while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
+    }
+    ts_trial_outcome_dev oc;
+    solve_finish(in, st, oc);
+    k3_store_results(tm, a, t, w, N, st.cur, oc);
+    __syncwarp();
+  }
+}
+constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 
 // ---------------------------------------------------------------------------------------------
 // Phase-split launch mode: the same solver phases as separate kernels, driven in lockstep by the

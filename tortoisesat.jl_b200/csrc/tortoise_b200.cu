@@ -77,6 +77,8 @@ int ts_create(ts_ctx** out, int device_id) {
   snprintf(c->name, sizeof(c->name), "%s", prop.name);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreate(&c->ev_k3[0]) != cudaSuccess || cudaEventCreate(&c->ev_k3[1]) != cudaSuccess ||
+      cudaEventCreate(&c->ev_k3[2]) != cudaSuccess ||
       cudaMalloc(&c->d_tabG, sizeof(TS_IGRF12_G)) != cudaSuccess || cudaMalloc(&c->d_tabH, sizeof(TS_IGRF12_H)) != cudaSuccess ||
       cudaMalloc(&c->d_flag, 64) != cudaSuccess) {
     ts_destroy(c);
@@ -98,13 +100,15 @@ int ts_create(ts_ctx** out, int device_id) {
 void ts_destroy(ts_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < 20; ++i)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->d_tabG) cudaFree(c->d_tabG);
   if (c->d_tabH) cudaFree(c->d_tabH);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int i = 0; i < 3; ++i)
+    if (c->ev_k3[i]) cudaEventDestroy(c->ev_k3[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -112,6 +116,24 @@ void ts_destroy(ts_ctx* c) {
 const char* ts_last_error(const ts_ctx* c) { return c ? c->err : "null context"; }
 int64_t ts_launch_count(const ts_ctx* c) { return c ? c->launches : 0; }
 double ts_last_kernel_ms(const ts_ctx* c) { return c ? c->last_kernel_ms : 0.0; }
+int ts_k3_last_split(ts_ctx* c, double* persistent_ms, double* straggler_ms, int64_t* n_parked) {
+  if (!c) return TS_ERR_ARG;
+  if (persistent_ms) *persistent_ms = 0.0;
+  if (straggler_ms) *straggler_ms = 0.0;
+  if (n_parked) *n_parked = 0;
+  if (!c->k3_timed) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  float a = 0.f, b = 0.f;
+  TS_CUDA(c, cudaEventElapsedTime(&a, c->ev_k3[0], c->ev_k3[1]));
+  TS_CUDA(c, cudaEventElapsedTime(&b, c->ev_k3[1], c->ev_k3[2]));
+  unsigned np = 0;
+  if (c->d_k3_parked) TS_CUDA(c, cudaMemcpy(&np, c->d_k3_parked, sizeof(np), cudaMemcpyDeviceToHost));
+  if (persistent_ms) *persistent_ms = a;
+  if (straggler_ms) *straggler_ms = b;
+  if (n_parked) *n_parked = (int64_t)np;
+  return TS_OK;
+}
 
 int ts_device_info(ts_ctx* c, int* sm_count, char* name, int name_len) {
   if (!c) return TS_ERR_ARG;
@@ -365,6 +387,8 @@ static double slew_angle(const double* x0, const double* xf) {
 //               phase, so the hot loop fits the instruction cache and finished trials free their SM slots
 // TS_K3_MODE=persistent|phased overrides the automatic choice.  Returns with all work complete on the stream
 // (the phased mode synchronises to poll the active-trial counter).
+// inner iterations a trial may use in the 4-trials-per-warp kernel once the queue is empty (see k3_wide_kernel)
+constexpr int K3_SUSPEND_AFTER_DEFAULT = 200;
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
   const int64_t n_trials = a.n_trials;
   int64_t Nmax = 0, Nmin = INT64_MAX;
@@ -428,14 +452,53 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   a.w_base = (double*)p_work;
   a.per_slot = per_slot + (per_slot & 1);
   a.queue = (unsigned long long*)p_q;
-  a.wide_mode = 1;
-  if (const char* m = getenv("TS_K3_WIDE")) a.wide_mode = atoi(m) ? 1 : 0;
   a.tail_share = 1;
   if (const char* m = getenv("TS_K3_TAIL")) a.tail_share = atoi(m) ? 1 : 0;
+  // straggler hand-over (k3_wide_kernel): allowance of inner iterations in the 4-trials-per-warp kernel
+  a.suspend_after = K3_SUSPEND_AFTER_DEFAULT;
+  if (const char* m = getenv("TS_K3_SUSPEND")) a.suspend_after = std::max(0, atoi(m));
+  if (phased) a.suspend_after = 0;
+  a.park_cap = 0;
+  a.park_count = (unsigned*)p_q + 8;
+  a.queue2 = (unsigned long long*)p_q + 2;
+  a.park_state = nullptr;
+  a.park_trial = nullptr;
+  a.park_data = nullptr;
+  a.park_order = nullptr;
+  if (a.suspend_after > 0) {
+    // places for every trial that can be resident when the queue runs dry (bounded by 16 GB of parking space)
+    int64_t cap = std::min<int64_t>(n_trials, slots);
+    cap = std::min<int64_t>(cap, (int64_t)(16e9 / (27.0 * 8.0 * (double)Nmax)));
+    void *p_ps, *p_pd;
+    if ((rc = scratch_reserve(c, 15, (size_t)cap * (sizeof(TrialState) + 8 + 4) + 64, &p_ps))) return rc;
+    if ((rc = scratch_reserve(c, 16, (size_t)cap * 27 * (size_t)Nmax * sizeof(double) + 64, &p_pd))) return rc;
+    a.park_cap = (int)cap;
+    a.park_state = (TrialState*)p_ps;
+    a.park_trial = (int64_t*)((char*)p_ps + (size_t)cap * sizeof(TrialState));
+    a.park_data = (double*)p_pd;
+    a.park_order = (int*)((char*)p_ps + (size_t)cap * (sizeof(TrialState) + 8));
+  }
   if (!phased) {
+    c->k3_timed = true;
+    c->d_k3_parked = a.park_count;
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
     k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
     c->launches++;
     TS_CUDA(c, cudaGetLastError());
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+    if (a.park_cap > 0) {
+      // one warp per parked trial; the grid cannot depend on the (device-side) count, idle blocks exit at once
+      int occ_w = 0;
+      TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_wide_kernel, 32, K3_WIDE_SMEM_BYTES));
+      if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
+      const int blocks_w = (int)std::min<int64_t>(std::min<int64_t>(a.park_cap, (int64_t)c->sm_count * occ_w), blocks);
+      k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
+      k3_wide_kernel<<<blocks_w, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
+      c->launches += 2;
+      TS_CUDA(c, cudaGetLastError());
+      TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+    }
     return TS_OK;
   }
   // ---- phased mode

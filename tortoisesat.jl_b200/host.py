@@ -124,6 +124,8 @@ def load_library():
     L.ts_synchronize.argtypes = [C.c_void_p]
     L.ts_last_kernel_ms.argtypes = [C.c_void_p]
     L.ts_last_kernel_ms.restype = C.c_double
+    L.ts_k3_last_split.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.ts_k3_last_split.restype = C.c_int
     L.ts_fp64_peak_probe.argtypes = [C.c_void_p, c_double_p]
     L.ts_igrf12_batch.argtypes = [C.c_void_p, C.c_double, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
     L.ts_magnetic_simulation_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
@@ -200,6 +202,12 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self.lib.ts_last_kernel_ms(self.h))
+
+    def k3_last_split(self):
+        """(persistent-kernel ms, straggler-kernel ms, trials handed over) of the most recent AL-iLQR solve."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._check(self.lib.ts_k3_last_split(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, int(n.value)
 
     def synchronize(self):
         self._check(self.lib.ts_synchronize(self.h))
