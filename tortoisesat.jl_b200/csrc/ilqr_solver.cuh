@@ -318,44 +318,75 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
         for (int i = 0; i < 7; ++i) s[i] = sm[L::SVEC + i];
         // ---- P1: column products
         double Qxxc[7], Quxc[3], Qx = 0.0;
-        if (lane < 7) {
-          double a[7], m[7];
-          for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
-          for (int i = 0; i < 7; ++i) {
+        if constexpr (W >= 10) {
+          // whole-warp team: lane c < 10 owns column c of [A|B] -- the three control columns run on lanes 7..9 in
+          // the same instruction stream as the state columns instead of a second pass on lanes 0..2
+          // (same sums in the same order as the narrow path below)
+          if (lane < 10) {
+            double a[7], m[7], g[10];
+            for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
+            for (int i = 0; i < 7; ++i) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * a[l];
+              m[i] = t;
+            }
+            for (int r = 0; r < 10; ++r) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += rec[r * 7 + l] * m[l];
+              g[r] = t;
+            }
             double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * a[l];
-            m[i] = t;
+            for (int l = 0; l < 7; ++l) t += a[l] * s[l];
+            if (lane < 7) {
+              for (int i = 0; i < 7; ++i) Qxxc[i] = g[i] + ((i == lane) ? sc * in.Qd[i] : 0.0);
+              for (int c = 0; c < 3; ++c) Quxc[c] = g[7 + c];
+              Qx = rec[70 + lane] + t;
+            } else {
+              const int cl = lane - 7;
+              for (int c = 0; c < 3; ++c) sm[L::QUU + c * 3 + cl] = g[7 + c] + ((c == cl) ? rec[80 + c] : 0.0);
+              sm[L::QUU + 9 + cl] = rec[77 + cl] + t;
+            }
           }
-          for (int i = 0; i < 7; ++i) {
+        } else {
+          if (lane < 7) {
+            double a[7], m[7];
+            for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
+            for (int i = 0; i < 7; ++i) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * a[l];
+              m[i] = t;
+            }
+            for (int i = 0; i < 7; ++i) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += rec[i * 7 + l] * m[l];
+              Qxxc[i] = t + ((i == lane) ? sc * in.Qd[i] : 0.0);
+            }
+            for (int c = 0; c < 3; ++c) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
+              Quxc[c] = t;
+            }
             double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += rec[i * 7 + l] * m[l];
-            Qxxc[i] = t + ((i == lane) ? sc * in.Qd[i] : 0.0);
+            for (int l = 0; l < 7; ++l) t += a[l] * s[l];
+            Qx = rec[70 + lane] + t;
           }
-          for (int c = 0; c < 3; ++c) {
+          if (lane < 3) {
+            double b[7], m[7];
+            for (int i = 0; i < 7; ++i) b[i] = rec[(7 + lane) * 7 + i];
+            for (int i = 0; i < 7; ++i) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * b[l];
+              m[i] = t;
+            }
+            for (int c = 0; c < 3; ++c) {
+              double t = 0.0;
+              for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
+              sm[L::QUU + c * 3 + lane] = t + ((c == lane) ? rec[80 + c] : 0.0);
+            }
             double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
-            Quxc[c] = t;
+            for (int l = 0; l < 7; ++l) t += b[l] * s[l];
+            sm[L::QUU + 9 + lane] = rec[77 + lane] + t;
           }
-          double t = 0.0;
-          for (int l = 0; l < 7; ++l) t += a[l] * s[l];
-          Qx = rec[70 + lane] + t;
-        }
-        if (lane < 3) {
-          double b[7], m[7];
-          for (int i = 0; i < 7; ++i) b[i] = rec[(7 + lane) * 7 + i];
-          for (int i = 0; i < 7; ++i) {
-            double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * b[l];
-            m[i] = t;
-          }
-          for (int c = 0; c < 3; ++c) {
-            double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += rec[(7 + c) * 7 + l] * m[l];
-            sm[L::QUU + c * 3 + lane] = t + ((c == lane) ? rec[80 + c] : 0.0);
-          }
-          double t = 0.0;
-          for (int l = 0; l < 7; ++l) t += b[l] * s[l];
-          sm[L::QUU + 9 + lane] = rec[77 + lane] + t;
         }
         tm.sync();
         // ---- P2: 3x3 solve (every lane, redundantly)
