@@ -136,16 +136,21 @@ struct K3Args {
   int64_t Nmax;      // padded to even
   unsigned long long* queue;
   int tail_share; // 1: finished siblings lend lanes + buffers to the line search of the group's last trial
-  // straggler hand-over (k3_wide_kernel): once the queue is empty, a trial that has used `suspend_after` inner
-  // iterations is parked (solver state + live arrays copied out) and finished by a whole warp in the second launch
-  int suspend_after;          // 0: never park
+  // straggler hand-over (k3_wide_kernel): once the queue is empty, a trial that has used its allowance of
+  // knot-iterations (inner iterations x horizon: the unit of sequential work) is parked -- solver state + live
+  // arrays copied out -- and finished by a whole warp in the second launch
+  long long park_budget;      // knot-iterations; 0: never park
   int park_cap;               // parking places
   unsigned* park_count;       // places handed out (may overshoot park_cap)
   TrialState* park_state;     // [park_cap]
   int64_t* park_trial;        // [park_cap] trial index
-  double* park_data;          // [park_cap][27 * Nmax]: current trajectory 10 | multipliers 6 | stage fields 10 | clock 1
+  long long* park_off;        // [park_cap] offset of the trial's arrays in park_data (doubles)
+  double* park_data;          // bump-allocated, 27 * N(even) doubles per parked trial:
+                              //   current trajectory 10N | multipliers 6N | stage fields 10N | clock N
+  long long park_data_cap;    // doubles
+  unsigned long long* park_used;  // doubles handed out
   unsigned long long* queue2; // work queue of the second launch
-  int* park_order;            // [park_cap] parking places, longest remaining iteration budget first
+  int* park_order;            // [park_cap] parking places, longest remaining work first
 };
 
 
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
       st.cur = team * 9;   // trajectory buffers are addressed in the warp's 36-buffer space from here on
     }
     bool stored = !have;
-    bool may_park = a.suspend_after > 0;
+    bool may_park = a.park_budget > 0;
     // ---- iterate: one iLQR iteration per pass for every unfinished team; the warp re-converges here
     for (;;) {
       if (!stored && st.phase == PH_DONE) {  // finished: write results now, so the slot's buffers can be lent out
@@ -281,31 +286,40 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
       }
       // straggler hand-over: nothing left in the queue and this trial is past its iteration allowance -> park it
       // (between two iterations, so its whole state is TrialState + the four live arrays) for k3_wide_kernel
-      if (may_park && !stored && st.phase == PH_BACKWARD && st.inner_total >= a.suspend_after) {  // team-uniform
-        unsigned place = 0xffffffffu;   // lane 0 decides for the team (the queue may move between two lanes' reads)
+      if (may_park && !stored && st.phase == PH_BACKWARD && (long long)st.inner_total * inp->N >= a.park_budget) {  // team-uniform
+        // lane 0 decides for the team (the queue may move between two lanes' reads)
+        unsigned place = 0xffffffffu;
+        long long off = 0;
+        const int N = inp->N;
+        const long long Ne = N + (N & 1);
         if (tm.ln == 0 && *(volatile unsigned long long*)a.queue >= (unsigned long long)a.n_trials) {
-          place = atomicAdd(a.park_count, 1u);
-          if (place >= (unsigned)a.park_cap) place = 0xfffffffeu;
+          place = 0xfffffffeu;
+          off = (long long)atomicAdd(a.park_used, (unsigned long long)(27 * Ne));
+          if (off + 27 * Ne <= a.park_data_cap) {
+            place = atomicAdd(a.park_count, 1u);
+            if (place >= (unsigned)a.park_cap) place = 0xfffffffeu;
+          }
         }
         place = __shfl_sync(tm.mask, place, 0, TEAM);
+        off = __shfl_sync(tm.mask, off, 0, TEAM);
         if (place == 0xffffffffu) {
           // queue not drained yet: fresh trials keep every lane busy, stay
         } else if (place < (unsigned)a.park_cap) {
-          const int N = inp->N;
-          double* pd = a.park_data + (int64_t)place * (27 * a.Nmax);
+          double* pd = a.park_data + off;
           const double* xc = xu_buf<TEAM>(w, st.cur);
           for (int i = tm.ln; i < N * 10; i += TEAM) pd[i] = xc[i];
-          for (int i = tm.ln; i < N * 6; i += TEAM) pd[10 * a.Nmax + i] = w.lam[i];
-          for (int i = tm.ln; i < N * 10; i += TEAM) pd[16 * a.Nmax + i] = w.bk[i];
-          for (int i = tm.ln; i < N; i += TEAM) pd[26 * a.Nmax + i] = w.clk[i];
+          for (int i = tm.ln; i < N * 6; i += TEAM) pd[10 * Ne + i] = w.lam[i];
+          for (int i = tm.ln; i < N * 10; i += TEAM) pd[16 * Ne + i] = w.bk[i];
+          for (int i = tm.ln; i < N; i += TEAM) pd[26 * Ne + i] = w.clk[i];
           if (tm.ln == 0) {
             a.park_state[place] = st;
             a.park_trial[place] = t;
+            a.park_off[place] = off;
           }
           st.phase = PH_DONE;
           stored = true;
         } else {
-          may_park = false;  // no place left: finish here
+          may_park = false;  // no room left: finish here
         }
       }
       const unsigned act = __ballot_sync(0xffffffffu, st.phase != PH_DONE);
@@ -456,8 +470,8 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
 // max_outer x max_inner iterations), and a lone 8-lane team leaves 3/4 of its warp's issue slots empty.
 // The per-trial arithmetic is that of the width-generic solver: outcomes do not depend on where a trial ran
 // (tests/test_hostsim_*.py run the same source at W = 8 and W = 32).
-// Between the two launches: order the parked trials by their remaining iteration BUDGET, largest first (counting
-// sort, one block).  The trials that will use every remaining iteration (the non-converging ones sit at a low
+// Between the two launches: order the parked trials by their remaining BUDGET of knot-iterations (remaining
+// inner iterations x horizon), largest first (counting sort, one block).  The trials that will use every remaining iteration (the non-converging ones sit at a low
 // outer count) then start in the first wave, and the short ones fill the warps that free up: longest-
 // processing-time-first on the only estimate available.
 __global__ void __launch_bounds__(1024, 1) k3_park_order_kernel(const K3Args a) {
@@ -468,13 +482,14 @@ __global__ void __launch_bounds__(1024, 1) k3_park_order_kernel(const K3Args a) 
   const int tid = threadIdx.x;
   hist[tid] = 0;
   __syncthreads();
-  const long long full = (long long)a.opts.max_outer * a.opts.max_inner;
+  const double full = (double)a.opts.max_outer * a.opts.max_inner * (double)a.Nmax;
   auto bin_of = [&](unsigned i) {
     const TrialState& st = a.park_state[i];
     long long rem = (long long)(a.opts.max_outer - st.outer) * a.opts.max_inner + (a.opts.max_inner - st.it);
     if (rem < 0) rem = 0;
-    if (rem > full) rem = full;
-    return 1023 - (int)((rem * 1023) / (full > 0 ? full : 1));   // bin 0 = largest budget
+    double f = (double)rem * (double)a.N_i[a.park_trial[i]] / (full > 0.0 ? full : 1.0);   // remaining knot-iterations, relative
+    if (f > 1.0) f = 1.0;
+    return 1023 - (int)(f * 1023.0);   // bin 0 = most remaining work
   };
   for (unsigned i = tid; i < n; i += 1024) atomicAdd(&hist[bin_of(i)], 1);
   __syncthreads();
@@ -516,11 +531,12 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
     const int64_t t = a.park_trial[idx];
     const TrialIn& in = k3_load_trial(tm, a, t);
     const int N = in.N;
-    const double* pd = a.park_data + (int64_t)idx * (27 * a.Nmax);
+    const long long Ne = N + (N & 1);
+    const double* pd = a.park_data + a.park_off[idx];
     for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];
-    for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * a.Nmax + i];
-    for (int i = lane32; i < N * 10; i += 32) w.bk[i] = pd[16 * a.Nmax + i];
-    for (int i = lane32; i < N; i += 32) w.clk[i] = pd[26 * a.Nmax + i];
+    for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * Ne + i];
+    for (int i = lane32; i < N * 10; i += 32) w.bk[i] = pd[16 * Ne + i];
+    for (int i = lane32; i < N; i += 32) w.clk[i] = pd[26 * Ne + i];
     TrialState st = a.park_state[idx];
     st.cur = 0;
     __syncwarp();

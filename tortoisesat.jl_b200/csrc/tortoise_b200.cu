@@ -420,6 +420,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   std::vector<int64_t> order((size_t)n_trials);
   std::iota(order.begin(), order.end(), (int64_t)0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return N_i_host[x] > N_i_host[y]; });
+  const std::vector<int64_t> order_by_N = order;
   if (difficulty_host && n_trials >= 8) {
     size_t lo = 0;
     while (lo < (size_t)n_trials) {
@@ -454,29 +455,42 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   a.queue = (unsigned long long*)p_q;
   a.tail_share = 1;
   if (const char* m = getenv("TS_K3_TAIL")) a.tail_share = atoi(m) ? 1 : 0;
-  // straggler hand-over (k3_wide_kernel): allowance of inner iterations in the 4-trials-per-warp kernel
-  a.suspend_after = K3_SUSPEND_AFTER_DEFAULT;
-  if (const char* m = getenv("TS_K3_SUSPEND")) a.suspend_after = std::max(0, atoi(m));
-  if (phased) a.suspend_after = 0;
+  // straggler hand-over (k3_wide_kernel): allowance of the 4-trials-per-warp kernel, in inner iterations of a
+  // trial of MEAN horizon; trials are charged in knot-iterations, so a long-horizon trial is handed over sooner
+  int suspend_after = K3_SUSPEND_AFTER_DEFAULT;
+  if (const char* m = getenv("TS_K3_SUSPEND")) suspend_after = std::max(0, atoi(m));
+  if (phased) suspend_after = 0;
+  double N_sum = 0.0;
+  for (int64_t t = 0; t < n_trials; ++t) N_sum += (double)N_i_host[t];
+  a.park_budget = (long long)((double)suspend_after * N_sum / (double)n_trials);
+  if (suspend_after > 0 && a.park_budget < 1) a.park_budget = 1;
   a.park_cap = 0;
   a.park_count = (unsigned*)p_q + 8;
+  a.park_used = (unsigned long long*)p_q + 5;
   a.queue2 = (unsigned long long*)p_q + 2;
   a.park_state = nullptr;
   a.park_trial = nullptr;
+  a.park_off = nullptr;
   a.park_data = nullptr;
+  a.park_data_cap = 0;
   a.park_order = nullptr;
-  if (a.suspend_after > 0) {
-    // places for every trial that can be resident when the queue runs dry (bounded by 16 GB of parking space)
-    int64_t cap = std::min<int64_t>(n_trials, slots);
-    cap = std::min<int64_t>(cap, (int64_t)(16e9 / (27.0 * 8.0 * (double)Nmax)));
+  if (suspend_after > 0) {
+    // a place for every trial that can be resident when the queue runs dry; array space for the `cap` longest
+    // horizons (order[] is sorted by horizon, descending), bounded by 32 GB
+    const int64_t cap = std::min<int64_t>(n_trials, slots);
+    double need = 0.0;
+    for (int64_t i = 0; i < cap; ++i) need += 27.0 * (double)(N_i_host[order_by_N[(size_t)i]] + 1);
+    need = std::min(need, 32e9 / 8.0);
     void *p_ps, *p_pd;
-    if ((rc = scratch_reserve(c, 15, (size_t)cap * (sizeof(TrialState) + 8 + 4) + 64, &p_ps))) return rc;
-    if ((rc = scratch_reserve(c, 16, (size_t)cap * 27 * (size_t)Nmax * sizeof(double) + 64, &p_pd))) return rc;
+    if ((rc = scratch_reserve(c, 15, (size_t)cap * (sizeof(TrialState) + 8 + 8 + 4) + 64, &p_ps))) return rc;
+    if ((rc = scratch_reserve(c, 16, (size_t)need * sizeof(double) + 64, &p_pd))) return rc;
     a.park_cap = (int)cap;
     a.park_state = (TrialState*)p_ps;
     a.park_trial = (int64_t*)((char*)p_ps + (size_t)cap * sizeof(TrialState));
+    a.park_off = (long long*)((char*)p_ps + (size_t)cap * (sizeof(TrialState) + 8));
+    a.park_order = (int*)((char*)p_ps + (size_t)cap * (sizeof(TrialState) + 16));
     a.park_data = (double*)p_pd;
-    a.park_order = (int*)((char*)p_ps + (size_t)cap * (sizeof(TrialState) + 8));
+    a.park_data_cap = (long long)need;
   }
   if (!phased) {
     c->k3_timed = true;
