@@ -183,3 +183,41 @@ def test_straggler_handover_does_not_change_results(engine):
         assert np.max(np.abs(ref[3]["c_max"] - other[3]["c_max"])) < 1e-10
         assert np.max(np.abs(ref[0] - other[0])) < 1e-10 and np.max(np.abs(ref[1] - other[1])) < 1e-10
         assert np.max(np.abs(ref[2] - other[2])) <= 1e-9 * np.max(np.abs(ref[2]))
+
+
+def test_straggler_handover_multi_wave(engine):
+    """More trials than resident team slots (several waves through the persistent kernel): parking only starts once
+    the queue is empty, the parked set is bounded by the resident slots, and results do not depend on it."""
+    import os
+    rng = np.random.default_rng(79)
+    qf = np.array([np.sqrt(2) / 2, np.sqrt(2) / 2, 0, 0])
+    base = S.build_slew([0, 6771, 96.6, 0, 0, 90], S.J_1U, qf, qf, t_final=8.0, tf=2400.0, alpha=0.1)
+    sm, _ = engine.device_info()
+    n = sm * 8 * 4 + 700                      # one full wave of 8 warps/SM x 4 teams, plus a partial second wave
+    x0 = np.tile(base.x0, (n, 1))
+    ang = np.where(np.arange(n) % 4 == 0, rng.uniform(40, 120, size=n), rng.uniform(0.5, 5.0, size=n))
+    for i in range(n):
+        dq = S.quat_axis_angle(rng.normal(size=3), ang[i])
+        x0[i, 3:7] = np.array([qf[0] * dq[0] - qf[1:] @ dq[1:], *(qf[0] * dq[1:] + dq[0] * qf[1:] + np.cross(qf[1:], dq[1:]))])
+    Qd, Qfd, Rd = engine.slew_weights_batch(x0, np.tile(base.xf, (n, 1)), np.tile(base.J.reshape(-1), (n, 1)), [base.t_final] * n,
+                                            dt=0.2, alpha=0.1, beta=1e3)
+    args = dict(N_i=[base.N] * n, x0=x0, xf=np.tile(base.xf, (n, 1)), Jmat=np.tile(base.J.reshape(-1), (n, 1)), Qd=Qd, Qfd=Qfd, Rd=Rd,
+                B_eci=base.B, B_offs=[0] * n, B_rows=[base.B.shape[0]] * n, index_scale=[base.index_scale] * n,
+                clock_rate=[base.clock_rate] * n, dt=base.dt, want_K=False)
+    import tortoisesat.jl_b200 as tb
+    go = _gpu_opts(tb, S.orc.default_ilqr_opts())
+    go.max_outer = 6
+    outs = []
+    try:
+        for flag in ("0", "4"):
+            os.environ["TS_K3_SUSPEND"] = flag
+            X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
+            outs.append((X.copy(), U.copy(), out.copy(), engine.k3_last_split()[2]))
+    finally:
+        os.environ.pop("TS_K3_SUSPEND", None)
+    ref, other = outs
+    assert ref[3] == 0 and 0 < other[3] <= sm * 8 * 4
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
+        assert np.array_equal(ref[2][f], other[2][f]), f
+    assert np.max(np.abs(ref[2]["J"] - other[2]["J"]) / np.abs(ref[2]["J"])) < 1e-10
+    assert np.max(np.abs(ref[0] - other[0])) < 1e-10 and np.max(np.abs(ref[1] - other[1])) < 1e-10
