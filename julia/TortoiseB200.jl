@@ -115,7 +115,20 @@ function igrf12(date::Number, r::Number, λ::Number, Ω::Number; show_warns = tr
     Bn, Be, Bd = igrf12_batch(date, [Float64(r)], [Float64(λ)], [Float64(Ω)])
     [Bn[1]; Be[1]; Bd[1]]
 end
-# igrf_data(altitude, year): the 1000 x 1000 x 3 map       reference src/magnetic_toolbox.jl:108-121
+# igrf_data(altitude, year): the 1000 x 1000 x 3 map       reference src/magnetic_toolbox.jl:108-127
+# Returned behind the reference's call shape mag_field(i,j,c) (monte_carlo.jl:90-96).  The reference wraps the array in
+# a cubic B-spline interpolant with periodic extrapolation but evaluates it at integer nodes only, where an
+# interpolating spline returns the data: node values + periodic index wrap; non-integer arguments are rejected.
+struct MagFieldMap
+    grid::Array{Float64,3}
+end
+function (m::MagFieldMap)(i, j, c)
+    (isinteger(i) && isinteger(j) && isinteger(c)) || error("mag_field(i,j,c): only integer grid nodes are supported")
+    n0, n1, n2 = size(m.grid)
+    m.grid[mod(Int(i) - 1, n0) + 1, mod(Int(j) - 1, n1) + 1, mod(Int(c) - 1, n2) + 1]
+end
+Base.size(m::MagFieldMap) = size(m.grid)
+Base.getindex(m::MagFieldMap, I...) = getindex(m.grid, I...)
 function igrf_data(altitude, year::Int64)
     R_E = 6378; N = 1000
     lat = collect(range(-π / 2, length = N, π / 2)); long = collect(range(-π, length = N, π))
@@ -126,7 +139,7 @@ function igrf_data(altitude, year::Int64)
         k = (i - 1) * N + j
         mag_field[i, j, :] = [Bn[k], Be[k], Bd[k]] / 1.e9
     end
-    mag_field        # (the B-spline wrapper of :124-125 is outside the hot path)
+    MagFieldMap(mag_field)
 end
 
 # ----------------------------------------------------------------------------- K2: orbit + field table

@@ -92,3 +92,22 @@ def test_linearity_in_coefficients_full_size(engine):
     mid = 0.5 * (outs[0] + outs[2])
     err = (outs[1] - mid).norm(dim=0) / outs[1].norm(dim=0)
     assert float(err.max()) < 1e-12
+
+
+def test_igrf_data_map_call_shape(engine, orc):
+    """igrf_data (magnetic_toolbox.jl:108-127): the lat/long map behind the reference's mag_field(i,j,c) call shape
+    (monte_carlo.jl:90-96) -- node values in Tesla, 1-based indices, periodic extrapolation; includes both pole rows."""
+    import tortoisesat.jl_b200 as tb
+    n = 64
+    mf = tb.host.igrf_data(400, 2019, n=n)
+    assert mf.shape == (n, n, 3)
+    lat = np.linspace(-math.pi / 2, math.pi / 2, n)
+    lon = np.linspace(-math.pi, math.pi, n)
+    for (i, j) in [(1, 1), (n, n), (n, 7), (17, 33), (1, 40)]:
+        ref = np.array(orc.igrf12_batch(2019.0, [(400 + 6378) * 1000.0], [lat[i - 1]], [lon[j - 1]])[:3]).ravel() / 1e9
+        got = np.array([mf(i, j, c) for c in (1, 2, 3)])
+        assert np.linalg.norm(got - ref) <= TOL * np.linalg.norm(ref), (i, j)
+    assert mf(n + 5, 3 - n, 4) == mf(5, 3, 1)            # extrapolate(..., Periodic())
+    assert np.asarray(mf)[4, 2, 0] == mf(5, 3, 1)
+    with pytest.raises(ValueError):
+        mf(1.5, 2, 1)

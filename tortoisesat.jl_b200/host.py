@@ -452,17 +452,46 @@ def igrf12(date, r, lat, lon, show_warns=True):
     return np.array([Bn[0], Be[0], Bd[0]])
 
 
+class MagFieldMap:
+    """What igrf_data returns in the reference: the n x n x 3 map (Tesla) behind a callable
+    ``mag_field(i, j, c)`` with 1-based indices (monte_carlo.jl:90-96).  The reference wraps the
+    array in a cubic B-spline interpolant with periodic extrapolation (magnetic_toolbox.jl:124-125)
+    but only ever evaluates it at integer grid nodes, where an interpolating spline returns the
+    data itself: this object returns the node values and wraps indices periodically (period n per
+    axis, 3 for the component axis).  Non-integer arguments are rejected -- the reference has no
+    caller for them and its boundary condition (Cubic(Reflect(OnCell()))) is not pinned by any test."""
+
+    def __init__(self, grid):
+        self.grid = np.ascontiguousarray(grid, dtype=np.float64)
+
+    def __call__(self, i, j, c):
+        for v in (i, j, c):
+            if int(v) != v:
+                raise ValueError("mag_field(i,j,c): only integer grid nodes are supported")
+        n0, n1, n2 = self.grid.shape
+        return float(self.grid[(int(i) - 1) % n0, (int(j) - 1) % n1, (int(c) - 1) % n2])
+
+    def __array__(self, dtype=None, copy=None):
+        return self.grid if dtype is None else self.grid.astype(dtype)
+
+    @property
+    def shape(self):
+        return self.grid.shape
+
+    def __getitem__(self, idx):
+        return self.grid[idx]
+
+
 def igrf_data(altitude, year, n=1000):
-    """igrf_data(altitude, year) (magnetic_toolbox.jl:108-121): the n x n x 3
-    lat/long map in Tesla.  (The cubic B-spline wrapper of :124-125 is not part of
-    the hot path.)"""
+    """igrf_data(altitude, year) (magnetic_toolbox.jl:108-127): the n x n x 3 lat/long map in Tesla
+    (one K1 launch for the n^2 points) behind the reference's ``mag_field(i,j,c)`` call shape."""
     R_E = 6378
     lat = np.linspace(-np.pi / 2, np.pi / 2, n)
     lon = np.linspace(-np.pi, np.pi, n)
     LA, LO = np.meshgrid(lat, lon, indexing="ij")
     r = np.full(LA.size, (altitude + R_E) * 1000.0)
     Bn, Be, Bd = default_engine().igrf12_batch(year, r, LA.ravel(), LO.ravel())
-    return np.stack([Bn, Be, Bd], axis=-1).reshape(n, n, 3) / 1.0e9
+    return MagFieldMap(np.stack([Bn, Be, Bd], axis=-1).reshape(n, n, 3) / 1.0e9)
 
 
 class params:
