@@ -19,6 +19,8 @@ struct ts_ctx {
   cudaEvent_t ev_k3[3] = {nullptr, nullptr, nullptr};  // K3: start | persistent kernel done | straggler kernel done
   unsigned* d_k3_parked = nullptr;                     // device word holding the number of parked trials of the last K3 run
   bool k3_timed = false;
+  cudaStream_t pipe[2] = {nullptr, nullptr};           // K1 host-pointer path: double-buffered copy/compute pipeline
+  cudaEvent_t pipe_ev = nullptr;
   char err[512] = {0};
   char name[128] = {0};
   int64_t launches = 0;

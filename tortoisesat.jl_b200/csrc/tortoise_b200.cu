@@ -109,6 +109,9 @@ void ts_destroy(ts_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int i = 0; i < 3; ++i)
     if (c->ev_k3[i]) cudaEventDestroy(c->ev_k3[i]);
+  for (int i = 0; i < 2; ++i)
+    if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
+  if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -170,6 +173,77 @@ int ts_fp64_peak_probe(ts_ctx* c, double* tflops_out) {
   return TS_OK;
 }
 
+static void k1_launch(ts_ctx* c, cudaStream_t st, double date, int64_t n, const double* r, const double* la, const double* lo,
+                      double* bn, double* be, double* bd) {
+  const unsigned blocks = (unsigned)((n + K1_THREADS - 1) / K1_THREADS);
+  if (igrf_nmax_for_date(date) == 13)
+    k1_igrf12_batch<13><<<blocks, K1_THREADS, 0, st>>>(c->d_tabG, c->d_tabH, date, n, r, la, lo, bn, be, bd, c->d_flag);
+  else
+    k1_igrf12_batch<10><<<blocks, K1_THREADS, 0, st>>>(c->d_tabG, c->d_tabH, date, n, r, la, lo, bn, be, bd, c->d_flag);
+  c->launches++;
+}
+
+// Host-pointer path of ts_igrf12_batch: the call is PCIe-bound (24 B in + 24 B out per point against ~20 ns of
+// FP64 work per 1000 points), so the points go through two device staging sets on two streams: the upload of
+// chunk k+1 and the download of chunk k-1 overlap the kernel of chunk k (full-duplex link), and no device
+// memory is allocated per call.
+static int igrf12_host_pipeline(ts_ctx* c, double date, int64_t n, const double* r_m, const double* lat, const double* lon,
+                                double* Bn, double* Be, double* Bd) {
+  constexpr int64_t CHUNK = 1 << 22;
+  for (int i = 0; i < 2; ++i)
+    if (!c->pipe[i]) TS_CUDA(c, cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+  if (!c->pipe_ev) TS_CUDA(c, cudaEventCreateWithFlags(&c->pipe_ev, cudaEventDisableTiming));
+  const int64_t chunk = std::min<int64_t>(CHUNK, n);
+  double* stage[2];
+  int rc;
+  for (int i = 0; i < 2; ++i) {
+    void* p;
+    if ((rc = scratch_reserve(c, 17 + i, (size_t)chunk * 6 * sizeof(double), &p))) return rc;
+    stage[i] = (double*)p;
+  }
+  TS_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  TS_CUDA(c, cudaEventRecord(c->pipe_ev, c->stream));
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> ev((size_t)n_chunks * 2, nullptr);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaError_t err = cudaSuccess;
+  for (int i = 0; i < 2 && err == cudaSuccess; ++i) err = cudaStreamWaitEvent(c->pipe[i], c->pipe_ev, 0);
+  for (int64_t k = 0; k < n_chunks && err == cudaSuccess; ++k) {
+    cudaStream_t st = c->pipe[k & 1];
+    double* d = stage[k & 1];
+    const int64_t o = k * chunk, m = std::min<int64_t>(chunk, n - o);
+    const size_t b = (size_t)m * sizeof(double);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d, r_m + o, b, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d + chunk, lat + o, b, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d + 2 * chunk, lon + o, b, cudaMemcpyHostToDevice, st);
+    cudaEventRecord(ev[(size_t)k * 2], st);
+    k1_launch(c, st, date, m, d, d + chunk, d + 2 * chunk, d + 3 * chunk, d + 4 * chunk, d + 5 * chunk);
+    cudaEventRecord(ev[(size_t)k * 2 + 1], st);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(Bn + o, d + 3 * chunk, b, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(Be + o, d + 4 * chunk, b, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(Bd + o, d + 5 * chunk, b, cudaMemcpyDeviceToHost, st);
+  }
+  for (int i = 0; i < 2; ++i) {
+    const cudaError_t e2 = cudaStreamSynchronize(c->pipe[i]);
+    if (err == cudaSuccess) err = e2;
+  }
+  double ms_sum = 0.0;
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    float ms = 0.f;
+    if (err == cudaSuccess && cudaEventElapsedTime(&ms, ev[(size_t)k * 2], ev[(size_t)k * 2 + 1]) == cudaSuccess) ms_sum += ms;
+  }
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  if (err != cudaSuccess) return fail(c, TS_ERR_CUDA, "ts_igrf12_batch (host pipeline): %s", cudaGetErrorString(err));
+  c->last_kernel_ms = ms_sum;
+  int bad = 0;
+  TS_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (bad) return fail(c, TS_ERR_DOMAIN, "The latitude must be between -pi/2 and +pi/2 rad and the longitude between -pi and +pi rad.");
+  return TS_OK;
+}
+
 int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const double* lat, const double* lon, double* Bn,
                     double* Be, double* Bd, int pointers_are_device) {
   if (!c) return TS_ERR_ARG;
@@ -178,32 +252,12 @@ int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const 
     return fail(c, TS_ERR_DATE, "This IGRF version will not work for years outside the interval [1900, 2025).");
   if (n == 0) return TS_OK;
   TS_CUDA(c, cudaSetDevice(c->device));
-  const size_t bytes = (size_t)n * sizeof(double);
-  DevBuf dr, dla, dlo, dbn, dbe, dbd;
-  int rc;
-  if ((rc = dev_in(c, dr, r_m, bytes, pointers_are_device))) return rc;
-  if ((rc = dev_in(c, dla, lat, bytes, pointers_are_device))) return rc;
-  if ((rc = dev_in(c, dlo, lon, bytes, pointers_are_device))) return rc;
-  if ((rc = dev_out(c, dbn, Bn, bytes, pointers_are_device))) return rc;
-  if ((rc = dev_out(c, dbe, Be, bytes, pointers_are_device))) return rc;
-  if ((rc = dev_out(c, dbd, Bd, bytes, pointers_are_device))) return rc;
+  if (!pointers_are_device) return igrf12_host_pipeline(c, date, n, r_m, lat, lon, Bn, Be, Bd);
   TS_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
-  const unsigned blocks = (unsigned)((n + K1_THREADS - 1) / K1_THREADS);
   KernelTimer t(c);
-  if (igrf_nmax_for_date(date) == 13)
-    k1_igrf12_batch<13><<<blocks, K1_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, date, n, (const double*)dr.d,
-                                                               (const double*)dla.d, (const double*)dlo.d, (double*)dbn.d,
-                                                               (double*)dbe.d, (double*)dbd.d, c->d_flag);
-  else
-    k1_igrf12_batch<10><<<blocks, K1_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, date, n, (const double*)dr.d,
-                                                               (const double*)dla.d, (const double*)dlo.d, (double*)dbn.d,
-                                                               (double*)dbe.d, (double*)dbd.d, c->d_flag);
+  k1_launch(c, c->stream, date, n, r_m, lat, lon, Bn, Be, Bd);
   t.stop();
-  c->launches++;
   TS_CUDA(c, cudaGetLastError());
-  if ((rc = dev_back(c, dbn, Bn, bytes))) return rc;
-  if ((rc = dev_back(c, dbe, Be, bytes))) return rc;
-  if ((rc = dev_back(c, dbd, Bd, bytes))) return rc;
   int bad = 0;
   TS_CUDA(c, cudaMemcpyAsync(&bad, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   TS_CUDA(c, cudaStreamSynchronize(c->stream));
