@@ -375,9 +375,10 @@ def main():
     total_trials = world * n
     solve_s = float(np.mean(solve_ms)) * 1e-3
     ach = float(np.mean(flops_solve)) / solve_s / 1e12
-    # HBM traffic of K3 per knot-iteration, from the ncu --set full capture profiles/k3_prof_r1b_summary.txt
-    # (2368 trials, N = 300: dram read 32.88 GB + write 52.74 GB over 6.19e7 knot-iterations)
-    K3_DRAM_BYTES_PER_KNOT_ITER = 1383.0
+    # HBM traffic of K3 per knot-iteration, from the ncu --set full captures summarised in profiles/
+    # (k3_narrow_r1e: 4736 trials, N = 300, 8 warps/SM: dram read 73.4 GB + write 131.2 GB over 1.24e8 knot-iterations
+    #  = 1650 B; k3_wide_r1d, one warp per trial with all 21 candidates written: 2050 B)
+    K3_DRAM_BYTES_PER_KNOT_ITER = 1650.0
     knot_iters = float(np.sum((out["N"] - 1).astype(np.float64) * out["inner_iters"]))
     h2d = n * (8 + 8 + 9 + 3) * 8 + n * 4 + len(fo) * (6 * 8 + 56)
     d2h = n * 64 + 8 * len(fo)
@@ -394,8 +395,8 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "k3_alilqr_kernel + k3_wide_kernel (one AL-iLQR solve: 4-trials-per-warp launch, "
                                                       "then one warp per straggler)", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": ach / peak_fp64, "traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters,
-                         "traffic_source": "1383 B per knot-iteration (ncu --set full, dram__bytes_read+write, capture of "
-                                           "tools/k3_small.py 2368: 85.6 GB / 6.19e7 knot-iterations) x this run's knot-iterations",
+                         "traffic_source": "1650 B per knot-iteration (ncu --set full, dram__bytes_read+write, capture of "
+                                           "tools/k3_small.py 4736: 204.6 GB / 1.24e8 knot-iterations) x this run's knot-iterations",
                          "hbm_gbs_from_traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters / solve_s / 1e9, "hbm_peak_gbs": hbm_peak,
                          "peak_source": "measured live: register-resident DFMA micro-benchmark (ts_fp64_peak_probe); "
                                         "MEASURED_PEAKS.json has no FP64 row",
