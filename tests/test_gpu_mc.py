@@ -1,6 +1,7 @@
 """GPU: slew preparation, K4 TVLQR replay and the fused Monte-Carlo path vs the CPU oracle."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -10,6 +11,7 @@ from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
 GM = S.GM
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _perturb(q0, qn):
@@ -185,3 +187,39 @@ def test_fused_monte_carlo_sweep_and_no_cutoff(engine):
     cfg2 = host.default_mc_config(n, shared_orbit=False, run_tvlqr=False, tf=2400.0, cutoff=1.0)
     out2, st2 = engine.monte_carlo_run(cfg2, kep, fo, x0, xf, Jm)
     assert np.all(out2["status"] == 5) and st2.n_no_cutoff == n
+
+
+def test_bench_ensemble_sample_matches_oracle(engine):
+    """The first 16 trials of bench.py's configs[2] ensemble at FULL size (N = 2044 knots, random attitudes on S^3,
+    20 x 50 AL-iLQR iterations; several of them go through the straggler hand-over): identical status and
+    outer / inner / line-search counters, converged cost and constraint violation to 1e-6 (north_star's bar)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench as B
+    from tortoisesat.jl_b200 import host
+    n = 16
+    tr = B.make_trials("mc_fixed_orbit", 4096, 0)
+    sub = dict(tr)
+    for k in ("x0", "xf", "Jm", "qn"):
+        sub[k] = tr[k][:n]
+    cfg = B.mc_config(host, sub, n)
+    cfg.run_tvlqr = 0
+    fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
+    fo[0] = tr["fo"][0]
+    out, st = engine.monte_carlo_run(cfg, tr["kep"], fo, sub["x0"], sub["xf"], sub["Jm"], q_noise0=sub["qn"])
+    assert engine.k3_last_split()[2] > 0                      # the one-warp-per-trial launch was exercised
+    slews, base = [], None
+    f = tr["fo"][0]
+    for t in range(n):
+        s = S.build_slew(tr["kep"][0], B.J_1U, tr["x0"][t, 3:7], B.QF, mjd=f[1], igrf_date=f[2], field_radius_m=f[3], tf=2400.0,
+                         cutoff=tr["cutoff"], alpha=0.1, **({} if base is None else dict(t_final=base.t_final)))
+        base = base or s
+        slews.append(s)
+    Xs, Us, Ks, ref = S.oracle_solve(slews, nthreads=orc.lib().orc_max_threads(), want_K=False)
+    for t in range(n):
+        g, r = out[t], ref[t]
+        assert g["N"] == slews[t].N == 2044
+        for fld in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
+            assert g[fld] == r[fld], (t, fld, g, r)
+        assert abs(g["J"] - r["J"]) <= 1e-6 * abs(r["J"])
+        assert abs(g["c_max"] - r["c_max"]) <= 1e-6 * max(1.0, r["c_max"])
