@@ -466,6 +466,13 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   const int64_t warps = phased ? groups : std::min(groups, max_warps);
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
+  // the one-warp-per-trial launch uses four slots (36 trajectory buffers) per warp: up to a full wave of warps,
+  // never more than there can be parked trials
+  int occ_w = 0;
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_wide_kernel, 32, K3_WIDE_SMEM_BYTES));
+  if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
+  const int64_t wide_warps = std::min<int64_t>(std::min<int64_t>(n_trials, slots), (int64_t)c->sm_count * occ_w);
+  const int64_t arena_slots = std::max<int64_t>(slots, wide_warps * 4);
   // Queue order.  (1) sort by horizon (descending): the four teams of a warp get similar trip counts.
   // (2) within a run of (nearly) equal horizons, sort by slew angle and DEAL the trials round-robin over the
   // groups of four, so each warp gets one trial of every difficulty quartile: the makespan of a single-wave
@@ -499,7 +506,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   void *p_work, *p_q;
   Nmax += (Nmax & 1);  // even: keeps every per-knot record 16-byte aligned for the asynchronous copies
   const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1);
-  if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)slots + 256, &p_work))) return rc;
+  if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)arena_slots + 256, &p_work))) return rc;
   if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
   TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
   a.order = d_order;
@@ -557,10 +564,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
     if (a.park_cap > 0) {
       // one warp per parked trial; the grid cannot depend on the (device-side) count, idle blocks exit at once
-      int occ_w = 0;
-      TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_wide_kernel, 32, K3_WIDE_SMEM_BYTES));
-      if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
-      const int blocks_w = (int)std::min<int64_t>(std::min<int64_t>(a.park_cap, (int64_t)c->sm_count * occ_w), blocks);
+      const int blocks_w = (int)std::min<int64_t>(a.park_cap, wide_warps);
       k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
       k3_wide_kernel<<<blocks_w, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
       c->launches += 2;
