@@ -73,7 +73,9 @@ struct SmL {
   static constexpr int SVEC = SCOL + 56;           // [8]        new s
   static constexpr int KQ = SVEC + 8;              // [7][6]     K(:,j), Qux(:,j)
   static constexpr int QUU = KQ + 42;              // [9] Quu, [3] Qu
-  static constexpr int BWD_END = QUU + 12;
+  static constexpr int MM = QUU + 12;              // whole-warp team only: [10][8] M = S*[A|B], [10] q = [A|B]'*s
+  static constexpr int QV = MM + 80;
+  static constexpr int BWD_END = QUU + 12 + (W >= 32 ? 92 : 0);
   static constexpr int FWD = 0;                    // [2][W][FWD_REC] staged chunks of the forward pass (overlay)
   static constexpr int FWD_END = 2 * W * FWD_REC;
   static constexpr int WORK = (BWD_END > FWD_END ? BWD_END : FWD_END) + ((BWD_END > FWD_END ? BWD_END : FWD_END) & 1);
@@ -311,43 +313,118 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       for (int kk = kk_hi; kk >= 0; --kk) {
         const double* rec = sm + L::REC0 + kk * REC;
         const int k = base + kk;
-        // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
-        double S[28], s[7];
-        for (int i = 0; i < 7; ++i)
-          for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[L::SCOL + j * 8 + i] + sm[L::SCOL + i * 8 + j]);
-        for (int i = 0; i < 7; ++i) s[i] = sm[L::SVEC + i];
-        // ---- P1: column products
-        double Qxxc[7], Quxc[3], Qx = 0.0;
-        if constexpr (W >= 10) {
-          // whole-warp team: lane c < 10 owns column c of [A|B] -- the three control columns run on lanes 7..9 in
-          // the same instruction stream as the state columns instead of a second pass on lanes 0..2
-          // (same sums in the same order as the narrow path below)
-          if (lane < 10) {
-            double a[7], m[7], g[10];
-            for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
-            for (int i = 0; i < 7; ++i) {
-              double t = 0.0;
-              for (int l = 0; l < 7; ++l) t += S[sym_idx(i, l)] * a[l];
-              m[i] = t;
+        if constexpr (W >= 32) {
+          // ================= whole-warp team: the knot step spread over 30 lanes =================
+          // The narrow team gives each of its lanes a whole column (119 FMAs in a row); a warp that works on ONE
+          // trial has lanes to spare, so here every lane computes at most three 7-term dot products per stage:
+          //   A  M(i,c) = S(i,:)*[A|B](:,c)      lane (i = lane%7, g = lane/7 < 4) takes c = g, g+4, g+8;
+          //      q(c)   = [A|B](:,c)'*s           lanes 28..31
+          //   B  G(r,c) = [A|B](:,r)'*M(:,c)      lane (i,g): Qxx(i,j) for j = g, g+4 (kept in registers for P3);
+          //                                       lanes 0..20 one entry of Qux, lanes 21..29 one entry of Quu
+          //   P2 3x3 Cholesky in every lane; each lane solves the (at most three) gain columns it needs itself
+          //   P3 lane (i,g): S_new(i,j) for j = g, g+4; the lanes with i == j also s_new(j)
+          // Every dot product and sum is evaluated in the order of the narrow path below: same results bit for bit.
+          // (written without divergent branches: lanes that have no task in a stage compute a clamped duplicate
+          //  and only their stores are predicated -- a divergent side branch costs its full latency again)
+          const int li = lane % 7, lg = lane / 7;
+          const bool rowlane = lane < 28;
+          const int j0 = lg < 4 ? lg : 3, j1 = lg + 4 < 7 ? lg + 4 : 6;   // clamped; validity in has_j1
+          const bool has_j1 = rowlane && lg + 4 < 7;
+          {  // ---- stage A: lanes 0..27 one row of S against up to three columns; lanes 28..31 the vector s
+            double X[7];
+            for (int l = 0; l < 7; ++l) {
+              const double srow = 0.5 * (sm[L::SCOL + l * 8 + li] + sm[L::SCOL + li * 8 + l]);
+              X[l] = rowlane ? srow : sm[L::SVEC + l];
             }
-            for (int r = 0; r < 10; ++r) {
+            const int c0 = rowlane ? lg : lane - 28;
+            for (int q = 0; q < 3; ++q) {
+              const int c = c0 + 4 * q;
+              const int cc = c < 10 ? c : 9;
               double t = 0.0;
-              for (int l = 0; l < 7; ++l) t += rec[r * 7 + l] * m[l];
-              g[r] = t;
-            }
-            double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += a[l] * s[l];
-            if (lane < 7) {
-              for (int i = 0; i < 7; ++i) Qxxc[i] = g[i] + ((i == lane) ? sc * in.Qd[i] : 0.0);
-              for (int c = 0; c < 3; ++c) Quxc[c] = g[7 + c];
-              Qx = rec[70 + lane] + t;
-            } else {
-              const int cl = lane - 7;
-              for (int c = 0; c < 3; ++c) sm[L::QUU + c * 3 + cl] = g[7 + c] + ((c == cl) ? rec[80 + c] : 0.0);
-              sm[L::QUU + 9 + cl] = rec[77 + cl] + t;
+              for (int l = 0; l < 7; ++l) t += X[l] * rec[cc * 7 + l];
+              if (c < 10) sm[rowlane ? (L::MM + c * 8 + li) : (L::QV + c)] = t;
             }
           }
+          tm.sync();
+          double Qxx0, Qxx1;
+          {  // ---- stage B
+            double arow[7];
+            for (int l = 0; l < 7; ++l) arow[l] = rec[li * 7 + l];
+            double t = 0.0;
+            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j0 * 8 + l];
+            Qxx0 = t + ((li == j0) ? sc * in.Qd[li] : 0.0);
+            t = 0.0;
+            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j1 * 8 + l];
+            Qxx1 = t + ((li == j1) ? sc * in.Qd[li] : 0.0);
+            const bool isux = lane < 21;
+            const int u = isux ? lane : (lane < 30 ? lane - 21 : 0);
+            const int rr = u % 3, cc = isux ? u / 3 : 7 + u / 3;
+            t = 0.0;
+            for (int l = 0; l < 7; ++l) t += rec[(7 + rr) * 7 + l] * sm[L::MM + cc * 8 + l];
+            const double tq = t + ((rr == cc - 7) ? rec[80 + rr] : 0.0);
+            if (lane < 30) sm[isux ? (L::KQ + cc * 3 + rr) : (L::QUU + rr * 3 + (cc - 7))] = isux ? t : tq;   // Qux(rr,cc) | Quu(rr,cc-7)
+          }
+          tm.sync();
+          double Quu[9], Qu[3], Qr[9], Lc[9];
+          for (int i = 0; i < 9; ++i) Quu[i] = sm[L::QUU + i];
+          for (int i = 0; i < 3; ++i) Qu[i] = rec[77 + i] + sm[L::QV + 7 + i];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
+          if (!chol3(Qr, Lc)) {
+            not_pd = true;  // identical decision in every lane
+            break;
+          }
+          double d[3], Quud[3];
+          {
+            const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
+            chol3_solve(Lc, nb, d);
+            for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
+          }
+          for (int l = 0; l < 3; ++l) {
+            dV1 += d[l] * Qu[l];
+            dV2 += 0.5 * d[l] * Quud[l];
+          }
+          double* kdk = w.kd + (long long)k * 24;
+          {  // ---- gains this lane needs, then its entries of the new value function
+            double Quxi[3], Ki[3];
+            for (int c = 0; c < 3; ++c) Quxi[c] = sm[L::KQ + li * 3 + c];
+            {
+              const double nb[3] = {-Quxi[0], -Quxi[1], -Quxi[2]};
+              chol3_solve(Lc, nb, Ki);
+            }
+            if (lane < 7)
+              for (int c = 0; c < 3; ++c) kdk[li * 3 + c] = Ki[c];
+            if (lane == 7)
+              for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
+            for (int q = 0; q < 2; ++q) {
+              const int j = q ? j1 : j0;
+              const bool valid = q ? has_j1 : rowlane;
+              double Quxj[3], Kj[3], QuuK[3];
+              for (int c = 0; c < 3; ++c) Quxj[c] = sm[L::KQ + j * 3 + c];
+              const double nb[3] = {-Quxj[0], -Quxj[1], -Quxj[2]};
+              chol3_solve(Lc, nb, Kj);
+              for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kj[0] + Quu[i * 3 + 1] * Kj[1] + Quu[i * 3 + 2] * Kj[2];
+              double t = q ? Qxx1 : Qxx0;
+              for (int l = 0; l < 3; ++l) t += Ki[l] * QuuK[l];
+              for (int l = 0; l < 3; ++l) t += Ki[l] * Quxj[l];
+              for (int l = 0; l < 3; ++l) t += Quxi[l] * Kj[l];
+              double ts = rec[70 + j] + sm[L::QV + j];   // new s(j): stored by the lane that holds column j's gain (li == j)
+              for (int l = 0; l < 3; ++l) ts += Kj[l] * Quud[l];
+              for (int l = 0; l < 3; ++l) ts += Kj[l] * Qu[l];
+              for (int l = 0; l < 3; ++l) ts += Quxj[l] * d[l];
+              if (valid) sm[L::SCOL + j * 8 + li] = t;
+              if (valid && li == j) sm[L::SVEC + j] = ts;
+            }
+          }
+          tm.sync();
         } else {
+          // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
+          double S[28], s[7];
+          for (int i = 0; i < 7; ++i)
+            for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[L::SCOL + j * 8 + i] + sm[L::SCOL + i * 8 + j]);
+          for (int i = 0; i < 7; ++i) s[i] = sm[L::SVEC + i];
+          // ---- P1: column products
+          double Qxxc[7], Quxc[3], Qx = 0.0;
           if (lane < 7) {
             double a[7], m[7];
             for (int i = 0; i < 7; ++i) a[i] = rec[lane * 7 + i];
@@ -387,59 +464,59 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             for (int l = 0; l < 7; ++l) t += b[l] * s[l];
             sm[L::QUU + 9 + lane] = rec[77 + lane] + t;
           }
-        }
-        tm.sync();
-        // ---- P2: 3x3 solve (every lane, redundantly)
-        double Quu[9], Qu[3], Qr[9], L[9];
-        for (int i = 0; i < 9; ++i) Quu[i] = sm[L::QUU + i];
-        for (int i = 0; i < 3; ++i) Qu[i] = sm[L::QUU + 9 + i];
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
-        if (!chol3(Qr, L)) {
-          not_pd = true;  // identical decision in every lane of the team
-          break;
-        }
-        double Kc[3] = {0.0, 0.0, 0.0}, d[3], Quud[3], QuuK[3] = {0.0, 0.0, 0.0};
-        {
-          const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
-          chol3_solve(L, nb, d);
-          for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
-        }
-        double* kdk = w.kd + (long long)k * 24;
-        if (lane < 7) {
-          const double nb[3] = {-Quxc[0], -Quxc[1], -Quxc[2]};
-          chol3_solve(L, nb, Kc);
-          for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kc[0] + Quu[i * 3 + 1] * Kc[1] + Quu[i * 3 + 2] * Kc[2];
-          for (int c = 0; c < 3; ++c) {
-            sm[L::KQ + lane * 6 + c] = Kc[c];
-            sm[L::KQ + lane * 6 + 3 + c] = Quxc[c];
-            kdk[lane * 3 + c] = Kc[c];
+          tm.sync();
+          // ---- P2: 3x3 solve (every lane, redundantly)
+          double Quu[9], Qu[3], Qr[9], L[9];
+          for (int i = 0; i < 9; ++i) Quu[i] = sm[L::QUU + i];
+          for (int i = 0; i < 3; ++i) Qu[i] = sm[L::QUU + 9 + i];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
+          if (!chol3(Qr, L)) {
+            not_pd = true;  // identical decision in every lane of the team
+            break;
           }
-        } else {
-          for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
-        }
-        for (int l = 0; l < 3; ++l) {
-          dV1 += d[l] * Qu[l];
-          dV2 += 0.5 * d[l] * Quud[l];
-        }
-        tm.sync();
-        // ---- P3: new S column / s entry
-        if (lane < 7) {
-          for (int i = 0; i < 7; ++i) {
-            const double* kq = sm + L::KQ + i * 6;
-            double t = Qxxc[i];
-            for (int l = 0; l < 3; ++l) t += kq[l] * QuuK[l];
-            for (int l = 0; l < 3; ++l) t += kq[l] * Quxc[l];
-            for (int l = 0; l < 3; ++l) t += kq[3 + l] * Kc[l];
-            sm[L::SCOL + lane * 8 + i] = t;
+          double Kc[3] = {0.0, 0.0, 0.0}, d[3], Quud[3], QuuK[3] = {0.0, 0.0, 0.0};
+          {
+            const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
+            chol3_solve(L, nb, d);
+            for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
           }
-          double t = Qx;
-          for (int l = 0; l < 3; ++l) t += Kc[l] * Quud[l];
-          for (int l = 0; l < 3; ++l) t += Kc[l] * Qu[l];
-          for (int l = 0; l < 3; ++l) t += Quxc[l] * d[l];
-          sm[L::SVEC + lane] = t;
+          double* kdk = w.kd + (long long)k * 24;
+          if (lane < 7) {
+            const double nb[3] = {-Quxc[0], -Quxc[1], -Quxc[2]};
+            chol3_solve(L, nb, Kc);
+            for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kc[0] + Quu[i * 3 + 1] * Kc[1] + Quu[i * 3 + 2] * Kc[2];
+            for (int c = 0; c < 3; ++c) {
+              sm[L::KQ + lane * 6 + c] = Kc[c];
+              sm[L::KQ + lane * 6 + 3 + c] = Quxc[c];
+              kdk[lane * 3 + c] = Kc[c];
+            }
+          } else {
+            for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
+          }
+          for (int l = 0; l < 3; ++l) {
+            dV1 += d[l] * Qu[l];
+            dV2 += 0.5 * d[l] * Quud[l];
+          }
+          tm.sync();
+          // ---- P3: new S column / s entry
+          if (lane < 7) {
+            for (int i = 0; i < 7; ++i) {
+              const double* kq = sm + L::KQ + i * 6;
+              double t = Qxxc[i];
+              for (int l = 0; l < 3; ++l) t += kq[l] * QuuK[l];
+              for (int l = 0; l < 3; ++l) t += kq[l] * Quxc[l];
+              for (int l = 0; l < 3; ++l) t += kq[3 + l] * Kc[l];
+              sm[L::SCOL + lane * 8 + i] = t;
+            }
+            double t = Qx;
+            for (int l = 0; l < 3; ++l) t += Kc[l] * Quud[l];
+            for (int l = 0; l < 3; ++l) t += Kc[l] * Qu[l];
+            for (int l = 0; l < 3; ++l) t += Quxc[l] * d[l];
+            sm[L::SVEC + lane] = t;
+          }
+          tm.sync();
         }
-        tm.sync();
       }
     }
     if (!not_pd) break;
