@@ -491,9 +491,9 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               sm[L::KQ + lane * 6 + 3 + c] = Quxc[c];
               kdk[lane * 3 + c] = Kc[c];
             }
-          } else {
-            for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
           }
+          if (lane == 7)  // (predicated stores, not an else-branch: a divergent side path costs its latency again)
+            for (int c = 0; c < 3; ++c) kdk[21 + c] = d[c];
           for (int l = 0; l < 3; ++l) {
             dV1 += d[l] * Qu[l];
             dV2 += 0.5 * d[l] * Quud[l];

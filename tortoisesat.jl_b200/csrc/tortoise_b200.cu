@@ -442,7 +442,7 @@ static double slew_angle(const double* x0, const double* xf) {
 // TS_K3_MODE=persistent|phased overrides the automatic choice.  Returns with all work complete on the stream
 // (the phased mode synchronises to poll the active-trial counter).
 // inner iterations a trial may use in the 4-trials-per-warp kernel once the queue is empty (see k3_wide_kernel)
-constexpr int K3_SUSPEND_AFTER_DEFAULT = 200;
+constexpr int K3_SUSPEND_AFTER_DEFAULT = 150;
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
   const int64_t n_trials = a.n_trials;
   int64_t Nmax = 0, Nmin = INT64_MAX;
