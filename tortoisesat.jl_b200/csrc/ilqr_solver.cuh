@@ -153,20 +153,19 @@ TS_HD bool inv3_gj(const double A[9], double out[9]) {
 // entries at [3],[6],[7] and the RECIPROCALS of the diagonal at [0],[4],[8] so that the two
 // triangular solves per lane need no division (3 divisions per knot instead of 15).
 TS_HD bool chol3(const double A[9], double L[9]) {
-  for (int i = 0; i < 9; ++i) L[i] = 0.0;
-  double s = A[0];
-  if (!(s > 0.0)) return false;
-  L[0] = rnorm(s);
+  // straight-line: the three pivot tests are combined at the end (a non-positive pivot makes the later entries
+  // NaN/inf, which nobody reads because the factorisation is then rejected) -- no branch on the critical path
+  L[1] = L[2] = L[5] = 0.0;
+  const double s0 = A[0];
+  L[0] = rnorm(s0);
   L[3] = A[3] * L[0];
   L[6] = A[6] * L[0];
-  s = A[4] - L[3] * L[3];
-  if (!(s > 0.0)) return false;
-  L[4] = rnorm(s);
+  const double s1 = A[4] - L[3] * L[3];
+  L[4] = rnorm(s1);
   L[7] = (A[7] - L[6] * L[3]) * L[4];
-  s = A[8] - L[6] * L[6] - L[7] * L[7];
-  if (!(s > 0.0)) return false;
-  L[8] = rnorm(s);
-  return true;
+  const double s2 = A[8] - L[6] * L[6] - L[7] * L[7];
+  L[8] = rnorm(s2);
+  return (s0 > 0.0) & (s1 > 0.0) & (s2 > 0.0);
 }
 TS_HD void chol3_solve(const double L[9], const double b[3], double x[3]) {
   double y[3];
