@@ -4,7 +4,7 @@
 // warp intrinsics emulated by 8 OS threads + barriers, so the kernel's logic,
 // indexing and synchronisation points can be checked against the oracle here
 // (no GPU in the build container).  Never linked into the product library.
-#include <barrier>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -15,9 +15,28 @@
 
 using namespace ts;
 
+// Sense-reversing barrier that spins briefly and then yields: the emulated teams synchronise three times per
+// knot, and a futex sleep/wake per synchronisation (std::barrier) made the CPU suite system-time bound.
+struct SpinBarrier {
+  explicit SpinBarrier(int n_) : n(n_) {}
+  void arrive_and_wait() {
+    const int g = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+      count.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (gen.load(std::memory_order_acquire) == g)
+        if (++spins > 200) std::this_thread::yield();
+    }
+  }
+  std::atomic<int> count{0}, gen{0};
+  const int n;
+};
+
 template <int W_>
 struct TeamSharedT {
-  std::barrier<> bar{W_};
+  SpinBarrier bar{W_};
   double xch[W_];
   unsigned bits[W_];
   std::vector<double> sm = std::vector<double>(SmL<W_>::TOTAL, 0.0);

@@ -65,7 +65,7 @@ def test_team_solver_matches_oracle(angle, tfin, mask, status):
     assert np.max(np.abs(U - Us[0])) < 1e-9
 
 
-@pytest.mark.parametrize("angle,tfin,mask", [(5.0, 24.0, 0x7F), (20.0, 12.0, 0x7F)])   # short horizons: 32 emulated lanes are slow
+@pytest.mark.parametrize("angle,tfin,mask", [(5.0, 60.0, 0x7F), (20.0, 30.0, 0x7F)])
 def test_wide_team_matches_oracle(angle, tfin, mask):
     """The whole-warp (32-lane) team used for a warp's straggler: 32 knots linearised per chunk, all 21 line-search
     candidates in one batch.  Must take the same iteration path as the sequential oracle."""
@@ -83,7 +83,7 @@ def test_wide_team_matches_oracle(angle, tfin, mask):
 def test_team_width_does_not_change_results():
     """A trial may start in an 8-lane team and be finished by a whole warp (straggler hand-over): the solver must be
     bit-identical at both widths -- same trajectories, gains, cost and counters."""
-    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 20.0), np.array([1.0, 0, 0, 0]), t_final=12.0)
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 20.0), np.array([1.0, 0, 0, 0]), t_final=30.0)
     o = orc.default_ilqr_opts()
     X8, U8, K8, o8 = S.hostsim_solve(s, o, width=8)
     X32, U32, K32, o32 = S.hostsim_solve(s, o, width=32)
