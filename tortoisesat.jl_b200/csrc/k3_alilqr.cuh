@@ -1,19 +1,23 @@
-// K3 -- batched AL-iLQR.  Persistent warps; each warp runs FOUR trials at a time,
-// one per 8-lane team (ilqr_solver.cuh), pulling groups of four trials from an
-// atomic queue (trials pre-sorted by horizon on the host so that the four teams of
-// a warp have similar trip counts and stay convergent).
+// K3 -- batched AL-iLQR, two launches.
 //
-// Why 8-lane teams and not one trial per warp: an FP64 warp instruction occupies
-// the SM sub-partition's 16-lane DFMA pipe for 2 issue cycles whatever the number
-// of active lanes, and the sequential parts of iLQR (Riccati recursion, rollouts)
-// expose at most ~10-way parallelism per knot.  Four trials per warp quadruple the
-// useful lanes per issued instruction while still giving 1024 resident warps for a
-// 4096-trial ensemble ("K3 mapping").
+// k3_alilqr_kernel: persistent warps; each warp runs FOUR trials at a time, one per 8-lane team (ilqr_solver.cuh),
+// pulling groups of four trials from an atomic queue (trials pre-sorted by horizon on the host so that the four
+// teams of a warp have similar trip counts, then dealt by slew angle).  Finished teams lend their lanes and
+// trajectory buffers to the unfinished trials of their warp.
+// k3_wide_kernel: once the queue is empty, trials that have used their allowance of knot-iterations are parked by
+// the first kernel and finished here, ONE trial per warp (32-lane team), longest remaining budget first.
 //
-// Working set per trial (HBM/L2, streamed): 9 trajectory buffers (current + 8
-// line-search candidates) x N x 10, gains N x 24, multipliers N x 6 doubles.
-// Shared memory per team: 6336 B (knot records of the current 8-knot chunk and the
-// Riccati exchange buffers).
+// Why 8-lane teams first and not one trial per warp throughout: an FP64 warp instruction occupies the SM
+// sub-partition's 16-lane DFMA pipe for 2 issue cycles whatever the number of active lanes, and the sequential
+// parts of iLQR (Riccati recursion, rollouts) expose limited parallelism per knot, so four trials per warp are the
+// throughput-efficient mapping (3.9 vs 7.4 warp-ms per trial-iteration).  But a single-wave ensemble ends with a
+// long tail of stragglers whose LATENCY is the makespan, and a whole warp per trial halves that latency
+// ("K3"; measurements in profiles/README.md).
+//
+// Working set per trial (HBM/L2, streamed): 9 trajectory buffers (current + 8 line-search candidates; a wide warp
+// uses the 36 buffers of its four slots) x N x 10, gains N x 24, multipliers N x 6 doubles.
+// Shared memory per 8-lane team: 6912 B (knot records of the current 8-knot chunk, Riccati exchange buffers,
+// staged forward-pass chunks, the trial's read-only parameters); 26 KB per wide warp.
 #pragma once
 #include "common.cuh"
 #include "ilqr_solver.cuh"
