@@ -42,6 +42,14 @@ for n in ntr:
           "inner mean/max", out["inner_iters"].mean(), out["inner_iters"].max(), "ls mean", out["ls_rollouts"].mean(), flush=True)
     print("   K3 split: persistent %.0f ms, straggler kernel %.0f ms, %d trials handed over" % eng.k3_last_split(),
           "| inner-iteration quantiles 50/75/90/95/99:", np.percentile(out["inner_iters"], [50, 75, 90, 95, 99]).tolist(), flush=True)
+    # angle correlation: could the slew angle predict the long trials?
+    qfv = np.asarray(base.xf[3:7]); dots = np.abs(q0[:n] @ qfv); ang = 2 * np.degrees(np.arccos(np.clip(dots, 0, 1)))
+    itn = out["inner_iters"].astype(float)
+    order_a = np.argsort(-ang); order_i = np.argsort(-itn)
+    top = min(1184, n // 3)
+    print("   angle vs iterations: corr %.3f | of the %d longest trials, %d are among the %d largest angles | mean iters by angle quartile:" % (
+        np.corrcoef(ang, itn)[0, 1], top, len(set(order_a[:top]) & set(order_i[:top])), top),
+        [round(float(itn[order_a[k * n // 4:(k + 1) * n // 4]].mean()), 1) for k in range(4)], flush=True)
     its = out["inner_iters"].astype(float)
     i = int(np.argmax(its))
     kn = its * base.N

@@ -107,11 +107,15 @@ struct TrialWork {
   double* clk;   // [Nmax]         clock state
   double* bk;    // [Nmax][10]     field vectors of the three rk3 stages of each knot (9 used)
   long long Nmax;
+  double* const* tab = nullptr;  // whole-warp team under the iteration queue (k3_queue_kernel): table of the 33 buffers
 };
 
 // trajectory buffer i in the warp's buffer space: slot i/9, buffer i%9 (a team that owns a single slot uses 0..8)
 template <int W>
 TS_HD double* xu_buf(const TrialWork& w, int i) {
+  if constexpr (W >= 32) {
+    if (w.tab) return w.tab[i];
+  }
   return w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10);
 }
 

@@ -557,6 +557,120 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
 constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 
 // ---------------------------------------------------------------------------------------------
+// Iteration-queue mode: ONE persistent launch, one warp per SM-resident slot, every warp a 32-lane team.
+// The unit of scheduling is one iLQR ITERATION of one trial: a warp pops a trial from a FIFO queue, runs one
+// iteration (backward sweep + one 21-candidate forward batch), and pushes the trial back unless it is finished.
+// All trials therefore advance at the same rate (processor sharing), the stragglers end up alone on their warps
+// exactly when there are fewer active trials than warps, and nothing has to be predicted or handed over.
+// Used for ensembles of more trials than resident team slots (several waves), where it beats the two-launch
+// scheme above (8192 slews: 15.6 s vs 16.7 s); for a single wave the 4-trials-per-warp kernel's higher
+// throughput wins (4096 slews: 9.05 s vs 8.15 s).
+//   * queue: array that never wraps (a trial is pushed at most once per inner iteration), head/tail counters;
+//     a warp that finds it empty EXITS: then every active trial is held by another live warp, and since the number
+//     of active trials only falls, live warps >= active trials stays true -- there is no waiting anywhere except
+//     the few instructions between a producer's slot reservation and its store.
+//   * buffers: a trial owns the ONE trajectory buffer that holds its current trajectory, a warp owns 32 candidate
+//     buffers; when a candidate is accepted the trial takes that buffer and the warp keeps the trial's old one
+//     (a pointer swap -- no copy).  Multipliers, stage field vectors and clock live per trial, gains per warp.
+//   * visibility between warps: writer __syncwarp + __threadfence before publishing the queue slot; reader
+//     __threadfence after popping (invalidates the SM's L1, which may hold the trial's lines from an earlier visit).
+constexpr int K3Q_INIT_BIT = 1 << 30;
+struct K3QArgs {
+  K3Args a;
+  double* pool;             // (n_trials + 32 * warps) trajectory buffers of buf_stride doubles
+  int64_t buf_stride;       // Nmax * 10
+  double* trial_arr;        // per trial: multipliers 6 Nmax | stage fields 10 Nmax | clock Nmax
+  double* kd_warp;          // per warp: 24 Nmax
+  TrialState* states;       // per trial
+  double** cur_ptr;         // per trial: its current trajectory buffer
+  int* queue;               // entries: trial + 1 (| K3Q_INIT_BIT for the first visit); 0 = not written yet
+  unsigned* head;
+  unsigned* tail;
+};
+constexpr int K3Q_SMEM_BYTES = (SmL<32>::TOTAL + 40) * 8;
+
+__global__ void __launch_bounds__(32, 1) k3_queue_kernel(const K3QArgs q) {
+  extern __shared__ __align__(16) double k3_smem[];
+  const K3Args& a = q.a;
+  const int lane32 = threadIdx.x & 31;
+  const int64_t gwarp = blockIdx.x;
+  GpuWideTeam tm;
+  tm.ln = lane32;
+  tm.sm = k3_smem;
+  double** tab = reinterpret_cast<double**>(k3_smem + SmL<32>::TOTAL);
+  tab[1 + lane32] = q.pool + ((int64_t)a.n_trials + gwarp * 32 + lane32) * q.buf_stride;
+  if (lane32 == 0) tab[0] = nullptr;
+  __syncwarp();
+  TrialWork w;
+  w.Nmax = a.Nmax;
+  w.xu_warp = nullptr;
+  w.slot_stride = 0;
+  w.kd = q.kd_warp + gwarp * 24 * a.Nmax;
+  w.tab = tab;
+  for (;;) {
+    int item = 0;
+    if (lane32 == 0) {
+      for (;;) {
+        const unsigned h = *(volatile unsigned*)q.head;
+        const unsigned t = *(volatile unsigned*)q.tail;
+        if (h >= t) break;                                   // empty: every active trial is in another warp's hands
+        if (atomicCAS(q.head, h, h + 1u) == h) {
+          while ((item = *(volatile int*)(q.queue + h)) == 0) {}   // producer is between its reservation and its store
+          break;
+        }
+      }
+      __threadfence();
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item == 0) break;
+    const bool first = (item & K3Q_INIT_BIT) != 0;
+    const int64_t t = (int64_t)((item & ~K3Q_INIT_BIT) - 1);
+    const TrialIn& in = k3_load_trial(tm, a, t);
+    w.lam = q.trial_arr + t * 17 * a.Nmax;
+    w.bk = w.lam + 6 * a.Nmax;
+    w.clk = w.bk + 10 * a.Nmax;
+    TrialState st;
+    if (lane32 == 0) tab[0] = first ? q.pool + t * q.buf_stride : q.cur_ptr[t];
+    __syncwarp();
+    w.xu = tab[0];
+    if (first) {
+      solve_init(tm, in, a.opts, w, st);
+    } else {
+      st = q.states[t];
+    }
+    if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
+    while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
+    __syncwarp();
+    if (st.cur != 0) {   // the accepted candidate's buffer goes with the trial, the warp keeps the old current one
+      if (lane32 == 0) {
+        double* nb = tab[st.cur];
+        tab[st.cur] = tab[0];
+        tab[0] = nb;
+      }
+      st.cur = 0;
+      __syncwarp();
+    }
+    if (st.phase == PH_DONE) {
+      ts_trial_outcome_dev oc;
+      solve_finish(in, st, oc);
+      k3_store_results(tm, a, t, w, in.N, 0, oc);
+    } else {
+      if (lane32 == 0) {
+        q.states[t] = st;
+        q.cur_ptr[t] = tab[0];
+      }
+      __syncwarp();
+      if (lane32 == 0) {
+        __threadfence();
+        const unsigned pos = atomicAdd(q.tail, 1u);
+        *(volatile int*)(q.queue + pos) = (int)(t + 1);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Phase-split launch mode: the same solver phases as separate kernels, driven in lockstep by the
 // host (init, then rounds of [backward, forward x3] until every trial is done, then finish).
 // All resident warps of a launch execute the same phase -> one hot loop in the instruction cache

@@ -453,10 +453,12 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   // measured (profiles/README.md): the phased mode is ~10-25% SLOWER than the persistent kernel on the 4096-trial
   // ensemble (every round waits for the slowest trial's phase), so it is opt-in only.
   bool phased = false;
+  int queue_override = -1;   // -1: automatic
   (void)Nmin;
   if (const char* m = getenv("TS_K3_MODE")) {
-    if (!strcmp(m, "persistent")) phased = false;
-    if (!strcmp(m, "phased")) phased = true;
+    if (!strcmp(m, "persistent") || !strcmp(m, "teams")) queue_override = 0;
+    if (!strcmp(m, "phased")) phased = true, queue_override = 0;
+    if (!strcmp(m, "queue")) queue_override = 1;
   }
   int occ = 0;
   TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
@@ -464,6 +466,10 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   const int64_t groups = (n_trials + 3) / 4;
   const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
   const int64_t warps = phased ? groups : std::min(groups, max_warps);
+  // More trials than resident team slots (several waves): the iteration queue balances them perfectly and was
+  // measured faster (8192 slews: 15.6 s vs 16.7 s); a single wave is faster with four trials per warp plus the
+  // straggler hand-over (4096 slews: 8.15 s vs 9.05 s).
+  const bool queue_mode = queue_override >= 0 ? queue_override == 1 : (n_trials > max_warps * 4);
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
   // the one-warp-per-trial launch uses four slots (36 trajectory buffers) per warp: up to a full wave of warps,
@@ -505,6 +511,72 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
   void *p_work, *p_q;
   Nmax += (Nmax & 1);  // even: keeps every per-knot record 16-byte aligned for the asynchronous copies
+  if (queue_mode) {
+    // ---- iteration-queue mode (k3_queue_kernel): one launch, one trial-iteration per work item
+    int occ_q = 0;
+    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k3_queue_kernel, 32, K3Q_SMEM_BYTES));
+    if (occ_q < 1) return fail(c, TS_ERR_CUDA, "k3 queue kernel does not fit on an SM");
+    const int64_t qwarps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_q);
+    const int64_t buf_stride = Nmax * 10;
+    const int64_t items = n_trials * ((int64_t)a.opts.max_outer * a.opts.max_inner + 2);
+    if (items > 0x7ffffff0ll) return fail(c, TS_ERR_ARG, "iteration queue too long (n_trials x max iterations)");
+    const size_t b_pool = (size_t)(n_trials + 32 * qwarps) * (size_t)buf_stride * sizeof(double);
+    const size_t b_trial = (size_t)n_trials * 17 * (size_t)Nmax * sizeof(double);
+    const size_t b_kd = (size_t)qwarps * 24 * (size_t)Nmax * sizeof(double);
+    const size_t b_state = (size_t)n_trials * (sizeof(TrialState) + sizeof(double*));
+    const size_t b_queue = (size_t)items * sizeof(int);
+    void *p_pool, *p_tr, *p_st, *p_qu;
+    if ((rc = scratch_reserve(c, 6, b_pool + 256, &p_pool))) return rc;
+    if ((rc = scratch_reserve(c, 16, b_trial + b_kd + 256, &p_tr))) return rc;
+    if ((rc = scratch_reserve(c, 15, b_state + 64, &p_st))) return rc;
+    if ((rc = scratch_reserve(c, 19, b_queue + 64, &p_qu))) return rc;
+    if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
+    std::vector<int> first((size_t)n_trials);
+    for (int64_t i = 0; i < n_trials; ++i) first[(size_t)i] = (int)(order[(size_t)i] + 1) | K3Q_INIT_BIT;
+    TS_CUDA(c, cudaMemsetAsync(p_qu, 0, b_queue, c->stream));
+    TS_CUDA(c, cudaMemcpyAsync(p_qu, first.data(), (size_t)n_trials * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    unsigned ht[16] = {0};
+    ht[1] = (unsigned)n_trials;   // head = 0, tail = n_trials
+    TS_CUDA(c, cudaMemcpyAsync(p_q, ht, 64, cudaMemcpyHostToDevice, c->stream));
+    TS_CUDA(c, cudaStreamSynchronize(c->stream));   // `first` and `ht` are host temporaries
+    a.order = d_order;
+    a.Nmax = Nmax;
+    a.w_base = nullptr;
+    a.per_slot = 0;
+    a.queue = nullptr;
+    a.tail_share = 0;
+    a.park_budget = 0;
+    a.park_cap = 0;
+    a.park_count = nullptr;
+    a.park_used = nullptr;
+    a.queue2 = nullptr;
+    a.park_state = nullptr;
+    a.park_trial = nullptr;
+    a.park_off = nullptr;
+    a.park_data = nullptr;
+    a.park_data_cap = 0;
+    a.park_order = nullptr;
+    K3QArgs q;
+    q.a = a;
+    q.pool = (double*)p_pool;
+    q.buf_stride = buf_stride;
+    q.trial_arr = (double*)p_tr;
+    q.kd_warp = (double*)((char*)p_tr + b_trial);
+    q.states = (TrialState*)p_st;
+    q.cur_ptr = (double**)((char*)p_st + (size_t)n_trials * sizeof(TrialState));
+    q.queue = (int*)p_qu;
+    q.head = (unsigned*)p_q;
+    q.tail = (unsigned*)p_q + 1;
+    c->k3_timed = true;
+    c->d_k3_parked = nullptr;
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
+    k3_queue_kernel<<<(unsigned)qwarps, 32, K3Q_SMEM_BYTES, c->stream>>>(q);
+    c->launches++;
+    TS_CUDA(c, cudaGetLastError());
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+    return TS_OK;
+  }
   const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1);
   if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)arena_slots + 256, &p_work))) return rc;
   if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
