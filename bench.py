@@ -392,8 +392,8 @@ def main():
                        "converged": conv, "no_cutoff": int(vec[2]), "mean_inner_iters": float(vec[7] / max(1.0, vec[0] - vec[2])),
                        "mean_ls_rollouts": float(vec[8] / max(1.0, vec[0] - vec[2])),
                        "mean_slew_time_s": float(vec[4] / max(1.0, vec[0] - vec[2])), "fail_slew": int(vec[3])},
-            "roofline": {"bound": "fp64", "kernel": "k3_alilqr_kernel + k3_wide_kernel (one AL-iLQR solve: 4-trials-per-warp launch, "
-                                                      "then one warp per straggler)", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "K3 AL-iLQR solve: k3_alilqr_kernel (4 trials per warp) + k3_wide_kernel (one warp per "
+                                                      "straggler) for a single wave of trials, k3_queue_kernel for more", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": ach / peak_fp64, "traffic": K3_DRAM_BYTES_PER_KNOT_ITER * knot_iters,
                          "traffic_source": "1650 B per knot-iteration (ncu --set full, dram__bytes_read+write, capture of "
                                            "tools/k3_small.py 4736: 204.6 GB / 1.24e8 knot-iterations) x this run's knot-iterations",
