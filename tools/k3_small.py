@@ -7,11 +7,12 @@ import slew_setup as S
 import tortoisesat.jl_b200 as tb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-same = len(sys.argv) > 2 and sys.argv[2] == "same"   # identical trials: every warp of an SM stays in the same phase
+same = len(sys.argv) > 2 and sys.argv[2] == "same"
+tfin = float(sys.argv[3]) if len(sys.argv) > 3 else 60.0   # horizon: N = tfin / 0.2   # identical trials: every warp of an SM stays in the same phase
 eng = tb.Engine(0)
 rng = np.random.default_rng(5)
 qf = np.array([1.0, 0, 0, 0])
-base = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 5.0), qf, t_final=60.0)
+base = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 5.0), qf, t_final=tfin)
 x0 = np.tile(base.x0, (n, 1))
 for i in range(n):
     if i == 0 or not same:
