@@ -609,3 +609,117 @@ def qrot(q, r):
     """qrot.jl:1-3 (host helper)."""
     q, r = np.asarray(q, dtype=float), np.asarray(r, dtype=float)
     return r + 2 * np.cross(q[1:], np.cross(q[1:], r) + q[0] * r)
+
+
+def q_inv(q):
+    """q_inv (attitude_controller.jl:164-166)."""
+    q = np.asarray(q, dtype=float)
+    return np.concatenate([[q[0]], -q[1:4]])
+
+
+def hat(x):
+    """hat (magnetic_toolbox.jl:142-146)."""
+    x = np.asarray(x, dtype=float)
+    return np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]])
+
+
+def DerivFunction(x, u, B_ECI, J, N, tf, t0=0.0):
+    """DerivFunction(dx,x,u) (DerivFunction.jl:1-56) as a function: returns dx (8).  B_ECI, J, N, tf, t0 are
+    the globals the reference's version reads (field row floor(x[8]*N+1), clock rate 1/(tf-t0), u*1e-2)."""
+    return default_engine().dynamics_batch(0, np.asarray(x, dtype=float).reshape(1, 8), np.asarray(u, dtype=float).reshape(1, 3),
+                                           B_ECI, J, index_scale=float(N), clock_rate=1.0 / (tf - t0))[0]
+
+
+def gain_simulator(x, u, B_ECI, J, N, tf, t0=0.0):
+    """gain_simulator(dx,x,u) (gain_simulator.jl:1-53) as a function: the noise-free simulator (u/100)."""
+    return default_engine().dynamics_batch(1, np.asarray(x, dtype=float).reshape(1, 8), np.asarray(u, dtype=float).reshape(1, 3),
+                                           B_ECI, J, index_scale=float(N), clock_rate=1.0 / (tf - t0))[0]
+
+
+def bryson_weights(x0, xf, J, t_final, t0=0.0, dt=0.2, alpha=10.0, beta=1e3):
+    """Bryson-rule LQR weights from the eigen-axis guess (TortoiseSat.jl:157-168): returns (Q, R, Qf) 8x8, 3x3, 8x8."""
+    Qd, Qfd, Rd = default_engine().slew_weights_batch(np.asarray(x0, dtype=float).reshape(1, 8), np.asarray(xf, dtype=float).reshape(1, 8),
+                                                      np.asarray(J, dtype=float).reshape(1, 9), [t_final], t0=t0, dt=dt, alpha=alpha,
+                                                      beta=beta)
+    return np.diag(Qd[0]), np.diag(Rd[0]), np.diag(Qfd[0])
+
+
+def solve_slew(x0, xf, J, Q, R, Qf, B_ECI, N, dt, N_field=None, tf_scope=5400.0, t0=0.0, U0=None, opts=None):
+    """The TrajectoryOptimization.jl block of TortoiseSat.jl:145-146,169,178-199 for ONE slew (batch of 1):
+    rk3(Model(DerivFunction,8,3)), LQRObjective(Q,R,Qf,xf,N), BoundConstraint(u in [-1,1]), goal_constraint(xf),
+    AugmentedLagrangianSolver, solve!.  B_ECI (rows x 3) is the field table the reference keeps in a global; N_field and
+    tf_scope are the globals N and tf that DerivFunction reads.  Returns X (8 x N), U (3 x N-1), K (3 x 8 x N-1) in the
+    reference's column-per-knot shapes, and the outcome record."""
+    B = np.ascontiguousarray(B_ECI, dtype=float).reshape(-1, 3)
+    N = int(N)
+    X, U, K, out, offs = default_engine().alilqr_solve_batch(
+        [N], np.asarray(x0, dtype=float).reshape(1, 8), np.asarray(xf, dtype=float).reshape(1, 8),
+        np.asarray(J, dtype=float).reshape(1, 9), np.diag(np.asarray(Q, dtype=float)).reshape(1, 8),
+        np.diag(np.asarray(Qf, dtype=float)).reshape(1, 8), np.diag(np.asarray(R, dtype=float)).reshape(1, 3), B, [0], [B.shape[0]],
+        [float(N if N_field is None else N_field)], [1.0 / (tf_scope - t0)], dt, U0=U0, opts=opts, want_K=True)
+    return X.T.copy(), U[:N - 1].T.copy(), np.transpose(K[:N - 1], (1, 2, 0)).copy(), out[0]
+
+
+def attitude_simulation(f, f_gains, integration, X_lqr, U_lqr, dt_lqr, x0_lqr, t0, tf, Q_lqr, R_lqr, Qf_lqr, *, B_ECI, J,
+                        N_field=None, tf_scope=5400.0, noise_mode=2, seed=0, q_final=(1.0, 0.0, 0.0, 0.0)):
+    """attitude_simulation(f!,f_gains!,integration,X_lqr,U_lqr,dt_lqr,x0_lqr,t0,tf,Q_lqr,R_lqr,Qf_lqr) -> (X_sim,U_sim,dX,K)
+    (attitude_controller.jl:1-48).  f, f_gains and integration are accepted for signature compatibility: the library
+    implements simulator / gain_simulator / rk4 (simulator.jl, gain_simulator.jl, attitude_controller.jl:122-145).
+    X_lqr is 8 x N, U_lqr 3 x (N-1) as in the reference; the noise is Philox(seed) instead of Julia's global RNG."""
+    X_lqr = np.asarray(X_lqr, dtype=float)
+    N = X_lqr.shape[1]
+    o = default_tvlqr_opts()
+    o.dt, o.t0, o.noise_mode, o.seed = float(dt_lqr), float(t0), int(noise_mode), int(seed)
+    for i in range(6):
+        o.Qd[i], o.Qfd[i] = float(np.asarray(Q_lqr)[i, i]), float(np.asarray(Qf_lqr)[i, i])
+    for i in range(3):
+        o.Rd[i] = float(np.asarray(R_lqr)[i, i])
+    Up = np.zeros((N, 3))
+    Ul = np.asarray(U_lqr, dtype=float)
+    Up[:Ul.shape[1]] = Ul.T
+    B = np.ascontiguousarray(B_ECI, dtype=float).reshape(-1, 3)
+    Xs, Us, dX, K, nsim, slew, offs = default_engine().tvlqr_sim_batch(
+        [N], X_lqr.T.copy(), Up, np.asarray(x0_lqr, dtype=float).reshape(1, 8), np.asarray(J, dtype=float).reshape(1, 9), B, [0],
+        [B.shape[0]], [float(N if N_field is None else N_field)], [1.0 / (tf_scope - t0)], [float(tf)], np.asarray(q_final, dtype=float),
+        opts=o)
+    n = int(nsim[0])
+    return Xs[:n].T.copy(), Us[:n].T.copy(), dX[:n].T.copy(), np.transpose(K[:N - 1], (1, 2, 0)).copy()
+
+
+def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=58155.0, igrf_date=2019.0, t0=0.0, tf=60 * 40.0,
+                cutoff=30.0, N=5000, J=None, q_0=None, q_final=(np.sqrt(2) / 2, np.sqrt(2) / 2, 0.0, 0.0), alpha=1.0e-1, beta=1.0e3,
+                seed=0, run_tvlqr=True, ilqr=None, rng=None):
+    """The loop of monte_carlo.jl:118-262 (solver block of TortoiseSat.jl:178-199) for number_sims trials in ONE
+    library call.  Returns the arrays the script leaves in globals (monte_carlo.jl:52-66,237-240): A (number_sims x 6),
+    t_final, slew_time, fails, plus the per-trial outcome records and the statistics block.  Randomisation as in
+    monte_carlo.jl:122-127,207 (RAAN and anomaly uniform in [0,360), q_0 uniform on S^3, initial attitude noise
+    randn(3)*(pi/180)^2), from numpy's generator instead of Julia's global RNG."""
+    rng = np.random.default_rng(seed) if rng is None else rng
+    n = int(number_sims)
+    J = np.diag([0.00125, 0.00125, 0.00125]) if J is None else np.asarray(J, dtype=float)
+    A = np.zeros((n, 6))
+    A[:, 1], A[:, 2] = alt + R_E, inclination
+    A[:, 3], A[:, 5] = rng.random(n) * 360, rng.random(n) * 360
+    fo = np.zeros(n, dtype=FIELD_OPTS_DTYPE)
+    for i in range(n):
+        fo[i] = (GM_EARTH, MJD_0, igrf_date, (alt + R_E) * 1000.0, 0.0, 0.0, 0)
+    x0, xf = np.zeros((n, 8)), np.zeros((n, 8))
+    if q_0 is None:
+        q = rng.normal(size=(n, 4))
+        x0[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    else:
+        x0[:, 3:7] = np.asarray(q_0, dtype=float)
+    xf[:, 3:7], xf[:, 7] = np.asarray(q_final, dtype=float), 1.0
+    qn = rng.normal(size=(n, 3)) * (np.pi / 180) ** 2
+    cfg = default_mc_config(n, shared_orbit=False, run_tvlqr=run_tvlqr, t0=t0, tf=tf, N_scope=int(N), cutoff=cutoff, dt=0.2,
+                            alpha=alpha, beta=beta)
+    if ilqr is not None:
+        cfg.ilqr = ilqr
+    cfg.tvlqr.noise_mode, cfg.tvlqr.seed = 2, int(seed)
+    for i in range(6):                                   # monte_carlo.jl:69-71,216-226
+        cfg.tvlqr.Qd[i], cfg.tvlqr.Qfd[i] = 10.0, 1000.0
+    for i in range(3):
+        cfg.tvlqr.Rd[i] = 0.5e3
+    out, st = default_engine().monte_carlo_run(cfg, A, fo, x0, xf, np.tile(J.reshape(-1), (n, 1)), q_noise0=qn)
+    fails = (out["slew_time"] == out["t_final"]).astype(float)     # monte_carlo.jl:257-261
+    return dict(A=A, t_final=out["t_final"].copy(), slew_time=out["slew_time"].copy(), fails=fails, outcomes=out, stats=st)
