@@ -435,12 +435,13 @@ static double slew_angle(const double* x0, const double* xf) {
 }
 
 // Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
-// Two launch modes (same solver code, ilqr_solver.cuh):
-//   persistent  one kernel, warps pull groups of 4 trials from a queue (ragged horizons)
-//   phased      host-driven lockstep of phase kernels (uniform horizons): every resident warp runs the same
-//               phase, so the hot loop fits the instruction cache and finished trials free their SM slots
-// TS_K3_MODE=persistent|phased overrides the automatic choice.  Returns with all work complete on the stream
-// (the phased mode synchronises to poll the active-trial counter).
+// Three launch schemes over the same solver code (ilqr_solver.cuh), see k3_alilqr.cuh:
+//   teams   k3_alilqr_kernel (warps pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel
+//           (stragglers handed over to one warp each); automatic when all trials fit the resident team slots
+//   queue   k3_queue_kernel: one launch, 32-lane warps, one trial-ITERATION per work item; automatic otherwise
+//   phased  host-driven lockstep of per-phase kernels -- a measured, slower alternative, opt-in only
+// TS_K3_MODE=teams|queue|phased overrides the automatic choice.  The work is queued on the context's stream
+// (the phased mode synchronises to poll the active-trial counter; the queue mode once, after its set-up copies).
 // inner iterations a trial may use in the 4-trials-per-warp kernel once the queue is empty (see k3_wide_kernel)
 constexpr int K3_SUSPEND_AFTER_DEFAULT = 150;
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
