@@ -209,7 +209,7 @@ def test_straggler_handover_multi_wave(engine):
     go.max_outer = 6
     outs = []
     try:
-        os.environ["TS_K3_MODE"] = "teams"      # (the automatic choice for a multi-wave ensemble is the iteration queue)
+        os.environ["TS_K3_MODE"] = "teams"
         for flag in ("0", "4"):
             os.environ["TS_K3_SUSPEND"] = flag
             X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
@@ -220,21 +220,18 @@ def test_straggler_handover_multi_wave(engine):
         os.environ.pop("TS_K3_SUSPEND", None)
         os.environ.pop("TS_K3_MODE", None)
     ref, other = outs
-    assert ref[3] == 0 and 0 < other[3] <= sm * 8 * 4
-    # iteration-queue mode (one trial-iteration per work item, trials migrate between warps; a separate compilation
-    # of the solver whose FMA contraction differs in the last bit): same status and outer count everywhere, costs to
-    # the parity tolerance, and the identical inner path on (nearly) every trial of this deliberately hard ensemble
-    for f in ("status", "outer_iters"):
-        assert np.array_equal(ref[2][f], outq[f]), f
-    assert np.max(np.abs(ref[2]["J"] - outq["J"]) / np.abs(ref[2]["J"])) < 1e-6
-    same = (ref[2]["inner_iters"] == outq["inner_iters"]) & (ref[2]["ls_rollouts"] == outq["ls_rollouts"])
-    assert same.mean() > 0.99
-    o_all = np.concatenate([np.arange(offs[t], offs[t + 1]) for t in np.nonzero(same)[0]])
-    assert np.max(np.abs(ref[0][o_all] - Xq[o_all])) < 1e-9
-    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
-        assert np.array_equal(ref[2][f], other[2][f]), f
-    assert np.max(np.abs(ref[2]["J"] - other[2]["J"]) / np.abs(ref[2]["J"])) < 1e-10
-    assert np.max(np.abs(ref[0] - other[0])) < 1e-10 and np.max(np.abs(ref[1] - other[1])) < 1e-10
+    assert ref[3] == 0 and 0 < other[3] <= n
+    # Both alternatives run (most of) every trial in the 32-lane kernels -- separate compilations of the solver whose
+    # FMA contraction differs in the last bit: same status and outer count everywhere, costs to the parity tolerance,
+    # and the identical inner path on (nearly) every trial of this deliberately hard ensemble.
+    for Xo, outo in ((other[0], other[2]), (Xq, outq)):
+        for f in ("status", "outer_iters"):
+            assert np.array_equal(ref[2][f], outo[f]), f
+        assert np.max(np.abs(ref[2]["J"] - outo["J"]) / np.abs(ref[2]["J"])) < 1e-6
+        same = (ref[2]["inner_iters"] == outo["inner_iters"]) & (ref[2]["ls_rollouts"] == outo["ls_rollouts"])
+        assert same.mean() > 0.99
+        o_all = np.concatenate([np.arange(offs[t], offs[t + 1]) for t in np.nonzero(same)[0]])
+        assert np.max(np.abs(ref[0][o_all] - Xo[o_all])) < 1e-9
 
 
 @pytest.mark.parametrize("mode", ["teams", "queue"])

@@ -144,6 +144,7 @@ struct K3Args {
   // knot-iterations (inner iterations x horizon: the unit of sequential work) is parked -- solver state + live
   // arrays copied out -- and finished by a whole warp in the second launch
   long long park_budget;      // knot-iterations; 0: never park
+  long long park_budget_early; // a trial past this many knot-iterations is parked even while the queue still has work
   int park_cap;               // parking places
   unsigned* park_count;       // places handed out (may overshoot park_cap)
   TrialState* park_state;     // [park_cap]
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
         long long off = 0;
         const int N = inp->N;
         const long long Ne = N + (N & 1);
-        if (tm.ln == 0 && *(volatile unsigned long long*)a.queue >= (unsigned long long)a.n_trials) {
+        if (tm.ln == 0 && (*(volatile unsigned long long*)a.queue >= (unsigned long long)a.n_trials ||
+                           (long long)st.inner_total * N >= a.park_budget_early)) {
           place = 0xfffffffeu;
           off = (long long)atomicAdd(a.park_used, (unsigned long long)(27 * Ne));
           if (off + 27 * Ne <= a.park_data_cap) {
@@ -562,9 +564,9 @@ constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 // iteration (backward sweep + one 21-candidate forward batch), and pushes the trial back unless it is finished.
 // All trials therefore advance at the same rate (processor sharing), the stragglers end up alone on their warps
 // exactly when there are fewer active trials than warps, and nothing has to be predicted or handed over.
-// Used for ensembles of more trials than resident team slots (several waves), where it beats the two-launch
-// scheme above (8192 slews: 15.6 s vs 16.7 s); for a single wave the 4-trials-per-warp kernel's higher
-// throughput wins (4096 slews: 9.05 s vs 8.15 s).
+// Opt-in (TS_K3_MODE=queue).  It beat the two-launch scheme above on multi-wave ensembles (8192 slews: 15.6 s vs
+// 16.7 s) until that scheme learned to park long trials while its queue still has work (14.5 s); for a single wave
+// the 4-trials-per-warp kernel's higher throughput wins anyway (4096 slews: 9.05 s vs 8.15 s).
 //   * queue: array that never wraps (a trial is pushed at most once per inner iteration), head/tail counters;
 //     a warp that finds it empty EXITS: then every active trial is held by another live warp, and since the number
 //     of active trials only falls, live warps >= active trials stays true -- there is no waiting anywhere except

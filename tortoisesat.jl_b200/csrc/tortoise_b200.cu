@@ -437,13 +437,14 @@ static double slew_angle(const double* x0, const double* xf) {
 // Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
 // Three launch schemes over the same solver code (ilqr_solver.cuh), see k3_alilqr.cuh:
 //   teams   k3_alilqr_kernel (warps pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel
-//           (stragglers handed over to one warp each); automatic when all trials fit the resident team slots
-//   queue   k3_queue_kernel: one launch, 32-lane warps, one trial-ITERATION per work item; automatic otherwise
+//           (stragglers handed over to one warp each); the default
+//   queue   k3_queue_kernel: one launch, 32-lane warps, one trial-ITERATION per work item; opt-in
 //   phased  host-driven lockstep of per-phase kernels -- a measured, slower alternative, opt-in only
 // TS_K3_MODE=teams|queue|phased overrides the automatic choice.  The work is queued on the context's stream
 // (the phased mode synchronises to poll the active-trial counter; the queue mode once, after its set-up copies).
 // inner iterations a trial may use in the 4-trials-per-warp kernel once the queue is empty (see k3_wide_kernel)
 constexpr int K3_SUSPEND_AFTER_DEFAULT = 150;
+constexpr double K3_EARLY_FACTOR_DEFAULT = 2.0;
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
   const int64_t n_trials = a.n_trials;
   int64_t Nmax = 0, Nmin = INT64_MAX;
@@ -467,10 +468,10 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   const int64_t groups = (n_trials + 3) / 4;
   const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
   const int64_t warps = phased ? groups : std::min(groups, max_warps);
-  // More trials than resident team slots (several waves): the iteration queue balances them perfectly and was
-  // measured faster (8192 slews: 15.6 s vs 16.7 s); a single wave is faster with four trials per warp plus the
-  // straggler hand-over (4096 slews: 8.15 s vs 9.05 s).
-  const bool queue_mode = queue_override >= 0 ? queue_override == 1 : (n_trials > max_warps * 4);
+  // Measured (profiles/README.md): the team kernels win for a single wave (4096 slews: 8.1 s vs 9.05 s) and, since
+  // trials past twice their allowance are parked even while the queue still has work, also for several waves
+  // (8192 slews: 14.5 s vs 15.6 s) -- the iteration queue is opt-in (TS_K3_MODE=queue).
+  const bool queue_mode = queue_override == 1;
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
   // the one-warp-per-trial launch uses four slots (36 trajectory buffers) per warp: up to a full wave of warps,
@@ -547,6 +548,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     a.queue = nullptr;
     a.tail_share = 0;
     a.park_budget = 0;
+    a.park_budget_early = 0;
     a.park_cap = 0;
     a.park_count = nullptr;
     a.park_used = nullptr;
@@ -598,6 +600,11 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   for (int64_t t = 0; t < n_trials; ++t) N_sum += (double)N_i_host[t];
   a.park_budget = (long long)((double)suspend_after * N_sum / (double)n_trials);
   if (suspend_after > 0 && a.park_budget < 1) a.park_budget = 1;
+  // multi-wave ensembles: a trial that has used EARLY_FACTOR x the allowance is parked even while fresh trials are
+  // still queued, so that it stops holding its warp's group back (TS_K3_EARLY overrides; 0 = only when drained)
+  double early = K3_EARLY_FACTOR_DEFAULT;
+  if (const char* m = getenv("TS_K3_EARLY")) early = atof(m);
+  a.park_budget_early = early > 0.0 ? (long long)(early * (double)a.park_budget) : (long long)4e18;
   a.park_cap = 0;
   a.park_count = (unsigned*)p_q + 8;
   a.park_used = (unsigned long long*)p_q + 5;
@@ -611,7 +618,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   if (suspend_after > 0) {
     // a place for every trial that can be resident when the queue runs dry; array space for the `cap` longest
     // horizons (order[] is sorted by horizon, descending), bounded by 32 GB
-    const int64_t cap = std::min<int64_t>(n_trials, slots);
+    const int64_t cap = early > 0.0 ? n_trials : std::min<int64_t>(n_trials, slots);
     double need = 0.0;
     for (int64_t i = 0; i < cap; ++i) need += 27.0 * (double)(N_i_host[order_by_N[(size_t)i]] + 1);
     need = std::min(need, 32e9 / 8.0);
