@@ -65,7 +65,7 @@ def test_team_solver_matches_oracle(angle, tfin, mask, status):
     assert np.max(np.abs(U - Us[0])) < 1e-9
 
 
-@pytest.mark.parametrize("angle,tfin,mask", [(5.0, 60.0, 0x7F), (20.0, 30.0, 0x7F)])
+@pytest.mark.parametrize("angle,tfin,mask", [(5.0, 60.0, 0x7F), (20.0, 30.0, 0x7F), (8.0, 40.0, 0xFF)])
 def test_wide_team_matches_oracle(angle, tfin, mask):
     """The whole-warp (32-lane) team used for a warp's straggler: 32 knots linearised per chunk, all 21 line-search
     candidates in one batch.  Must take the same iteration path as the sequential oracle."""
@@ -90,6 +90,26 @@ def test_team_width_does_not_change_results():
     for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "N", "J", "c_max"):
         assert o8[f] == o32[f], f
     assert np.array_equal(X8, X32) and np.array_equal(U8, U32) and np.array_equal(K8, K32)
+
+
+def test_wide_team_stage_cost_dt_3u_inertia_and_gains():
+    """The 30-lane Riccati step of the whole-warp team with a non-spherical inertia, dt-scaled stage cost and a knot
+    count that is not a multiple of 32: gains, trajectories and counters against the oracle AND bit-identical to
+    the 8-lane team."""
+    s = S.build_slew([0, 6871, 51.6, 30, 0, 10], S.J_3U, S.quat_axis_angle([0, 1, 0], 3.0), np.array([1.0, 0, 0, 0]), t_final=50.0)
+    o = orc.default_ilqr_opts()
+    o.stage_cost_dt = 1
+    o.max_outer = 6
+    Xs, Us, Ks, out = S.oracle_solve([s], o)
+    X8, U8, K8, o8 = S.hostsim_solve(s, o, width=8)
+    X32, U32, K32, o32 = S.hostsim_solve(s, o, width=32)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "J", "c_max"):
+        assert o8[f] == o32[f], f
+    assert np.array_equal(X8, X32) and np.array_equal(U8, U32) and np.array_equal(K8, K32)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
+        assert o32[f] == out[0][f], f
+    assert abs(o32["J"] - out[0]["J"]) <= 1e-6 * abs(out[0]["J"])
+    assert np.max(np.abs(K32 - Ks[0])) <= 1e-8 * np.max(np.abs(Ks[0]))
 
 
 def test_stage_cost_dt_and_3u_inertia():
