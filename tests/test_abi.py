@@ -44,3 +44,21 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("liboracle", "orc_", "import oracle", "from oracle", "oracle/"):
                     assert needle not in src, (f, needle)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in host.py (and the Julia structs, which copy them) must have the sizes the C compiler gives
+    the structs of include/tortoise_b200.h -- compiled here with gcc, no GPU needed."""
+    import ctypes as C
+    import subprocess
+    from tortoisesat.jl_b200 import host
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "tortoise_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ts_ilqr_opts), '
+                   'sizeof(ts_tvlqr_opts), sizeof(ts_field_opts), sizeof(ts_mc_config), sizeof(ts_mc_stats), sizeof(ts_trial_outcome));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    mine = [C.sizeof(host.IlqrOpts), C.sizeof(host.TvlqrOpts), C.sizeof(host.FieldOpts), C.sizeof(host.McConfig), C.sizeof(host.McStats),
+            host.OUTCOME_DTYPE.itemsize]
+    assert sizes == mine, (sizes, mine)
+    assert host.FIELD_OPTS_DTYPE.itemsize == sizes[2]
