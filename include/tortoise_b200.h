@@ -59,6 +59,10 @@ double ts_last_kernel_ms(const ts_ctx* ctx);
 /* diagnostics of the most recent AL-iLQR solve on ctx (K3): device time of the persistent 4-trials-per-warp
  * kernel, of the straggler kernel (one warp per trial), and how many trials were handed from one to the other */
 int ts_k3_last_split(ts_ctx* ctx, double* persistent_ms, double* straggler_ms, int64_t* n_parked);
+/* per-trial SM-cycle counters of the most recent AL-iLQR solve on ctx (profiling aid; trial order of that call, or the
+ * order of the trials that reached the solver in ts_monte_carlo_run): cycles3 = n_trials x 3 HOST doubles
+ * [backward pass, forward pass (line search), linearisation share of the backward pass].                        */
+int ts_k3_last_cycles(ts_ctx* ctx, int64_t n_trials, double* cycles3);
 
 /* Measures the FP64 FMA peak of the bound GPU with a register-resident DFMA
  * micro-benchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64 row). */
@@ -133,6 +137,26 @@ typedef struct ts_ilqr_opts {
   double bp_reg_increase, bp_reg_max, bp_reg_min, bp_reg_fp; /* 1.6, 1e8, 1e-8, 10 */
   double max_cost_value, max_state_value, max_control_value; /* 1e8 each */
   double u_max, u_min;      /* BoundConstraint(n,m,u_max=1,u_min=-1)  (TortoiseSat.jl:178) */
+  /* Assumption registry: TrajectoryOptimization.jl v0.1.2 is not in the reference tree, so every
+   * choice its call sites do not pin is a named switch; 0 = the frozen default, 1 = the alternative reading.
+   * tests/test_assumption_flips.py flips each one (oracle and kernel agree under every setting).            */
+  int32_t a2_active_ge;           /* A2: inequality active when c >= 0 (default c > 0) or lambda > 0          */
+  int32_t a3_grad_over_N;         /* A3: Todorov gradient averaged over N knots (default N-1 controls)         */
+  int32_t a4_no_intermediate;     /* A4: final tolerances on every outer iteration (default: intermediate ones
+                                         on all but the last)                                                 */
+  int32_t a5_dual_active_only;    /* A5: dual update on active inequalities only (default: all, then max(0,.)) */
+  int32_t a6_penalty_conditional; /* A6: penalty x scaling only if c_max > constraint_decrease_ratio x previous
+                                         c_max (default: every outer iteration, every constraint)             */
+  int32_t a7_carry_cost;          /* A7: J_prev of an inner solve = last cost under the OLD multipliers
+                                         (default: re-evaluated with the new lambda, mu)                      */
+  double constraint_decrease_ratio; /* 0.25 (only read when a6_penalty_conditional = 1)                       */
+  /* K3 launch scheme (no effect on results): a trial is handed from the 4-trials-per-warp kernel to the
+   * one-warp-per-trial kernel once it has used k3_suspend_after inner iterations of a mean-horizon trial and the
+   * queue is empty (0 = never), or k3_early_factor x that while fresh trials are still queued (0 = never early);
+   * k3_tail_share: finished teams lend their lanes to their warp's unfinished trials.                         */
+  int32_t k3_suspend_after;       /* 150 */
+  int32_t k3_tail_share;          /* 1   */
+  double k3_early_factor;         /* 2.0 */
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);
 
@@ -170,12 +194,15 @@ int ts_alilqr_solve_batch(ts_ctx* ctx, int64_t n_trials, const int64_t* N_i, con
 /* ---- slew preparation: eigen-axis guess + Bryson weights ---------------------- *
  * eigen_axis_slew(x0,xf,t) [src/eigen_axis_slew.jl:1-38] over t = t0:dt:t_final[t], followed by
  * Bryson's rule [src/TortoiseSat.jl:157-168; alpha = 10 there, 0.1 in src/monte_carlo.jl:169;
- * beta = 1e3].  HOST arrays: x0, xf (8 per trial), Jmat (9), t_final (1) -> Qd, Qfd (8), Rd (3).
+ * beta = 1e3].  eigen_axis_fix = 0 reproduces eigen_axis_slew.jl:16 literally: `qmult([q2;-q2[2:4]],q1)` hands qmult
+ * a 7-vector of which it reads entries 1 and 2:4, i.e. the error quaternion is qmult(q_f, q_0) WITHOUT the conjugate;
+ * eigen_axis_fix = 1 uses conj(q_f) (x) q_0 (the evident intent; same theta_f whenever either attitude is the identity).
+ * HOST arrays: x0, xf (8 per trial), Jmat (9), t_final (1) -> Qd, Qfd (8), Rd (3).
  * Optional guess outputs (nullable): w_guess (ragged nt x 3) / q_guess (ragged nt x 4) at row
  * offsets goffs[t] (host, n_trials entries), nt = length(t0:dt:t_final[t]).                   */
 int ts_slew_weights_batch(ts_ctx* ctx, int64_t n_trials, const double* x0, const double* xf, const double* Jmat,
-                          const double* t_final, double t0, double dt, double alpha, double beta, double* Qd, double* Qfd,
-                          double* Rd, const int64_t* goffs, double* w_guess, double* q_guess);
+                          const double* t_final, double t0, double dt, double alpha, double beta, int eigen_axis_fix,
+                          double* Qd, double* Qfd, double* Rd, const int64_t* goffs, double* w_guess, double* q_guess);
 
 /* ---- K4: batched TVLQR closed-loop replay -------------------------------------- */
 typedef struct ts_tvlqr_opts {
@@ -222,6 +249,10 @@ typedef struct ts_mc_config {
   double cutoff;         /* condition-number cutoff (30 / 50 / 100)                                   */
   double dt;             /* 0.2                                                                       */
   double alpha, beta;    /* Bryson weights                                                            */
+  int32_t eigen_axis_fix;    /* see ts_slew_weights_batch; 0 = literal reference                          */
+  int32_t keep_trajectories; /* 1: X, U, X_sim, U_sim and the fine field tables of this run stay resident in HBM
+                                    for ts_mc_fetch_trajectories (the `states`, `control_inputs`, `sim_states`,
+                                    `sim_control_inputs`, `B_ECI_total` arrays of monte_carlo.jl:52-66)       */
   ts_ilqr_opts ilqr;
   ts_tvlqr_opts tvlqr;
 } ts_mc_config;
@@ -229,6 +260,7 @@ typedef struct ts_mc_stats {
   int64_t n_trials, n_converged, n_no_cutoff, n_fail_slew;
   double sum_slew_time, sum_slew_time_sq, sum_t_final, sum_inner_iters, sum_ls_rollouts, sum_knots, flops;
   double ms_field, ms_prep, ms_solve, ms_tvlqr; /* device time of each stage (CUDA events) */
+  int64_t n_status[6];                          /* trials per TS_ST_* code                  */
 } ts_mc_stats;
 /* HOST inputs: kep6 (n x 6, or 1 x 6 if shared_orbit), fopts (n, or 1; only GM, mjd, igrf_date,
  * field_radius_m are read), x0, xf (n x 8), Jmat (n x 9), q_noise0 (n x 3, nullable: initial
@@ -237,6 +269,41 @@ typedef struct ts_mc_stats {
 int ts_monte_carlo_run(ts_ctx* ctx, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts, const double* x0,
                        const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
                        ts_trial_outcome* out, ts_mc_stats* stats);
+
+/* Trajectories of the most recent ts_monte_carlo_run on ctx that had cfg->keep_trajectories = 1 (they stay in HBM until
+ * the next Monte-Carlo run on ctx).  Layout call: knot_offs (n_trials+1, HOST) -- trial t owns knots
+ * [knot_offs[t], knot_offs[t+1]) (none if its status is TS_ST_NO_CUTOFF); row_offs (n_trials+1, HOST) -- trial t's
+ * fine field table starts at row row_offs[t] and has 2*N_t rows (a shared-orbit run has ONE table: every row_offs[t]
+ * is 0 and row_offs[n_trials] = 2N).  Fetch call: any of the HOST outputs may be null; X, X_sim: knots x 8 (states of
+ * monte_carlo.jl:200, sim_states :232; rows >= N_sim of a trial's X_sim are 0), U, U_sim: knots x 3 (last row of each
+ * trial unused = 0), B_eci: rows x 3 Tesla (B_ECI_total, monte_carlo.jl:149; rows the solver cannot index are 0).   */
+int ts_mc_trajectory_layout(ts_ctx* ctx, int64_t n_trials, int64_t* knot_offs, int64_t* row_offs);
+int ts_mc_fetch_trajectories(ts_ctx* ctx, double* X, double* U, double* X_sim, double* U_sim, double* B_eci);
+
+/* ---- igrf12syn: the Fortran-style twin of igrf12 -------------------------------------------- *
+ * igrf12syn(isv, date, itype, alt, colat, elong) [src/igrf.jl:335-534] at n points.  isv 0 = main field, 1 = secular
+ * variation; itype 1 = geodetic (alt = height above the WGS-84 ellipsoid, km), 2 = geocentric (alt = radius, km);
+ * colat in [0,180] deg, elong in [0,360] deg.  Outputs x (north), y (east), z (down), f (total) in nT (nT/yr for isv 1).
+ * Returns TS_ERR_DATE for dates outside [1900, 2025] (igrf.jl:343-345).                                              */
+int ts_igrf12syn_batch(ts_ctx* ctx, int isv, double date, int itype, int64_t n, const double* alt_km, const double* colat_deg,
+                       const double* elong_deg, double* x, double* y, double* z, double* f, int pointers_are_device);
+
+/* ---- several GPUs of one node behind one handle ---------------------------------------------- *
+ * ts_create_multi owns one ts_ctx per device, one host thread per device while a call runs, and (for n_devices > 1)
+ * one NCCL communicator per device (libnccl.so.2 is loaded on first use; the single-GPU entry points never need it).
+ * ts_multi_monte_carlo_run shards the trials round-robin (trial t -> device t mod n_devices: horizons are ragged),
+ * runs ts_monte_carlo_run on every shard concurrently, gathers the 64-byte outcome records with ncclAllGather and
+ * sums the statistics with ncclAllReduce; `out` comes back in the caller's trial order.  Same arguments as
+ * ts_monte_carlo_run (a shared orbit is replicated on every device).  stats->ms_* = max over devices.               */
+typedef struct ts_multi ts_multi;
+int ts_create_multi(ts_multi** out, const int* device_ids, int n_devices);
+void ts_destroy_multi(ts_multi* m);
+const char* ts_multi_last_error(const ts_multi* m);
+int ts_multi_device_count(const ts_multi* m);
+ts_ctx* ts_multi_ctx(ts_multi* m, int i); /* the i-th device's context (borrowed) */
+int ts_multi_monte_carlo_run(ts_multi* m, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts,
+                             const double* x0, const double* xf, const double* Jmat, const double* q_noise0,
+                             const uint32_t* stream_id, ts_trial_outcome* out, ts_mc_stats* stats);
 
 /* ---- element-wise batch versions of the reference's building blocks (all HOST pointers) --- *
  * Correctness / drop-in paths for callers that use the small functions on their own; the fused

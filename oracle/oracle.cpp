@@ -133,7 +133,11 @@ void orc_rk3_jacobian(const orc_dyn* d, const double* x8, const double* u3, doub
 
 // ---------------------------------------------------------------- slew prep
 void orc_eigen_axis_slew(const double* x0, const double* xf, const double* t, int64_t nt, double* w, double* q) {
-  eigen_axis_slew(x0, xf, t, nt, w, q);
+  eigen_axis_slew(x0, xf, t, nt, w, q, 0);
+}
+// conj_fix = 1: conj(q_f) (x) q_0 instead of the reference's literal qmult(q_f, q_0) (eigen_axis_slew.jl:16)
+void orc_eigen_axis_slew_mode(const double* x0, const double* xf, const double* t, int64_t nt, double* w, double* q, int conj_fix) {
+  eigen_axis_slew(x0, xf, t, nt, w, q, conj_fix);
 }
 void orc_bryson_weights(const double* w, int64_t nt, const double* J9, double dt, double alpha, double beta, double* Qd,
                         double* Qfd, double* Rd) {
@@ -147,6 +151,11 @@ struct orc_ilqr_opts {
   double penalty_initial, penalty_scaling, penalty_max, dual_max;
   double ls_lower, ls_upper, bp_reg_increase, bp_reg_max, bp_reg_min, bp_reg_fp;
   double max_cost_value, max_state_value, max_control_value, u_max, u_min;
+  int32_t a2_active_ge, a3_grad_over_N, a4_no_intermediate, a5_dual_active_only, a6_penalty_conditional, a7_carry_cost;
+  double constraint_decrease_ratio;
+  // launch-scheme fields of the product's ts_ilqr_opts (same layout; meaningless on the CPU)
+  int32_t k3_suspend_after, k3_tail_share;
+  double k3_early_factor;
 };
 static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   IlqrOpts o;
@@ -161,6 +170,9 @@ static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   o.bp_reg_max = s->bp_reg_max; o.bp_reg_min = s->bp_reg_min; o.bp_reg_fp = s->bp_reg_fp;
   o.max_cost_value = s->max_cost_value; o.max_state_value = s->max_state_value;
   o.max_control_value = s->max_control_value; o.u_max = s->u_max; o.u_min = s->u_min;
+  o.a2_active_ge = s->a2_active_ge; o.a3_grad_over_N = s->a3_grad_over_N; o.a4_no_intermediate = s->a4_no_intermediate;
+  o.a5_dual_active_only = s->a5_dual_active_only; o.a6_penalty_conditional = s->a6_penalty_conditional;
+  o.a7_carry_cost = s->a7_carry_cost; o.constraint_decrease_ratio = s->constraint_decrease_ratio;
   return o;
 }
 void orc_ilqr_default_opts(orc_ilqr_opts* s) {
@@ -175,6 +187,10 @@ void orc_ilqr_default_opts(orc_ilqr_opts* s) {
   s->bp_reg_max = o.bp_reg_max; s->bp_reg_min = o.bp_reg_min; s->bp_reg_fp = o.bp_reg_fp;
   s->max_cost_value = o.max_cost_value; s->max_state_value = o.max_state_value;
   s->max_control_value = o.max_control_value; s->u_max = o.u_max; s->u_min = o.u_min;
+  s->a2_active_ge = o.a2_active_ge; s->a3_grad_over_N = o.a3_grad_over_N; s->a4_no_intermediate = o.a4_no_intermediate;
+  s->a5_dual_active_only = o.a5_dual_active_only; s->a6_penalty_conditional = o.a6_penalty_conditional;
+  s->a7_carry_cost = o.a7_carry_cost; s->constraint_decrease_ratio = o.constraint_decrease_ratio;
+  s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0;
 }
 
 // Batched solve.  Per trial t: N_i[t] knots, ragged arrays addressed through

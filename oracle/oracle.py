@@ -41,7 +41,11 @@ class IlqrOpts(C.Structure):
                [(k, C.c_double) for k in ("cost_tol", "cost_tol_intermediate", "grad_tol", "grad_tol_intermediate",
                                           "constraint_tol", "penalty_initial", "penalty_scaling", "penalty_max", "dual_max",
                                           "ls_lower", "ls_upper", "bp_reg_increase", "bp_reg_max", "bp_reg_min", "bp_reg_fp",
-                                          "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")]
+                                          "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")] + \
+               [(k, C.c_int32) for k in ("a2_active_ge", "a3_grad_over_N", "a4_no_intermediate", "a5_dual_active_only",
+                                         "a6_penalty_conditional", "a7_carry_cost")] + \
+               [("constraint_decrease_ratio", C.c_double), ("k3_suspend_after", C.c_int32), ("k3_tail_share", C.c_int32),
+                ("k3_early_factor", C.c_double)]
 
 
 class Outcome(C.Structure):
@@ -90,6 +94,7 @@ def lib():
         L.orc_rk3_step.argtypes = [C.POINTER(Dyn), C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.orc_rk3_jacobian.argtypes = [C.POINTER(Dyn), C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_eigen_axis_slew.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_eigen_axis_slew_mode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_bryson_weights.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
         L.orc_ilqr_default_opts.argtypes = [C.POINTER(IlqrOpts)]

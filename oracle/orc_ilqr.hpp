@@ -43,6 +43,14 @@ struct IlqrOpts {
   int stage_cost_dt = 0;             // A1: 0 = stage cost not scaled by dt (default)
   int goal_mask = 0x7F;              // Q2: bit i set -> terminal equality on state i (0xFF = literal)
   double u_max = 1.0, u_min = -1.0;  // BoundConstraint(n,m,u_max=1,u_min=-1)
+  // Assumption registry of SURVEY.md App. C: 0 = the frozen default, 1 = the named alternative (flip-tested)
+  int a2_active_ge = 0;            // A2: inequality active when c >= 0 (default: c > 0) or lambda > 0
+  int a3_grad_over_N = 0;          // A3: Todorov gradient averaged over N (default: N-1 controls)
+  int a4_no_intermediate = 0;      // A4: final tolerances on every outer iteration (default: intermediate on all but the last)
+  int a5_dual_active_only = 0;     // A5: dual update only on active inequalities (default: all, then max(0,.))
+  int a6_penalty_conditional = 0;  // A6: penalties scaled only if c_max > ratio * previous c_max (default: every outer iteration)
+  int a7_carry_cost = 0;           // A7: J_prev of an inner solve = last cost under the OLD multipliers (default: re-evaluated)
+  double constraint_decrease_ratio = 0.25;
 };
 
 enum {
@@ -108,7 +116,7 @@ inline double al_cost(const IlqrProblem& p, const IlqrOpts& o, const Work& w, co
     bound_c(o, u, c);
     for (int i = 0; i < nb; ++i) {
       const double lam = w.lam_b[k * nb + i], mu = w.mu_b[k * nb + i];
-      const bool act = (c[i] > 0.0) || (lam > 0.0);
+      const bool act = (o.a2_active_ge ? (c[i] >= 0.0) : (c[i] > 0.0)) || (lam > 0.0);
       Jc += lam * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
       cmax = std::max(cmax, std::max(0.0, c[i]));
     }
@@ -220,8 +228,8 @@ restart:
       luu[i] = sc * p.Rd[i];
       const double lp = w.lam_b[k * nb + i], mp = w.mu_b[k * nb + i];
       const double ln = w.lam_b[k * nb + 3 + i], mn = w.mu_b[k * nb + 3 + i];
-      const bool ap = (c[i] > 0.0) || (lp > 0.0);
-      const bool an = (c[3 + i] > 0.0) || (ln > 0.0);
+      const bool ap = (o.a2_active_ge ? (c[i] >= 0.0) : (c[i] > 0.0)) || (lp > 0.0);
+      const bool an = (o.a2_active_ge ? (c[3 + i] >= 0.0) : (c[3 + i] > 0.0)) || (ln > 0.0);
       lu[i] += (lp + (ap ? mp * c[i] : 0.0)) - (ln + (an ? mn * c[3 + i] : 0.0));
       luu[i] += (ap ? mp : 0.0) + (an ? mn : 0.0);
     }
@@ -372,14 +380,15 @@ inline void alilqr_solve(const IlqrProblem& p, const IlqrOpts& o, const double* 
   for (int64_t k = 0; k < N - 1; ++k) step(p, &w.X[k * n], &w.U[k * m], &w.X[(k + 1) * n]);
 
   int status = ST_MAX_OUTER, outer = 0, inner_total = 0, ls_total = 0;
-  double J = 0, c_max = 0;
+  double J = 0, c_max = 0, c_max_prev = INFINITY;
   for (int oi = 1; oi <= o.max_outer; ++oi) {
     outer = oi;
-    const bool last = (oi == o.max_outer);
+    const bool last = (oi == o.max_outer) || o.a4_no_intermediate;
     const double ctol = last ? o.cost_tol : o.cost_tol_intermediate;
     const double gtol = last ? o.grad_tol : o.grad_tol_intermediate;
     Reg reg;
     double J_prev = al_cost(p, o, w, w.X.data(), w.U.data(), nullptr);
+    if (o.a7_carry_cost && oi > 1) J_prev = J;  // A7 alternative: the cost carried over from the previous inner solve
     J = J_prev;
     int dJ_zero = 0;
     bool abort_trial = false;
@@ -446,20 +455,25 @@ inline void alilqr_solve(const IlqrProblem& p, const IlqrOpts& o, const double* 
         for (int i = 0; i < m; ++i) mxv = std::max(mxv, std::fabs(w.d[k * m + i]) / (std::fabs(w.U[k * m + i]) + 1.0));
         g += mxv;
       }
-      g /= (double)(N - 1);
+      g /= (double)(o.a3_grad_over_N ? N : N - 1);
       if ((0.0 < dJ && dJ < ctol) || g < gtol || dJ_zero > o.dJ_counter_limit) break;
     }
     J = al_cost(p, o, w, w.X.data(), w.U.data(), &c_max);
     if (abort_trial) break;
     // dual + penalty update (A5, A6) with constraint values at the final trajectory
+    const bool grow = !o.a6_penalty_conditional || (c_max > o.constraint_decrease_ratio * c_max_prev);
+    c_max_prev = c_max;
     for (int64_t k = 0; k < N - 1; ++k) {
       double c[nb];
       bound_c(o, &w.U[k * m], c);
       for (int i = 0; i < nb; ++i) {
-        double l = w.lam_b[k * nb + i] + w.mu_b[k * nb + i] * c[i];
+        const double l0 = w.lam_b[k * nb + i];
+        const bool act = (o.a2_active_ge ? (c[i] >= 0.0) : (c[i] > 0.0)) || (l0 > 0.0);
+        double l = l0 + w.mu_b[k * nb + i] * c[i];
         l = std::min(std::max(l, -o.dual_max), o.dual_max);
+        if (o.a5_dual_active_only && !act) l = l0;
         w.lam_b[k * nb + i] = std::max(0.0, l);
-        w.mu_b[k * nb + i] = std::min(w.mu_b[k * nb + i] * o.penalty_scaling, o.penalty_max);
+        if (grow) w.mu_b[k * nb + i] = std::min(w.mu_b[k * nb + i] * o.penalty_scaling, o.penalty_max);
       }
     }
     for (int i = 0; i < n; ++i) {
@@ -467,7 +481,7 @@ inline void alilqr_solve(const IlqrProblem& p, const IlqrOpts& o, const double* 
       const double e = w.X[(N - 1) * n + i] - p.xf[i];
       double l = w.lam_g[i] + w.mu_g[i] * e;
       w.lam_g[i] = std::min(std::max(l, -o.dual_max), o.dual_max);
-      w.mu_g[i] = std::min(w.mu_g[i] * o.penalty_scaling, o.penalty_max);
+      if (grow) w.mu_g[i] = std::min(w.mu_g[i] * o.penalty_scaling, o.penalty_max);
     }
     if (c_max < o.constraint_tol) {
       status = ST_CONVERGED;

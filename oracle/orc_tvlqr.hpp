@@ -198,11 +198,16 @@ inline int64_t attitude_simulation(const DynCtx& dyn, const TvlqrOpts& o, int64_
 }
 
 // reference src/eigen_axis_slew.jl:1-38.  t has nt entries; outputs nt x 3, nt x 4.
+// :16 reads `q_e = qmult([q2;-q2[2:4]],q1)`: the first argument is a 7-vector of which qmult (qmult.jl:1-3) reads only
+// entries 1 and 2:4, i.e. the LITERAL product is qmult(q2, q1) -- no conjugate.  conj_fix = 0 reproduces that;
+// conj_fix = 1 is the evident intent conj(q2) (x) q1 (identical whenever one of the two attitudes is the identity up to
+// the sign of the axis, which is why the shipped scripts never notice).
 inline void eigen_axis_slew(const double x0[7], const double xf[7], const double* t, int64_t nt, double* w_guess,
-                            double* q_guess) {
+                            double* q_guess, int conj_fix = 0) {
   const double* q1 = x0 + 3;
   const double* q2 = xf + 3;
-  const double q2c[4] = {q2[0], -q2[1], -q2[2], -q2[3]};
+  const double sg = conj_fix ? -1.0 : 1.0;
+  const double q2c[4] = {q2[0], sg * q2[1], sg * q2[2], sg * q2[3]};
   double qe[4];
   qmult(q2c, q1, qe);
   const double theta_f = 2 * std::acos(qe[0]);

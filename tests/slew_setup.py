@@ -139,19 +139,28 @@ def hostsim_solve(s, opts=None, width=8):
     return X, U[:-1], K[:-1].reshape(-1, 3, 8), out[0]
 
 
+def oracle_tvlqr_opts(noise_mode=0, seed=0, dt=0.2, dt_squared=1, R=7.5e3):
+    """Oracle TvlqrOpts with the constants of TortoiseSat.jl:251-260 (R = 7.5e3) / monte_carlo.jl:216-227 (R = 0.5e3).
+    Touches only the oracle (bench.py's CPU legs must not load the product library)."""
+    o = orc.TvlqrOpts()
+    o.dt, o.t0, o.dt_squared, o.noise_mode, o.seed = dt, 0.0, dt_squared, noise_mode, seed
+    for i in range(6):
+        o.Qd[i], o.Qfd[i] = 10.0, 1000.0
+    for i in range(3):
+        o.Rd[i] = R
+    return o
+
+
 def tvlqr_opts_pair(noise_mode=0, seed=0, dt=0.2, literal=0, dt_squared=1, R=7.5e3):
-    """(oracle TvlqrOpts, product TvlqrOpts) with the constants of TortoiseSat.jl:251-260."""
+    """(oracle TvlqrOpts, product TvlqrOpts) with the same constants; GPU tests only (loads the product library)."""
     import tortoisesat.jl_b200 as tb
     g = tb.host.default_tvlqr_opts()
     g.dt, g.noise_mode, g.seed, g.literal_postproc, g.dt_squared = dt, noise_mode, seed, literal, dt_squared
     for i in range(3):
         g.Rd[i] = R
-    o = orc.TvlqrOpts()
-    o.dt, o.t0, o.dt_squared, o.noise_mode, o.seed = dt, 0.0, dt_squared, noise_mode, seed
+    o = oracle_tvlqr_opts(noise_mode, seed, dt, dt_squared, R)
     for i in range(6):
-        o.Qd[i], o.Qfd[i] = g.Qd[i], g.Qfd[i]
-    for i in range(3):
-        o.Rd[i] = g.Rd[i]
+        assert (o.Qd[i], o.Qfd[i]) == (g.Qd[i], g.Qfd[i])
     return o, g
 
 

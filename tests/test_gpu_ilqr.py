@@ -128,11 +128,10 @@ def test_lane_lending_does_not_change_results(engine):
     go = _gpu_opts(tb, o)
     go.max_outer = 8
     outs = []
-    for flag in ("1", "0"):
-        os.environ["TS_K3_TAIL"] = flag
+    for flag in (1, 0):
+        go.k3_tail_share = flag
         X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
         outs.append((X.copy(), U.copy(), out.copy()))
-    os.environ.pop("TS_K3_TAIL", None)
     a, b = outs
     for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
         assert np.array_equal(a[2][f], b[2][f]), f
@@ -164,13 +163,10 @@ def test_straggler_handover_does_not_change_results(engine):
     go = _gpu_opts(tb, o)
     go.max_outer = 8
     outs = []
-    try:
-        for flag in ("0", "3", "40"):
-            os.environ["TS_K3_SUSPEND"] = flag
-            X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
-            outs.append((X.copy(), U.copy(), K.copy(), out.copy()))
-    finally:
-        os.environ.pop("TS_K3_SUSPEND", None)
+    for flag in (0, 3, 40):
+        go.k3_suspend_after = flag
+        X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
+        outs.append((X.copy(), U.copy(), K.copy(), out.copy()))
     ref = outs[0]
     assert ref[3]["inner_iters"].max() > 40 and ref[3]["inner_iters"].min() < 40   # some trials are handed over, some are not
     # The two kernels are separate compilations of the same solver source (FMA contraction may differ in the last
@@ -208,23 +204,16 @@ def test_straggler_handover_multi_wave(engine):
     go = _gpu_opts(tb, S.orc.default_ilqr_opts())
     go.max_outer = 6
     outs = []
-    try:
-        os.environ["TS_K3_MODE"] = "teams"
-        for flag in ("0", "4"):
-            os.environ["TS_K3_SUSPEND"] = flag
-            X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
-            outs.append((X.copy(), U.copy(), out.copy(), engine.k3_last_split()[2]))
-        os.environ["TS_K3_MODE"] = "queue"
-        Xq, Uq, Kq, outq, offs = engine.alilqr_solve_batch(**args, opts=go)
-    finally:
-        os.environ.pop("TS_K3_SUSPEND", None)
-        os.environ.pop("TS_K3_MODE", None)
-    ref, other = outs
-    assert ref[3] == 0 and 0 < other[3] <= n
-    # Both alternatives run (most of) every trial in the 32-lane kernels -- separate compilations of the solver whose
+    for flag, early in ((0, 2.0), (4, 2.0), (4, 0.0)):
+        go.k3_suspend_after, go.k3_early_factor = flag, early
+        X, U, K, out, offs = engine.alilqr_solve_batch(**args, opts=go)
+        outs.append((X.copy(), U.copy(), out.copy(), engine.k3_last_split()[2]))
+    ref, other, late = outs
+    assert ref[3] == 0 and 0 < other[3] <= n and 0 < late[3] <= other[3]
+    # The hand-over runs (most of) every trial in the 32-lane kernel -- a separate compilation of the solver whose
     # FMA contraction differs in the last bit: same status and outer count everywhere, costs to the parity tolerance,
     # and the identical inner path on (nearly) every trial of this deliberately hard ensemble.
-    for Xo, outo in ((other[0], other[2]), (Xq, outq)):
+    for Xo, outo in ((other[0], other[2]), (late[0], late[2])):
         for f in ("status", "outer_iters"):
             assert np.array_equal(ref[2][f], outo[f]), f
         assert np.max(np.abs(ref[2]["J"] - outo["J"]) / np.abs(ref[2]["J"])) < 1e-6
@@ -234,11 +223,9 @@ def test_straggler_handover_multi_wave(engine):
         assert np.max(np.abs(ref[0][o_all] - Xo[o_all])) < 1e-9
 
 
-@pytest.mark.parametrize("mode", ["teams", "queue"])
-def test_launch_modes_match_oracle(engine, mode):
-    """Both K3 launch schemes -- four trials per warp + straggler hand-over ("teams") and the iteration queue
-    ("queue", the automatic choice for multi-wave ensembles) -- against the oracle on a ragged batch with gains."""
-    import os
+def test_handover_matches_oracle(engine):
+    """Four trials per warp + straggler hand-over after 10 inner iterations against the oracle on a ragged batch with
+    gains (most trials finish in the one-warp-per-trial kernel)."""
     rng = np.random.default_rng(5)
     slews = []
     for i in range(12):
@@ -246,11 +233,36 @@ def test_launch_modes_match_oracle(engine, mode):
                          np.array([1.0, 0, 0, 0]), t_final=float(rng.integers(20, 50)))
         slews.append(s)
     import tortoisesat.jl_b200 as tb
-    try:
-        os.environ["TS_K3_MODE"] = mode
-        os.environ["TS_K3_SUSPEND"] = "10"
-        same = _check(engine, slews, orc.default_ilqr_opts(), tb)
-    finally:
-        os.environ.pop("TS_K3_MODE", None)
-        os.environ.pop("TS_K3_SUSPEND", None)
+    o = orc.default_ilqr_opts()
+    o.k3_suspend_after = 10
+    same = _check(engine, slews, o, tb)
+    assert engine.k3_last_split()[2] > 0
     assert same >= 10
+
+
+FLAGS = ["stage_cost_dt", "a2_active_ge", "a3_grad_over_N", "a4_no_intermediate", "a5_dual_active_only", "a6_penalty_conditional",
+         "a7_carry_cost"]
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+def test_assumption_flips_on_gpu(engine, flag):
+    """SURVEY App. C assumption registry: under every alternative reading the kernel still follows the oracle
+    (GPU twin of tests/test_assumption_flips.py), in both kernels (hand-over after 20 iterations)."""
+    import tortoisesat.jl_b200 as tb
+    qf = np.array([1.0, 0, 0, 0])
+    slews = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], a), qf, t_final=30.0) for a in (2.0, 5.0, 10.0)]
+    o = orc.default_ilqr_opts()
+    setattr(o, flag, 1)
+    o.k3_suspend_after = 20
+    assert _check(engine, slews, o, tb) >= 2
+
+
+def test_cycle_diagnostics_are_separate_from_outcomes(engine):
+    """ts_alilqr_solve_batch returns outcome records whose t_final / slew_time / flops are 0 (they belong to the fused
+    Monte-Carlo path); the SM-cycle counters come through ts_k3_last_cycles."""
+    import tortoisesat.jl_b200 as tb
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], 2.0), np.array([1.0, 0, 0, 0]), t_final=30.0)
+    X, U, K, out, offs = engine.alilqr_solve_batch(**_pack([s, s]), opts=_gpu_opts(tb, orc.default_ilqr_opts()))
+    assert np.all(out["t_final"] == 0) and np.all(out["slew_time"] == 0) and np.all(out["flops"] == 0)
+    cyc = engine.k3_last_cycles(2)
+    assert cyc.shape == (2, 3) and np.all(cyc[:, 0] > 0) and np.all(cyc[:, 1] > 0) and np.all(cyc[:, 2] <= cyc[:, 0])

@@ -1,62 +1,118 @@
-"""GPU probe: K3 throughput on the configs[2] ensemble (fixed orbit, random attitudes)."""
-import json, math, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np
-import slew_setup as S
-from oracle import oracle as orc
-import tortoisesat.jl_b200 as tb
+"""GPU probe on the BENCHMARK ensembles (bench.make_trials): where the solves end up, and why.
 
-ntr = [int(a) for a in sys.argv[1:]] or [256, 1024, 4096]
+  python tools/mc_probe.py <mc_fixed_orbit|mc_sweep> <n_trials> [--suspend a,b,...] [--flips] [--why]
+
+Per run: K3 time and its split between the two kernels, per-status histogram, inner-iteration quantiles.
+--why     keeps the trajectories and decomposes c_max of the non-converged trials: which constraint (control bound
+          |u| <= 1 or a goal component) holds c_max above the 1e-3 tolerance, and the per-outer progress.
+--flips   re-runs the ensemble under each alternative of the SURVEY App. C assumption registry (A1..A7) and counts the
+          trials whose status / outer-iteration count change: the spec risk of the unpinned solver details.
+Writes gpurun_out/mc_probe_<workload>_<n>.json.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import bench as B
+import tortoisesat.jl_b200 as tb
+from tortoisesat.jl_b200 import host
+
+workload = sys.argv[1] if len(sys.argv) > 1 else "mc_fixed_orbit"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+args = sys.argv[3:]
+suspends = [150]
+for i, a in enumerate(args):
+    if a == "--suspend":
+        suspends = [int(x) for x in args[i + 1].split(",")]
 eng = tb.Engine(0)
-rng = np.random.default_rng(2026)
-qf = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])
-kep = [0, 6771.0, 96.6, 0.0, 0.0, 90.0]
-base = S.build_slew(kep, S.J_1U, np.array([1.0, 0, 0, 0]), qf, tf=2400.0, cutoff=30.0, alpha=0.1)
-print("N", base.N, "t_final", base.t_final, flush=True)
-T = max(ntr)
-q0 = rng.normal(size=(T, 4)); q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
-L = orc.lib()
-Qd = np.zeros((T, 8)); Qfd = np.zeros((T, 8)); Rd = np.zeros((T, 3))
-nt = base.t.shape[0]
-t0 = time.time()
-for i in range(T):
-    x0 = np.concatenate([[0, 0, 0], q0[i]])
-    w_g = np.zeros((nt, 3)); q_g = np.zeros((nt, 4))
-    L.orc_eigen_axis_slew(orc.P(x0), orc.P(orc.f64(base.xf[:7])), orc.P(base.t), nt, orc.P(w_g), orc.P(q_g))
-    L.orc_bryson_weights(orc.P(w_g), nt, orc.P(orc.f64(base.J)), base.dt, 0.1, 1e3, orc.P(Qd[i]), orc.P(Qfd[i]), orc.P(Rd[i]))
-print("weights host s", time.time() - t0, flush=True)
-x0 = np.concatenate([np.zeros((T, 3)), q0, np.zeros((T, 1))], axis=1)
-xf = np.tile(base.xf, (T, 1))
-res = {}
-for n in ntr:
-    args = dict(N_i=[base.N] * n, x0=x0[:n], xf=xf[:n], Jmat=np.tile(base.J.reshape(-1), (n, 1)), Qd=Qd[:n], Qfd=Qfd[:n], Rd=Rd[:n],
-                B_eci=base.B, B_offs=[0] * n, B_rows=[base.B.shape[0]] * n, index_scale=[base.index_scale] * n,
-                clock_rate=[base.clock_rate] * n, dt=base.dt, want_K=False)
-    t0 = time.time()
-    X, U, K, out, offs = eng.alilqr_solve_batch(**args)
-    wall = time.time() - t0
-    ms = eng.last_kernel_ms()
-    st = np.bincount(out["status"], minlength=5)
-    print(n, "kernel ms", ms, "wall s", wall, "trials/s", n / (ms * 1e-3), "status", st.tolist(), "outer mean", out["outer_iters"].mean(),
-          "inner mean/max", out["inner_iters"].mean(), out["inner_iters"].max(), "ls mean", out["ls_rollouts"].mean(), flush=True)
-    print("   K3 split: persistent %.0f ms, straggler kernel %.0f ms, %d trials handed over" % eng.k3_last_split(),
-          "| inner-iteration quantiles 50/75/90/95/99:", np.percentile(out["inner_iters"], [50, 75, 90, 95, 99]).tolist(), flush=True)
-    # angle correlation: could the slew angle predict the long trials?
-    qfv = np.asarray(base.xf[3:7]); dots = np.abs(q0[:n] @ qfv); ang = 2 * np.degrees(np.arccos(np.clip(dots, 0, 1)))
-    itn = out["inner_iters"].astype(float)
-    order_a = np.argsort(-ang); order_i = np.argsort(-itn)
-    top = min(1184, n // 3)
-    print("   angle vs iterations: corr %.3f | of the %d longest trials, %d are among the %d largest angles | mean iters by angle quartile:" % (
-        np.corrcoef(ang, itn)[0, 1], top, len(set(order_a[:top]) & set(order_i[:top])), top),
-        [round(float(itn[order_a[k * n // 4:(k + 1) * n // 4]].mean()), 1) for k in range(4)], flush=True)
-    its = out["inner_iters"].astype(float)
-    i = int(np.argmax(its))
-    kn = its * base.N
-    print("   slowest trial per knot-iter: bwd %.0f (lin %.0f) fwd %.0f | median trial: bwd %.0f (lin %.0f) fwd %.0f" % (
-        out["t_final"][i] / kn[i], out["flops"][i] / kn[i], out["slew_time"][i] / kn[i], np.median(out["t_final"] / kn),
-        np.median(out["flops"] / kn), np.median(out["slew_time"] / kn)), flush=True)
-    res[n] = dict(ms=ms, trials_per_s=n / (ms * 1e-3), status=st.tolist(), inner_mean=float(out["inner_iters"].mean()),
-                  inner_max=int(out["inner_iters"].max()), ls_mean=float(out["ls_rollouts"].mean()))
-os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/mc_probe.json", "w"), indent=1)
+tr = B.make_trials(workload, n, 0)
+fo = np.zeros(len(tr["fo"]), dtype=host.FIELD_OPTS_DTYPE)
+for i, f in enumerate(tr["fo"]):
+    fo[i] = f
+sid = np.arange(n).astype(np.uint32)
+STAT = ["converged", "max_outer", "cost_blowup", "reg_max", "nan", "no_cutoff"]
+res = {"workload": workload, "n": n, "runs": []}
+
+
+def run(cfg, label):
+    out, st = eng.monte_carlo_run(cfg, tr["kep"], fo, tr["x0"], tr["xf"], tr["Jm"], q_noise0=tr["qn"], stream_id=sid)
+    act = out["status"] != 5
+    it = out["inner_iters"][act].astype(float)
+    hist = np.bincount(out["status"], minlength=6).tolist()
+    rec = dict(label=label, ms_solve=st.ms_solve, ms_field=st.ms_field, ms_tvlqr=st.ms_tvlqr, split=list(eng.k3_last_split()),
+               status=dict(zip(STAT, hist)), inner_q=np.percentile(it, [50, 75, 90, 95, 99, 100]).tolist(), inner_mean=float(it.mean()),
+               ls_mean=float(out["ls_rollouts"][act].mean()), outer_q=np.percentile(out["outer_iters"][act], [50, 90, 100]).tolist(),
+               N_q=np.percentile(out["N"][act], [0, 50, 90, 100]).tolist(), fail_slew=int(st.n_fail_slew),
+               trials_per_s=n / (1e-3 * (st.ms_field + st.ms_prep + st.ms_solve + st.ms_tvlqr)))
+    print(json.dumps(rec), flush=True)
+    res["runs"].append(rec)
+    return out, st
+
+
+base_out = None
+for s in suspends:
+    cfg = B.mc_config(host, tr, n)
+    cfg.ilqr.k3_suspend_after = s
+    out, st = run(cfg, "suspend=%d" % s)
+    if base_out is None:
+        base_out = out.copy()
+
+if "--why" in args:
+    cfg = B.mc_config(host, tr, n)
+    cfg.keep_trajectories = 1
+    out, st = run(cfg, "keep_trajectories")
+    t = eng.mc_trajectories(n, want=("X", "U"))
+    ko = t["knot_offs"]
+    xf = tr["xf"]
+    rows = []
+    for i in np.nonzero(out["status"] == 1)[0]:
+        X = t["X"][ko[i]:ko[i + 1]]
+        U = t["U"][ko[i]:ko[i + 1] - 1]
+        ub = float(np.max(np.abs(U)) - 1.0)
+        ge = np.abs(X[-1, :7] - xf[i, :7])
+        rows.append((ub, float(ge[:3].max()), float(ge[3:7].max()), float(out["c_max"][i]), int(out["inner_iters"][i])))
+    rows = np.array(rows) if rows else np.zeros((0, 5))
+    why = {}
+    if len(rows):
+        dom = np.argmax(rows[:, :3], axis=1)
+        why = dict(n_max_outer=int(len(rows)), binding_control_bound=int((dom == 0).sum()), binding_goal_rate=int((dom == 1).sum()),
+                   binding_goal_attitude=int((dom == 2).sum()), c_max_q=np.percentile(rows[:, 3], [0, 10, 50, 90, 100]).tolist(),
+                   u_excess_q=np.percentile(rows[:, 0], [0, 50, 100]).tolist(), goal_q_err_q=np.percentile(rows[:, 2], [0, 50, 100]).tolist(),
+                   inner_q=np.percentile(rows[:, 4], [0, 50, 100]).tolist(),
+                   frac_within_2x_tol=float((rows[:, 3] < 2e-3).mean()), frac_within_10x_tol=float((rows[:, 3] < 1e-2).mean()))
+    # slew angle vs outcome
+    qf = xf[:, 3:7]
+    ang = 2 * np.degrees(np.arccos(np.clip(np.abs(np.sum(tr["x0"][:, 3:7] * qf, axis=1)), 0, 1)))
+    why["angle_deg_mean_by_status"] = {STAT[k]: float(ang[out["status"] == k].mean()) for k in range(6) if (out["status"] == k).any()}
+    why["corr_angle_inner"] = float(np.corrcoef(ang, out["inner_iters"])[0, 1])
+    print("why:", json.dumps(why), flush=True)
+    res["why"] = why
+
+if "--flips" in args:
+    flips = {}
+    for flag in ["stage_cost_dt", "a2_active_ge", "a3_grad_over_N", "a4_no_intermediate", "a5_dual_active_only", "a6_penalty_conditional",
+                 "a7_carry_cost"]:
+        cfg = B.mc_config(host, tr, n)
+        setattr(cfg.ilqr, flag, 1)
+        out, st = run(cfg, "flip " + flag)
+        flips[flag] = dict(status_changed=int((out["status"] != base_out["status"]).sum()),
+                           outer_changed=int((out["outer_iters"] != base_out["outer_iters"]).sum()),
+                           inner_changed=int((out["inner_iters"] != base_out["inner_iters"]).sum()),
+                           converged=int((out["status"] == 0).sum()), converged_default=int((base_out["status"] == 0).sum()))
+        print("flip", flag, flips[flag], flush=True)
+    # the eigen-axis conjugate "fix" (ADVICE r1): how much does the literal qmult(q_f, q_0) matter for the ensemble?
+    cfg = B.mc_config(host, tr, n)
+    cfg.eigen_axis_fix = 1
+    out, st = run(cfg, "eigen_axis_fix=1")
+    flips["eigen_axis_fix"] = dict(status_changed=int((out["status"] != base_out["status"]).sum()),
+                                   outer_changed=int((out["outer_iters"] != base_out["outer_iters"]).sum()),
+                                   converged=int((out["status"] == 0).sum()), converged_default=int((base_out["status"] == 0).sum()))
+    print("flip eigen_axis_fix", flips["eigen_axis_fix"], flush=True)
+    res["flips"] = flips
+
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "mc_probe_%s_%d.json" % (workload, n)), "w"), indent=1)

@@ -19,6 +19,8 @@ struct ts_ctx {
   cudaEvent_t ev_k3[3] = {nullptr, nullptr, nullptr};  // K3: start | persistent kernel done | straggler kernel done
   unsigned* d_k3_parked = nullptr;                     // device word holding the number of parked trials of the last K3 run
   bool k3_timed = false;
+  int k3_park_cap = 0;                                 // parking places of the last K3 run
+  int64_t k3_diag_n = 0;                               // trials covered by the K3 cycle diagnostics (scratch slot 19)
   cudaStream_t pipe[2] = {nullptr, nullptr};           // K1 host-pointer path: double-buffered copy/compute pipeline
   cudaEvent_t pipe_ev = nullptr;
   char err[512] = {0};
@@ -27,10 +29,18 @@ struct ts_ctx {
   double last_kernel_ms = 0.0;
   double* d_tabG = nullptr;  // 104 x 25
   double* d_tabH = nullptr;  // 91 x 25
+  double* d_tabGH = nullptr; // 3450 (igrf12syn)
   int* d_flag = nullptr;     // generic device error/flag word
+  // trajectories of the last ts_monte_carlo_run with keep_trajectories (device pointers into the scratch arenas)
+  struct McLast {
+    bool valid = false;
+    int64_t n = 0, knots = 0, rows = 0;
+    std::vector<int64_t> knot_offs, row_offs;
+    double *d_X = nullptr, *d_U = nullptr, *d_Xs = nullptr, *d_Us = nullptr, *d_B = nullptr;
+  } mc_last;
   // grow-only scratch arenas
-  void* scratch[20] = {};
-  size_t scratch_bytes[20] = {};
+  void* scratch[32] = {};
+  size_t scratch_bytes[32] = {};
 };
 
 namespace ts {

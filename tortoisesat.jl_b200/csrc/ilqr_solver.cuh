@@ -40,6 +40,12 @@ struct ts_ilqr_opts_dev {
   double penalty_initial, penalty_scaling, penalty_max, dual_max;
   double ls_lower, ls_upper, bp_reg_increase, bp_reg_max, bp_reg_min, bp_reg_fp;
   double max_cost_value, max_state_value, max_control_value, u_max, u_min;
+  // assumption registry of SURVEY.md App. C (0 = frozen default, 1 = named alternative)
+  int32_t a2_active_ge, a3_grad_over_N, a4_no_intermediate, a5_dual_active_only, a6_penalty_conditional, a7_carry_cost;
+  double constraint_decrease_ratio;
+  // K3 launch scheme (host side only)
+  int32_t k3_suspend_after, k3_tail_share;
+  double k3_early_factor;
 };
 // 64-byte per-trial record (C ABI: ts_trial_outcome).
 struct ts_trial_outcome_dev {
@@ -107,15 +113,11 @@ struct TrialWork {
   double* clk;   // [Nmax]         clock state
   double* bk;    // [Nmax][10]     field vectors of the three rk3 stages of each knot (9 used)
   long long Nmax;
-  double* const* tab = nullptr;  // whole-warp team under the iteration queue (k3_queue_kernel): table of the 33 buffers
 };
 
 // trajectory buffer i in the warp's buffer space: slot i/9, buffer i%9 (a team that owns a single slot uses 0..8)
 template <int W>
 TS_HD double* xu_buf(const TrialWork& w, int i) {
-  if constexpr (W >= 32) {
-    if (w.tab) return w.tab[i];
-  }
   return w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10);
 }
 
@@ -206,7 +208,7 @@ TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double s
   double c[6];
   bound_c(o, u, c);
   for (int i = 0; i < 6; ++i) {
-    const bool act = (c[i] > 0.0) || (lam[i] > 0.0);
+    const bool act = (o.a2_active_ge ? (c[i] >= 0.0) : (c[i] > 0.0)) || (lam[i] > 0.0);
     Jc += lam[i] * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
     cmax = fmax(cmax, fmax(0.0, c[i]));
   }
@@ -258,8 +260,8 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
     double lu = sc * in.Rd[i] * u[i];
     double luu = sc * in.Rd[i];
     const double lp = lam[i], ln = lam[3 + i];
-    const bool ap = (c6[i] > 0.0) || (lp > 0.0);
-    const bool an = (c6[3 + i] > 0.0) || (ln > 0.0);
+    const bool ap = (o.a2_active_ge ? (c6[i] >= 0.0) : (c6[i] > 0.0)) || (lp > 0.0);
+    const bool an = (o.a2_active_ge ? (c6[3 + i] >= 0.0) : (c6[3 + i] > 0.0)) || (ln > 0.0);
     lu += (lp + (ap ? mu * c6[i] : 0.0)) - (ln + (an ? mu * c6[3 + i] : 0.0));
     luu += (ap ? mu : 0.0) + (an ? mu : 0.0);
     rec[77 + i] = lu;
@@ -658,7 +660,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
   }
   r.J = Jc;
   r.cmax = cmax;
-  r.grad = gsum / (double)(N - 1);
+  r.grad = gsum / (double)(o.a3_grad_over_N ? N : N - 1);
   return r;
 }
 
@@ -668,7 +670,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
 enum { PH_BACKWARD = 0, PH_FORWARD = 1, PH_DONE = 2 };
 struct TrialState {
   double mu, lam_g[8];
-  double J_prev, J, c_max, rho, drho, dV1, dV2, clk_absmax;
+  double J_prev, J, c_max, c_max_prev, rho, drho, dV1, dV2, clk_absmax;
   long long cyc_bwd, cyc_fwd, cyc_lin;
   int it, outer, dJ_zero, inner_total, ls_total, status, cur, phase, b0, pad_;
 };
@@ -737,6 +739,7 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
   st.cyc_bwd = st.cyc_fwd = st.cyc_lin = 0;
   st.clk_absmax = clk_absmax;
   st.c_max = 0.0;
+  st.c_max_prev = INFINITY;
   st.J_prev = trajectory_cost(tm, in, o, w, w.xu, sc, st.mu, st.lam_g, st.c_max);
   st.J = st.J_prev;
   st.phase = (o.max_outer < 1) ? PH_DONE : PH_BACKWARD;
@@ -749,8 +752,7 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
   const int lane = tm.lane();
   const int N = in.N;
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
-  const long long bstride = w.Nmax * 10;
-  const bool last = (st.outer == o.max_outer);
+  const bool last = (st.outer == o.max_outer) || o.a4_no_intermediate;
   const double ctol = last ? o.cost_tol : o.cost_tol_intermediate;
   const double gtol = last ? o.grad_tol : o.grad_tol_intermediate;
   st.phase = PH_BACKWARD;
@@ -781,8 +783,10 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
     bound_c(o, xu_c + (long long)k * 10 + 7, c6);
     double* lam = w.lam + (long long)k * 6;
     for (int i = 0; i < 6; ++i) {
-      double l = lam[i] + st.mu * c6[i];
+      const double l0 = lam[i];
+      double l = l0 + st.mu * c6[i];
       l = fmin(fmax(l, -o.dual_max), o.dual_max);
+      if (o.a5_dual_active_only && !((o.a2_active_ge ? (c6[i] >= 0.0) : (c6[i] > 0.0)) || (l0 > 0.0))) l = l0;
       lam[i] = fmax(0.0, l);
     }
   }
@@ -792,7 +796,9 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
     const double l = st.lam_g[i] + st.mu * e;
     st.lam_g[i] = fmin(fmax(l, -o.dual_max), o.dual_max);
   }
-  st.mu = fmin(st.mu * o.penalty_scaling, o.penalty_max);
+  if (!o.a6_penalty_conditional || st.c_max > o.constraint_decrease_ratio * st.c_max_prev)
+    st.mu = fmin(st.mu * o.penalty_scaling, o.penalty_max);
+  st.c_max_prev = st.c_max;
   tm.sync();
   if (st.c_max < o.constraint_tol) {
     st.status = ST_CONVERGED;
@@ -806,7 +812,8 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
     st.rho = 0.0;
     st.drho = 0.0;
     double cm;
-    st.J_prev = trajectory_cost(tm, in, o, w, xu_c, sc, st.mu, st.lam_g, cm);
+    const double Jnew = trajectory_cost(tm, in, o, w, xu_c, sc, st.mu, st.lam_g, cm);
+    st.J_prev = o.a7_carry_cost ? st.J : Jnew;
   }
 }
 
@@ -814,7 +821,6 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
 template <class Team>
 TS_FN void solve_backward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, const TrialWork& w, TrialState& st) {
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
-  const long long bstride = w.Nmax * 10;
   ++st.it;
   ++st.inner_total;
   const long long t0 = ts_clock();
@@ -841,7 +847,6 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   const int lane = tm.lane();
   const int N = in.N;
   const double sc = o.stage_cost_dt ? in.dt : 1.0;
-  const long long bstride = w.Nmax * 10;
   const long long t0 = ts_clock();
   const double* xu_cur = xu_buf<Team::W>(w, st.cur);
   const int n_cand = o.max_linesearch + 1;
@@ -895,9 +900,16 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
       g += mxg;
     }
-  const double grad = tm.sum(g) / (double)(N - 1);
+  const double grad = tm.sum(g) / (double)(o.a3_grad_over_N ? N : N - 1);
   st.cyc_fwd += ts_clock() - t0;
-  solve_after_forward(tm, in, o, w, st, st.J_prev, grad);
+  // the kept trajectory's cost: J_prev in the default reading; under A7 J_prev may still be the carried-over value, so
+  // the cost under the current multipliers is evaluated like the oracle does (al_cost of the unchanged trajectory)
+  double Jkeep = st.J_prev;
+  if (o.a7_carry_cost) {
+    double cm;
+    Jkeep = trajectory_cost(tm, in, o, w, xu_cur, sc, st.mu, st.lam_g, cm);
+  }
+  solve_after_forward(tm, in, o, w, st, Jkeep, grad);
 }
 
 TS_HD void solve_finish(const TrialIn& in, const TrialState& st, ts_trial_outcome_dev& out) {
@@ -908,10 +920,15 @@ TS_HD void solve_finish(const TrialIn& in, const TrialState& st, ts_trial_outcom
   out.N = in.N;
   out.J = st.J;
   out.c_max = st.c_max;
-  // diagnostics of the low-level solve (SM cycles): backward pass, forward pass, linearisation share
-  out.t_final = (double)st.cyc_bwd;
-  out.slew_time = (double)st.cyc_fwd;
-  out.flops = (double)st.cyc_lin;
+  out.t_final = 0.0;    // filled by the fused Monte-Carlo path; the low-level solve has no field pass / replay
+  out.slew_time = 0.0;
+  out.flops = 0.0;
+}
+// per-trial SM-cycle diagnostics (ts_k3_last_cycles): backward pass, forward pass, linearisation share of the backward pass
+TS_HD void solve_diag(const TrialState& st, double* diag3) {
+  diag3[0] = (double)st.cyc_bwd;
+  diag3[1] = (double)st.cyc_fwd;
+  diag3[2] = (double)st.cyc_lin;
 }
 
 // The whole solve as one loop over phases (persistent-kernel mode and the host lane-emulator).

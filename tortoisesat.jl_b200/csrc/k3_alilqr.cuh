@@ -134,10 +134,21 @@ struct K3Args {
   double* U;             // ragged (N-1) x 3 at offs*3
   double* K;             // nullable, ragged (N-1) x 3 x 8 at offs*24
   ts_trial_outcome_dev* out;
-  // work arena: one contiguous block per team slot [xu 9x | kd | lam | bk | clk] (2 MB pages: ~2 per trial)
+  double* diag;          // nullable; 3 per trial: SM cycles in the backward pass, the forward pass, the linearisation
+  // work arena of the first launch: one contiguous block per team slot [xu 9x | kd | lam | bk | clk], RAGGED by warp:
+  // warp w starts with the w-th group of four of the horizon-sorted queue and only ever pulls shorter trials later,
+  // so its four slots are sized for that first group (warp_cap[w] knots, even) and start at w_base + warp_off[w].
+  // A single long-horizon outlier therefore costs one warp's worth of memory, not (slots x its horizon).
   double* w_base;
-  int64_t per_slot;  // doubles per slot (even)
-  int64_t Nmax;      // padded to even
+  const long long* warp_off;  // [warps] doubles
+  const int* warp_cap;        // [warps] knots (even)
+  int64_t n_warps;            // warps of the first launch (the dynamic queue starts behind their static first groups)
+  int64_t Nmax;               // longest horizon of the ensemble, padded to even
+  // region pool of the second launch: a wide warp takes 261 x N doubles per trial ([22 buffers x 10 | kd 24 | lam 6 |
+  // bk 10 | clk 1] x N), bump-allocated, and keeps its region for later trials that fit
+  double* pool;
+  unsigned long long* pool_used;  // doubles handed out
+  long long pool_cap;             // doubles
   unsigned long long* queue;
   int tail_share; // 1: finished siblings lend lanes + buffers to the line search of the group's last trial
   // straggler hand-over (k3_wide_kernel): once the queue is empty, a trial that has used its allowance of
@@ -196,7 +207,8 @@ __device__ __forceinline__ const TrialIn& k3_load_trial(const Team& tm, const K3
 // Writes a finished trial's results in the reference's shapes: X (N x 8 incl. clock), U, K (3 x 8 per knot).
 template <class Team>
 __device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a, int64_t t, const TrialWork& w, int N, int cur,
-                                                 const ts_trial_outcome_dev& oc) {
+                                                 const ts_trial_outcome_dev& oc, const TrialState& st) {
+  if (tm.ln == 0 && a.diag) solve_diag(st, a.diag + t * 3);
   const double* xu = xu_buf<Team::W>(w, cur);
   double* Xo = a.X + a.offs[t] * 8;
   double* Uo = a.U + a.offs[t] * 3;
@@ -223,6 +235,9 @@ __device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a
 }
 
 constexpr int K3_WARPS_PER_BLOCK = 1;
+constexpr int K3_SLOT_DOUBLES_PER_KNOT = 90 + 24 + 6 + 10 + 1;      // narrow team slot: 9 buffers x 10 | kd | lam | bk | clk
+constexpr int K3_WIDE_BUFFERS = 22;                                 // current trajectory + up to 21 line-search candidates
+constexpr int K3_WIDE_DOUBLES_PER_KNOT = K3_WIDE_BUFFERS * 10 + 24 + 6 + 10 + 1;
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
 // index of the n-th set bit (n = 0, 1, ...) of a 4-bit mask
@@ -254,19 +269,29 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
   tm.shift = team * 8;
   tm.mask = 0xffu << tm.shift;
   tm.sm = warp_smem + team * TEAM_SMEM_DOUBLES;
+  (void)slot;
   TrialWork w;
-  w.Nmax = a.Nmax;
-  w.xu = a.w_base + slot * a.per_slot;
-  w.xu_warp = a.w_base + (gwarp * 4) * a.per_slot;
-  w.slot_stride = a.per_slot;
-  w.kd = w.xu + 90 * a.Nmax;
-  w.lam = w.kd + 24 * a.Nmax;
-  w.bk = w.lam + 6 * a.Nmax;
-  w.clk = w.bk + 10 * a.Nmax;
+  const long long cap = a.warp_cap[gwarp];          // knots every slot of this warp can hold
+  const long long per_slot = cap * K3_SLOT_DOUBLES_PER_KNOT;
+  double* const warp_base = a.w_base + a.warp_off[gwarp];
+  w.Nmax = cap;
+  w.xu = warp_base + team * per_slot;
+  w.xu_warp = warp_base;
+  w.slot_stride = per_slot;
+  w.kd = w.xu + 90 * cap;
+  w.lam = w.kd + 24 * cap;
+  w.bk = w.lam + 6 * cap;
+  w.clk = w.bk + 10 * cap;
+  bool first_pull = true;
   for (;;) {
     unsigned long long base = 0;
-    if (lane32 == 0) base = atomicAdd(a.queue, 4ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    if (first_pull) {
+      base = (unsigned long long)gwarp * 4ull;        // static first group: the one this warp's slots were sized for
+      first_pull = false;
+    } else {
+      if (lane32 == 0) base = atomicAdd(a.queue, 4ull);   // a.queue starts at 4 * n_warps
+      base = __shfl_sync(0xffffffffu, base, 0);
+    }
     if ((int64_t)base >= a.n_trials) break;
     const int64_t qi = (int64_t)base + team;
     const bool have = qi < a.n_trials;
@@ -286,7 +311,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
       if (!stored && st.phase == PH_DONE) {  // finished: write results now, so the slot's buffers can be lent out
         ts_trial_outcome_dev oc;
         solve_finish(*inp, st, oc);
-        k3_store_results(tm, a, t, w, inp->N, st.cur, oc);
+        k3_store_results(tm, a, t, w, inp->N, st.cur, oc, st);
         stored = true;
       }
       // straggler hand-over: nothing left in the queue and this trial is past its iteration allowance -> park it
@@ -371,11 +396,11 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
         const TrialIn* in_w = reinterpret_cast<const TrialIn*>(warp_smem + wt * TEAM_SMEM_DOUBLES + SM_TRIAL);
         __builtin_assume(__isShared(in_w));
         TrialWork ww = w;   // gains / multipliers / field vectors of the trial being rolled out
-        ww.xu = a.w_base + (gwarp * 4 + wt) * a.per_slot;
-        ww.kd = ww.xu + 90 * a.Nmax;
-        ww.lam = ww.kd + 24 * a.Nmax;
-        ww.bk = ww.lam + 6 * a.Nmax;
-        ww.clk = ww.bk + 10 * a.Nmax;
+        ww.xu = warp_base + wt * per_slot;
+        ww.kd = ww.xu + 90 * cap;
+        ww.lam = ww.kd + 24 * cap;
+        ww.bk = ww.lam + 6 * cap;
+        ww.clk = ww.bk + 10 * cap;
         const int n_cand = a.opts.max_linesearch + 1;
         const int c = b0_w + 8 * part + tm.ln;
         const bool live = fwd_w && (c < n_cand);
@@ -458,8 +483,13 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
                 for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
                 g += mxg;
               }
-              const double gr = tm.sum(g) / (double)(inp->N - 1);
-              solve_after_forward(tm, *inp, a.opts, w, st, st.J_prev, gr);
+              const double gr = tm.sum(g) / (double)(a.opts.a3_grad_over_N ? inp->N : inp->N - 1);
+              double Jkeep = st.J_prev;
+              if (a.opts.a7_carry_cost) {  // see solve_forward: under A7 J_prev may be the carried-over value
+                double cm;
+                Jkeep = trajectory_cost(tm, *inp, a.opts, w, xc, sc, st.mu, st.lam_g, cm);
+              }
+              solve_after_forward(tm, *inp, a.opts, w, st, Jkeep, gr);
             }
           }
         }
@@ -517,15 +547,12 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
   GpuWideTeam tm;
   tm.ln = lane32;
   tm.sm = k3_smem;
+  (void)gwarp;
   TrialWork w;
-  w.Nmax = a.Nmax;
-  w.xu = a.w_base + (gwarp * 4) * a.per_slot;   // the warp's four slots = 36 trajectory buffers, 33 used
-  w.xu_warp = w.xu;
-  w.slot_stride = a.per_slot;
-  w.kd = w.xu + 90 * a.Nmax;
-  w.lam = w.kd + 24 * a.Nmax;
-  w.bk = w.lam + 6 * a.Nmax;
-  w.clk = w.bk + 10 * a.Nmax;
+  w.Nmax = 0;
+  w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
+  w.slot_stride = 0;
+  long long region_cap = 0;   // knots the warp's current region can hold
   unsigned n_parked = *a.park_count;
   if (n_parked > (unsigned)a.park_cap) n_parked = (unsigned)a.park_cap;
   for (;;) {
@@ -538,6 +565,29 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
     const TrialIn& in = k3_load_trial(tm, a, t);
     const int N = in.N;
     const long long Ne = N + (N & 1);
+    if (Ne > region_cap) {  // first trial of this warp, or one longer than its region: take a new region from the pool
+      unsigned long long off = 0;
+      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * K3_WIDE_DOUBLES_PER_KNOT));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if ((long long)(off + Ne * K3_WIDE_DOUBLES_PER_KNOT) > a.pool_cap) {
+        // cannot happen: the host sizes the pool for the park_cap longest horizons; fail loudly rather than corrupt
+        if (lane32 == 0) {
+          ts_trial_outcome_dev oc = {};
+          oc.status = ST_NAN;
+          oc.N = N;
+          a.out[t] = oc;
+        }
+        continue;
+      }
+      region_cap = Ne;
+      w.Nmax = Ne;                                   // buffer i of the warp = xu_warp + i * Ne * 10 (see xu_buf)
+      w.slot_stride = 9 * Ne * 10;
+      w.xu = w.xu_warp = a.pool + off;
+      w.kd = w.xu + (long long)K3_WIDE_BUFFERS * 10 * Ne;
+      w.lam = w.kd + 24 * Ne;
+      w.bk = w.lam + 6 * Ne;
+      w.clk = w.bk + 10 * Ne;
+    }
     const double* pd = a.park_data + a.park_off[idx];
     for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];
     for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * Ne + i];
@@ -552,185 +602,10 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
     }
     ts_trial_outcome_dev oc;
     solve_finish(in, st, oc);
-    k3_store_results(tm, a, t, w, N, st.cur, oc);
+    k3_store_results(tm, a, t, w, N, st.cur, oc, st);
     __syncwarp();
   }
 }
 constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
-
-// ---------------------------------------------------------------------------------------------
-// Iteration-queue mode: ONE persistent launch, one warp per SM-resident slot, every warp a 32-lane team.
-// The unit of scheduling is one iLQR ITERATION of one trial: a warp pops a trial from a FIFO queue, runs one
-// iteration (backward sweep + one 21-candidate forward batch), and pushes the trial back unless it is finished.
-// All trials therefore advance at the same rate (processor sharing), the stragglers end up alone on their warps
-// exactly when there are fewer active trials than warps, and nothing has to be predicted or handed over.
-// Opt-in (TS_K3_MODE=queue).  It beat the two-launch scheme above on multi-wave ensembles (8192 slews: 15.6 s vs
-// 16.7 s) until that scheme learned to park long trials while its queue still has work (14.5 s); for a single wave
-// the 4-trials-per-warp kernel's higher throughput wins anyway (4096 slews: 9.05 s vs 8.15 s).
-//   * queue: array that never wraps (a trial is pushed at most once per inner iteration), head/tail counters;
-//     a warp that finds it empty EXITS: then every active trial is held by another live warp, and since the number
-//     of active trials only falls, live warps >= active trials stays true -- there is no waiting anywhere except
-//     the few instructions between a producer's slot reservation and its store.
-//   * buffers: a trial owns the ONE trajectory buffer that holds its current trajectory, a warp owns 32 candidate
-//     buffers; when a candidate is accepted the trial takes that buffer and the warp keeps the trial's old one
-//     (a pointer swap -- no copy).  Multipliers, stage field vectors and clock live per trial, gains per warp.
-//   * visibility between warps: writer __syncwarp + __threadfence before publishing the queue slot; reader
-//     __threadfence after popping (invalidates the SM's L1, which may hold the trial's lines from an earlier visit).
-constexpr int K3Q_INIT_BIT = 1 << 30;
-struct K3QArgs {
-  K3Args a;
-  double* pool;             // (n_trials + 32 * warps) trajectory buffers of buf_stride doubles
-  int64_t buf_stride;       // Nmax * 10
-  double* trial_arr;        // per trial: multipliers 6 Nmax | stage fields 10 Nmax | clock Nmax
-  double* kd_warp;          // per warp: 24 Nmax
-  TrialState* states;       // per trial
-  double** cur_ptr;         // per trial: its current trajectory buffer
-  int* queue;               // entries: trial + 1 (| K3Q_INIT_BIT for the first visit); 0 = not written yet
-  unsigned* head;
-  unsigned* tail;
-};
-constexpr int K3Q_SMEM_BYTES = (SmL<32>::TOTAL + 40) * 8;
-
-__global__ void __launch_bounds__(32, 1) k3_queue_kernel(const K3QArgs q) {
-  extern __shared__ __align__(16) double k3_smem[];
-  const K3Args& a = q.a;
-  const int lane32 = threadIdx.x & 31;
-  const int64_t gwarp = blockIdx.x;
-  GpuWideTeam tm;
-  tm.ln = lane32;
-  tm.sm = k3_smem;
-  double** tab = reinterpret_cast<double**>(k3_smem + SmL<32>::TOTAL);
-  tab[1 + lane32] = q.pool + ((int64_t)a.n_trials + gwarp * 32 + lane32) * q.buf_stride;
-  if (lane32 == 0) tab[0] = nullptr;
-  __syncwarp();
-  TrialWork w;
-  w.Nmax = a.Nmax;
-  w.xu_warp = nullptr;
-  w.slot_stride = 0;
-  w.kd = q.kd_warp + gwarp * 24 * a.Nmax;
-  w.tab = tab;
-  for (;;) {
-    int item = 0;
-    if (lane32 == 0) {
-      for (;;) {
-        const unsigned h = *(volatile unsigned*)q.head;
-        const unsigned t = *(volatile unsigned*)q.tail;
-        if (h >= t) break;                                   // empty: every active trial is in another warp's hands
-        if (atomicCAS(q.head, h, h + 1u) == h) {
-          while ((item = *(volatile int*)(q.queue + h)) == 0) {}   // producer is between its reservation and its store
-          break;
-        }
-      }
-      __threadfence();
-    }
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item == 0) break;
-    const bool first = (item & K3Q_INIT_BIT) != 0;
-    const int64_t t = (int64_t)((item & ~K3Q_INIT_BIT) - 1);
-    const TrialIn& in = k3_load_trial(tm, a, t);
-    w.lam = q.trial_arr + t * 17 * a.Nmax;
-    w.bk = w.lam + 6 * a.Nmax;
-    w.clk = w.bk + 10 * a.Nmax;
-    TrialState st;
-    if (lane32 == 0) tab[0] = first ? q.pool + t * q.buf_stride : q.cur_ptr[t];
-    __syncwarp();
-    w.xu = tab[0];
-    if (first) {
-      solve_init(tm, in, a.opts, w, st);
-    } else {
-      st = q.states[t];
-    }
-    if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
-    while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
-    __syncwarp();
-    if (st.cur != 0) {   // the accepted candidate's buffer goes with the trial, the warp keeps the old current one
-      if (lane32 == 0) {
-        double* nb = tab[st.cur];
-        tab[st.cur] = tab[0];
-        tab[0] = nb;
-      }
-      st.cur = 0;
-      __syncwarp();
-    }
-    if (st.phase == PH_DONE) {
-      ts_trial_outcome_dev oc;
-      solve_finish(in, st, oc);
-      k3_store_results(tm, a, t, w, in.N, 0, oc);
-    } else {
-      if (lane32 == 0) {
-        q.states[t] = st;
-        q.cur_ptr[t] = tab[0];
-      }
-      __syncwarp();
-      if (lane32 == 0) {
-        __threadfence();
-        const unsigned pos = atomicAdd(q.tail, 1u);
-        *(volatile int*)(q.queue + pos) = (int)(t + 1);
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Phase-split launch mode: the same solver phases as separate kernels, driven in lockstep by the
-// host (init, then rounds of [backward, forward x3] until every trial is done, then finish).
-// All resident warps of a launch execute the same phase -> one hot loop in the instruction cache
-// and a per-kernel register allocation; finished trials release their SM slots immediately.
-// One work slot per trial (slot = queue index).  Used when the ensemble has (nearly) uniform
-// horizons; ragged ensembles use the persistent kernel above.
-enum { K3P_INIT = 10, K3P_FINISH = 11 };
-
-__device__ __forceinline__ void k3_team_setup(const K3Args& a, GpuTeam& tm, TrialWork& w, int64_t& qi, double* smem) {
-  const int lane32 = threadIdx.x & 31;
-  const int team = lane32 >> 3;
-  qi = (int64_t)blockIdx.x * 4 + team;
-  tm.ln = lane32 & 7;
-  tm.shift = team * 8;
-  tm.mask = 0xffu << tm.shift;
-  tm.sm = smem + team * TEAM_SMEM_DOUBLES;
-  w.Nmax = a.Nmax;
-  w.xu = a.w_base + qi * a.per_slot;
-  w.xu_warp = w.xu;
-  w.slot_stride = a.per_slot;
-  w.kd = w.xu + 90 * a.Nmax;
-  w.lam = w.kd + 24 * a.Nmax;
-  w.bk = w.lam + 6 * a.Nmax;
-  w.clk = w.bk + 10 * a.Nmax;
-}
-
-template <int PHASE>
-__global__ void __launch_bounds__(32, 1) k3_phase_kernel(const K3Args a, TrialState* __restrict__ states, int* __restrict__ n_active) {
-  extern __shared__ __align__(16) double k3_smem[];
-  GpuTeam tm;
-  TrialWork w;
-  int64_t qi;
-  k3_team_setup(a, tm, w, qi, k3_smem);
-  if (qi >= a.n_trials) return;
-  TrialState st;
-  if (PHASE != K3P_INIT) {
-    st = states[qi];
-    if (PHASE == PH_BACKWARD && st.phase != PH_BACKWARD) return;
-    if (PHASE == PH_FORWARD && st.phase != PH_FORWARD) return;
-  }
-  const int64_t t = a.order ? a.order[qi] : qi;
-  const TrialIn& in = k3_load_trial(tm, a, t);
-  if (PHASE == K3P_INIT) solve_init(tm, in, a.opts, w, st);
-  if (PHASE == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
-  if (PHASE == PH_FORWARD) {
-    solve_forward(tm, in, a.opts, w, st);
-    if (st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
-  }
-  if (PHASE == PH_BACKWARD && st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
-  if (PHASE == K3P_INIT && st.phase == PH_DONE && tm.ln == 0) atomicSub(n_active, 1);
-  if (PHASE == K3P_FINISH) {
-    ts_trial_outcome_dev oc;
-    solve_finish(in, st, oc);
-    k3_store_results(tm, a, t, w, in.N, st.cur, oc);
-    return;
-  }
-  tm.sync();
-  if (tm.ln == 0) states[qi] = st;
-}
 
 }  // namespace ts

@@ -78,6 +78,7 @@ struct PrepArgs {
   const double* Jmat;     // 9
   const double* t_final;  // per trial
   double t0, dt, alpha, beta;
+  int conj_fix;           // 0: the reference's literal qmult(q_f, q_0) (eigen_axis_slew.jl:16); 1: conj(q_f) (x) q_0
   double* Qd;             // 8 per trial
   double* Qfd;
   double* Rd;             // 3
@@ -94,7 +95,10 @@ __global__ void __launch_bounds__(128) k_slew_prep(const PrepArgs a) {
   const double* xf = a.xf + t * 8;
   const double* J = a.Jmat + t * 9;
   const double q1[4] = {x0[3], x0[4], x0[5], x0[6]};
-  const double q2c[4] = {xf[3], -xf[4], -xf[5], -xf[6]};
+  // eigen_axis_slew.jl:16 passes the 7-vector [q2; -q2[2:4]] to qmult, which reads entries 1 and 2:4 only: the literal
+  // error quaternion is qmult(q2, q1), NOT conj(q2) (x) q1.  Reproduced by default; conj_fix = 1 is the evident intent.
+  const double sg = a.conj_fix ? -1.0 : 1.0;
+  const double q2c[4] = {xf[3], sg * xf[4], sg * xf[5], sg * xf[6]};
   double qe[4];
   qmult(q2c, q1, qe);
   const double theta_f = 2 * acos(qe[0]);

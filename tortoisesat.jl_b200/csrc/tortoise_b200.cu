@@ -8,6 +8,7 @@
 #include "k3_alilqr.cuh"
 #include "k4_tvlqr.cuh"
 #include "k5_unitops.cuh"
+#include "k6_igrf12syn.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -80,12 +81,13 @@ int ts_create(ts_ctx** out, int device_id) {
       cudaEventCreate(&c->ev_k3[0]) != cudaSuccess || cudaEventCreate(&c->ev_k3[1]) != cudaSuccess ||
       cudaEventCreate(&c->ev_k3[2]) != cudaSuccess ||
       cudaMalloc(&c->d_tabG, sizeof(TS_IGRF12_G)) != cudaSuccess || cudaMalloc(&c->d_tabH, sizeof(TS_IGRF12_H)) != cudaSuccess ||
-      cudaMalloc(&c->d_flag, 64) != cudaSuccess) {
+      cudaMalloc(&c->d_tabGH, sizeof(TS_IGRF12_GH)) != cudaSuccess || cudaMalloc(&c->d_flag, 64) != cudaSuccess) {
     ts_destroy(c);
     return TS_ERR_CUDA;
   }
   cudaMemcpy(c->d_tabG, TS_IGRF12_G, sizeof(TS_IGRF12_G), cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_tabH, TS_IGRF12_H, sizeof(TS_IGRF12_H), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_tabGH, TS_IGRF12_GH, sizeof(TS_IGRF12_GH), cudaMemcpyHostToDevice);
   IgrfConsts h;
   igrf_host_constants(h);
   if (cudaMemcpyToSymbol(c_igrf, &h, sizeof(h)) != cudaSuccess) {
@@ -100,10 +102,11 @@ int ts_create(ts_ctx** out, int device_id) {
 void ts_destroy(ts_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 20; ++i)
+  for (int i = 0; i < 32; ++i)
     if (c->scratch[i]) cudaFree(c->scratch[i]);
   if (c->d_tabG) cudaFree(c->d_tabG);
   if (c->d_tabH) cudaFree(c->d_tabH);
+  if (c->d_tabGH) cudaFree(c->d_tabGH);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -134,7 +137,17 @@ int ts_k3_last_split(ts_ctx* c, double* persistent_ms, double* straggler_ms, int
   if (c->d_k3_parked) TS_CUDA(c, cudaMemcpy(&np, c->d_k3_parked, sizeof(np), cudaMemcpyDeviceToHost));
   if (persistent_ms) *persistent_ms = a;
   if (straggler_ms) *straggler_ms = b;
+  if (np > (unsigned)c->k3_park_cap) np = (unsigned)c->k3_park_cap;   // the device counter may overshoot the parking places
   if (n_parked) *n_parked = (int64_t)np;
+  return TS_OK;
+}
+
+int ts_k3_last_cycles(ts_ctx* c, int64_t n_trials, double* cycles3) {
+  if (!c || !cycles3 || n_trials < 0) return TS_ERR_ARG;
+  if (n_trials > c->k3_diag_n || !c->scratch[19]) return fail(c, TS_ERR_ARG, "ts_k3_last_cycles: the last solve covered %lld trials", (long long)c->k3_diag_n);
+  TS_CUDA(c, cudaSetDevice(c->device));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  TS_CUDA(c, cudaMemcpy(cycles3, c->scratch[19], (size_t)n_trials * 3 * sizeof(double), cudaMemcpyDeviceToHost));
   return TS_OK;
 }
 
@@ -263,6 +276,35 @@ int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const 
   TS_CUDA(c, cudaStreamSynchronize(c->stream));
   t.read();
   if (bad) return fail(c, TS_ERR_DOMAIN, "The latitude must be between -pi/2 and +pi/2 rad and the longitude between -pi and +pi rad.");
+  return TS_OK;
+}
+
+// igrf12syn(isv,date,itype,alt,colat,elong) [src/igrf.jl:335-534] at n points
+int ts_igrf12syn_batch(ts_ctx* c, int isv, double date, int itype, int64_t n, const double* alt_km, const double* colat_deg,
+                       const double* elong_deg, double* x, double* y, double* z, double* f, int pad) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!alt_km || !colat_deg || !elong_deg || !x || !y || !z || !f))) return fail(c, TS_ERR_ARG, "ts_igrf12syn_batch: null array or n<0");
+  if (isv != 0 && isv != 1) return fail(c, TS_ERR_ARG, "ts_igrf12syn_batch: isv must be 0 or 1");
+  if (itype != 1 && itype != 2) return fail(c, TS_ERR_ARG, "ts_igrf12syn_batch: itype must be 1 (geodetic) or 2 (geocentric)");
+  if (!(date >= 1900.0 && date <= 2025.0))
+    return fail(c, TS_ERR_DATE, "This IGRF version will not work for years outside the interval [1900, 2025).");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  int rc;
+  DevBuf da, dc, de, ox, oy, oz, of;
+  const size_t b = (size_t)n * sizeof(double);
+  if ((rc = dev_in(c, da, alt_km, b, pad)) || (rc = dev_in(c, dc, colat_deg, b, pad)) || (rc = dev_in(c, de, elong_deg, b, pad))) return rc;
+  if ((rc = dev_out(c, ox, x, b, pad)) || (rc = dev_out(c, oy, y, b, pad)) || (rc = dev_out(c, oz, z, b, pad)) || (rc = dev_out(c, of, f, b, pad))) return rc;
+  const SynEpoch ep = igrf12syn_epoch(isv, date);
+  KernelTimer tm(c);
+  k6_igrf12syn<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->d_tabGH, ep, itype, n, (const double*)da.d, (const double*)dc.d,
+                                                                   (const double*)de.d, (double*)ox.d, (double*)oy.d, (double*)oz.d, (double*)of.d);
+  tm.stop();
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  if ((rc = dev_back(c, ox, x, b)) || (rc = dev_back(c, oy, y, b)) || (rc = dev_back(c, oz, z, b)) || (rc = dev_back(c, of, f, b))) return rc;
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  tm.read();
   return TS_OK;
 }
 
@@ -424,6 +466,9 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->ls_lower = 1e-8; o->ls_upper = 10.0; o->bp_reg_increase = 1.6; o->bp_reg_max = 1e8; o->bp_reg_min = 1e-8;
   o->bp_reg_fp = 10.0; o->max_cost_value = 1e8; o->max_state_value = 1e8; o->max_control_value = 1e8;
   o->u_max = 1.0; o->u_min = -1.0;
+  o->a2_active_ge = 0; o->a3_grad_over_N = 0; o->a4_no_intermediate = 0; o->a5_dual_active_only = 0;
+  o->a6_penalty_conditional = 0; o->a7_carry_cost = 0; o->constraint_decrease_ratio = 0.25;
+  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0;
 }
 
 // slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
@@ -434,44 +479,20 @@ static double slew_angle(const double* x0, const double* xf) {
   return 2.0 * acos(c > 1.0 ? 1.0 : c);
 }
 
-// Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted).
-// Three launch schemes over the same solver code (ilqr_solver.cuh), see k3_alilqr.cuh:
-//   teams   k3_alilqr_kernel (warps pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel
-//           (stragglers handed over to one warp each); the default
-//   queue   k3_queue_kernel: one launch, 32-lane warps, one trial-ITERATION per work item; opt-in
-//   phased  host-driven lockstep of per-phase kernels -- a measured, slower alternative, opt-in only
-// TS_K3_MODE=teams|queue|phased overrides the automatic choice.  The work is queued on the context's stream
-// (the phased mode synchronises to poll the active-trial counter; the queue mode once, after its set-up copies).
-// inner iterations a trial may use in the 4-trials-per-warp kernel once the queue is empty (see k3_wide_kernel)
-constexpr int K3_SUSPEND_AFTER_DEFAULT = 150;
-constexpr double K3_EARLY_FACTOR_DEFAULT = 2.0;
+// Launch K3 on device-resident per-trial arrays (a.* device pointers except where noted): k3_alilqr_kernel (warps
+// pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel (stragglers handed over to one warp each).
+// The launch scheme is controlled by ts_ilqr_opts.k3_* (suspend_after, early_factor, tail_share).  Work is queued on
+// the context's stream; nothing here synchronises.
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
   const int64_t n_trials = a.n_trials;
-  int64_t Nmax = 0, Nmin = INT64_MAX;
-  for (int64_t t = 0; t < n_trials; ++t) {
-    Nmax = std::max(Nmax, N_i_host[t]);
-    Nmin = std::min(Nmin, N_i_host[t]);
-  }
-  // measured (profiles/README.md): the phased mode is ~10-25% SLOWER than the persistent kernel on the 4096-trial
-  // ensemble (every round waits for the slowest trial's phase), so it is opt-in only.
-  bool phased = false;
-  int queue_override = -1;   // -1: automatic
-  (void)Nmin;
-  if (const char* m = getenv("TS_K3_MODE")) {
-    if (!strcmp(m, "persistent") || !strcmp(m, "teams")) queue_override = 0;
-    if (!strcmp(m, "phased")) phased = true, queue_override = 0;
-    if (!strcmp(m, "queue")) queue_override = 1;
-  }
+  int64_t Nmax = 0;
+  for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
   int occ = 0;
   TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
   if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
   const int64_t groups = (n_trials + 3) / 4;
   const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
-  const int64_t warps = phased ? groups : std::min(groups, max_warps);
-  // Measured (profiles/README.md): the team kernels win for a single wave (4096 slews: 8.1 s vs 9.05 s) and, since
-  // trials past twice their allowance are parked even while the queue still has work, also for several waves
-  // (8192 slews: 14.5 s vs 15.6 s) -- the iteration queue is opt-in (TS_K3_MODE=queue).
-  const bool queue_mode = queue_override == 1;
+  const int64_t warps = std::min(groups, max_warps);
   const int blocks = (int)((warps + K3_WARPS_PER_BLOCK - 1) / K3_WARPS_PER_BLOCK);
   const int64_t slots = (int64_t)blocks * K3_WARPS_PER_BLOCK * 4;
   // the one-warp-per-trial launch uses four slots (36 trajectory buffers) per warp: up to a full wave of warps,
@@ -479,8 +500,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   int occ_w = 0;
   TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_wide_kernel, 32, K3_WIDE_SMEM_BYTES));
   if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
-  const int64_t wide_warps = std::min<int64_t>(std::min<int64_t>(n_trials, slots), (int64_t)c->sm_count * occ_w);
-  const int64_t arena_slots = std::max<int64_t>(slots, wide_warps * 4);
+  const int64_t wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w);
   // Queue order.  (1) sort by horizon (descending): the four teams of a warp get similar trip counts.
   // (2) within a run of (nearly) equal horizons, sort by slew angle and DEAL the trials round-robin over the
   // groups of four, so each warp gets one trial of every difficulty quartile: the makespan of a single-wave
@@ -511,99 +531,63 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   int rc;
   int64_t* d_order = nullptr;
   if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
-  void *p_work, *p_q;
+  void *p_work, *p_q, *p_diag;
   Nmax += (Nmax & 1);  // even: keeps every per-knot record 16-byte aligned for the asynchronous copies
-  if (queue_mode) {
-    // ---- iteration-queue mode (k3_queue_kernel): one launch, one trial-iteration per work item
-    int occ_q = 0;
-    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k3_queue_kernel, 32, K3Q_SMEM_BYTES));
-    if (occ_q < 1) return fail(c, TS_ERR_CUDA, "k3 queue kernel does not fit on an SM");
-    const int64_t qwarps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_q);
-    const int64_t buf_stride = Nmax * 10;
-    const int64_t items = n_trials * ((int64_t)a.opts.max_outer * a.opts.max_inner + 2);
-    if (items > 0x7ffffff0ll) return fail(c, TS_ERR_ARG, "iteration queue too long (n_trials x max iterations)");
-    const size_t b_pool = (size_t)(n_trials + 32 * qwarps) * (size_t)buf_stride * sizeof(double);
-    const size_t b_trial = (size_t)n_trials * 17 * (size_t)Nmax * sizeof(double);
-    const size_t b_kd = (size_t)qwarps * 24 * (size_t)Nmax * sizeof(double);
-    const size_t b_state = (size_t)n_trials * (sizeof(TrialState) + sizeof(double*));
-    const size_t b_queue = (size_t)items * sizeof(int);
-    void *p_pool, *p_tr, *p_st, *p_qu;
-    if ((rc = scratch_reserve(c, 6, b_pool + 256, &p_pool))) return rc;
-    if ((rc = scratch_reserve(c, 16, b_trial + b_kd + 256, &p_tr))) return rc;
-    if ((rc = scratch_reserve(c, 15, b_state + 64, &p_st))) return rc;
-    if ((rc = scratch_reserve(c, 19, b_queue + 64, &p_qu))) return rc;
-    if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
-    std::vector<int> first((size_t)n_trials);
-    for (int64_t i = 0; i < n_trials; ++i) first[(size_t)i] = (int)(order[(size_t)i] + 1) | K3Q_INIT_BIT;
-    TS_CUDA(c, cudaMemsetAsync(p_qu, 0, b_queue, c->stream));
-    TS_CUDA(c, cudaMemcpyAsync(p_qu, first.data(), (size_t)n_trials * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    unsigned ht[16] = {0};
-    ht[1] = (unsigned)n_trials;   // head = 0, tail = n_trials
-    TS_CUDA(c, cudaMemcpyAsync(p_q, ht, 64, cudaMemcpyHostToDevice, c->stream));
-    TS_CUDA(c, cudaStreamSynchronize(c->stream));   // `first` and `ht` are host temporaries
-    a.order = d_order;
-    a.Nmax = Nmax;
-    a.w_base = nullptr;
-    a.per_slot = 0;
-    a.queue = nullptr;
-    a.tail_share = 0;
-    a.park_budget = 0;
-    a.park_budget_early = 0;
-    a.park_cap = 0;
-    a.park_count = nullptr;
-    a.park_used = nullptr;
-    a.queue2 = nullptr;
-    a.park_state = nullptr;
-    a.park_trial = nullptr;
-    a.park_off = nullptr;
-    a.park_data = nullptr;
-    a.park_data_cap = 0;
-    a.park_order = nullptr;
-    K3QArgs q;
-    q.a = a;
-    q.pool = (double*)p_pool;
-    q.buf_stride = buf_stride;
-    q.trial_arr = (double*)p_tr;
-    q.kd_warp = (double*)((char*)p_tr + b_trial);
-    q.states = (TrialState*)p_st;
-    q.cur_ptr = (double**)((char*)p_st + (size_t)n_trials * sizeof(TrialState));
-    q.queue = (int*)p_qu;
-    q.head = (unsigned*)p_q;
-    q.tail = (unsigned*)p_q + 1;
-    c->k3_timed = true;
-    c->d_k3_parked = nullptr;
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
-    k3_queue_kernel<<<(unsigned)qwarps, 32, K3Q_SMEM_BYTES, c->stream>>>(q);
-    c->launches++;
-    TS_CUDA(c, cudaGetLastError());
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
-    return TS_OK;
+  // ragged arena: warp w's four slots are sized for its static first group (the w-th of the horizon-sorted queue; the
+  // dealing above permutes only inside runs of nearly equal horizons, so the group's maximum is taken explicitly)
+  const int64_t n_warps = (int64_t)blocks * K3_WARPS_PER_BLOCK;
+  std::vector<long long> warp_off((size_t)n_warps);
+  std::vector<int> warp_cap((size_t)n_warps);
+  long long arena = 0;
+  {
+    int64_t later_max = 0;   // longest horizon among the trials pulled dynamically (queue positions >= 4 * n_warps)
+    for (int64_t q = 4 * n_warps; q < n_trials; ++q) later_max = std::max(later_max, N_i_host[order[(size_t)q]]);
+    for (int64_t w = 0; w < n_warps; ++w) {
+      int64_t cap = later_max;
+      for (int64_t q = 4 * w; q < std::min<int64_t>(4 * w + 4, n_trials); ++q) cap = std::max(cap, N_i_host[order[(size_t)q]]);
+      cap = std::max<int64_t>(cap, 2);
+      cap += (cap & 1);
+      warp_off[(size_t)w] = arena;
+      warp_cap[(size_t)w] = (int)cap;
+      arena += 4 * cap * K3_SLOT_DOUBLES_PER_KNOT;
+    }
   }
-  const int64_t per_slot = Nmax * (90 + 24 + 6 + 10 + 1);
-  if ((rc = scratch_reserve(c, 6, (size_t)(per_slot + 1) * sizeof(double) * (size_t)arena_slots + 256, &p_work))) return rc;
-  if ((rc = scratch_reserve(c, 4, 64, &p_q))) return rc;
-  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 64, c->stream));
+  if ((rc = scratch_reserve(c, 6, (size_t)(arena + 2) * sizeof(double) + 256, &p_work))) return rc;
+  long long* d_woff = nullptr;
+  int* d_wcap = nullptr;
+  if ((rc = upload(c, 23, warp_off.data(), (size_t)n_warps, &d_woff))) return rc;
+  if ((rc = upload(c, 24, warp_cap.data(), (size_t)n_warps, &d_wcap))) return rc;
+  if ((rc = scratch_reserve(c, 4, 128, &p_q))) return rc;
+  if ((rc = scratch_reserve(c, 19, (size_t)n_trials * 3 * sizeof(double) + 64, &p_diag))) return rc;
+  {
+    unsigned long long h_q[16] = {0};
+    h_q[0] = (unsigned long long)(4 * n_warps);   // the dynamic queue starts behind the static first groups
+    TS_CUDA(c, cudaMemcpyAsync(p_q, h_q, 128, cudaMemcpyHostToDevice, c->stream));
+  }
+  TS_CUDA(c, cudaMemsetAsync(p_diag, 0, (size_t)n_trials * 3 * sizeof(double), c->stream));
   a.order = d_order;
   a.Nmax = Nmax;
   a.w_base = (double*)p_work;
-  a.per_slot = per_slot + (per_slot & 1);
+  a.warp_off = d_woff;
+  a.warp_cap = d_wcap;
+  a.n_warps = n_warps;
+  a.pool = nullptr;
+  a.pool_used = (unsigned long long*)p_q + 10;
+  a.pool_cap = 0;
   a.queue = (unsigned long long*)p_q;
-  a.tail_share = 1;
-  if (const char* m = getenv("TS_K3_TAIL")) a.tail_share = atoi(m) ? 1 : 0;
+  a.diag = (double*)p_diag;
+  c->k3_diag_n = n_trials;
+  a.tail_share = a.opts.k3_tail_share ? 1 : 0;
   // straggler hand-over (k3_wide_kernel): allowance of the 4-trials-per-warp kernel, in inner iterations of a
   // trial of MEAN horizon; trials are charged in knot-iterations, so a long-horizon trial is handed over sooner
-  int suspend_after = K3_SUSPEND_AFTER_DEFAULT;
-  if (const char* m = getenv("TS_K3_SUSPEND")) suspend_after = std::max(0, atoi(m));
-  if (phased) suspend_after = 0;
+  const int suspend_after = std::max(0, (int)a.opts.k3_suspend_after);
   double N_sum = 0.0;
   for (int64_t t = 0; t < n_trials; ++t) N_sum += (double)N_i_host[t];
   a.park_budget = (long long)((double)suspend_after * N_sum / (double)n_trials);
   if (suspend_after > 0 && a.park_budget < 1) a.park_budget = 1;
-  // multi-wave ensembles: a trial that has used EARLY_FACTOR x the allowance is parked even while fresh trials are
-  // still queued, so that it stops holding its warp's group back (TS_K3_EARLY overrides; 0 = only when drained)
-  double early = K3_EARLY_FACTOR_DEFAULT;
-  if (const char* m = getenv("TS_K3_EARLY")) early = atof(m);
+  // multi-wave ensembles: a trial that has used early_factor x the allowance is parked even while fresh trials are
+  // still queued, so that it stops holding its warp's group back (0 = only once the queue has drained)
+  const double early = a.opts.k3_early_factor;
   a.park_budget_early = early > 0.0 ? (long long)(early * (double)a.park_budget) : (long long)4e18;
   a.park_cap = 0;
   a.park_count = (unsigned*)p_q + 8;
@@ -618,11 +602,26 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   if (suspend_after > 0) {
     // a place for every trial that can be resident when the queue runs dry; array space for the `cap` longest
     // horizons (order[] is sorted by horizon, descending), bounded by 32 GB
-    const int64_t cap = early > 0.0 ? n_trials : std::min<int64_t>(n_trials, slots);
-    double need = 0.0;
-    for (int64_t i = 0; i < cap; ++i) need += 27.0 * (double)(N_i_host[order_by_N[(size_t)i]] + 1);
-    need = std::min(need, 32e9 / 8.0);
-    void *p_ps, *p_pd;
+    int64_t cap = early > 0.0 ? n_trials : std::min<int64_t>(n_trials, slots);
+    // memory of the hand-over: 27 N doubles of parked state per trial + a 261 N region per trial in the worst case
+    // (no region is ever re-used); the parking places are limited to what fits 60% of the free device memory
+    size_t free_b = 0, total_b = 0;
+    TS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    const double budget = 0.6 * (double)(free_b + c->scratch_bytes[16] + c->scratch_bytes[25]) / 8.0;
+    double need = 0.0, pool_need = 0.0;
+    int64_t cap_fit = 0;
+    for (int64_t i = 0; i < cap; ++i) {
+      const double Ne = (double)(N_i_host[order_by_N[(size_t)i]] + 1);
+      if (need + pool_need + (27.0 + K3_WIDE_DOUBLES_PER_KNOT) * Ne > budget) break;
+      need += 27.0 * Ne;
+      pool_need += (double)K3_WIDE_DOUBLES_PER_KNOT * Ne;
+      cap_fit = i + 1;
+    }
+    cap = cap_fit;
+    void *p_ps, *p_pd, *p_pool;
+    if ((rc = scratch_reserve(c, 25, (size_t)pool_need * sizeof(double) + 256, &p_pool))) return rc;
+    a.pool = (double*)p_pool;
+    a.pool_cap = (long long)pool_need;
     if ((rc = scratch_reserve(c, 15, (size_t)cap * (sizeof(TrialState) + 8 + 8 + 4) + 64, &p_ps))) return rc;
     if ((rc = scratch_reserve(c, 16, (size_t)need * sizeof(double) + 64, &p_pd))) return rc;
     a.park_cap = (int)cap;
@@ -633,51 +632,24 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     a.park_data = (double*)p_pd;
     a.park_data_cap = (long long)need;
   }
-  if (!phased) {
-    c->k3_timed = true;
-    c->d_k3_parked = a.park_count;
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
-    k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
-    c->launches++;
-    TS_CUDA(c, cudaGetLastError());
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
-    TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
-    if (a.park_cap > 0) {
-      // one warp per parked trial; the grid cannot depend on the (device-side) count, idle blocks exit at once
-      const int blocks_w = (int)std::min<int64_t>(a.park_cap, wide_warps);
-      k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
-      k3_wide_kernel<<<blocks_w, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
-      c->launches += 2;
-      TS_CUDA(c, cudaGetLastError());
-      TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
-    }
-    return TS_OK;
-  }
-  // ---- phased mode
-  void* p_st;
-  if ((rc = scratch_reserve(c, 15, (size_t)slots * sizeof(TrialState) + 64, &p_st))) return rc;
-  TrialState* d_states = (TrialState*)p_st;
-  int* d_active = (int*)p_q + 4;
-  int h_active = (int)n_trials;
-  TS_CUDA(c, cudaMemcpyAsync(d_active, &h_active, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  const int smem = 4 * TEAM_SMEM_DOUBLES * 8;
-  k3_phase_kernel<K3P_INIT><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
-  c->launches++;
-  const int n_batches = (a.opts.max_linesearch + 1 + TEAM - 1) / TEAM;
-  const long long max_rounds = (long long)a.opts.max_outer * a.opts.max_inner + 8;
-  for (long long round = 0; round < max_rounds; ++round) {
-    k3_phase_kernel<PH_BACKWARD><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
-    for (int b = 0; b < n_batches; ++b) k3_phase_kernel<PH_FORWARD><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
-    c->launches += 1 + n_batches;
-    if ((round & 7) == 7 || round < 2) {
-      TS_CUDA(c, cudaMemcpyAsync(&h_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      TS_CUDA(c, cudaStreamSynchronize(c->stream));
-      if (h_active <= 0) break;
-    }
-  }
-  k3_phase_kernel<K3P_FINISH><<<blocks, 32, smem, c->stream>>>(a, d_states, d_active);
+  c->k3_timed = true;
+  c->d_k3_parked = a.park_count;
+  c->k3_park_cap = a.park_cap;
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
+  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
   c->launches++;
   TS_CUDA(c, cudaGetLastError());
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+  if (a.park_cap > 0) {
+    // one warp per parked trial; the grid cannot depend on the (device-side) count, idle blocks exit at once
+    const int blocks_w = (int)std::max<int64_t>(1, std::min<int64_t>(a.park_cap, wide_warps));
+    k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
+    k3_wide_kernel<<<blocks_w, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
+    c->launches += 2;
+    TS_CUDA(c, cudaGetLastError());
+    TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+  }
   return TS_OK;
 }
 
@@ -768,7 +740,7 @@ void ts_tvlqr_default_opts(ts_tvlqr_opts* o) {
 }
 
 int ts_slew_weights_batch(ts_ctx* c, int64_t n, const double* x0, const double* xf, const double* Jmat, const double* t_final,
-                          double t0, double dt, double alpha, double beta, double* Qd, double* Qfd, double* Rd,
+                          double t0, double dt, double alpha, double beta, int eigen_axis_fix, double* Qd, double* Qfd, double* Rd,
                           const int64_t* goffs, double* w_guess, double* q_guess) {
   if (!c) return TS_ERR_ARG;
   if (n < 0 || (n > 0 && (!x0 || !xf || !Jmat || !t_final || !Qd || !Qfd || !Rd))) return fail(c, TS_ERR_ARG, "ts_slew_weights_batch: null argument");
@@ -795,7 +767,7 @@ int ts_slew_weights_batch(ts_ctx* c, int64_t n, const double* x0, const double* 
   if (q_guess && (rc = scratch_reserve(c, 8, (size_t)total * 4 * 8, &p_q))) return rc;
   PrepArgs a;
   a.n_trials = n; a.x0 = d_f; a.xf = d_f + 8 * T; a.Jmat = d_f + 16 * T; a.t_final = d_f + 25 * T;
-  a.t0 = t0; a.dt = dt; a.alpha = alpha; a.beta = beta;
+  a.t0 = t0; a.dt = dt; a.alpha = alpha; a.beta = beta; a.conj_fix = eigen_axis_fix ? 1 : 0;
   a.Qd = (double*)p_o; a.Qfd = a.Qd + 8 * T; a.Rd = a.Qd + 16 * T;
   a.goffs = d_g; a.w_guess = (double*)p_w; a.q_guess = (double*)p_q;
   KernelTimer tm(c);
@@ -909,9 +881,10 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
   const int64_t nf = cfg->shared_orbit ? 1 : n;
   const size_t NF = (size_t)nf;
   int rc;
-  cudaEvent_t e[6];
-  for (int i = 0; i < 6; ++i) cudaEventCreate(&e[i]);
-  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]); } } evg{e};
+  cudaEvent_t e[7];
+  for (int i = 0; i < 7; ++i) cudaEventCreate(&e[i]);
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 7; ++i) cudaEventDestroy(e[i]); } } evg{e};
+  c->mc_last.valid = false;
 
   // ---- stage 1: scoping pass (2*N_scope samples per orbit) + gramian cutoff
   std::vector<ts_field_opts> fo(NF);
@@ -952,6 +925,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
   }
   k2c_gramian_cutoff<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, (double*)p_Bs, d_offs_s, d_rows_s, d_dts, d_cuts, nullptr, d_idx);
   c->launches++;
+  cudaEventRecord(e[6], c->stream);   // end of the scoping stage on the device (the host sync below is not device time)
   TS_CUDA(c, cudaGetLastError());
   std::vector<int64_t> idx(NF);
   TS_CUDA(c, cudaMemcpyAsync(idx.data(), d_idx, NF * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1028,9 +1002,13 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
       if (q_noise0) {
         const double* qn = q_noise0 + 3 * t;
         const double th = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2]);
-        const double sh = sin(th / 2);
-        const double qp[4] = {cos(th / 2), qn[0] / th * sh, qn[1] / th * sh, qn[2] / th * sh};
-        ts::qmult(q0, qp, xl + 3);
+        if (th > 1e-300) {
+          const double sh = sin(th / 2);
+          const double qp[4] = {cos(th / 2), qn[0] / th * sh, qn[1] / th * sh, qn[2] / th * sh};
+          ts::qmult(q0, qp, xl + 3);
+        } else {  // a zero row = "no initial perturbation" (the reference's r_noise = q_noise/0 would be NaN)
+          for (int i = 0; i < 4; ++i) xl[3 + i] = q0[i];
+        }
       } else {
         for (int i = 0; i < 4; ++i) xl[3 + i] = q0[i];
       }
@@ -1045,7 +1023,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     const size_t b_B = (size_t)offs_f[nf] * 3 * 8, b_w = 19 * NA * 8, b_X = (size_t)knots * 8 * 8, b_U = (size_t)knots * 3 * 8,
                  b_o = NA * sizeof(ts_trial_outcome), b_s = NA * 16;
     void* p_blk;
-    if ((rc = scratch_reserve(c, 8, b_B + b_w + b_X + b_U + b_o + b_s + 512, &p_blk))) return rc;
+    if ((rc = scratch_reserve(c, 22, b_B + b_w + b_X + b_U + b_o + b_s + 512, &p_blk))) return rc;   // slot 22: only this path uses it (kept trajectories)
     char* w = (char*)p_blk;
     double* d_Bf = (double*)w; w += b_B;
     double* d_Qd = (double*)w; w += b_w;
@@ -1053,7 +1031,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     double* d_U = (double*)w; w += b_U;
     ts_trial_outcome_dev* d_out = (ts_trial_outcome_dev*)w; w += b_o;
     int64_t* d_nsim = (int64_t*)w; double* d_slew = (double*)(w + NA * 8);
-    cudaEventRecord(e[1], c->stream);  // (stage-1 time = e0..sync above; fine pass added below)
+    cudaEventRecord(e[1], c->stream);  // fine pass starts
     k2a_orbit_euler<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, d_kep, d_fo2, d_offs_f, d_lim, (double*)p_pos2, nullptr);
     c->launches++;
     {
@@ -1067,7 +1045,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     // ---- stage 3: eigen-axis guess + Bryson weights
     PrepArgs pa;
     pa.n_trials = na; pa.x0 = d_f; pa.xf = d_f + 8 * NA; pa.Jmat = d_f + 16 * NA; pa.t_final = d_f + 25 * NA;
-    pa.t0 = cfg->t0; pa.dt = cfg->dt; pa.alpha = cfg->alpha; pa.beta = cfg->beta;
+    pa.t0 = cfg->t0; pa.dt = cfg->dt; pa.alpha = cfg->alpha; pa.beta = cfg->beta; pa.conj_fix = cfg->eigen_axis_fix ? 1 : 0;
     pa.Qd = d_Qd; pa.Qfd = d_Qd + 8 * NA; pa.Rd = d_Qd + 16 * NA;
     pa.goffs = nullptr; pa.w_guess = nullptr; pa.q_guess = nullptr;
     k_slew_prep<<<(unsigned)((na + 127) / 128), 128, 0, c->stream>>>(pa);
@@ -1087,6 +1065,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     if ((rc = k3_launch(c, ka, hi.data(), diff.data()))) return rc;
     cudaEventRecord(e[4], c->stream);
     // ---- stage 5: TVLQR replay + slew-time rule
+    double *d_Xs_keep = nullptr, *d_Us_keep = nullptr;
     if (cfg->run_tvlqr) {
       void* p_K;
       if ((rc = scratch_reserve(c, 9, (size_t)knots * 18 * 8, &p_K))) return rc;
@@ -1104,6 +1083,15 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
       if (k4.opts.noise_mode == 1) k4.opts.noise_mode = 2;  // no explicit array in the fused path
       k4.opts.literal_postproc = 0;                          // needs X_sim storage; fused path uses the fixed rule (Q12)
       k4.noise = nullptr; k4.X_sim = nullptr; k4.U_sim = nullptr; k4.dX = nullptr; k4.K = (double*)p_K;
+      if (cfg->keep_trajectories) {
+        void *p_xs, *p_us;
+        if ((rc = scratch_reserve(c, 20, (size_t)knots * 8 * 8 + 64, &p_xs))) return rc;
+        if ((rc = scratch_reserve(c, 21, (size_t)knots * 3 * 8 + 64, &p_us))) return rc;
+        TS_CUDA(c, cudaMemsetAsync(p_xs, 0, (size_t)knots * 8 * 8, c->stream));
+        TS_CUDA(c, cudaMemsetAsync(p_us, 0, (size_t)knots * 3 * 8, c->stream));
+        k4.X_sim = (double*)p_xs; k4.U_sim = (double*)p_us;
+        d_Xs_keep = k4.X_sim; d_Us_keep = k4.U_sim;
+      }
       k4.N_sim = d_nsim; k4.slew_time = d_slew;
       k4_tvlqr_kernel<<<(unsigned)((na + 63) / 64), 64, 0, c->stream>>>(k4);
       c->launches++;
@@ -1116,7 +1104,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     if (cfg->run_tvlqr) TS_CUDA(c, cudaMemcpyAsync(slew.data(), d_slew, NA * 8, cudaMemcpyDeviceToHost, c->stream));
     TS_CUDA(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e[0], e[1]); ms_field = ms;
+    cudaEventElapsedTime(&ms, e[0], e[6]); ms_field = ms;
     cudaEventElapsedTime(&ms, e[1], e[2]); ms_field += ms;
     cudaEventElapsedTime(&ms, e[2], e[3]); ms_prep = ms;
     cudaEventElapsedTime(&ms, e[3], e[4]); ms_solve = ms;
@@ -1129,6 +1117,20 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
       const double kn = (double)(Nf[f] - 1);
       out[t].flops = kn * ((double)oa[a].inner_iters * FL_ITER + (double)oa[a].ls_rollouts * FL_ROLL) + (cfg->run_tvlqr ? kn * FL_TVLQR : 0.0);
     }
+    if (cfg->keep_trajectories) {
+      ts_ctx::McLast& L = c->mc_last;
+      L.n = n; L.knots = knots; L.rows = offs_f[nf];
+      L.knot_offs.assign((size_t)n + 1, 0);
+      L.row_offs.assign((size_t)n + 1, 0);
+      for (int64_t t = 0; t < n; ++t) {
+        const int64_t f = cfg->shared_orbit ? 0 : t;
+        L.knot_offs[t + 1] = L.knot_offs[t] + (Nf[f] >= 2 ? Nf[f] : 0);
+        L.row_offs[t] = cfg->shared_orbit ? 0 : offs_f[f];
+      }
+      L.row_offs[n] = offs_f[nf];
+      L.d_X = d_X; L.d_U = d_U; L.d_Xs = d_Xs_keep; L.d_Us = d_Us_keep; L.d_B = d_Bf;
+      L.valid = true;
+    }
   }
   c->last_kernel_ms = ms_field + ms_prep + ms_solve + ms_tvlqr;
   if (stats) {
@@ -1136,6 +1138,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     stats->flops = field_samples * FL_FIELD;
     for (int64_t t = 0; t < n; ++t) {
       const ts_trial_outcome& o = out[t];
+      if (o.status >= 0 && o.status < 6) stats->n_status[o.status]++;
       if (o.status == TS_ST_NO_CUTOFF) { stats->n_no_cutoff++; continue; }
       if (o.status == TS_ST_CONVERGED) stats->n_converged++;
       stats->sum_t_final += o.t_final;
@@ -1150,6 +1153,32 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     }
     stats->ms_field = ms_field; stats->ms_prep = ms_prep; stats->ms_solve = ms_solve; stats->ms_tvlqr = ms_tvlqr;
   }
+  return TS_OK;
+}
+
+int ts_mc_trajectory_layout(ts_ctx* c, int64_t n_trials, int64_t* knot_offs, int64_t* row_offs) {
+  if (!c) return TS_ERR_ARG;
+  const ts_ctx::McLast& L = c->mc_last;
+  if (!L.valid) return fail(c, TS_ERR_ARG, "no Monte-Carlo run with keep_trajectories = 1 on this context");
+  if (n_trials != L.n) return fail(c, TS_ERR_ARG, "the kept run had %lld trials", (long long)L.n);
+  if (knot_offs) memcpy(knot_offs, L.knot_offs.data(), (size_t)(L.n + 1) * 8);
+  if (row_offs) memcpy(row_offs, L.row_offs.data(), (size_t)(L.n + 1) * 8);
+  return TS_OK;
+}
+
+int ts_mc_fetch_trajectories(ts_ctx* c, double* X, double* U, double* X_sim, double* U_sim, double* B_eci) {
+  if (!c) return TS_ERR_ARG;
+  const ts_ctx::McLast& L = c->mc_last;
+  if (!L.valid) return fail(c, TS_ERR_ARG, "no Monte-Carlo run with keep_trajectories = 1 on this context");
+  if ((X_sim || U_sim) && !L.d_Xs) return fail(c, TS_ERR_ARG, "the kept run had run_tvlqr = 0: no X_sim / U_sim");
+  TS_CUDA(c, cudaSetDevice(c->device));
+  const size_t K = (size_t)L.knots;
+  if (X) TS_CUDA(c, cudaMemcpyAsync(X, L.d_X, K * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (U) TS_CUDA(c, cudaMemcpyAsync(U, L.d_U, K * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (X_sim) TS_CUDA(c, cudaMemcpyAsync(X_sim, L.d_Xs, K * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (U_sim) TS_CUDA(c, cudaMemcpyAsync(U_sim, L.d_Us, K * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (B_eci) TS_CUDA(c, cudaMemcpyAsync(B_eci, L.d_B, (size_t)L.rows * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
   return TS_OK;
 }
 
@@ -1234,3 +1263,5 @@ int ts_rk3_step_batch(ts_ctx* c, int64_t n, const double* x, const double* u, co
 }
 
 }  // extern "C"
+
+#include "multi.cuh"

@@ -115,11 +115,13 @@ TS_HD void simulator7(const Inertia& I, const double x[7], const double u[3], co
   if (nz) {
     for (int i = 0; i < 3; ++i) om[i] = x[i] + nz[i];
     const double th = sqrt(nz[3] * nz[3] + nz[4] * nz[4] + nz[5] * nz[5]);
-    const double sh = sin(th / 2);
-    const double qn[4] = {cos(th / 2), nz[3] / th * sh, nz[4] / th * sh, nz[5] / th * sh};
-    double q2[4];
-    qmult(q, qn, q2);
-    for (int i = 0; i < 4; ++i) q[i] = q2[i];
+    if (th > 1e-300) {  // a zero attitude perturbation is the identity (the reference's q_noise/0 would be NaN)
+      const double sh = sin(th / 2);
+      const double qn[4] = {cos(th / 2), nz[3] / th * sh, nz[4] / th * sh, nz[5] / th * sh};
+      double q2[4];
+      qmult(q, qn, q2);
+      for (int i = 0; i < 4; ++i) q[i] = q2[i];
+    }
     for (int i = 0; i < 3; ++i) Bf[i] = Bn[i] + nz[6 + i];
   }
   const double w4[4] = {0.0, om[0], om[1], om[2]};

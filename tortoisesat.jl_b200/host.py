@@ -37,7 +37,11 @@ class IlqrOpts(C.Structure):
                [(k, C.c_double) for k in ("cost_tol", "cost_tol_intermediate", "grad_tol", "grad_tol_intermediate",
                                           "constraint_tol", "penalty_initial", "penalty_scaling", "penalty_max", "dual_max",
                                           "ls_lower", "ls_upper", "bp_reg_increase", "bp_reg_max", "bp_reg_min", "bp_reg_fp",
-                                          "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")]
+                                          "max_cost_value", "max_state_value", "max_control_value", "u_max", "u_min")] + \
+               [(k, C.c_int32) for k in ("a2_active_ge", "a3_grad_over_N", "a4_no_intermediate", "a5_dual_active_only",
+                                         "a6_penalty_conditional", "a7_carry_cost")] + \
+               [("constraint_decrease_ratio", C.c_double), ("k3_suspend_after", C.c_int32), ("k3_tail_share", C.c_int32),
+                ("k3_early_factor", C.c_double)]
 
 
 class TvlqrOpts(C.Structure):
@@ -56,7 +60,8 @@ class McConfig(C.Structure):
     """ts_mc_config"""
     _fields_ = [("n_trials", C.c_int64), ("shared_orbit", C.c_int32), ("run_tvlqr", C.c_int32), ("t0", C.c_double),
                 ("tf", C.c_double), ("N_scope", C.c_int64), ("cutoff", C.c_double), ("dt", C.c_double), ("alpha", C.c_double),
-                ("beta", C.c_double), ("ilqr", IlqrOpts), ("tvlqr", TvlqrOpts)]
+                ("beta", C.c_double), ("eigen_axis_fix", C.c_int32), ("keep_trajectories", C.c_int32), ("ilqr", IlqrOpts),
+                ("tvlqr", TvlqrOpts)]
 
 
 class McStats(C.Structure):
@@ -64,7 +69,7 @@ class McStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_trials", "n_converged", "n_no_cutoff", "n_fail_slew")] + \
                [(k, C.c_double) for k in ("sum_slew_time", "sum_slew_time_sq", "sum_t_final", "sum_inner_iters",
                                           "sum_ls_rollouts", "sum_knots", "flops", "ms_field", "ms_prep", "ms_solve",
-                                          "ms_tvlqr")]
+                                          "ms_tvlqr")] + [("n_status", C.c_int64 * 6)]
 
 
 def default_tvlqr_opts():
@@ -75,12 +80,16 @@ def default_tvlqr_opts():
 
 def default_mc_config(n_trials, shared_orbit=True, run_tvlqr=True, t0=0.0, tf=2400.0, N_scope=5000, cutoff=30.0, dt=0.2,
                       alpha=0.1, beta=1e3):
-    """Defaults = the constants of src/monte_carlo.jl:37-78,169-171."""
+    """Defaults = the constants of src/monte_carlo.jl:37-78,169-171,227 (R_lqr = 0.5e3 there; TortoiseSat.jl:260 uses
+    7.5e3, which is what ts_tvlqr_default_opts returns)."""
     cfg = McConfig()
     cfg.n_trials, cfg.shared_orbit, cfg.run_tvlqr = n_trials, int(shared_orbit), int(run_tvlqr)
     cfg.t0, cfg.tf, cfg.N_scope, cfg.cutoff, cfg.dt, cfg.alpha, cfg.beta = t0, tf, N_scope, cutoff, dt, alpha, beta
+    cfg.eigen_axis_fix, cfg.keep_trajectories = 0, 0
     cfg.ilqr = default_ilqr_opts()
     cfg.tvlqr = default_tvlqr_opts()
+    for i in range(3):
+        cfg.tvlqr.Rd[i] = 0.5e3                                      # monte_carlo.jl:227
     return cfg
 
 
@@ -126,7 +135,20 @@ def load_library():
     L.ts_last_kernel_ms.restype = C.c_double
     L.ts_k3_last_split.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.ts_k3_last_split.restype = C.c_int
+    L.ts_k3_last_cycles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.ts_fp64_peak_probe.argtypes = [C.c_void_p, c_double_p]
+    L.ts_mc_trajectory_layout.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ts_mc_fetch_trajectories.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.ts_igrf12syn_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
+    L.ts_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+    L.ts_destroy_multi.argtypes = [C.c_void_p]
+    L.ts_destroy_multi.restype = None
+    L.ts_multi_last_error.argtypes = [C.c_void_p]
+    L.ts_multi_last_error.restype = C.c_char_p
+    L.ts_multi_device_count.argtypes = [C.c_void_p]
+    L.ts_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.ts_multi_ctx.restype = C.c_void_p
+    L.ts_multi_monte_carlo_run.argtypes = [C.c_void_p, C.POINTER(McConfig)] + [C.c_void_p] * 8 + [C.POINTER(McStats)]
     L.ts_igrf12_batch.argtypes = [C.c_void_p, C.c_double, C.c_int64] + [C.c_void_p] * 6 + [C.c_int]
     L.ts_magnetic_simulation_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
     L.ts_magnetic_gramian_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int]
@@ -143,7 +165,7 @@ def load_library():
                                     C.c_void_p, C.c_double, C.c_void_p]
     L.ts_tvlqr_default_opts.argtypes = [C.POINTER(TvlqrOpts)]
     L.ts_tvlqr_default_opts.restype = None
-    L.ts_slew_weights_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_double] * 4 + [C.c_void_p] * 6
+    L.ts_slew_weights_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_double] * 4 + [C.c_int] + [C.c_void_p] * 6
     L.ts_tvlqr_sim_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 14 + [C.POINTER(TvlqrOpts)] + [C.c_void_p] * 7 + [C.c_int]
     L.ts_monte_carlo_run.argtypes = [C.c_void_p, C.POINTER(McConfig)] + [C.c_void_p] * 8 + [C.POINTER(McStats)]
     L.ts_alilqr_solve_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 13 + [C.c_double, C.c_void_p,
@@ -364,8 +386,10 @@ class Engine:
         return xn
 
     # -- prep / K4 / fused MC ----------------------------------------------
-    def slew_weights_batch(self, x0, xf, Jmat, t_final, t0=0.0, dt=0.2, alpha=10.0, beta=1e3, want_guess=False):
-        """eigen_axis_slew + Bryson weights (eigen_axis_slew.jl:1-38, TortoiseSat.jl:157-168)."""
+    def slew_weights_batch(self, x0, xf, Jmat, t_final, t0=0.0, dt=0.2, alpha=10.0, beta=1e3, want_guess=False, eigen_axis_fix=False):
+        """eigen_axis_slew + Bryson weights (eigen_axis_slew.jl:1-38, TortoiseSat.jl:157-168).  eigen_axis_fix=False
+        reproduces the reference's literal error quaternion qmult(q_f, q_0) (eigen_axis_slew.jl:16); True uses
+        conj(q_f) (x) q_0."""
         x0 = _f64(np.atleast_2d(x0))
         T = x0.shape[0]
         xf, Jmat, t_final = _f64(np.asarray(xf).reshape(T, 8)), _f64(np.asarray(Jmat).reshape(T, 9)), _f64(np.asarray(t_final).reshape(T))
@@ -376,7 +400,7 @@ class Engine:
             goffs = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
             wg, qg = np.zeros((int(goffs[-1]), 3)), np.zeros((int(goffs[-1]), 4))
         self._check(self.lib.ts_slew_weights_batch(self.h, T, _ptr(x0), _ptr(xf), _ptr(Jmat), _ptr(t_final), t0, dt, alpha, beta,
-                                                   _ptr(Qd), _ptr(Qfd), _ptr(Rd), None if goffs is None else _ptr(goffs),
+                                                   int(bool(eigen_axis_fix)), _ptr(Qd), _ptr(Qfd), _ptr(Rd), None if goffs is None else _ptr(goffs),
                                                    None if wg is None else _ptr(wg), None if qg is None else _ptr(qg)))
         if want_guess:
             return Qd, Qfd, Rd, wg, qg, goffs
@@ -428,6 +452,81 @@ class Engine:
         self._check(self.lib.ts_monte_carlo_run(self.h, C.byref(cfg), _ptr(kep6), fopts.ctypes.data, _ptr(x0), _ptr(xf), _ptr(Jmat),
                                                 None if qn is None else _ptr(qn), None if sid is None else _ptr(sid),
                                                 out.ctypes.data, C.byref(st)))
+        return out, st
+
+    def k3_last_cycles(self, n_trials):
+        """(n_trials, 3) SM cycles of the last AL-iLQR solve: backward pass, forward pass, linearisation share."""
+        cyc = np.zeros((int(n_trials), 3))
+        self._check(self.lib.ts_k3_last_cycles(self.h, int(n_trials), _ptr(cyc)))
+        return cyc
+
+    def mc_trajectories(self, n_trials, want=("X", "U", "X_sim", "U_sim", "B_eci")):
+        """Trajectories of the last monte_carlo_run with cfg.keep_trajectories = 1: dict with knot_offs, row_offs and the
+        requested arrays (`states`, `control_inputs`, `sim_states`, `sim_control_inputs`, `B_ECI_total` of
+        monte_carlo.jl:52-66, ragged by knot_offs / row_offs)."""
+        n = int(n_trials)
+        ko, ro = np.zeros(n + 1, dtype=np.int64), np.zeros(n + 1, dtype=np.int64)
+        self._check(self.lib.ts_mc_trajectory_layout(self.h, n, _ptr(ko), _ptr(ro)))
+        K, R = int(ko[-1]), int(ro[-1])
+        res = {"knot_offs": ko, "row_offs": ro}
+        shapes = {"X": (K, 8), "U": (K, 3), "X_sim": (K, 8), "U_sim": (K, 3), "B_eci": (R, 3)}
+        for k in want:
+            res[k] = np.zeros(shapes[k])
+        g = lambda k: _ptr(res[k]) if k in res else None
+        self._check(self.lib.ts_mc_fetch_trajectories(self.h, g("X"), g("U"), g("X_sim"), g("U_sim"), g("B_eci")))
+        return res
+
+    def igrf12syn_batch(self, isv, date, itype, alt, colat, elong):
+        """igrf12syn (igrf.jl:335-534) at n points: alt km, colat/elong degrees -> x, y, z, f (nT)."""
+        alt, colat, elong = _f64(np.atleast_1d(alt)), _f64(np.atleast_1d(colat)), _f64(np.atleast_1d(elong))
+        n = alt.shape[0]
+        o = [np.zeros(n) for _ in range(4)]
+        self._check(self.lib.ts_igrf12syn_batch(self.h, int(isv), float(date), int(itype), n, _ptr(alt), _ptr(colat), _ptr(elong),
+                                                _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), _ptr(o[3]), 0))
+        return tuple(o)
+
+
+class MultiEngine:
+    """Several GPUs of one node behind one handle (ts_create_multi): the library owns one context, one host thread and
+    one NCCL communicator per device; trials are sharded round-robin."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.ts_create_multi(C.byref(h), ids, len(devices))
+        if rc != 0 or not h.value:
+            raise TortoiseError(rc, "ts_create_multi failed (no usable CUDA devices / NCCL?) -- there is no CPU fallback")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.ts_destroy_multi(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_count(self):
+        return int(self.lib.ts_multi_device_count(self.h))
+
+    def monte_carlo_run(self, cfg, kep6, fopts, x0, xf, Jmat, q_noise0=None, stream_id=None):
+        n = int(cfg.n_trials)
+        kep6 = _f64(np.atleast_2d(kep6))
+        fopts = np.ascontiguousarray(fopts, dtype=FIELD_OPTS_DTYPE)
+        x0, xf, Jmat = _f64(np.asarray(x0).reshape(n, 8)), _f64(np.asarray(xf).reshape(n, 8)), _f64(np.asarray(Jmat).reshape(n, 9))
+        qn = None if q_noise0 is None else _f64(np.asarray(q_noise0).reshape(n, 3))
+        sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.uint32)
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        st = McStats()
+        rc = self.lib.ts_multi_monte_carlo_run(self.h, C.byref(cfg), _ptr(kep6), fopts.ctypes.data, _ptr(x0), _ptr(xf), _ptr(Jmat),
+                                               None if qn is None else _ptr(qn), None if sid is None else _ptr(sid),
+                                               out.ctypes.data, C.byref(st))
+        if rc != 0:
+            raise TortoiseError(rc, (self.lib.ts_multi_last_error(self.h) or b"").decode())
         return out, st
 
 
@@ -688,12 +787,15 @@ def attitude_simulation(f, f_gains, integration, X_lqr, U_lqr, dt_lqr, x0_lqr, t
 
 def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=58155.0, igrf_date=2019.0, t0=0.0, tf=60 * 40.0,
                 cutoff=30.0, N=5000, J=None, q_0=None, q_final=(np.sqrt(2) / 2, np.sqrt(2) / 2, 0.0, 0.0), alpha=1.0e-1, beta=1.0e3,
-                seed=0, run_tvlqr=True, ilqr=None, rng=None):
+                seed=0, run_tvlqr=True, ilqr=None, rng=None, random_attitudes=False, trajectories=True, eigen_axis_fix=False):
     """The loop of monte_carlo.jl:118-262 (solver block of TortoiseSat.jl:178-199) for number_sims trials in ONE
     library call.  Returns the arrays the script leaves in globals (monte_carlo.jl:52-66,237-240): A (number_sims x 6),
-    t_final, slew_time, fails, plus the per-trial outcome records and the statistics block.  Randomisation as in
-    monte_carlo.jl:122-127,207 (RAAN and anomaly uniform in [0,360), q_0 uniform on S^3, initial attitude noise
-    randn(3)*(pi/180)^2), from numpy's generator instead of Julia's global RNG."""
+    t_final, slew_time, fails, and -- with trajectories=True -- the per-trial lists `states` (8 x N_i), `control_inputs`
+    (3 x N_i-1), `sim_states` (8 x N_sim_i), `sim_control_inputs` (3 x N_sim_i), `B_ECI_total` (2N_i x 3), `t_total`, plus
+    the outcome records and the statistics block.  Randomisation as in monte_carlo.jl:122-127,207 (RAAN and anomaly
+    uniform in [0,360); q_0 = [1,0,0,0] for every trial as at monte_carlo.jl:108-111 unless random_attitudes=True, which
+    draws q_0 uniformly on S^3 -- the BASELINE configs[2] ensemble; initial attitude noise randn(3)*(pi/180)^2), from
+    numpy's generator instead of Julia's global RNG."""
     rng = np.random.default_rng(seed) if rng is None else rng
     n = int(number_sims)
     J = np.diag([0.00125, 0.00125, 0.00125]) if J is None else np.asarray(J, dtype=float)
@@ -704,11 +806,11 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
     for i in range(n):
         fo[i] = (GM_EARTH, MJD_0, igrf_date, (alt + R_E) * 1000.0, 0.0, 0.0, 0)
     x0, xf = np.zeros((n, 8)), np.zeros((n, 8))
-    if q_0 is None:
+    if random_attitudes:
         q = rng.normal(size=(n, 4))
         x0[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
     else:
-        x0[:, 3:7] = np.asarray(q_0, dtype=float)
+        x0[:, 3:7] = np.asarray((1.0, 0.0, 0.0, 0.0) if q_0 is None else q_0, dtype=float)
     xf[:, 3:7], xf[:, 7] = np.asarray(q_final, dtype=float), 1.0
     qn = rng.normal(size=(n, 3)) * (np.pi / 180) ** 2
     cfg = default_mc_config(n, shared_orbit=False, run_tvlqr=run_tvlqr, t0=t0, tf=tf, N_scope=int(N), cutoff=cutoff, dt=0.2,
@@ -720,6 +822,20 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
         cfg.tvlqr.Qd[i], cfg.tvlqr.Qfd[i] = 10.0, 1000.0
     for i in range(3):
         cfg.tvlqr.Rd[i] = 0.5e3
-    out, st = default_engine().monte_carlo_run(cfg, A, fo, x0, xf, np.tile(J.reshape(-1), (n, 1)), q_noise0=qn)
+    cfg.eigen_axis_fix, cfg.keep_trajectories = int(bool(eigen_axis_fix)), int(bool(trajectories))
+    eng = default_engine()
+    out, st = eng.monte_carlo_run(cfg, A, fo, x0, xf, np.tile(J.reshape(-1), (n, 1)), q_noise0=qn)
     fails = (out["slew_time"] == out["t_final"]).astype(float)     # monte_carlo.jl:257-261
-    return dict(A=A, t_final=out["t_final"].copy(), slew_time=out["slew_time"].copy(), fails=fails, outcomes=out, stats=st)
+    res = dict(A=A, t_final=out["t_final"].copy(), slew_time=out["slew_time"].copy(), fails=fails, outcomes=out, stats=st)
+    if trajectories:
+        tr = eng.mc_trajectories(n, want=("X", "U", "X_sim", "U_sim", "B_eci") if run_tvlqr else ("X", "U", "B_eci"))
+        ko, ro = tr["knot_offs"], tr["row_offs"]
+        sl = lambda a, t, last=0: a[ko[t]:ko[t + 1] - last].T.copy()
+        res["states"] = [sl(tr["X"], t) for t in range(n)]                       # monte_carlo.jl:200
+        res["control_inputs"] = [sl(tr["U"], t, 1) for t in range(n)]            # :201
+        res["B_ECI_total"] = [tr["B_eci"][ro[t]:ro[t] + 2 * (ko[t + 1] - ko[t])].copy() for t in range(n)]   # :149
+        res["t_total"] = [t0 + 0.2 * np.arange(ko[t + 1] - ko[t] + 1) for t in range(n)]                      # :144
+        if run_tvlqr:
+            res["sim_states"] = [sl(tr["X_sim"], t) for t in range(n)]           # :232
+            res["sim_control_inputs"] = [sl(tr["U_sim"], t) for t in range(n)]   # :233
+    return res
