@@ -5,10 +5,16 @@
 // cpu_baseline / --impl reference legs -- never by the product library.
 //
 // PARITY STATUS: the reference has no tests, fixtures or golden vectors
-//  and cannot run here (no Julia).  IGRF is pinned by the
-// reference's own two independent implementations + tables agreeing (igrf12 vs
-// igrf12syn) and by an independent numpy restatement (tests/golden/).  Orbit,
-// dynamics, AL-iLQR and TVLQR are "parity unpinned" against real Julia output.
+//  and cannot run here (no Julia).  Everything whose source
+// IS in /root/reference (IGRF, orbit, field table, gramian cutoff, eigen-axis
+// slew, Bryson weights, dynamics, rk3/rk4, TVLQR replay, MC post-processing) is
+// pinned to tests/golden/ref_fixtures.json, the output of a line-by-line numpy
+// transliteration of those sources (tests/golden/gen_ref_fixtures.py), and IGRF
+// additionally to the reference's second implementation + table (igrf12syn) and
+// to mpmath goldens.  AL-iLQR: TrajectoryOptimization.jl v0.1.2 is not vendored
+// => PARITY UNPINNED against the real package; the algorithm is the frozen spec
+// of SURVEY.md App. C, cross-checked by a second independent implementation
+// (same fixture file) and with every unpinned choice a flip-tested switch.
 #include <omp.h>
 
 #include <cstdint>
@@ -257,6 +263,120 @@ int64_t orc_attitude_simulation(const orc_dyn* d, const orc_tvlqr_opts* o, int64
 double orc_mc_slew_time(const double* X_sim, int64_t N_sim, const double* q_final, double t_final, double time_step,
                         double w_limit, double ang_limit, int literal, int64_t trial_index_1based) {
   return mc_slew_time(X_sim, N_sim, q_final, t_final, time_step, w_limit, ang_limit, literal, trial_index_1based);
+}
+
+// ---------------------------------------------------------------- whole Monte-Carlo pipeline (CPU baseline)
+// The loop body of reference src/monte_carlo.jl:118-262 with the solver block of src/TortoiseSat.jl:178-199, one trial
+// per OpenMP task (schedule(dynamic,1): trials differ by 10x in work): scoping field pass -> gramian cutoff -> fine
+// field table -> eigen-axis guess + Bryson weights -> AL-iLQR -> TVLQR replay with Philox noise -> slew-time rule.
+// Mirrors ts_monte_carlo_run of the product argument for argument (a shared orbit is scoped once, as the fused GPU
+// path does).  cpu_seconds (nullable, n_trials): per-trial CPU time, so that a bounded sample can be scaled by SUMS.
+struct orc_mc_config {
+  int64_t n_trials;
+  int32_t shared_orbit, run_tvlqr;
+  double t0, tf;
+  int64_t N_scope;
+  double cutoff, dt, alpha, beta;
+  int32_t eigen_axis_fix, keep_trajectories;
+  orc_ilqr_opts ilqr;
+  orc_tvlqr_opts tvlqr;   // NB: product layout has more fields behind `seed`; only this prefix is read
+};
+int orc_mc_run(const orc_mc_config* cfg, const double* kep6, const orc_field_opts* fopts, const double* x0, const double* xf,
+               const double* Jmat, const double* q_noise0, const uint32_t* stream_id, IlqrOutcome* out, double* cpu_seconds,
+               int nthreads) {
+  const int64_t n = cfg->n_trials;
+  const IlqrOpts o = make_opts(&cfg->ilqr);
+  if (nthreads < 1) nthreads = 1;
+  struct Orbit {
+    int64_t idx = 0, N = 0;
+    double t_final = 0;
+    std::vector<double> B;
+  };
+  auto scope = [&](int64_t f, Orbit& ob) {
+    FieldOpts fo{fopts[f].GM, fopts[f].mjd, fopts[f].igrf_date, fopts[f].field_radius_m, cfg->t0, cfg->tf, cfg->N_scope};
+    std::vector<double> B0((size_t)2 * cfg->N_scope * 3), G((size_t)2 * cfg->N_scope * 9);
+    magnetic_simulation(kep6 + f * 6, fo, B0.data(), nullptr, nullptr);
+    magnetic_gramian(B0.data(), 2 * cfg->N_scope, (cfg->tf - cfg->t0) / (double)cfg->N_scope, G.data());
+    ob.idx = condition_based_time(G.data(), 2 * cfg->N_scope, cfg->cutoff);
+    if (ob.idx <= 0) return;
+    ob.t_final = (double)ob.idx * (cfg->tf - cfg->t0) / (double)cfg->N_scope;
+    ob.N = (int64_t)std::floor((ob.t_final - cfg->t0) / cfg->dt);
+    if (ob.N < 2) { ob.N = 0; return; }
+    FieldOpts f2 = fo;
+    f2.tf = ob.t_final;
+    f2.N = ob.N;
+    ob.B.assign((size_t)2 * ob.N * 3, 0.0);
+    magnetic_simulation(kep6 + f * 6, f2, ob.B.data(), nullptr, nullptr);
+  };
+  Orbit shared;
+  if (cfg->shared_orbit) scope(0, shared);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+  for (int64_t t = 0; t < n; ++t) {
+    const double t_start = omp_get_wtime();
+    Orbit own;
+    if (!cfg->shared_orbit) scope(t, own);
+    const Orbit& ob = cfg->shared_orbit ? shared : own;
+    IlqrOutcome& r = out[t];
+    std::memset(&r, 0, sizeof(r));
+    if (ob.N < 2) {
+      r.status = 5;  // NO_CUTOFF (magnetic_toolbox.jl:23: tf_index stays 0)
+      if (cpu_seconds) cpu_seconds[t] = omp_get_wtime() - t_start;
+      continue;
+    }
+    const int64_t N = ob.N;
+    const int64_t nt = range_len(cfg->t0, cfg->dt, ob.t_final);
+    std::vector<double> tt((size_t)nt), wg((size_t)nt * 3), qg((size_t)nt * 4);
+    for (int64_t i = 0; i < nt; ++i) tt[(size_t)i] = cfg->t0 + cfg->dt * (double)i;
+    eigen_axis_slew(x0 + t * 8, xf + t * 8, tt.data(), nt, wg.data(), qg.data(), cfg->eigen_axis_fix);
+    IlqrProblem p;
+    p.N = N;
+    p.dt = cfg->dt;
+    bryson_weights(wg.data(), nt, Jmat + t * 9, cfg->dt, cfg->alpha, cfg->beta, p.Qd, p.Qfd, p.Rd);
+    for (int i = 0; i < 8; ++i) {
+      p.x0[i] = x0[t * 8 + i];
+      p.xf[i] = xf[t * 8 + i];
+    }
+    p.dyn.B_eci = ob.B.data();
+    p.dyn.B_rows = 2 * N;
+    p.dyn.index_scale = (double)N;
+    p.dyn.clock_rate = 1.0 / (cfg->tf - cfg->t0);
+    for (int i = 0; i < 9; ++i) p.dyn.J[i] = Jmat[t * 9 + i];
+    inv3(p.dyn.J, p.dyn.Jinv);
+    std::vector<double> X((size_t)N * 8), U((size_t)N * 3);
+    alilqr_solve(p, o, nullptr, X.data(), U.data(), nullptr, &r);
+    r.t_final = ob.t_final;
+    if (cfg->run_tvlqr) {
+      double x0l[8];
+      for (int i = 0; i < 3; ++i) x0l[i] = x0[t * 8 + i];
+      const double* q0 = x0 + t * 8 + 3;
+      if (q_noise0) {  // TortoiseSat.jl:231-234
+        const double* qn = q_noise0 + t * 3;
+        const double th = std::sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2]);
+        const double qp[4] = {std::cos(th / 2), qn[0] / th * std::sin(th / 2), qn[1] / th * std::sin(th / 2), qn[2] / th * std::sin(th / 2)};
+        qmult(q0, qp, x0l + 3);
+      } else {
+        for (int i = 0; i < 4; ++i) x0l[3 + i] = q0[i];
+      }
+      x0l[7] = 0.0;
+      TvlqrOpts tv;
+      tv.dt = cfg->dt; tv.t0 = cfg->t0; tv.tf = ob.t_final; tv.dt_squared = cfg->tvlqr.dt_squared;
+      for (int i = 0; i < 6; ++i) { tv.Qd[i] = cfg->tvlqr.Qd[i]; tv.Qfd[i] = cfg->tvlqr.Qfd[i]; }
+      for (int i = 0; i < 3; ++i) tv.Rd[i] = cfg->tvlqr.Rd[i];
+      const uint32_t sid = stream_id ? stream_id[t] : (uint32_t)t;
+      std::vector<double> gen;
+      if (cfg->tvlqr.noise_mode != 0) {
+        gen.resize((size_t)N * 36);
+        for (int64_t k = 0; k < N; ++k)
+          for (int s4 = 0; s4 < 4; ++s4) tvlqr_noise(cfg->tvlqr.seed, sid, (uint32_t)k, (uint32_t)s4, &gen[(size_t)k * 36 + s4 * 9]);
+      }
+      std::vector<double> Xs((size_t)N * 8), Us((size_t)N * 3), dX((size_t)N * 6), K((size_t)N * 18);
+      const int64_t ns = attitude_simulation(p.dyn, tv, N, X.data(), U.data(), x0l, gen.empty() ? nullptr : gen.data(), Xs.data(),
+                                             Us.data(), dX.data(), K.data());
+      r.slew_time = mc_slew_time(Xs.data(), ns, xf + t * 8 + 3, ob.t_final, cfg->dt, 0.05, 0.08727, 0, t + 1);
+    }
+    if (cpu_seconds) cpu_seconds[t] = omp_get_wtime() - t_start;
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------- Philox

@@ -59,6 +59,14 @@ class TvlqrOpts(C.Structure):
                 ("Rd", C.c_double * 3), ("dt_squared", C.c_int32), ("noise_mode", C.c_int32), ("seed", C.c_uint64)]
 
 
+class McConfig(C.Structure):
+    """orc_mc_config (oracle.cpp): the oracle's own layout of the Monte-Carlo configuration."""
+    _fields_ = [("n_trials", C.c_int64), ("shared_orbit", C.c_int32), ("run_tvlqr", C.c_int32), ("t0", C.c_double),
+                ("tf", C.c_double), ("N_scope", C.c_int64), ("cutoff", C.c_double), ("dt", C.c_double), ("alpha", C.c_double),
+                ("beta", C.c_double), ("eigen_axis_fix", C.c_int32), ("keep_trajectories", C.c_int32), ("ilqr", IlqrOpts),
+                ("tvlqr", TvlqrOpts)]
+
+
 OUTCOME_DTYPE = np.dtype([("status", "<i4"), ("outer_iters", "<i4"), ("inner_iters", "<i4"), ("ls_rollouts", "<i4"),
                           ("N", "<i8"), ("J", "<f8"), ("c_max", "<f8"), ("t_final", "<f8"), ("slew_time", "<f8"),
                           ("flops", "<f8")])
@@ -110,6 +118,7 @@ def lib():
         L.orc_mc_slew_time.restype = C.c_double
         L.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
         L.orc_tvlqr_noise.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_mc_run.argtypes = [C.POINTER(McConfig)] + [C.c_void_p] * 9 + [C.c_int]
         L.orc_max_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -206,3 +215,37 @@ def default_ilqr_opts():
     o = IlqrOpts()
     lib().orc_ilqr_default_opts(C.byref(o))
     return o
+
+
+FIELD_OPTS_DTYPE = np.dtype([("GM", "<f8"), ("mjd", "<f8"), ("igrf_date", "<f8"), ("field_radius_m", "<f8"), ("t0", "<f8"),
+                             ("tf", "<f8"), ("N", "<i8")])
+
+
+def mc_config(n_trials, shared_orbit=True, run_tvlqr=True, t0=0.0, tf=2400.0, N_scope=5000, cutoff=30.0, dt=0.2, alpha=0.1, beta=1e3,
+              noise_mode=2, seed=0, R_lqr=0.5e3):
+    """Constants of src/monte_carlo.jl:37-78,169-171,216-227."""
+    cfg = McConfig()
+    cfg.n_trials, cfg.shared_orbit, cfg.run_tvlqr = n_trials, int(shared_orbit), int(run_tvlqr)
+    cfg.t0, cfg.tf, cfg.N_scope, cfg.cutoff, cfg.dt, cfg.alpha, cfg.beta = t0, tf, N_scope, cutoff, dt, alpha, beta
+    lib().orc_ilqr_default_opts(C.byref(cfg.ilqr))
+    cfg.tvlqr.dt, cfg.tvlqr.t0, cfg.tvlqr.dt_squared, cfg.tvlqr.noise_mode, cfg.tvlqr.seed = dt, t0, 1, noise_mode, seed
+    for i in range(6):
+        cfg.tvlqr.Qd[i], cfg.tvlqr.Qfd[i] = 10.0, 1000.0
+    for i in range(3):
+        cfg.tvlqr.Rd[i] = R_lqr
+    return cfg
+
+
+def mc_run(cfg, kep6, fopts, x0, xf, Jmat, q_noise0=None, stream_id=None, nthreads=1):
+    """The whole per-trial pipeline (orc_mc_run), OpenMP over trials.  Returns (outcomes, per-trial CPU seconds)."""
+    n = int(cfg.n_trials)
+    kep6 = f64(np.atleast_2d(kep6))
+    fopts = np.ascontiguousarray(fopts, dtype=FIELD_OPTS_DTYPE)
+    x0, xf, Jmat = f64(np.asarray(x0).reshape(n, 8)), f64(np.asarray(xf).reshape(n, 8)), f64(np.asarray(Jmat).reshape(n, 9))
+    qn = None if q_noise0 is None else f64(np.asarray(q_noise0).reshape(n, 3))
+    sid = None if stream_id is None else np.ascontiguousarray(stream_id, dtype=np.uint32)
+    out = np.zeros(n, dtype=OUTCOME_DTYPE)
+    secs = np.zeros(n)
+    lib().orc_mc_run(C.byref(cfg), P(kep6), fopts.ctypes.data, P(x0), P(xf), P(Jmat), P(qn), None if sid is None else sid.ctypes.data,
+                     out.ctypes.data, P(secs), int(nthreads))
+    return out, secs

@@ -131,3 +131,32 @@ def test_host_pipeline_matches_device_path(engine):
     lat[-3] = 1.6
     with pytest.raises(tb.TortoiseError):
         engine.igrf12_batch(2019.0, r, lat, lon)
+
+
+@pytest.mark.parametrize("date,isv,itype", [(2019.0, 0, 2), (2019.0, 0, 1), (2017.3, 1, 2), (2003.7, 0, 2), (1987.25, 0, 1), (1996.0, 1, 1)])
+def test_igrf12syn_batch_vs_oracle(engine, orc, date, isv, itype):
+    """ts_igrf12syn_batch (K6) -- the Fortran-style twin igrf12syn(isv,date,itype,alt,colat,elong) of igrf.jl:335-534 --
+    against the oracle's restatement, and (geocentric main field) against igrf12 itself as the reference's own
+    cross-check does (igrf.jl:283-287)."""
+    rng = np.random.default_rng(12)
+    n = 20_000
+    colat = np.degrees(np.arccos(2 * rng.random(n) - 1))
+    elong = 360.0 * rng.random(n)
+    alt = (6371.2 + 300 + 900 * rng.random(n)) if itype == 2 else (300 + 900 * rng.random(n))
+    colat[:3] = [0.0, 180.0, 90.0]                      # poles: the st == 0 branch of igrf.jl:511-515
+    x, y, z, f = engine.igrf12syn_batch(isv, date, itype, alt, colat, elong)
+    ref = np.array([orc.igrf12syn(isv, date, itype, alt[i], colat[i], elong[i]) for i in range(0, n, 97)] +
+                   [orc.igrf12syn(isv, date, itype, alt[i], colat[i], elong[i]) for i in range(3)])
+    got = np.stack([x, y, z, f], -1)
+    got = np.concatenate([got[0:n:97], got[:3]])
+    scale = np.abs(ref[:, 3:4])
+    assert np.max(np.abs(got - ref) / scale) <= 1e-11
+    if isv == 0 and itype == 2:
+        lat = np.radians(90.0 - colat[3:])
+        lon = np.radians(elong[3:])
+        lon = np.where(lon > math.pi, lon - 2 * math.pi, lon)
+        bn, be, bd = engine.igrf12_batch(date, alt[3:] * 1000.0, lat, lon)
+        e = np.linalg.norm(np.stack([bn - x[3:], be - y[3:], bd - z[3:]], -1), axis=-1) / f[3:]
+        assert e.max() < 1e-9                          # two implementations, two coefficient tables (SURVEY section 4)
+    with pytest.raises(Exception):
+        engine.igrf12syn_batch(0, 2031.0, 2, [6771.0], [90.0], [0.0])

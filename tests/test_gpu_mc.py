@@ -107,11 +107,12 @@ def _oracle_trial(kep, fo, x0, xf, J, cfg, qn, sid):
     s = S.build_slew(kep, J, x0[3:7], xf[3:7], mjd=fo["mjd"], igrf_date=fo["igrf_date"], field_radius_m=fo["field_radius_m"],
                      t0=cfg.t0, tf=cfg.tf, N_scope=int(cfg.N_scope), cutoff=cfg.cutoff, dt=cfg.dt, alpha=cfg.alpha, beta=cfg.beta)
     Xs, Us, Ks, out = S.oracle_solve([s])
-    o, g = S.tvlqr_opts_pair(noise_mode=2, seed=int(cfg.tvlqr.seed))
+    o, g = S.tvlqr_opts_pair(noise_mode=2, seed=int(cfg.tvlqr.seed), R=float(cfg.tvlqr.Rd[0]))
     x0l = s.x0.copy()
     x0l[3:7] = _perturb(s.x0[3:7], qn)
     x0l[7] = 0
     a = S.oracle_tvlqr(s, Xs[0], Us[0], x0l, o, trial=sid)
+    _oracle_trial.last = (Xs[0], Us[0], a)
     return s, out[0], a[5]
 
 
@@ -223,3 +224,170 @@ def test_bench_ensemble_sample_matches_oracle(engine):
             assert g[fld] == r[fld], (t, fld, g, r)
         assert abs(g["J"] - r["J"]) <= 1e-6 * abs(r["J"])
         assert abs(g["c_max"] - r["c_max"]) <= 1e-6 * max(1.0, r["c_max"])
+
+
+def test_monte_carlo_trajectories_match_oracle(engine):
+    """keep_trajectories = 1: the arrays monte_carlo.jl leaves in globals (states, control_inputs, sim_states,
+    sim_control_inputs, B_ECI_total; monte_carlo.jl:52-66,149,200-201,232-233) come back through
+    ts_mc_fetch_trajectories and equal the oracle's per-trial pipeline."""
+    from tortoisesat.jl_b200 import host
+    rng = np.random.default_rng(33)
+    n = 3
+    cfg = host.default_mc_config(n, shared_orbit=False, run_tvlqr=True, tf=2400.0, cutoff=30.0, alpha=0.1)
+    cfg.tvlqr.noise_mode, cfg.tvlqr.seed, cfg.keep_trajectories = 2, 515, 1
+    assert cfg.tvlqr.Rd[0] == 0.5e3                                    # monte_carlo.jl:227 (ADVICE r1)
+    kep = np.zeros((n, 6))
+    fo = np.zeros(n, dtype=host.FIELD_OPTS_DTYPE)
+    for t in range(n):
+        kep[t] = [0, 6771.0, 96.6, rng.uniform(0, 360), 0, rng.uniform(0, 360)]
+        fo[t] = (GM, 58155.0, 2019.0, 6771000.0, 0, 0, 0)
+    qf = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])
+    x0 = np.zeros((n, 8))
+    x0[:, 3] = 1.0                                                     # q_0 = identity, as monte_carlo.jl:108-111
+    x0[1, 3:7] = S.quat_axis_angle([0.2, 1, -0.4], 50.0)              # and one trial with both attitudes non-identity
+    xf = np.tile(np.concatenate([[0, 0, 0], qf, [1.0]]), (n, 1))
+    Jm = np.tile(S.J_1U.reshape(-1), (n, 1))
+    qn = rng.normal(size=(n, 3)) * (math.pi / 180) ** 2
+    out, st = engine.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn, stream_id=np.arange(7, 7 + n))
+    tr = engine.mc_trajectories(n)
+    ko, ro = tr["knot_offs"], tr["row_offs"]
+    assert ko[-1] == out["N"].sum() and sum(st.n_status) == n
+    for t in range(n):
+        s, ref, slew = _oracle_trial(kep[t], fo[t], x0[t], xf[t], S.J_1U, cfg, qn[t], 7 + t)
+        Xo, Uo, a = _oracle_trial.last
+        assert (out[t]["status"], out[t]["outer_iters"], out[t]["inner_iters"]) == (ref["status"], ref["outer_iters"], ref["inner_iters"])
+        N = s.N
+        assert ko[t + 1] - ko[t] == N
+        assert np.max(np.abs(tr["X"][ko[t]:ko[t + 1]] - Xo)) < 1e-8
+        assert np.max(np.abs(tr["U"][ko[t]:ko[t + 1] - 1] - Uo)) < 1e-7
+        ns = a[4]
+        assert np.max(np.abs(tr["X_sim"][ko[t]:ko[t] + ns] - a[0])) < 1e-7      # replay of a 1e-8-equal optimised slew
+        assert np.max(np.abs(tr["U_sim"][ko[t]:ko[t] + ns] - a[1])) < 1e-6
+        rows = 2 * N
+        Bg = tr["B_eci"][ro[t]:ro[t] + rows]
+        used = np.nonzero(np.any(Bg != 0, axis=1))[0]
+        assert len(used) > 8 and used[-1] < rows - 1
+        assert np.max(np.abs(Bg[used] - s.B[used])) < 1e-10 * np.max(np.abs(s.B))
+        assert out[t]["slew_time"] == slew
+    # the reference-named wrapper hands the same arrays back in the script's shapes
+    r = host.monte_carlo(number_sims=2, seed=3, trajectories=True)
+    assert len(r["states"]) == 2 and r["states"][0].shape[0] == 8 and r["control_inputs"][0].shape[0] == 3
+    assert r["sim_states"][0].shape == r["states"][0].shape and r["B_ECI_total"][0].shape[1] == 3
+    assert r["states"][0].shape[1] == r["outcomes"]["N"][0] == r["control_inputs"][0].shape[1] + 1
+
+
+def test_sweep_ensemble_sample_matches_oracle(engine):
+    """BASELINE configs[3] shape: the first trials of bench.py's magnetic-diversity sweep (per-trial inclination,
+    altitude, RAAN, anomaly, MJD, IGRF date; ragged horizons) against the oracle pipeline: same horizon, status,
+    outer / inner / line-search counters, J and c_max to 1e-6, same slew time."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench as B
+    from tortoisesat.jl_b200 import host
+    n = 24
+    tr = B.make_trials("mc_sweep", n, 0)
+    cfg = B.mc_config(host, tr, n)
+    fo = np.zeros(n, dtype=host.FIELD_OPTS_DTYPE)
+    for i, f in enumerate(tr["fo"]):
+        fo[i] = f
+    sid = np.arange(n).astype(np.uint32)
+    out, st = engine.monte_carlo_run(cfg, tr["kep"], fo, tr["x0"], tr["xf"], tr["Jm"], q_noise0=tr["qn"], stream_id=sid)
+    pick = [t for t in range(n) if out[t]["status"] != 5 and out[t]["N"] <= 2600][:8]    # bounded oracle time
+    assert len(pick) >= 6
+    import concurrent.futures as cf
+
+    def one(t):
+        return _oracle_trial_sweep(tr, fo, cfg, t)
+    with cf.ThreadPoolExecutor(8) as ex:                 # the oracle calls release the GIL (ctypes)
+        refs = list(ex.map(one, pick))
+    n_same = 0
+    for t, (s, ref, slew) in zip(pick, refs):
+        g = out[t]
+        assert g["N"] == s.N and abs(g["t_final"] - s.t_final) < 1e-9, (t, g, s.N)
+        assert g["status"] == ref["status"] and g["outer_iters"] == ref["outer_iters"], (t, g, ref)
+        assert abs(g["J"] - ref["J"]) <= 1e-6 * abs(ref["J"])
+        assert abs(g["c_max"] - ref["c_max"]) <= 1e-6 * max(1.0, ref["c_max"])
+        if g["inner_iters"] == ref["inner_iters"] and g["ls_rollouts"] == ref["ls_rollouts"]:
+            n_same += 1
+            assert g["slew_time"] == slew
+    assert n_same >= len(pick) - 1
+
+
+def _oracle_trial_sweep(tr, fo, cfg, t):
+    s = S.build_slew(tr["kep"][t], S.J_1U, tr["x0"][t, 3:7], tr["xf"][t, 3:7], mjd=fo[t]["mjd"], igrf_date=fo[t]["igrf_date"],
+                     field_radius_m=fo[t]["field_radius_m"], t0=cfg.t0, tf=cfg.tf, N_scope=int(cfg.N_scope), cutoff=cfg.cutoff,
+                     dt=cfg.dt, alpha=cfg.alpha, beta=cfg.beta)
+    Xs, Us, Ks, out = S.oracle_solve([s], want_K=False)
+    o = S.oracle_tvlqr_opts(noise_mode=2, seed=int(cfg.tvlqr.seed), R=float(cfg.tvlqr.Rd[0]))
+    x0l = s.x0.copy()
+    x0l[3:7] = _perturb(s.x0[3:7], tr["qn"][t])
+    x0l[7] = 0
+    a = S.oracle_tvlqr(s, Xs[0], Us[0], x0l, o, trial=t)
+    return s, out[0], a[5]
+
+
+def test_tvlqr_tracking_batch_matches_oracle(engine):
+    """BASELINE configs[4] shape: batched TVLQR tracking (simulator.jl / gain_simulator.jl through attitude_simulation)
+    of optimised slews with Philox disturbance draws, stand-alone through ts_tvlqr_sim_batch with DEVICE-side noise
+    generation, on a batch large enough to fill several warps: every trial against the oracle replay."""
+    qf = np.array([1.0, 0, 0, 0])
+    base = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P, S.quat_axis_angle([1, 0, 1], a), qf, t_final=tf_)
+            for a, tf_ in ((3.0, 40.0), (5.0, 60.0), (2.0, 30.0))]
+    Xs, Us, Ks, out = S.oracle_solve(base, nthreads=3)
+    n = 96
+    rng = np.random.default_rng(91)
+    idx = [i % 3 for i in range(n)]
+    o, g = S.tvlqr_opts_pair(noise_mode=2, seed=2024)
+    N_i = [base[i].N for i in idx]
+    Xl = np.concatenate([Xs[i] for i in idx])
+    Ul = np.concatenate([np.vstack([Us[i], np.zeros((1, 3))]) for i in idx])
+    x0l = []
+    for i in idx:
+        x = base[i].x0.copy()
+        x[3:7] = _perturb(base[i].x0[3:7], rng.normal(size=3) * (math.pi / 180) ** 2)
+        x[7] = 0
+        x0l.append(x)
+    rows = np.array([base[i].B.shape[0] for i in idx])
+    B_offs = np.concatenate([[0], np.cumsum(rows)])[:-1]
+    Xsim, Usim, dX, K, nsim, slew, offs = engine.tvlqr_sim_batch(
+        N_i, Xl, Ul, np.stack(x0l), np.stack([base[i].J.reshape(-1) for i in idx]), np.concatenate([base[i].B for i in idx]), B_offs, rows,
+        [base[i].index_scale for i in idx], [base[i].clock_rate for i in idx], [base[i].t_final for i in idx],
+        np.stack([base[i].xf[3:7] for i in idx]), opts=g, stream_id=np.arange(1000, 1000 + n))
+    for t, i in enumerate(idx):
+        a = S.oracle_tvlqr(base[i], Xs[i], Us[i], x0l[t], o, trial=1000 + t)
+        k = int(nsim[t])
+        assert k == a[4]
+        assert np.max(np.abs(Xsim[offs[t]:offs[t] + k] - a[0])) < 1e-10
+        assert np.max(np.abs(Usim[offs[t]:offs[t] + k] - a[1])) < 1e-9
+        assert slew[t] == a[5]
+
+
+def test_multi_gpu_handle_matches_single(engine):
+    """ts_create_multi: trials sharded round-robin over the devices of one node, outcomes gathered with NCCL; results
+    must not depend on the device count (Philox streams are keyed by the global trial id)."""
+    import torch
+    from tortoisesat.jl_b200 import host
+    ndev = torch.cuda.device_count()
+    rng = np.random.default_rng(5)
+    n = 10
+    cfg = host.default_mc_config(n, shared_orbit=True, run_tvlqr=True, tf=2400.0, cutoff=30.0, alpha=0.1)
+    cfg.tvlqr.noise_mode, cfg.tvlqr.seed = 2, 99
+    cfg.ilqr.max_outer = 4
+    kep = np.array([[0, 6771.0, 96.6, 0.0, 0.0, 90.0]])
+    fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
+    fo[0] = (GM, 58155.0, 2019.0, 6771000.0, 0, 0, 0)
+    q0 = rng.normal(size=(n, 4))
+    q0 /= np.linalg.norm(q0, axis=1, keepdims=True)
+    x0 = np.concatenate([np.zeros((n, 3)), q0, np.zeros((n, 1))], axis=1)
+    xf = np.tile(np.concatenate([[0, 0, 0], [math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0], [1.0]]), (n, 1))
+    Jm = np.tile(S.J_1U.reshape(-1), (n, 1))
+    qn = rng.normal(size=(n, 3)) * (math.pi / 180) ** 2
+    ref, st_ref = engine.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn, stream_id=np.arange(n))
+    for devs in ([0], list(range(min(ndev, 2)))):
+        m = host.MultiEngine(devs)
+        assert m.device_count() == len(devs)
+        out, st = m.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn)
+        m.close()
+        for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "N", "J", "c_max", "t_final", "slew_time"):
+            assert np.array_equal(out[f], ref[f]), (devs, f)
+        assert st.n_trials == n and st.n_converged == st_ref.n_converged and abs(st.sum_slew_time - st_ref.sum_slew_time) < 1e-9

@@ -10,6 +10,7 @@ library is missing or no GPU is usable.
 """
 from .host import (  # noqa: F401
     Engine,
+    MultiEngine,
     TortoiseError,
     lib_path,
     load_library,

@@ -144,8 +144,9 @@ struct K3Args {
   const int* warp_cap;        // [warps] knots (even)
   int64_t n_warps;            // warps of the first launch (the dynamic queue starts behind their static first groups)
   int64_t Nmax;               // longest horizon of the ensemble, padded to even
-  // region pool of the second launch: a wide warp takes 261 x N doubles per trial ([22 buffers x 10 | kd 24 | lam 6 |
-  // bk 10 | clk 1] x N), bump-allocated, and keeps its region for later trials that fit
+  // region pool of the second launch: a wide warp takes k3_wide_doubles_per_knot() x N doubles per trial ([22 buffers
+  // x 10 | kd 24 | lam 6 | bk 10 | clk 1] x N = 261 N by default), bump-allocated, and keeps its region for later trials
+  // that fit
   double* pool;
   unsigned long long* pool_used;  // doubles handed out
   long long pool_cap;             // doubles
@@ -236,8 +237,10 @@ __device__ __forceinline__ void k3_store_results(const Team& tm, const K3Args& a
 
 constexpr int K3_WARPS_PER_BLOCK = 1;
 constexpr int K3_SLOT_DOUBLES_PER_KNOT = 90 + 24 + 6 + 10 + 1;      // narrow team slot: 9 buffers x 10 | kd | lam | bk | clk
-constexpr int K3_WIDE_BUFFERS = 22;                                 // current trajectory + up to 21 line-search candidates
-constexpr int K3_WIDE_DOUBLES_PER_KNOT = K3_WIDE_BUFFERS * 10 + 24 + 6 + 10 + 1;
+// wide team: current trajectory + one buffer per line-search candidate of a batch (max_linesearch + 1 = 21 by default,
+// at most 32 per batch), then kd | lam | bk | clk
+__host__ __device__ inline int k3_wide_buffers(int max_linesearch) { return (max_linesearch + 1 < 32 ? max_linesearch + 1 : 32) + 1; }
+__host__ __device__ inline int k3_wide_doubles_per_knot(int max_linesearch) { return k3_wide_buffers(max_linesearch) * 10 + 24 + 6 + 10 + 1; }
 constexpr int K3_SMEM_BYTES = K3_WARPS_PER_BLOCK * 4 * TEAM_SMEM_DOUBLES * 8;
 
 // index of the n-th set bit (n = 0, 1, ...) of a 4-bit mask
@@ -553,6 +556,8 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
   w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
   w.slot_stride = 0;
   long long region_cap = 0;   // knots the warp's current region can hold
+  const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
+  const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
   unsigned n_parked = *a.park_count;
   if (n_parked > (unsigned)a.park_cap) n_parked = (unsigned)a.park_cap;
   for (;;) {
@@ -567,9 +572,9 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
     const long long Ne = N + (N & 1);
     if (Ne > region_cap) {  // first trial of this warp, or one longer than its region: take a new region from the pool
       unsigned long long off = 0;
-      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * K3_WIDE_DOUBLES_PER_KNOT));
+      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * dpk));
       off = __shfl_sync(0xffffffffu, off, 0);
-      if ((long long)(off + Ne * K3_WIDE_DOUBLES_PER_KNOT) > a.pool_cap) {
+      if ((long long)(off + Ne * dpk) > a.pool_cap) {
         // cannot happen: the host sizes the pool for the park_cap longest horizons; fail loudly rather than corrupt
         if (lane32 == 0) {
           ts_trial_outcome_dev oc = {};
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
       w.Nmax = Ne;                                   // buffer i of the warp = xu_warp + i * Ne * 10 (see xu_buf)
       w.slot_stride = 9 * Ne * 10;
       w.xu = w.xu_warp = a.pool + off;
-      w.kd = w.xu + (long long)K3_WIDE_BUFFERS * 10 * Ne;
+      w.kd = w.xu + (long long)nbuf * 10 * Ne;
       w.lam = w.kd + 24 * Ne;
       w.bk = w.lam + 6 * Ne;
       w.clk = w.bk + 10 * Ne;

@@ -612,9 +612,10 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     int64_t cap_fit = 0;
     for (int64_t i = 0; i < cap; ++i) {
       const double Ne = (double)(N_i_host[order_by_N[(size_t)i]] + 1);
-      if (need + pool_need + (27.0 + K3_WIDE_DOUBLES_PER_KNOT) * Ne > budget) break;
+      const double dpk = (double)k3_wide_doubles_per_knot(a.opts.max_linesearch);
+      if (need + pool_need + (27.0 + dpk) * Ne > budget) break;
       need += 27.0 * Ne;
-      pool_need += (double)K3_WIDE_DOUBLES_PER_KNOT * Ne;
+      pool_need += dpk * Ne;
       cap_fit = i + 1;
     }
     cap = cap_fit;
