@@ -67,6 +67,10 @@ int ts_k3_last_cycles(ts_ctx* ctx, int64_t n_trials, double* cycles3);
 /* Measures the FP64 FMA peak of the bound GPU with a register-resident DFMA
  * micro-benchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64 row). */
 int ts_fp64_peak_probe(ts_ctx* ctx, double* tflops_out);
+/* Latency micro-benchmark of the bound GPU (one warp): cycles4 = SM cycles per DEPENDENT operation for
+ * [DFMA, DADD/DMUL, rsqrt + DADD, shared-memory store -> __syncwarp -> load round trip] -- the quantities that bound
+ * the strictly sequential Riccati / rollout chains of K3 (profiles/README.md).                                  */
+int ts_fp64_latency_probe(ts_ctx* ctx, double* cycles4);
 
 /* ---- K1: batched IGRF-12 --------------------------------------------------- *
  * Replaces igrf12(date, r, lat, lon) [src/igrf.jl:67-274] (+ legendre.jl:254-292,

@@ -358,6 +358,48 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
   }
 }
 
+// Directional derivatives of the rk4 ZOH step (attitude_controller.jl:122-132,134-145) by JVPs through the four stages:
+// out[d*7 .. d*7+6] = d xn / d (x,u) . (vx_d, vu_d) for nd directions (dirs: nd x 10 = [vx(7) | vu(3)]).
+// Same register-resident scheme as rk3_jac7_jvp: four 11-double stage records + one direction in flight.
+TS_HD void rk4_jvp7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
+                    const double* B4, double h, int nd, const double* dirs, double* out) {
+  StagePt s1, s2, s3, s4;
+  double k1[7], k2[7], k3[7], k4[7], xs[7];
+  const double us[3] = {u[0] * 1.e-2, u[1] * 1.e-2, u[2] * 1.e-2};
+  stage_eval(I, x, us, B1, s1, k1);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k1[i] * h);
+  stage_eval(I, xs, us, B2, s2, k2);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k2[i] * h);
+  stage_eval(I, xs, us, B3, s3, k3);
+  for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i] * h;
+  stage_eval(I, xs, us, B4, s4, k4);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int d = 0; d < nd; ++d) {
+    double vx[7], vu[3], t1[7], t2[7], t3[7], t4[7], y[7];
+    for (int i = 0; i < 7; ++i) vx[i] = dirs[d * 10 + i];
+    for (int i = 0; i < 3; ++i) vu[i] = dirs[d * 10 + 7 + i];
+    stage_jvp(I, s1, us, vx, vu, t1);
+    for (int i = 0; i < 7; ++i) {
+      t1[i] *= h;
+      y[i] = vx[i] + 0.5 * t1[i];
+    }
+    stage_jvp(I, s2, us, y, vu, t2);
+    for (int i = 0; i < 7; ++i) {
+      t2[i] *= h;
+      y[i] = vx[i] + 0.5 * t2[i];
+    }
+    stage_jvp(I, s3, us, y, vu, t3);
+    for (int i = 0; i < 7; ++i) {
+      t3[i] *= h;
+      y[i] = vx[i] + t3[i];
+    }
+    stage_jvp(I, s4, us, y, vu, t4);
+    for (int i = 0; i < 7; ++i) out[d * 7 + i] = vx[i] + (t1[i] + 2.0 * t2[i] + 2.0 * t3[i] + t4[i] * h) * TS_SIXTH;
+  }
+}
+
 // rk4 ZOH step (attitude_controller.jl:122-132) with one field row per stage.
 template <int UMODE>
 TS_HD void rk4_jac7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,

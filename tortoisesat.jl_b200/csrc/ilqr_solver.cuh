@@ -115,10 +115,20 @@ struct TrialWork {
   long long Nmax;
 };
 
+// Work pointers always address global memory; when a TrialWork lives in shared memory (k3_wide_kernel) the compiler
+// can no longer infer that from the kernel parameters, and would fall back to generic LD/ST.
+template <class T>
+TS_HD T* gptr(T* p) {
+#ifdef __CUDA_ARCH__
+  __builtin_assume(__isGlobal(p));
+#endif
+  return p;
+}
+
 // trajectory buffer i in the warp's buffer space: slot i/9, buffer i%9 (a team that owns a single slot uses 0..8)
 template <int W>
 TS_HD double* xu_buf(const TrialWork& w, int i) {
-  return w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10);
+  return gptr(w.xu_warp + (long long)(i / 9) * w.slot_stride + (long long)(i % 9) * (w.Nmax * 10));
 }
 
 TS_HD int sym_idx(int i, int j) { return (i <= j) ? (i * 7 - i * (i - 1) / 2 + (j - i)) : (j * 7 - j * (j - 1) / 2 + (i - j)); }
@@ -194,6 +204,10 @@ TS_HD void bound_c(const ts_ilqr_opts_dev& o, const double u[3], double c[6]) {
   }
 }
 
+// A2: an inequality is active when c > 0 (default) or c >= 0; `c >= 0` is `c > -(smallest subnormal)`, so the switch
+// costs one uniform select instead of a second comparison per constraint.
+TS_HD double active_threshold(const ts_ilqr_opts_dev& o) { return o.a2_active_ge ? -4.9406564584124654e-324 : 0.0; }
+
 // Adds one knot's AL stage cost to Jc in the oracle's summation order; updates cmax.
 TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double sc, double mu, const double x[7], double e8,
                           const double u[3], const double lam[6], double& Jc, double& cmax) {
@@ -207,8 +221,9 @@ TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double s
   Jc += l * sc;
   double c[6];
   bound_c(o, u, c);
+  const double act_thr = active_threshold(o);
   for (int i = 0; i < 6; ++i) {
-    const bool act = (o.a2_active_ge ? (c[i] >= 0.0) : (c[i] > 0.0)) || (lam[i] > 0.0);
+    const bool act = (c[i] > act_thr) || (lam[i] > 0.0);
     Jc += lam[i] * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
     cmax = fmax(cmax, fmax(0.0, c[i]));
   }
@@ -245,8 +260,8 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
                                    int k, double sc, double mu, double* rec) {
   // all global inputs of the knot are loaded up front (one memory round trip, not one per use)
   const double* p = xu_cur + (long long)k * 10;
-  const double* bp = w.bk + (long long)k * 10;
-  const double* lp_ = w.lam + (long long)k * 6;
+  const double* bp = gptr(w.bk) + (long long)k * 10;
+  const double* lp_ = gptr(w.lam) + (long long)k * 6;
   double x[7], u[3], b[9], lam[6];
   for (int i = 0; i < 7; ++i) x[i] = p[i];
   for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
@@ -256,12 +271,13 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
   for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
   double c6[6];
   bound_c(o, u, c6);
+  const double act_thr = active_threshold(o);
   for (int i = 0; i < 3; ++i) {
     double lu = sc * in.Rd[i] * u[i];
     double luu = sc * in.Rd[i];
     const double lp = lam[i], ln = lam[3 + i];
-    const bool ap = (o.a2_active_ge ? (c6[i] >= 0.0) : (c6[i] > 0.0)) || (lp > 0.0);
-    const bool an = (o.a2_active_ge ? (c6[3 + i] >= 0.0) : (c6[3 + i] > 0.0)) || (ln > 0.0);
+    const bool ap = (c6[i] > act_thr) || (lp > 0.0);
+    const bool an = (c6[3 + i] > act_thr) || (ln > 0.0);
     lu += (lp + (ap ? mu * c6[i] : 0.0)) - (ln + (an ? mu * c6[3 + i] : 0.0));
     luu += (ap ? mu : 0.0) + (an ? mu : 0.0);
     rec[77 + i] = lu;
@@ -309,8 +325,8 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       if (base >= W) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
         const int kn = base - W + lane;
         tm.prefetch_l2(xu_cur + (long long)kn * 10);
-        tm.prefetch_l2(w.bk + (long long)kn * 10);
-        tm.prefetch_l2(w.lam + (long long)kn * 6);
+        tm.prefetch_l2(gptr(w.bk) + (long long)kn * 10);
+        tm.prefetch_l2(gptr(w.lam) + (long long)kn * 6);
       }
       int kk_hi = N - 2 - base;
       if (kk_hi > W - 1) kk_hi = W - 1;
@@ -389,7 +405,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             dV1 += d[l] * Qu[l];
             dV2 += 0.5 * d[l] * Quud[l];
           }
-          double* kdk = w.kd + (long long)k * 24;
+          double* kdk = gptr(w.kd) + (long long)k * 24;
           {  // ---- gains this lane needs, then its entries of the new value function
             double Quxi[3], Ki[3];
             for (int c = 0; c < 3; ++c) Quxi[c] = sm[L::KQ + li * 3 + c];
@@ -486,7 +502,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             chol3_solve(L, nb, d);
             for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
           }
-          double* kdk = w.kd + (long long)k * 24;
+          double* kdk = gptr(w.kd) + (long long)k * 24;
           if (lane < 7) {
             const double nb[3] = {-Quxc[0], -Quxc[1], -Quxc[2]};
             chol3_solve(L, nb, Kc);
@@ -544,10 +560,10 @@ TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
   if (tm.lane() < TEAM)
     for (int k = tm.lane(); k < N - 1; k += TEAM) {
       const double* p = xu + (long long)k * 10;
-      const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
-      add_stage_cost(in, o, sc, mu, p, e8, p + 7, w.lam + (long long)k * 6, Jc, cmax);
+      const double e8 = (in.Qd[7] != 0.0) ? (gptr(w.clk)[k] - in.xf[7]) : 0.0;
+      add_stage_cost(in, o, sc, mu, p, e8, p + 7, gptr(w.lam) + (long long)k * 6, Jc, cmax);
     }
-  if (tm.lane() == 0) add_terminal_cost(in, o, mu, xu + (long long)(N - 1) * 10, w.clk[N - 1] - in.xf[7], lam_g, Jc, cmax);
+  if (tm.lane() == 0) add_terminal_cost(in, o, mu, xu + (long long)(N - 1) * 10, gptr(w.clk)[N - 1] - in.xf[7], lam_g, Jc, cmax);
   cmax_out = tm.max(cmax);
   return tm.sum(Jc);
 }
@@ -566,9 +582,9 @@ TS_FN void stage_chunk(Team& tm, const TrialWork& w, const double* xu_cur, int b
   if (k < N - 1) {
     double* dst = buf + tm.lane() * FWD_REC;
     tm.stage16(dst, xu_cur + (long long)k * 10, 5);
-    tm.stage16(dst + 10, w.kd + (long long)k * 24, 12);
-    tm.stage16(dst + 34, w.lam + (long long)k * 6, 3);
-    tm.stage16(dst + 40, w.bk + (long long)k * 10, 5);
+    tm.stage16(dst + 10, gptr(w.kd) + (long long)k * 24, 12);
+    tm.stage16(dst + 34, gptr(w.lam) + (long long)k * 6, 3);
+    tm.stage16(dst + 40, gptr(w.bk) + (long long)k * 10, 5);
   }
   tm.stage_commit();
 }
@@ -616,7 +632,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
           t += alpha * kd[21 + i];
           ub[i] = t;
         }
-        const double e8 = (in.Qd[7] != 0.0) ? (w.clk[k] - in.xf[7]) : 0.0;
+        const double e8 = (in.Qd[7] != 0.0) ? (gptr(w.clk)[k] - in.xf[7]) : 0.0;
         add_stage_cost(in, o, sc, mu, xb, e8, ub, p + 34, Jc, cmax);
         {  // max_i |d_i| / (|u_i| + 1) with one division: pick the maximiser by cross-multiplication
           double na = fabs(kd[21]), da = fabs(ub[0]) + 1.0;
@@ -656,7 +672,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
     double* q = xu_cand + (long long)(N - 1) * 10;
     for (int i = 0; i < 7; ++i) q[i] = xb[i];
     q[7] = q[8] = q[9] = 0.0;
-    add_terminal_cost(in, o, mu, xb, w.clk[N - 1] - in.xf[7], lam_g, Jc, cmax);
+    add_terminal_cost(in, o, mu, xb, gptr(w.clk)[N - 1] - in.xf[7], lam_g, Jc, cmax);
   }
   r.J = Jc;
   r.cmax = cmax;
@@ -670,7 +686,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
 enum { PH_BACKWARD = 0, PH_FORWARD = 1, PH_DONE = 2 };
 struct TrialState {
   double mu, lam_g[8];
-  double J_prev, J, c_max, c_max_prev, rho, drho, dV1, dV2, clk_absmax;
+  double J_prev, J, J_true, c_max, c_max_prev, rho, drho, dV1, dV2, clk_absmax;
   long long cyc_bwd, cyc_fwd, cyc_lin;
   int it, outer, dJ_zero, inner_total, ls_total, status, cur, phase, b0, pad_;
 };
@@ -686,24 +702,24 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
     double x8 = in.clk0;
     for (int k = 0; k < N - 1; ++k) {
       const ClockStep cs = clock_rk3(x8, in.clock_rate, in.dt);
-      w.clk[k] = x8;
+      gptr(w.clk)[k] = x8;
       clk_absmax = fmax(clk_absmax, fabs(x8));
       const double tt[3] = {cs.t1, cs.t2, cs.t3};
       for (int s3 = 0; s3 < 3; ++s3) {
         const double* br = in.Bt + (long long)field_row(tt[s3], in.index_scale, in.B_rows) * 3;
-        for (int c = 0; c < 3; ++c) w.bk[(long long)k * 10 + s3 * 3 + c] = br[c];
+        for (int c = 0; c < 3; ++c) gptr(w.bk)[(long long)k * 10 + s3 * 3 + c] = br[c];
       }
-      w.bk[(long long)k * 10 + 9] = 0.0;
+      gptr(w.bk)[(long long)k * 10 + 9] = 0.0;
       x8 = cs.next;
     }
-    w.clk[N - 1] = x8;
+    gptr(w.clk)[N - 1] = x8;
     clk_absmax = fmax(clk_absmax, fabs(x8));
   }
   clk_absmax = tm.bcast(clk_absmax, 0);
-  for (int i = lane; i < (N - 1) * 6; i += Team::W) w.lam[i] = 0.0;
+  for (int i = lane; i < (N - 1) * 6; i += Team::W) gptr(w.lam)[i] = 0.0;
   tm.sync();
   if (lane == 0) {
-    double* xu = w.xu;
+    double* xu = gptr(w.xu);
     double xb[7];
     for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
     for (int k = 0; k < N - 1; ++k) {
@@ -712,7 +728,7 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
       double* q = xu + (long long)k * 10;
       for (int i = 0; i < 7; ++i) q[i] = xb[i];
       for (int i = 0; i < 3; ++i) q[7 + i] = u[i];
-      const double* b = w.bk + (long long)k * 10;
+      const double* b = gptr(w.bk) + (long long)k * 10;
       double xn[7];
       rk3_step7<0>(in.I, xb, u, b, b + 3, b + 6, in.dt, xn);
       for (int i = 0; i < 7; ++i) xb[i] = xn[i];
@@ -740,8 +756,9 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
   st.clk_absmax = clk_absmax;
   st.c_max = 0.0;
   st.c_max_prev = INFINITY;
-  st.J_prev = trajectory_cost(tm, in, o, w, w.xu, sc, st.mu, st.lam_g, st.c_max);
+  st.J_prev = trajectory_cost(tm, in, o, w, gptr(w.xu), sc, st.mu, st.lam_g, st.c_max);
   st.J = st.J_prev;
+  st.J_true = st.J_prev;
   st.phase = (o.max_outer < 1) ? PH_DONE : PH_BACKWARD;
 }
 
@@ -781,18 +798,18 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
   for (int k = lane; k < N - 1; k += Team::W) {
     double c6[6];
     bound_c(o, xu_c + (long long)k * 10 + 7, c6);
-    double* lam = w.lam + (long long)k * 6;
+    double* lam = gptr(w.lam) + (long long)k * 6;
     for (int i = 0; i < 6; ++i) {
       const double l0 = lam[i];
       double l = l0 + st.mu * c6[i];
       l = fmin(fmax(l, -o.dual_max), o.dual_max);
-      if (o.a5_dual_active_only && !((o.a2_active_ge ? (c6[i] >= 0.0) : (c6[i] > 0.0)) || (l0 > 0.0))) l = l0;
+      if (o.a5_dual_active_only && !((c6[i] > active_threshold(o)) || (l0 > 0.0))) l = l0;
       lam[i] = fmax(0.0, l);
     }
   }
   for (int i = 0; i < 8; ++i) {
     if (!(o.goal_mask & (1 << i))) continue;
-    const double e = ((i < 7) ? xu_c[(long long)(N - 1) * 10 + i] : w.clk[N - 1]) - in.xf[i];
+    const double e = ((i < 7) ? xu_c[(long long)(N - 1) * 10 + i] : gptr(w.clk)[N - 1]) - in.xf[i];
     const double l = st.lam_g[i] + st.mu * e;
     st.lam_g[i] = fmin(fmax(l, -o.dual_max), o.dual_max);
   }
@@ -812,8 +829,10 @@ TS_FN void solve_after_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_d
     st.rho = 0.0;
     st.drho = 0.0;
     double cm;
-    const double Jnew = trajectory_cost(tm, in, o, w, xu_c, sc, st.mu, st.lam_g, cm);
-    st.J_prev = o.a7_carry_cost ? st.J : Jnew;
+    // J_true: the current trajectory's cost under the NEW multipliers; J_prev: the line-search reference of the next
+    // iteration -- the same number in the default reading, the carried-over cost under A7
+    st.J_true = trajectory_cost(tm, in, o, w, xu_c, sc, st.mu, st.lam_g, cm);
+    st.J_prev = o.a7_carry_cost ? st.J : st.J_true;
   }
 }
 
@@ -895,21 +914,16 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   if (lane < TEAM)  // width-independent summation order, see trajectory_cost
     for (int k = lane; k < N - 1; k += TEAM) {
       const double* p = xu_cur + (long long)k * 10;
-      const double* kd = w.kd + (long long)k * 24;
+      const double* kd = gptr(w.kd) + (long long)k * 24;
       double mxg = 0.0;
       for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
       g += mxg;
     }
   const double grad = tm.sum(g) / (double)(o.a3_grad_over_N ? N : N - 1);
   st.cyc_fwd += ts_clock() - t0;
-  // the kept trajectory's cost: J_prev in the default reading; under A7 J_prev may still be the carried-over value, so
-  // the cost under the current multipliers is evaluated like the oracle does (al_cost of the unchanged trajectory)
-  double Jkeep = st.J_prev;
-  if (o.a7_carry_cost) {
-    double cm;
-    Jkeep = trajectory_cost(tm, in, o, w, xu_cur, sc, st.mu, st.lam_g, cm);
-  }
-  solve_after_forward(tm, in, o, w, st, Jkeep, grad);
+  // the kept trajectory's cost under the current multipliers (the oracle re-evaluates al_cost of the unchanged
+  // trajectory): J_prev, except in the first iteration of an inner solve under A7, where J_prev is the carried-over value
+  solve_after_forward(tm, in, o, w, st, (st.it == 1) ? st.J_true : st.J_prev, grad);
 }
 
 TS_HD void solve_finish(const TrialIn& in, const TrialState& st, ts_trial_outcome_dev& out) {

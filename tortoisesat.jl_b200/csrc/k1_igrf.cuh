@@ -57,6 +57,52 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
   if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
 }
 
+// Latency micro-benchmark (one warp): cycles per DEPENDENT operation for DFMA, DADD/DMUL pairs, rsqrt, and a shared-memory
+// store -> __syncwarp -> load round trip: the numbers that bound the strictly sequential Riccati / rollout chains of K3.
+__global__ void __launch_bounds__(32) fp64_latency_kernel(double* out, int iters, double a, double b) {
+  __shared__ double sm[64];
+  double x = threadIdx.x * 1e-9 + 1.0;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x = fma(x, a, b);
+  }
+  long long t1 = clock64();
+  double y = x;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      y = __dadd_rn(y, b);
+      y = __dmul_rn(y, a);
+    }
+  }
+  long long t2 = clock64();
+  double z = fabs(y) + 2.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z = rsqrt(z) + 2.0;
+  }
+  long long t3 = clock64();
+  double w = z;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[threadIdx.x] = w;
+      __syncwarp();
+      w = sm[(threadIdx.x + 1) & 31] + b;
+      __syncwarp();
+    }
+  }
+  long long t4 = clock64();
+  if (threadIdx.x == 0) {
+    out[0] = (double)(t1 - t0) / ((double)iters * 32);   // DFMA
+    out[1] = (double)(t2 - t1) / ((double)iters * 32);   // DADD / DMUL
+    out[2] = (double)(t3 - t2) / ((double)iters * 8);    // rsqrt + DADD
+    out[3] = (double)(t4 - t3) / ((double)iters * 8);    // STS + syncwarp + LDS + DADD + syncwarp
+    out[4] = w;
+  }
+}
+
 inline void igrf_host_constants(IgrfConsts& h) {
   memset(&h, 0, sizeof(h));
   for (int n = 1; n <= 13; ++n) {

@@ -487,12 +487,7 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(c
                 g += mxg;
               }
               const double gr = tm.sum(g) / (double)(a.opts.a3_grad_over_N ? inp->N : inp->N - 1);
-              double Jkeep = st.J_prev;
-              if (a.opts.a7_carry_cost) {  // see solve_forward: under A7 J_prev may be the carried-over value
-                double cm;
-                Jkeep = trajectory_cost(tm, *inp, a.opts, w, xc, sc, st.mu, st.lam_g, cm);
-              }
-              solve_after_forward(tm, *inp, a.opts, w, st, Jkeep, gr);
+              solve_after_forward(tm, *inp, a.opts, w, st, (st.it == 1) ? st.J_true : st.J_prev, gr);   // see solve_forward
             }
           }
         }
@@ -551,10 +546,17 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
   tm.ln = lane32;
   tm.sm = k3_smem;
   (void)gwarp;
-  TrialWork w;
-  w.Nmax = 0;
-  w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
-  w.slot_stride = 0;
+  // the warp's work pointers change with every region it takes from the pool, so they cannot be re-derived from kernel
+  // parameters the way the first launch does; they live in shared memory (one LDS per use) instead of eight 64-bit
+  // registers held across the whole solve in a kernel that already sits at the 255-register limit
+  __shared__ TrialWork w_sm;
+  TrialWork& w = w_sm;
+  if (lane32 == 0) {
+    w.Nmax = 0;
+    w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
+    w.slot_stride = 0;
+  }
+  __syncwarp();
   long long region_cap = 0;   // knots the warp's current region can hold
   const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
   const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
@@ -585,13 +587,17 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
         continue;
       }
       region_cap = Ne;
-      w.Nmax = Ne;                                   // buffer i of the warp = xu_warp + i * Ne * 10 (see xu_buf)
-      w.slot_stride = 9 * Ne * 10;
-      w.xu = w.xu_warp = a.pool + off;
-      w.kd = w.xu + (long long)nbuf * 10 * Ne;
-      w.lam = w.kd + 24 * Ne;
-      w.bk = w.lam + 6 * Ne;
-      w.clk = w.bk + 10 * Ne;
+      __syncwarp();
+      if (lane32 == 0) {
+        w.Nmax = Ne;                                   // buffer i of the warp = xu_warp + i * Ne * 10 (see xu_buf)
+        w.slot_stride = 9 * Ne * 10;
+        w.xu = w.xu_warp = a.pool + off;
+        w.kd = w.xu + (long long)nbuf * 10 * Ne;
+        w.lam = w.kd + 24 * Ne;
+        w.bk = w.lam + 6 * Ne;
+        w.clk = w.bk + 10 * Ne;
+      }
+      __syncwarp();
     }
     const double* pd = a.park_data + a.park_off[idx];
     for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];

@@ -1,11 +1,12 @@
-// K4 -- batched TVLQR replay, one thread per trial (tvlqr_solver.cuh), plus the
-// eigen-axis-slew / Bryson-weight preparation kernel.
+// K4 -- batched TVLQR replay in three launches (tvlqr_solver.cuh): K4a linearisation, one thread per (trial, knot);
+// K4b backward Riccati sweep and K4c closed-loop replay, one thread per trial -- plus the eigen-axis-slew /
+// Bryson-weight preparation kernel.
 //   attitude_simulation(...)      reference src/attitude_controller.jl:1-48 (+ :50-145)
 //   eigen_axis_slew(x0,xf,t)      src/eigen_axis_slew.jl:1-38
 //   Bryson weights                src/TortoiseSat.jl:157-168, src/monte_carlo.jl:165-176
-// A single backward sweep and a single forward sweep per trial: <1% of a trial's
-// FLOPs (~12 MFLOP vs ~2 GFLOP for the solve), latency-bound sequential
-// scans -- kept deliberately simple.
+// Round 1 ran all three phases in one thread per trial (255 registers, 5.5 KB of stack, 80 ms per 4096 trials and
+// 780 ms on the ragged sweep): the Jacobians were 70% of the work and sat inside the sequential scan.  They are now
+// their own fully parallel launch, and the two sequential scans are light (6x6 blocks, no spills in the loop).
 #pragma once
 #include "common.cuh"
 #include "tvlqr_solver.cuh"
@@ -36,9 +37,77 @@ struct K4Args {
   double* K;             // ragged N x 18 (scratch if the caller passes none)
   int64_t* N_sim;        // nullable
   double* slew_time;     // nullable
+  // linearisation scratch: AB[lin_total x 54] = projected (A 6x6 | B 6x3) per knot, lin_offs[t] = first knot of trial t
+  double* AB;
+  const int64_t* lin_offs;
+  int64_t lin_total;
 };
 
-__global__ void __launch_bounds__(64) k4_tvlqr_kernel(const K4Args a) {
+// ---- K4a: the linearisation, one thread per (trial, knot) -- ~70% of the replay's FLOPs and embarrassingly parallel
+// over knots (every knot's Jacobian depends only on the optimised trajectory).  lin_offs[t] = sum_{t' < t} (N_t' - 1).
+__global__ void __launch_bounds__(128) k4a_linearise_kernel(const K4Args a) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.lin_total) return;
+  // trial of knot g: largest t with lin_offs[t] <= g
+  int64_t lo = 0, hi = a.n_trials - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (a.lin_offs[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  const int64_t t = lo;
+  const int64_t k = g - a.lin_offs[t];
+  Inertia I;
+  for (int i = 0; i < 9; ++i) I.J[i] = a.Jmat[t * 9 + i];
+  inv3_gj(I.J, I.Jinv);
+  const double* X = a.X_lqr + a.offs[t] * 8;
+  const double* U = a.U_lqr + a.offs[t] * 3;
+  const double h = a.opts.dt_squared ? a.opts.dt * a.opts.dt : a.opts.dt;
+  double AB[54];
+  tvlqr_linearise_knot(I, X + k * 8, X + (k + 1) * 8, U + k * 3, a.B_eci + a.B_offs[t] * 3, a.B_rows[t], a.index_scale[t],
+                       a.clock_rate[t], h, AB);
+  double* o = a.AB + g * 54;
+  for (int i = 0; i < 54; ++i) o[i] = AB[i];
+}
+
+// ---- K4b: the backward Riccati sweep (sequential in k), one thread per trial, over the stored linearisations
+__global__ void __launch_bounds__(32) k4b_riccati_kernel(const K4Args a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_trials) return;
+  const int N = (int)a.N_i[t];
+  double S[36];
+  for (int i = 0; i < 36; ++i) S[i] = 0.0;
+  for (int i = 0; i < 6; ++i) S[i * 6 + i] = a.opts.Qfd[i];
+  const double* ab = a.AB + a.lin_offs[t] * 54;
+  double* K = a.K + a.offs[t] * 18;
+#pragma unroll 1
+  for (int k = N - 2; k >= 0; --k) tvlqr_riccati_step(a.opts, ab + (long long)k * 54, S, K + (long long)k * 18);
+}
+
+// ---- K4n: the disturbance draws of simulator.jl:5,10,22 (Philox4x32-10 + Box-Muller, counter-based on (seed, trial, step,
+// stage)) for every rk4 stage of every step, one thread per (trial, knot, stage).  In round 1 they were generated inside
+// the sequential replay, where the FP64 log / sincos of the Box-Muller transform were ~80% of its instructions.  The
+// draws overwrite the linearisation scratch (54 >= 36 doubles per knot), which K4b has consumed by then.
+__global__ void __launch_bounds__(128) k4n_noise_kernel(const K4Args a) {
+  const int64_t g4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g = g4 >> 2;
+  const int s4 = (int)(g4 & 3);
+  if (g >= a.lin_total) return;
+  int64_t lo = 0, hi = a.n_trials - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (a.lin_offs[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  const int64_t t = lo;
+  const int64_t k = g - a.lin_offs[t];
+  const uint32_t trial = a.stream_id ? a.stream_id[t] : (uint32_t)t;
+  double nz[9];
+  tvlqr_noise(a.opts.seed, trial, (uint32_t)k, (uint32_t)s4, nz);
+  double* o = a.AB + a.lin_offs[t] * 54 + (k * 4 + s4) * 9;
+  for (int i = 0; i < 9; ++i) o[i] = nz[i];
+}
+
+// ---- K4c: the closed-loop replay (sequential in k) + slew-time rule, one thread per trial
+__global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_trials) return;
   TvlqrIn in;
@@ -60,13 +129,28 @@ __global__ void __launch_bounds__(64) k4_tvlqr_kernel(const K4Args a) {
   in.trial_index_1based = (long long)in.trial + 1;
   ts_tvlqr_opts_dev o = a.opts;
   o.tf = a.t_final[t];
-  double* K = a.K + a.offs[t] * 18;
-  tvlqr_gains(in, o, K);
+  if (o.noise_mode == 2 && a.AB) {   // the Philox draws were pre-generated by K4n: replay them as an explicit array
+    in.noise = a.AB + a.lin_offs[t] * 54;
+    o.noise_mode = 1;
+  }
+  const double* K = a.K + a.offs[t] * 18;
   double slew = 0.0;
   const long long ns = tvlqr_replay(in, o, K, a.X_sim ? a.X_sim + a.offs[t] * 8 : nullptr, a.U_sim ? a.U_sim + a.offs[t] * 3 : nullptr,
                                     a.dX ? a.dX + a.offs[t] * 6 : nullptr, &slew);
   if (a.N_sim) a.N_sim[t] = ns;
   if (a.slew_time) a.slew_time[t] = slew;
+}
+
+// host: the three launches of K4 (a.AB / a.lin_offs / a.lin_total must be set)
+inline void k4_launch(ts_ctx* c, const K4Args& a) {
+  if (a.lin_total > 0) k4a_linearise_kernel<<<(unsigned)((a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
+  k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
+  if (a.opts.noise_mode == 2 && a.lin_total > 0) {
+    k4n_noise_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
+  c->launches += 3;
 }
 
 // eigen_axis_slew + Bryson weights, one thread per trial.  t_k = t0 + k*dt, k = 0..nt-1 with

@@ -186,6 +186,20 @@ int ts_fp64_peak_probe(ts_ctx* c, double* tflops_out) {
   return TS_OK;
 }
 
+int ts_fp64_latency_probe(ts_ctx* c, double* cycles4) {
+  if (!c || !cycles4) return TS_ERR_ARG;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  double* d = (double*)c->d_flag;   // 64 bytes
+  for (int rep = 0; rep < 2; ++rep) {
+    fp64_latency_kernel<<<1, 32, 0, c->stream>>>(d + 1, 2048, 1.0000001, 1e-9);
+    c->launches++;
+  }
+  TS_CUDA(c, cudaGetLastError());
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  TS_CUDA(c, cudaMemcpy(cycles4, d + 1, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  return TS_OK;
+}
+
 static void k1_launch(ts_ctx* c, cudaStream_t st, double date, int64_t n, const double* r, const double* la, const double* lo,
                       double* bn, double* be, double* bd) {
   const unsigned blocks = (unsigned)((n + K1_THREADS - 1) / K1_THREADS);
@@ -846,10 +860,18 @@ int ts_tvlqr_sim_batch(ts_ctx* c, int64_t n, const int64_t* N_i, const int64_t* 
   a.noise = (o.noise_mode == 1) ? (const double*)dNz.d : nullptr;
   a.X_sim = X_sim ? (double*)oX.d : nullptr; a.U_sim = U_sim ? (double*)oU.d : nullptr; a.dX = dX ? (double*)odX.d : nullptr;
   a.K = dK; a.N_sim = (int64_t*)p_o; a.slew_time = (double*)((int64_t*)p_o + T);
+  {
+    std::vector<int64_t> lin((size_t)T + 1, 0);
+    for (size_t t = 0; t < T; ++t) lin[t + 1] = lin[t] + (N_i[t] - 1);
+    int64_t* d_lin;
+    void* p_ab;
+    if ((rc = upload(c, 27, lin.data(), T + 1, &d_lin))) return rc;
+    if ((rc = scratch_reserve(c, 26, (size_t)lin[T] * 54 * 8 + 64, &p_ab))) return rc;
+    a.AB = (double*)p_ab; a.lin_offs = d_lin; a.lin_total = lin[T];
+  }
   KernelTimer tm(c);
-  k4_tvlqr_kernel<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(a);
+  k4_launch(c, a);
   tm.stop();
-  c->launches++;
   TS_CUDA(c, cudaGetLastError());
   if (X_sim && (rc = dev_back(c, oX, X_sim, (size_t)knots * 8 * 8))) return rc;
   if (U_sim && (rc = dev_back(c, oU, U_sim, (size_t)knots * 3 * 8))) return rc;
@@ -1094,8 +1116,16 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
         d_Xs_keep = k4.X_sim; d_Us_keep = k4.U_sim;
       }
       k4.N_sim = d_nsim; k4.slew_time = d_slew;
-      k4_tvlqr_kernel<<<(unsigned)((na + 63) / 64), 64, 0, c->stream>>>(k4);
-      c->launches++;
+      {
+        std::vector<int64_t> lin(NA + 1, 0);
+        for (size_t a2 = 0; a2 < NA; ++a2) lin[a2 + 1] = lin[a2] + (hi[a2] - 1);
+        int64_t* d_lin;
+        void* p_ab;
+        if ((rc = upload(c, 27, lin.data(), NA + 1, &d_lin))) return rc;
+        if ((rc = scratch_reserve(c, 26, (size_t)lin[NA] * 54 * 8 + 64, &p_ab))) return rc;
+        k4.AB = (double*)p_ab; k4.lin_offs = d_lin; k4.lin_total = lin[NA];
+      }
+      k4_launch(c, k4);
     }
     cudaEventRecord(e[5], c->stream);
     TS_CUDA(c, cudaGetLastError());

@@ -137,115 +137,138 @@ TS_HD void simulator7(const Inertia& I, const double x[7], const double u[3], co
   for (int i = 0; i < 4; ++i) dx[3 + i] = 0.5 * qd[i];
 }
 
-// Gains K ((N-1) x 18, row-major 3x6 per knot) -- attitude_lqr, both methods.
-TS_HD void tvlqr_gains(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, double* K) {
+// ---- attitude_lqr, first method (attitude_controller.jl:95-119) + the G(q) projection of the second (:59-81), for ONE
+// knot: the reduced discrete linearisation A (6x6), B (6x3) -> AB54 = [A row-major 36 | B row-major 18].
+// The reference takes the full 12x12 ForwardDiff Jacobian of rk4(f_augmented(gain_simulator)) with step dt^2 (Q6) and then
+// forms A = perm_Gn * Aq * perm_Gk, B = perm_Gn * Bq.  Here the 9 needed directional derivatives are taken directly:
+// the three rate directions, the three columns of G(q_k) in the quaternion block (Aq * perm_Gk without ever forming Aq's
+// four quaternion columns) and the three control directions -- the same numbers up to summation order (1e-16 relative).
+TS_HD void tvlqr_linearise_knot(const Inertia& I, const double* xk, const double* xn_, const double* uk, const double* Bt, long long B_rows,
+                                double index_scale, double clock_rate, double h, double* AB54) {
+  double tcl[4], nxt;
+  clock_rk4(xk[7], clock_rate, h, tcl, nxt);
+  const double* Br[4];
+  for (int s = 0; s < 4; ++s) Br[s] = Bt + (long long)field_row(tcl[s], index_scale, B_rows) * 3;
+  // G(q) = [-v'; s I + hat(v)]   (attitude_controller.jl:59-71), row-major 4x3
+  double Gn[12];
+  {
+    const double s = xn_[3], v0 = xn_[4], v1 = xn_[5], v2 = xn_[6];
+    const double g[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
+    for (int i = 0; i < 12; ++i) Gn[i] = g[i];
+  }
+  double dirs[90];
+  for (int i = 0; i < 90; ++i) dirs[i] = 0.0;
+  {
+    const double s = xk[3], v0 = xk[4], v1 = xk[5], v2 = xk[6];
+    const double Gk[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
+    for (int d = 0; d < 3; ++d) {
+      dirs[d * 10 + d] = 1.0;                                         // rate directions
+      for (int l = 0; l < 4; ++l) dirs[(3 + d) * 10 + 3 + l] = Gk[l * 3 + d];   // column d of G(q_k)
+      dirs[(6 + d) * 10 + 7 + d] = 1.0;                               // control directions
+    }
+  }
+  double cols[63];
+  rk4_jvp7(I, xk, uk, Br[0], Br[1], Br[2], Br[3], h, 9, dirs, cols);
+  // perm_Gn * column: rows 0..2 copy, rows 3..5 = Gn' * (quaternion rows)
+  for (int d = 0; d < 9; ++d) {
+    const double* c = cols + d * 7;
+    double r[6];
+    for (int i = 0; i < 3; ++i) r[i] = c[i];
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+      for (int l = 0; l < 4; ++l) s += Gn[l * 3 + i] * c[3 + l];
+      r[3 + i] = s;
+    }
+    if (d < 6)
+      for (int i = 0; i < 6; ++i) AB54[i * 6 + d] = r[i];
+    else
+      for (int i = 0; i < 6; ++i) AB54[36 + i * 3 + (d - 6)] = r[i];
+  }
+}
+
+// ---- attitude_lqr, second method (attitude_controller.jl:84-91): one backward Riccati step.
+// K = inv(R + B'SB) (B'SA) ; S <- Q + K'RK + (A-BK)'S(A-BK).  Kout: 3x6 row-major.
+TS_HD void tvlqr_riccati_step(const ts_tvlqr_opts_dev& o, const double* AB54, double S[36], double* Kout) {
+  const double* A = AB54;
+  const double* B = AB54 + 36;
+  double SB[18], SA[36], BSB[9], BSA[18], Minv[9], Kk[18], Acl[36], SAcl[36];
+  for (int i = 0; i < 6; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * B[l * 3 + j];
+      SB[i * 3 + j] = s;
+    }
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * A[l * 6 + j];
+      SA[i * 6 + j] = s;
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SB[l * 3 + j];
+      BSB[i * 3 + j] = s + ((i == j) ? o.Rd[i] : 0.0);
+    }
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SA[l * 6 + j];
+      BSA[i * 6 + j] = s;
+    }
+  }
+  inv3_general(BSB, Minv);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 3; ++l) s += Minv[i * 3 + l] * BSA[l * 6 + j];
+      Kk[i * 6 + j] = s;
+      Kout[i * 6 + j] = s;
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 3; ++l) s += B[i * 3 + l] * Kk[l * 6 + j];
+      Acl[i * 6 + j] = A[i * 6 + j] - s;
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * Acl[l * 6 + j];
+      SAcl[i * 6 + j] = s;
+    }
+  double Sn[36];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = (i == j) ? o.Qd[i] : 0.0;
+      double kr = 0.0;
+      for (int l = 0; l < 3; ++l) kr += Kk[l * 6 + i] * o.Rd[l] * Kk[l * 6 + j];
+      s += kr;
+      double t = 0.0;
+      for (int l = 0; l < 6; ++l) t += Acl[l * 6 + i] * SAcl[l * 6 + j];
+      Sn[i * 6 + j] = s + t;
+    }
+  for (int i = 0; i < 36; ++i) S[i] = Sn[i];
+}
+
+// Gains K ((N-1) x 18, row-major 3x6 per knot) -- attitude_lqr, both methods, for one trial in one thread (host
+// lane-emulator and small batches; the GPU path runs the linearisation as its own fully parallel kernel, K4a).
+// ABp: optional precomputed linearisations ((N-1) x 54); null -> computed on the fly.
+TS_HD void tvlqr_gains(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, double* K, const double* ABp = nullptr) {
   const int N = in.N;
   const double h = o.dt_squared ? o.dt * o.dt : o.dt;
   double S[36];
   for (int i = 0; i < 36; ++i) S[i] = 0.0;
   for (int i = 0; i < 6; ++i) S[i * 6 + i] = o.Qfd[i];
   for (int k = N - 2; k >= 0; --k) {
-    const double* xk = in.X_lqr + (long long)k * 8;
-    const double* xn_ = in.X_lqr + (long long)(k + 1) * 8;
-    double tcl[4], nxt;
-    clock_rk4(xk[7], in.clock_rate, h, tcl, nxt);
-    const double* Br[4];
-    for (int s = 0; s < 4; ++s) Br[s] = in.Bt + (long long)field_row(tcl[s], in.index_scale, in.B_rows) * 3;
-    double xo[7], AB[70];
-    rk4_jac7<1>(in.I, xk, in.U_lqr + (long long)k * 3, Br[0], Br[1], Br[2], Br[3], h, xo, AB);
-    // G(q) = [-v'; s I + hat(v)]   (attitude_controller.jl:59-71)
-    double Gk[12], Gn[12];
-    {
-      const double s = xk[3], v0 = xk[4], v1 = xk[5], v2 = xk[6];
-      const double g[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
-      for (int i = 0; i < 12; ++i) Gk[i] = g[i];
+    double AB[54];
+    const double* ab = AB;
+    if (ABp) {
+      ab = ABp + (long long)k * 54;
+    } else {
+      tvlqr_linearise_knot(in.I, in.X_lqr + (long long)k * 8, in.X_lqr + (long long)(k + 1) * 8, in.U_lqr + (long long)k * 3, in.Bt, in.B_rows,
+                           in.index_scale, in.clock_rate, h, AB);
     }
-    {
-      const double s = xn_[3], v0 = xn_[4], v1 = xn_[5], v2 = xn_[6];
-      const double g[12] = {-v0, -v1, -v2, s, -v2, v1, v2, s, -v0, -v1, v0, s};
-      for (int i = 0; i < 12; ++i) Gn[i] = g[i];
-    }
-    // T1 = perm_Gn * [Aq | Bq]  (6 x 10): rows 0..2 = rows 0..2 of AB; rows 3..5 = Gn' * rows 3..6
-    double T1[60];
-    for (int j = 0; j < 10; ++j) {
-      for (int i = 0; i < 3; ++i) T1[i * 10 + j] = AB[i * 10 + j];
-      for (int i = 0; i < 3; ++i) {
-        double s = 0.0;
-        // the reference multiplies the full 6x7 permutation matrix: zeros from the identity block first
-        for (int l = 0; l < 4; ++l) s += Gn[l * 3 + i] * AB[(3 + l) * 10 + j];
-        T1[(3 + i) * 10 + j] = s;
-      }
-    }
-    // A = T1[:, 0:7] * perm_Gk (6x6), B = T1[:, 7:10] (6x3)
-    double A[36], B[18];
-    for (int i = 0; i < 6; ++i) {
-      for (int j = 0; j < 3; ++j) A[i * 6 + j] = T1[i * 10 + j];
-      for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 4; ++l) s += T1[i * 10 + 3 + l] * Gk[l * 3 + j];
-        A[i * 6 + 3 + j] = s;
-      }
-      for (int j = 0; j < 3; ++j) B[i * 3 + j] = T1[i * 10 + 7 + j];
-    }
-    // K = inv(R + B'SB) (B'SA) ; S = Q + K'RK + (A-BK)'S(A-BK)
-    double SB[18], SA[36], BSB[9], BSA[18], Minv[9], Kk[18], Acl[36], SAcl[36];
-    for (int i = 0; i < 6; ++i) {
-      for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * B[l * 3 + j];
-        SB[i * 3 + j] = s;
-      }
-      for (int j = 0; j < 6; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * A[l * 6 + j];
-        SA[i * 6 + j] = s;
-      }
-    }
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SB[l * 3 + j];
-        BSB[i * 3 + j] = s + ((i == j) ? o.Rd[i] : 0.0);
-      }
-      for (int j = 0; j < 6; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SA[l * 6 + j];
-        BSA[i * 6 + j] = s;
-      }
-    }
-    inv3_general(BSB, Minv);
-    double* Kout = K + (long long)k * 18;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 6; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 3; ++l) s += Minv[i * 3 + l] * BSA[l * 6 + j];
-        Kk[i * 6 + j] = s;
-        Kout[i * 6 + j] = s;
-      }
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j < 6; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 3; ++l) s += B[i * 3 + l] * Kk[l * 6 + j];
-        Acl[i * 6 + j] = A[i * 6 + j] - s;
-      }
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j < 6; ++j) {
-        double s = 0.0;
-        for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * Acl[l * 6 + j];
-        SAcl[i * 6 + j] = s;
-      }
-    double Sn[36];
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j < 6; ++j) {
-        double s = (i == j) ? o.Qd[i] : 0.0;
-        double kr = 0.0;
-        for (int l = 0; l < 3; ++l) kr += Kk[l * 6 + i] * o.Rd[l] * Kk[l * 6 + j];
-        s += kr;
-        double t = 0.0;
-        for (int l = 0; l < 6; ++l) t += Acl[l * 6 + i] * SAcl[l * 6 + j];
-        Sn[i * 6 + j] = s + t;
-      }
-    for (int i = 0; i < 36; ++i) S[i] = Sn[i];
+    tvlqr_riccati_step(o, ab, S, K + (long long)k * 18);
   }
 }
 

@@ -137,6 +137,7 @@ def load_library():
     L.ts_k3_last_split.restype = C.c_int
     L.ts_k3_last_cycles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.ts_fp64_peak_probe.argtypes = [C.c_void_p, c_double_p]
+    L.ts_fp64_latency_probe.argtypes = [C.c_void_p, c_double_p]
     L.ts_mc_trajectory_layout.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.ts_mc_fetch_trajectories.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.ts_igrf12syn_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
@@ -453,6 +454,12 @@ class Engine:
                                                 None if qn is None else _ptr(qn), None if sid is None else _ptr(sid),
                                                 out.ctypes.data, C.byref(st)))
         return out, st
+
+    def fp64_latency_cycles(self):
+        """SM cycles per dependent DFMA, DADD/DMUL, rsqrt+DADD, and shared-memory round trip (ts_fp64_latency_probe)."""
+        v = (C.c_double * 4)()
+        self._check(self.lib.ts_fp64_latency_probe(self.h, v))
+        return dict(zip(("dfma", "dadd_dmul", "rsqrt_dadd", "smem_roundtrip"), [float(x) for x in v]))
 
     def k3_last_cycles(self, n_trials):
         """(n_trials, 3) SM cycles of the last AL-iLQR solve: backward pass, forward pass, linearisation share."""
