@@ -65,3 +65,25 @@ def test_shard_helpers():
     assert cover == list(range(65536 + 3))
     il = np.sort(np.concatenate([parallel.interleaved_shard(101, r, 4) for r in range(4)]))
     assert il.tolist() == list(range(101))
+
+
+def test_persistence_round_trip_and_retry_list(tmp_path):
+    """results in the on-disk shape of monte_carlo.jl:334-343 (same container and dataset names, .npz
+    instead of HDF5) and the `retry` list of monte_carlo.jl:269 (host logic only: no GPU needed)."""
+    import numpy as np
+    from tortoisesat.jl_b200 import host
+    n = 4
+    rng = np.random.default_rng(0)
+    res = dict(A=rng.random((n, 6)), t_final=np.array([100., 200., 300., 50.]), slew_time=np.array([50., 200., 120., 50.]),
+               fails=np.array([0., 1., 0., 1.]), outcomes=np.zeros(n, dtype=host.OUTCOME_DTYPE),
+               sim_states=[rng.random((8, 5 + i)) for i in range(n)], sim_control_inputs=[rng.random((3, 5 + i)) for i in range(n)],
+               B_ECI_total=[rng.random((10 + 2 * i, 3)) for i in range(n)], t_total=[np.arange(6 + i) * 0.2 for i in range(n)])
+    retry = host.save_monte_carlo(res, str(tmp_path), prefix="100")
+    assert retry.tolist() == [2, 4]                                     # findall(x -> x == 1., fails), 1-based
+    for name in ("100_A", "100_states_1", "100_control_4", "100_B_N_2", "100_t_total_3", "100_summary"):
+        assert (tmp_path / (name + ".npz")).exists()
+    assert set(np.load(tmp_path / "100_states_2.npz").files) == {"one_state", "states"}
+    back = host.load_monte_carlo(str(tmp_path), prefix="100")
+    assert back["retry"].tolist() == [2, 4] and np.array_equal(back["A"], res["A"])
+    for k in ("sim_states", "sim_control_inputs", "B_ECI_total", "t_total"):
+        assert all(np.array_equal(a, b) for a, b in zip(back[k], res[k]))

@@ -1,5 +1,6 @@
-// K4 -- batched TVLQR replay in three launches (tvlqr_solver.cuh): K4a linearisation, one thread per (trial, knot);
-// K4b backward Riccati sweep and K4c closed-loop replay, one thread per trial -- plus the eigen-axis-slew /
+// K4 -- batched TVLQR replay in four launches (tvlqr_solver.cuh): K4a linearisation, one thread per (trial, knot);
+// K4b backward Riccati sweep, one thread per trial; K4n stage records (noise, perturbation quaternions, field rows), one
+// thread per (trial, step, stage); K4c closed-loop replay, one thread per trial -- plus the eigen-axis-slew /
 // Bryson-weight preparation kernel.
 //   attitude_simulation(...)      reference src/attitude_controller.jl:1-48 (+ :50-145)
 //   eigen_axis_slew(x0,xf,t)      src/eigen_axis_slew.jl:1-38
@@ -39,6 +40,7 @@ struct K4Args {
   double* slew_time;     // nullable
   // linearisation scratch: AB[lin_total x 54] = projected (A 6x6 | B 6x3) per knot, lin_offs[t] = first knot of trial t
   double* AB;
+  double* clk;             // [lin_total] replay clock state per step (written by K4b, read by K4n)
   const int64_t* lin_offs;
   int64_t lin_total;
 };
@@ -81,13 +83,25 @@ __global__ void __launch_bounds__(32) k4b_riccati_kernel(const K4Args a) {
   double* K = a.K + a.offs[t] * 18;
 #pragma unroll 1
   for (int k = N - 2; k >= 0; --k) tvlqr_riccati_step(a.opts, ab + (long long)k * 54, S, K + (long long)k * 18);
+  // the replay's clock state at every step (the reference accumulates it through rk4: sequential, exact replica), so
+  // that K4n can look the stage field rows up in parallel
+  double x8 = a.x0_lqr[t * 8 + 7];
+  double* clk = a.clk + a.lin_offs[t];
+#pragma unroll 1
+  for (int k = 0; k < N - 1; ++k) {
+    clk[k] = x8;
+    double tcl[4], nxt;
+    clock_rk4(x8, a.clock_rate[t], a.opts.dt, tcl, nxt);
+    x8 = nxt;
+  }
 }
 
-// ---- K4n: the disturbance draws of simulator.jl:5,10,22 (Philox4x32-10 + Box-Muller, counter-based on (seed, trial, step,
-// stage)) for every rk4 stage of every step, one thread per (trial, knot, stage).  In round 1 they were generated inside
-// the sequential replay, where the FP64 log / sincos of the Box-Muller transform were ~80% of its instructions.  The
-// draws overwrite the linearisation scratch (54 >= 36 doubles per knot), which K4b has consumed by then.
-__global__ void __launch_bounds__(128) k4n_noise_kernel(const K4Args a) {
+// ---- K4n: the stage records of the replay (tvlqr_solver.cuh): for every rk4 stage of every step the disturbance draws of
+// simulator.jl:5,10,22 (Philox4x32-10 + Box-Muller, counter-based on (seed, trial, step, stage)), the perturbation
+// quaternion (sincos) and the perturbed field row of the stage's clock value -- one thread per (trial, step, stage).  In
+// round 1 all of this sat inside the sequential replay, where FP64 log / sincos / divisions were ~80% of its instructions.
+// The records (40 doubles per step) overwrite the linearisation scratch (54 per step), which K4b has consumed by then.
+__global__ void __launch_bounds__(128) k4n_records_kernel(const K4Args a) {
   const int64_t g4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t g = g4 >> 2;
   const int s4 = (int)(g4 & 3);
@@ -99,11 +113,20 @@ __global__ void __launch_bounds__(128) k4n_noise_kernel(const K4Args a) {
   }
   const int64_t t = lo;
   const int64_t k = g - a.lin_offs[t];
-  const uint32_t trial = a.stream_id ? a.stream_id[t] : (uint32_t)t;
-  double nz[9];
-  tvlqr_noise(a.opts.seed, trial, (uint32_t)k, (uint32_t)s4, nz);
-  double* o = a.AB + a.lin_offs[t] * 54 + (k * 4 + s4) * 9;
-  for (int i = 0; i < 9; ++i) o[i] = nz[i];
+  double tcl[4], nxt;
+  clock_rk4(a.clk[g], a.clock_rate[t], a.opts.dt, tcl, nxt);
+  const double* Bn = a.B_eci + (a.B_offs[t] + field_row(tcl[s4], a.index_scale[t], a.B_rows[t])) * 3;
+  double nzb[9];
+  const double* nz = nullptr;
+  if (a.opts.noise_mode == 1) nz = a.noise + a.offs[t] * 36 + (k * 4 + s4) * 9;
+  if (a.opts.noise_mode == 2) {
+    tvlqr_noise(a.opts.seed, a.stream_id ? a.stream_id[t] : (uint32_t)t, (uint32_t)k, (uint32_t)s4, nzb);
+    nz = nzb;
+  }
+  double rec[TV_REC];
+  tvlqr_stage_record(nz, Bn, rec);
+  double* o = a.AB + a.lin_offs[t] * 54 + (k * 4 + s4) * TV_REC;
+  for (int i = 0; i < TV_REC; ++i) o[i] = rec[i];
 }
 
 // ---- K4c: the closed-loop replay (sequential in k) + slew-time rule, one thread per trial
@@ -129,14 +152,10 @@ __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
   in.trial_index_1based = (long long)in.trial + 1;
   ts_tvlqr_opts_dev o = a.opts;
   o.tf = a.t_final[t];
-  if (o.noise_mode == 2 && a.AB) {   // the Philox draws were pre-generated by K4n: replay them as an explicit array
-    in.noise = a.AB + a.lin_offs[t] * 54;
-    o.noise_mode = 1;
-  }
   const double* K = a.K + a.offs[t] * 18;
   double slew = 0.0;
-  const long long ns = tvlqr_replay(in, o, K, a.X_sim ? a.X_sim + a.offs[t] * 8 : nullptr, a.U_sim ? a.U_sim + a.offs[t] * 3 : nullptr,
-                                    a.dX ? a.dX + a.offs[t] * 6 : nullptr, &slew);
+  const long long ns = tvlqr_replay_t<true>(in, o, K, a.X_sim ? a.X_sim + a.offs[t] * 8 : nullptr, a.U_sim ? a.U_sim + a.offs[t] * 3 : nullptr,
+                                            a.dX ? a.dX + a.offs[t] * 6 : nullptr, &slew, a.AB + a.lin_offs[t] * 54);
   if (a.N_sim) a.N_sim[t] = ns;
   if (a.slew_time) a.slew_time[t] = slew;
 }
@@ -145,12 +164,9 @@ __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
 inline void k4_launch(ts_ctx* c, const K4Args& a) {
   if (a.lin_total > 0) k4a_linearise_kernel<<<(unsigned)((a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
   k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
-  if (a.opts.noise_mode == 2 && a.lin_total > 0) {
-    k4n_noise_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
-    c->launches++;
-  }
+  if (a.lin_total > 0) k4n_records_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
   k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
-  c->launches += 3;
+  c->launches += 4;
 }
 
 // eigen_axis_slew + Bryson weights, one thread per trial.  t_k = t0 + k*dt, k = 0..nt-1 with

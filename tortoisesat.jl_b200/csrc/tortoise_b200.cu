@@ -866,8 +866,8 @@ int ts_tvlqr_sim_batch(ts_ctx* c, int64_t n, const int64_t* N_i, const int64_t* 
     int64_t* d_lin;
     void* p_ab;
     if ((rc = upload(c, 27, lin.data(), T + 1, &d_lin))) return rc;
-    if ((rc = scratch_reserve(c, 26, (size_t)lin[T] * 54 * 8 + 64, &p_ab))) return rc;
-    a.AB = (double*)p_ab; a.lin_offs = d_lin; a.lin_total = lin[T];
+    if ((rc = scratch_reserve(c, 26, (size_t)lin[T] * 55 * 8 + 64, &p_ab))) return rc;
+    a.AB = (double*)p_ab; a.clk = a.AB + (size_t)lin[T] * 54; a.lin_offs = d_lin; a.lin_total = lin[T];
   }
   KernelTimer tm(c);
   k4_launch(c, a);
@@ -1122,8 +1122,8 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
         int64_t* d_lin;
         void* p_ab;
         if ((rc = upload(c, 27, lin.data(), NA + 1, &d_lin))) return rc;
-        if ((rc = scratch_reserve(c, 26, (size_t)lin[NA] * 54 * 8 + 64, &p_ab))) return rc;
-        k4.AB = (double*)p_ab; k4.lin_offs = d_lin; k4.lin_total = lin[NA];
+        if ((rc = scratch_reserve(c, 26, (size_t)lin[NA] * 55 * 8 + 64, &p_ab))) return rc;
+        k4.AB = (double*)p_ab; k4.clk = k4.AB + (size_t)lin[NA] * 54; k4.lin_offs = d_lin; k4.lin_total = lin[NA];
       }
       k4_launch(c, k4);
     }

@@ -64,6 +64,29 @@ TS_HD void inv3_general(const double A[9], double out[9]) {
     for (int j = 0; j < 3; ++j) out[i * 3 + j] = M[i][3 + j];
 }
 
+#ifdef __CUDA_ARCH__
+#define TS_UNROLL _Pragma("unroll")
+#else
+#define TS_UNROLL
+#endif
+
+// inverse of a well-conditioned 3x3 (R + B'SB, symmetric positive definite and dominated by R) by the adjugate: no
+// pivot search, hence no dynamically indexed scratch in the sequential Riccati sweep
+TS_HD void inv3_adj(const double A[9], double out[9]) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double id = 1.0 / det;
+  out[0] = c00 * id;
+  out[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+  out[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+  out[3] = c01 * id;
+  out[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+  out[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+  out[6] = c02 * id;
+  out[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+  out[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
 struct TvlqrIn {
   int N;                 // knots of the optimised trajectory
   const double* X_lqr;   // N x 8
@@ -106,29 +129,47 @@ TS_HD void clock_rk4(double x8, double rate, double h, double t[4], double& next
 #endif
 }
 
-// simulator(dx,x,u) (simulator.jl:1-42) for the 7 dynamic states; nz = 9 scaled perturbations or null
-TS_HD void simulator7(const Inertia& I, const double x[7], const double u[3], const double* Bn, const double* nz, double dx[7]) {
-  double om[3] = {x[0], x[1], x[2]};
-  const double nq = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
-  double q[4] = {x[3] / nq, x[4] / nq, x[5] / nq, x[6] / nq};
-  double Bf[3] = {Bn[0], Bn[1], Bn[2]};
-  if (nz) {
-    for (int i = 0; i < 3; ++i) om[i] = x[i] + nz[i];
-    const double th = sqrt(nz[3] * nz[3] + nz[4] * nz[4] + nz[5] * nz[5]);
+// ---- stage records -----------------------------------------------------------------------------------------------------
+// Everything of one simulator() call (simulator.jl:1-42) that does not depend on the state, 10 doubles per rk4 stage:
+//   [0:3) omega_noise   (randn(3)*(.38pi/180)^2, :5)
+//   [3:7) the perturbation quaternion [cos(th/2); r sin(th/2)] of q_noise = randn(3)*(pi/180)^2 (:10-13); identity if none
+//   [7:10) B_ECI[floor(t*N+1),:] + B_N_noise (:22) -- the field row of the stage's clock value, already perturbed
+// The GPU path produces the records of all (trial, step, stage) in one fully parallel launch (K4n: Philox + Box-Muller +
+// sincos + field lookup), so the sequential replay only multiplies and adds; the host emulator builds them on the fly
+// with the same function, so both run the same arithmetic.
+constexpr int TV_REC = 10;
+TS_HD void tvlqr_stage_record(const double* nz9, const double* Bn, double rec[TV_REC]) {
+  rec[0] = rec[1] = rec[2] = 0.0;
+  rec[3] = 1.0;
+  rec[4] = rec[5] = rec[6] = 0.0;
+  for (int i = 0; i < 3; ++i) rec[7 + i] = Bn[i];
+  if (nz9) {
+    for (int i = 0; i < 3; ++i) rec[i] = nz9[i];
+    const double th = sqrt(nz9[3] * nz9[3] + nz9[4] * nz9[4] + nz9[5] * nz9[5]);
     if (th > 1e-300) {  // a zero attitude perturbation is the identity (the reference's q_noise/0 would be NaN)
       const double sh = sin(th / 2);
-      const double qn[4] = {cos(th / 2), nz[3] / th * sh, nz[4] / th * sh, nz[5] / th * sh};
-      double q2[4];
-      qmult(q, qn, q2);
-      for (int i = 0; i < 4; ++i) q[i] = q2[i];
+      rec[3] = cos(th / 2);
+      rec[4] = nz9[3] / th * sh;
+      rec[5] = nz9[4] / th * sh;
+      rec[6] = nz9[5] / th * sh;
     }
-    for (int i = 0; i < 3; ++i) Bf[i] = Bn[i] + nz[6 + i];
+    for (int i = 0; i < 3; ++i) rec[7 + i] = Bn[i] + nz9[6 + i];
   }
+}
+
+// simulator(dx,x,u) (simulator.jl:1-42) for the 7 dynamic states, from a stage record.  q/|q| is x * rsqrt(q.q) (one
+// rounding apart from the reference's four divisions, like the solver kernels; inside the 1e-10 rollout bar).
+TS_HD void simulator7_rec(const Inertia& I, const double x[7], const double u[3], const double* rec, double dx[7]) {
+  const double om[3] = {x[0] + rec[0], x[1] + rec[1], x[2] + rec[2]};
+  const double inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+  const double q0[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
+  double q[4];
+  qmult(q0, rec + 3, q);
   const double w4[4] = {0.0, om[0], om[1], om[2]};
   double qd[4], BB[3], tau[3], Jw[3], wJw[3];
   qmult(q, w4, qd);
-  qrot(q, Bf, BB);
-  const double us[3] = {u[0] / 100.0, u[1] / 100.0, u[2] / 100.0};
+  qrot(q, rec + 7, BB);
+  const double us[3] = {u[0] * 0.01, u[1] * 0.01, u[2] * 0.01};
   cross3(us, BB, tau);
   for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * om[0] + I.J[i * 3 + 1] * om[1] + I.J[i * 3 + 2] * om[2];
   cross3(om, Jw, wJw);
@@ -192,61 +233,85 @@ TS_HD void tvlqr_riccati_step(const ts_tvlqr_opts_dev& o, const double* AB54, do
   const double* A = AB54;
   const double* B = AB54 + 36;
   double SB[18], SA[36], BSB[9], BSA[18], Minv[9], Kk[18], Acl[36], SAcl[36];
+  TS_UNROLL
   for (int i = 0; i < 6; ++i) {
+    TS_UNROLL
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * B[l * 3 + j];
       SB[i * 3 + j] = s;
     }
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * A[l * 6 + j];
       SA[i * 6 + j] = s;
     }
   }
+  TS_UNROLL
   for (int i = 0; i < 3; ++i) {
+    TS_UNROLL
     for (int j = 0; j < 3; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SB[l * 3 + j];
       BSB[i * 3 + j] = s + ((i == j) ? o.Rd[i] : 0.0);
     }
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) s += B[l * 3 + i] * SA[l * 6 + j];
       BSA[i * 6 + j] = s;
     }
   }
-  inv3_general(BSB, Minv);
+  inv3_adj(BSB, Minv);
+  TS_UNROLL
   for (int i = 0; i < 3; ++i)
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 3; ++l) s += Minv[i * 3 + l] * BSA[l * 6 + j];
       Kk[i * 6 + j] = s;
       Kout[i * 6 + j] = s;
     }
+  TS_UNROLL
   for (int i = 0; i < 6; ++i)
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 3; ++l) s += B[i * 3 + l] * Kk[l * 6 + j];
       Acl[i * 6 + j] = A[i * 6 + j] - s;
     }
+  TS_UNROLL
   for (int i = 0; i < 6; ++i)
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * Acl[l * 6 + j];
       SAcl[i * 6 + j] = s;
     }
   double Sn[36];
+  TS_UNROLL
   for (int i = 0; i < 6; ++i)
+    TS_UNROLL
     for (int j = 0; j < 6; ++j) {
       double s = (i == j) ? o.Qd[i] : 0.0;
       double kr = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 3; ++l) kr += Kk[l * 6 + i] * o.Rd[l] * Kk[l * 6 + j];
       s += kr;
       double t = 0.0;
+      TS_UNROLL
       for (int l = 0; l < 6; ++l) t += Acl[l * 6 + i] * SAcl[l * 6 + j];
       Sn[i * 6 + j] = s + t;
     }
+  TS_UNROLL
   for (int i = 0; i < 36; ++i) S[i] = Sn[i];
 }
 
@@ -272,10 +337,31 @@ TS_HD void tvlqr_gains(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, double* K,
   }
 }
 
+// The four stage records of step k (40 doubles) when they are not pre-generated: clock -> field rows -> noise -> records.
+TS_HD void tvlqr_step_records(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, long long k, double x8, double recs[4 * TV_REC]) {
+  double tcl[4], nxt;
+  clock_rk4(x8, in.clock_rate, o.dt, tcl, nxt);
+  for (int s = 0; s < 4; ++s) {
+    const double* Bn = in.Bt + (long long)field_row(tcl[s], in.index_scale, in.B_rows) * 3;
+    double nzb[9];
+    const double* nz = nullptr;
+    if (o.noise_mode == 1) nz = in.noise + (k * 4 + s) * 9;
+    if (o.noise_mode == 2) {
+      tvlqr_noise(o.seed, in.trial, (uint32_t)k, (uint32_t)s, nzb);
+      nz = nzb;
+    }
+    tvlqr_stage_record(nz, Bn, recs + s * TV_REC);
+  }
+}
+
 // Closed-loop replay + slew-time detection.  Outputs nullable.  Returns N_sim; *slew_time_out as
-// monte_carlo.jl:237-262 (== t_final when the trial "fails").
-TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
-                             double* dX, double* slew_time_out) {
+// monte_carlo.jl:237-262 (== t_final when the trial "fails").  recs: pre-generated stage records (40 doubles per step,
+// K4n) or null -> built on the fly.  The slew-time rule is evaluated without sqrt / acos: |w| < w_limit is w.w < w_limit^2
+// and 2 acos(min(q_e1,1)) < ang_limit is q_e1 > cos(ang_limit/2) (acos is decreasing; identical decisions except within one
+// rounding of the thresholds).
+template <bool PRE>
+TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
+                               double* dX, double* slew_time_out, const double* recs) {
   const int N = in.N;
   long long N_sim = range_len(o.t0, o.dt, o.tf);
   if (N_sim > N) N_sim = range_len(o.t0, o.dt, o.tf - o.dt);
@@ -284,6 +370,8 @@ TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, cons
   for (int i = 0; i < 8; ++i) x[i] = in.x0[i];
   double slew = in.t_final;
   const double qi[4] = {in.q_final[0], -in.q_final[1], -in.q_final[2], -in.q_final[3]};
+  const double w2_limit = o.w_limit * o.w_limit;
+  const double cos_limit = cos(o.ang_limit / 2);
   // literal post-processing reads omega of column = trial index (quirk Q12): that column is only
   // known once the replay has reached it, so the literal mode evaluates the rule in a second pass.
   for (long long k = 0; k < N_sim; ++k) {
@@ -291,11 +379,9 @@ TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, cons
       for (int i = 0; i < 8; ++i) X_sim[k * 8 + i] = x[i];
     if (!o.literal_postproc) {
       const long long j = k + 1;
-      const double wn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-      double qe[4];
-      qmult(qi, x + 3, qe);
-      const double ang = 2 * acos(fmin(qe[0], 1.0));
-      if (j > 10 && wn < o.w_limit && ang < o.ang_limit && slew == in.t_final) slew = in.time_step * (double)j;
+      const double w2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+      const double qe0 = qi[0] * x[3] - (qi[1] * x[4] + qi[2] * x[5] + qi[3] * x[6]);   // scalar part of qmult(q_inv(q_final), q)
+      if (j > 10 && w2 < w2_limit && qe0 > cos_limit && slew == in.t_final) slew = in.time_step * (double)j;
     }
     if (k == N_sim - 1) {
       if (U_sim) U_sim[k * 3 + 0] = U_sim[k * 3 + 1] = U_sim[k * 3 + 2] = 0.0;
@@ -324,30 +410,24 @@ TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, cons
       for (int i = 0; i < 3; ++i) U_sim[k * 3 + i] = u[i];
     if (dX)
       for (int i = 0; i < 6; ++i) dX[k * 6 + i] = d6[i];
-    // rk4(simulator) with per-stage noise
+    // rk4(simulator) with per-stage records
     double tcl[4], nxt;
     clock_rk4(x[7], in.clock_rate, o.dt, tcl, nxt);
-    double k1[7], k2[7], k3[7], k4[7], xs[7], nzb[9];
-    const double* nz[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int s = 0; s < 4; ++s) {
-      const double* Bn = in.Bt + (long long)field_row(tcl[s], in.index_scale, in.B_rows) * 3;
-      if (o.noise_mode == 1) nz[s] = in.noise + (k * 4 + s) * 9;
-      if (o.noise_mode == 2) {
-        tvlqr_noise(o.seed, in.trial, (uint32_t)k, (uint32_t)s, nzb);
-        nz[s] = nzb;
-      }
-      double* ks = (s == 0) ? k1 : (s == 1) ? k2 : (s == 2) ? k3 : k4;
-      if (s == 0)
-        for (int i = 0; i < 7; ++i) xs[i] = x[i];
-      simulator7(in.I, xs, u, Bn, nz[s], ks);
-      for (int i = 0; i < 7; ++i) ks[i] = ks[i] * o.dt;
-      if (s == 0)
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
-      if (s == 1)
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k2[i] / 2.0;
-      if (s == 2)
-        for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i];
-    }
+    double rbuf[PRE ? 1 : 4 * TV_REC];
+    const double* rk = PRE ? recs + k * (4 * TV_REC) : rbuf;
+    if (!PRE) tvlqr_step_records(in, o, k, x[7], rbuf);
+    double k1[7], k2[7], k3[7], k4[7], xs[7];
+    simulator7_rec(in.I, x, u, rk, k1);
+    for (int i = 0; i < 7; ++i) k1[i] = k1[i] * o.dt;
+    for (int i = 0; i < 7; ++i) xs[i] = x[i] + k1[i] / 2.0;
+    simulator7_rec(in.I, xs, u, rk + TV_REC, k2);
+    for (int i = 0; i < 7; ++i) k2[i] = k2[i] * o.dt;
+    for (int i = 0; i < 7; ++i) xs[i] = x[i] + k2[i] / 2.0;
+    simulator7_rec(in.I, xs, u, rk + 2 * TV_REC, k3);
+    for (int i = 0; i < 7; ++i) k3[i] = k3[i] * o.dt;
+    for (int i = 0; i < 7; ++i) xs[i] = x[i] + k3[i];
+    simulator7_rec(in.I, xs, u, rk + 3 * TV_REC, k4);
+    for (int i = 0; i < 7; ++i) k4[i] = k4[i] * o.dt;
     for (int i = 0; i < 7; ++i) x[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) * TS_SIXTH;
     x[7] = nxt;
   }
@@ -365,6 +445,10 @@ TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, cons
   }
   if (slew_time_out) *slew_time_out = slew;
   return N_sim;
+}
+TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
+                             double* dX, double* slew_time_out) {
+  return tvlqr_replay_t<false>(in, o, K, X_sim, U_sim, dX, slew_time_out, nullptr);
 }
 
 }  // namespace ts

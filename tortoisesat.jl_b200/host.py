@@ -807,11 +807,12 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
     n = int(number_sims)
     J = np.diag([0.00125, 0.00125, 0.00125]) if J is None else np.asarray(J, dtype=float)
     A = np.zeros((n, 6))
-    A[:, 1], A[:, 2] = alt + R_E, inclination
+    alt_i = np.broadcast_to(np.asarray(alt, dtype=float), (n,))          # scalars as in monte_carlo.jl, or one value per trial
+    A[:, 1], A[:, 2] = alt_i + R_E, np.broadcast_to(np.asarray(inclination, dtype=float), (n,))
     A[:, 3], A[:, 5] = rng.random(n) * 360, rng.random(n) * 360
     fo = np.zeros(n, dtype=FIELD_OPTS_DTYPE)
     for i in range(n):
-        fo[i] = (GM_EARTH, MJD_0, igrf_date, (alt + R_E) * 1000.0, 0.0, 0.0, 0)
+        fo[i] = (GM_EARTH, MJD_0, igrf_date, (alt_i[i] + R_E) * 1000.0, 0.0, 0.0, 0)
     x0, xf = np.zeros((n, 8)), np.zeros((n, 8))
     if random_attitudes:
         q = rng.normal(size=(n, 4))
@@ -846,3 +847,71 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
             res["sim_states"] = [sl(tr["X_sim"], t) for t in range(n)]           # :232
             res["sim_control_inputs"] = [sl(tr["U_sim"], t) for t in range(n)]   # :233
     return res
+
+
+# ---------------------------------------------------------------------------
+# Result persistence + retry of failed trials (monte_carlo.jl:269,334-343, heatmap.jl:114-123)
+def save_monte_carlo(res, directory, prefix="100"):
+    """Writes the result of monte_carlo() in the layout of monte_carlo.jl:334-343: one container per array and per trial,
+    `<prefix>_A`, `<prefix>_states_<i>` (datasets `one_state`, `states` = sim_states[i], as the script writes them),
+    `<prefix>_control_<i>` (`control` = sim_control_inputs[i]), `<prefix>_B_N_<i>` (`B_ECI`), `<prefix>_t_total_<i>`
+    (`t_total`), i = 1..number_sims.  The reference uses HDF5 (`h5write`); this image has no HDF5 library, so each container
+    is a NumPy .npz archive holding the SAME dataset names (np.load(path)["states"] replaces h5read(path, "states")).
+    A `<prefix>_summary` container adds what the script keeps in globals: t_final, slew_time, fails, retry, outcomes."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    p = lambda name: os.path.join(directory, "%s_%s.npz" % (prefix, name))
+    n = res["A"].shape[0]
+    np.savez(p("A"), A=res["A"])
+    for i in range(n):
+        if "sim_states" in res:
+            np.savez(p("states_%d" % (i + 1)), one_state=res["sim_states"][i], states=res["sim_states"][i])
+            np.savez(p("control_%d" % (i + 1)), control=res["sim_control_inputs"][i])
+        if "B_ECI_total" in res:
+            np.savez(p("B_N_%d" % (i + 1)), B_ECI=res["B_ECI_total"][i])
+            np.savez(p("t_total_%d" % (i + 1)), t_total=res["t_total"][i])
+    retry = np.nonzero(res["fails"] == 1.0)[0] + 1                      # monte_carlo.jl:269 (1-based, like findall)
+    np.savez(p("summary"), t_final=res["t_final"], slew_time=res["slew_time"], fails=res["fails"], retry=retry,
+             outcomes=res["outcomes"])
+    return retry
+
+
+def load_monte_carlo(directory, prefix="100"):
+    """Inverse of save_monte_carlo: the arrays a resumed script needs (A, t_final, slew_time, fails, retry, and the
+    per-trial lists when they were written)."""
+    import os
+    p = lambda name: os.path.join(directory, "%s_%s.npz" % (prefix, name))
+    s = np.load(p("summary"))
+    res = dict(A=np.load(p("A"))["A"], t_final=s["t_final"], slew_time=s["slew_time"], fails=s["fails"], retry=s["retry"],
+               outcomes=s["outcomes"])
+    n = res["A"].shape[0]
+    if os.path.exists(p("states_1")):
+        res["sim_states"] = [np.load(p("states_%d" % (i + 1)))["states"] for i in range(n)]
+        res["sim_control_inputs"] = [np.load(p("control_%d" % (i + 1)))["control"] for i in range(n)]
+    if os.path.exists(p("B_N_1")):
+        res["B_ECI_total"] = [np.load(p("B_N_%d" % (i + 1)))["B_ECI"] for i in range(n)]
+        res["t_total"] = [np.load(p("t_total_%d" % (i + 1)))["t_total"] for i in range(n)]
+    return res
+
+
+def retry_failed(res, max_rounds=3, inclination=None, seed=1, **mc_kwargs):
+    """Re-runs the trials listed in `retry` (fails == 1) with fresh orbit draws, as paper_images/heatmap.jl:114-123 does
+    (`for i in retry`: new RAAN and anomaly, and -- when `inclination` is None, the heat-map variant -- a new inclination
+    rand*90, for those rows of A only), merging the new outcomes into `res` in place.  One library call per round; stops
+    when nothing fails.  Returns the 1-based indices still failing."""
+    rng = np.random.default_rng(seed)
+    for _ in range(max_rounds):
+        retry = np.nonzero(res["fails"] == 1.0)[0]
+        if retry.size == 0:
+            break
+        inc = rng.random(retry.size) * 90 if inclination is None else inclination          # heatmap.jl:120
+        sub = monte_carlo(number_sims=retry.size, rng=rng, inclination=inc, **mc_kwargs)
+        for k, i in enumerate(retry):
+            res["A"][i] = sub["A"][k]
+            for f in ("t_final", "slew_time", "fails"):
+                res[f][i] = sub[f][k]
+            res["outcomes"][i] = sub["outcomes"][k]
+            for f in ("states", "control_inputs", "sim_states", "sim_control_inputs", "B_ECI_total", "t_total"):
+                if f in res and f in sub:
+                    res[f][i] = sub[f][k]
+    return np.nonzero(res["fails"] == 1.0)[0] + 1
