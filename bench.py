@@ -39,13 +39,20 @@ QF = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0.0, 0.0])   # monte_carlo.jl
 SEED = 0x5EED
 FIELD_OPTS_DTYPE = np.dtype([("GM", "<f8"), ("mjd", "<f8"), ("igrf_date", "<f8"), ("field_radius_m", "<f8"), ("t0", "<f8"),
                              ("tf", "<f8"), ("N", "<i8")])
-# Algorithmic FLOP per unit (profiles/flop_counts_r2.json = counted with an instrumented scalar)
+# Algorithmic FLOP per unit.  Three models, all reported: (1) COUNTED kernel math -- the 7-state
+# JVP-linearisation + dense Riccati + rollout arithmetic the kernels execute, counted with an instrumented scalar
+# (tools/flopcount.cpp -> profiles/flop_counts_r2.json): the roofline numerator; (2) the same count on the oracle = the
+# literal reference algorithm (8-state, 11-seed forward-mode duals); (3) SURVEY 8d's round-1 ESTIMATE (6100 / 500).
 FL_ITER, FL_ROLL, FL_TVLQR, FL_IGRF = 6100.0, 500.0, 7700.0, 2243.0
+FL_MODELS = {"survey_estimate": (6100.0, 500.0)}
 try:
     _fc = json.load(open(os.path.join(ROOT, "profiles", "flop_counts_r2.json")))
     FL_ITER, FL_ROLL = float(_fc["per_knot_iteration"]), float(_fc["per_rollout_knot"])
     FL_TVLQR = float(_fc.get("tvlqr_per_knot", FL_TVLQR))
-    FLOP_SOURCE = "counted: profiles/flop_counts_r2.json (%s)" % _fc.get("how", "instrumented scalar")
+    FL_MODELS["reference_algorithm_counted"] = (float(_fc["oracle_per_knot_iteration"]), float(_fc["oracle_per_rollout_knot"]))
+    FLOP_SOURCE = "counted kernel math, %.0f FLOP per knot-iteration (JVP linearisation %d + cost gradients %d + Riccati step %d) + %.0f per " \
+                  "line-search rollout knot: tools/flopcount.cpp -> profiles/flop_counts_r2.json" % (
+                      FL_ITER, _fc["linearise"], _fc["cost_gradients"], _fc["riccati"], FL_ROLL)
 except Exception:
     FLOP_SOURCE = "SURVEY 8d estimate: 6100 per knot-iteration (rk3 Jacobian 2600 + Riccati step 3500) + 500 per rollout knot"
 # HBM traffic of K3 per knot-iteration: ncu dram__bytes_read+write of THIS configuration (N = 2044, 4096 trials)
@@ -403,7 +410,7 @@ def main():
         barrier()
         l0 = eng.launch_count()
         t0 = time.perf_counter()
-        acc = {k: [] for k in ("dev_ms", "call_s", "field", "prep", "solve", "tvlqr", "flops", "p_ms", "s_ms", "parked")}
+        acc = {k: [] for k in ("dev_ms", "call_s", "field", "prep", "solve", "tvlqr", "flops", "p_ms", "s_ms", "parked", "ki", "kr")}
         last = None
         for _ in range(steps):
             out, st, allout, vec, t_call = step()
@@ -413,6 +420,8 @@ def main():
                 acc[k].append(getattr(st, "ms_" + k))
             kn = (out["N"] - 1).astype(np.float64)
             acc["flops"].append(float(np.sum(kn * (out["inner_iters"] * FL_ITER + out["ls_rollouts"] * FL_ROLL))))
+            acc["ki"].append(float(np.sum(kn * out["inner_iters"])))
+            acc["kr"].append(float(np.sum(kn * out["ls_rollouts"])))
             sp = eng.k3_last_split()
             acc["p_ms"].append(sp[0])
             acc["s_ms"].append(sp[1])
@@ -448,6 +457,8 @@ def main():
                       "dram__bytes_read+write of this configuration) x this run's knot-iterations" % (K3_TRAFFIC["source"], K3_TRAFFIC["bytes_per_knot_iter"]),
                       "hbm_gbs_from_traffic": K3_TRAFFIC["bytes_per_knot_iter"] * knot_iters / solve_s / 1e9, "hbm_peak_gbs": hbm_peak,
                       "hbm_peak_source": hbm_src, "peak_source": peak_src, "flop_model": FLOP_SOURCE,
+                      "frac_other_flop_models": {k: (float(np.mean(acc["ki"])) * v[0] + float(np.mean(acc["kr"])) * v[1]) / solve_s / 1e12 / peak_fp64
+                                                 for k, v in FL_MODELS.items()},
                       "kernel_share_of_step": solve_s / float(np.mean(acc["dev_ms"]) * 1e-3)})
         res["h2d"] = int(n * (8 + 8 + 9 + 3) * 8 + n * 4 + len(fo) * (6 * 8 + 56))
         res["d2h"] = int(n * 64 + 8 * len(fo))

@@ -36,6 +36,16 @@ struct IgrfConsts {
   double leg_d[14];
   double dl_a[14][14];
   double dl_b[14][14];
+  // Rescaled recursion of the field kernels (igrf12_point): R[n][m] = P[n][m] / kap[n][m] with kap chosen so that the
+  // three-term recurrence loses one multiplication per (n,m):  R[n][m] = (rl_a[n][m] * c) * R[n-1][m] - R[n-2][m]
+  // (kap[m][m] = kap[m+1][m] = 1, kap[n][m] = leg_b[n][m] * kap[n-2][m]); the factor kap is folded into the staged Gauss
+  // coefficients, and the derivative constants are rescaled to give dP[n][m] / kap[n][m] directly:
+  //   dP'[n][0] = rd_0[n] * R[n][1];   dP'[n][m] = rd_a[n][m] * R[n][m-1] + rd_b[n][m] * R[n][m+1]
+  double kap[14][14];
+  double rl_a[14][14];
+  double rd_0[14];
+  double rd_a[14][14];
+  double rd_b[14][14];
 };
 // The library is built as ONE translation unit (csrc/tortoise_b200.cu), so the
 // definition lives here.
@@ -68,6 +78,10 @@ __device__ __forceinline__ void igrf_stage_coeffs(double2* s_gh, const double* _
       const double dh = interp ? __ddiv_rn(__dsub_rn(tabH[kh * 25 + c0 + 1], h0), 5.0) : tabH[kh * 25 + 24];
       v.y = __dadd_rn(h0, __dmul_rn(dh, dt));
     }
+    // the rescaling factor of the Legendre recursion (IgrfConsts::kap) rides on the coefficients
+    const double kp = c_igrf.kap[n][m];
+    v.x *= kp;
+    v.y *= kp;
     s_gh[k] = v;
     // (-m g, +m h): folds the factor -m of the d/dphi sum into the coefficients (igrf.jl:235)
     double2 vm;
@@ -83,10 +97,12 @@ __host__ __device__ inline int igrf_nmax_for_date(double date) {
   return (epoch < 1995) ? 10 : 13;
 }
 
-// Field at one point.  r in metres; lat, lon in rad; out (north, east, down) in nT.
-template <int NMAX>
-__device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, double r_m, double lat, double lon,
-                                             double& bn, double& be, double& bd) {
+// Field at one point.  r in metres; lat, lon in rad; out (north, east, down) in nT.  POLE: theta == 0 exactly (the
+// reference's pole branch, igrf.jl:235,270) -- a separate instantiation, so the 91 per-(n,m) selects between P and dP
+// are not paid by every other point.
+template <int NMAX, bool POLE>
+__device__ __forceinline__ void igrf12_point_t(const double2* __restrict__ s_gh, double r_m, double lat, double lon,
+                                               double& bn, double& be, double& bd) {
   const double PI = 3.141592653589793;
   const double theta = PI / 2 - lat;
   const double phi = (lon >= 0.0) ? lon : 2 * PI + lon;
@@ -117,7 +133,6 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
   const double ratio = a / r;
   const double inv_r = 1.0 / r;
   double fact = ratio;
-  const bool pole = (theta == 0.0);
 
   double dVr = 0.0, dVt = 0.0, dVp = 0.0;
   double Pm1[NMAX + 2], Pm2[NMAX + 2], Pn[NMAX + 2];
@@ -133,7 +148,7 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
       Pn[1] = s;
     } else {
 #pragma unroll
-      for (int m = 0; m <= n - 1; ++m) Pn[m] = c_igrf.leg_a[n][m] * c * Pm1[m] - c_igrf.leg_b[n][m] * Pm2[m];
+      for (int m = 0; m <= n - 1; ++m) Pn[m] = fma(c_igrf.rl_a[n][m] * c, Pm1[m], -Pm2[m]);   // rescaled rows: R = P / kap
       Pn[n] = s * c_igrf.leg_d[n] * Pm1[n - 1];
     }
     Pn[n + 1] = 0.0;
@@ -147,7 +162,7 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
     double aux_r, aux_t, aux_p = 0.0;
     {
       const double g = s_gh[k0].x;
-      const double dP0 = -c_igrf.dl_a[n][0] * Pn[1] + c_igrf.dl_b[n][0] * Pn[1];
+      const double dP0 = c_igrf.rd_0[n] * Pn[1];
       aux_r = g * Pn[0];  // -(n+1)/r is factored out of the sum over m (one DMUL per n instead of per (n,m))
       aux_t = g * dP0;
     }
@@ -156,16 +171,16 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
     for (int m = 1; m <= n; ++m) {
       const double2 gh = s_gh[k0 + m];
       double dPm;
-      if (m == n && m != 1)
-        dPm = c_igrf.dl_a[n][m] * Pn[m - 1];
+      if (m == n)
+        dPm = c_igrf.rd_a[n][m] * Pn[m - 1];                                   // (n = m = 1 reads the zero P[1][2]: same value)
       else
-        dPm = c_igrf.dl_a[n][m] * Pn[m - 1] + c_igrf.dl_b[n][m] * Pn[m + 1];
+        dPm = c_igrf.rd_a[n][m] * Pn[m - 1] + c_igrf.rd_b[n][m] * Pn[m + 1];
       const double2 ghm = s_gh[IGRF_NCOEF + k0 + m];
       const double GcHs = gh.x * cm[m] + gh.y * sm[m];
       const double mGsHc = ghm.x * sm[m] + ghm.y * cm[m];  // = -m (g sin - h cos)
       aux_r += GcHs * Pn[m];
       aux_t += GcHs * dPm;
-      aux_p += mGsHc * (pole ? dPm : Pn[m]);
+      aux_p += mGsHc * (POLE ? dPm : Pn[m]);
     }
     fact *= ratio;
     dVr += (cr * aux_r) * fact;
@@ -182,8 +197,27 @@ __device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, d
   dVp *= a;
   dVt *= a;
   bn = inv_r * dVt;
-  be = pole ? (-1.0 / r) * dVp : (-1.0 / (r * sin(theta))) * dVp;
+  be = POLE ? (-1.0 / r) * dVp : (-1.0 / (r * sin(theta))) * dVp;
   bd = dVr;
+}
+// the pole instantiation is kept out of line: it is taken by measure-zero inputs (the lat = +pi/2 row of a grid map) and
+// must not cost the common path registers
+template <int NMAX>
+__device__ __noinline__ void igrf12_point_pole(const double2* s_gh, double r_m, double lat, double lon, double* out3) {
+  igrf12_point_t<NMAX, true>(s_gh, r_m, lat, lon, out3[0], out3[1], out3[2]);
+}
+template <int NMAX>
+__device__ __forceinline__ void igrf12_point(const double2* __restrict__ s_gh, double r_m, double lat, double lon,
+                                             double& bn, double& be, double& bd) {
+  if (3.141592653589793 / 2 - lat == 0.0) {
+    double o[3];
+    igrf12_point_pole<NMAX>(s_gh, r_m, lat, lon, o);
+    bn = o[0];
+    be = o[1];
+    bd = o[2];
+  } else {
+    igrf12_point_t<NMAX, false>(s_gh, r_m, lat, lon, bn, be, bd);
+  }
 }
 
 }  // namespace ts

@@ -128,6 +128,20 @@ inline void igrf_host_constants(IgrfConsts& h) {
       }
     }
   }
+  // rescaled recursion (see IgrfConsts): kap, then the constants of R = P / kap and dP' = dP / kap
+  for (int n = 0; n <= 13; ++n)
+    for (int m = 0; m <= 13; ++m) h.kap[n][m] = 1.0;
+  for (int m = 0; m <= 13; ++m)
+    for (int n = m + 2; n <= 13; ++n) h.kap[n][m] = h.leg_b[n][m] * h.kap[n - 2][m];
+  for (int n = 2; n <= 13; ++n)
+    for (int m = 0; m <= n - 1; ++m) h.rl_a[n][m] = h.leg_a[n][m] * h.kap[n - 1][m] / h.kap[n][m];
+  for (int n = 1; n <= 13; ++n) {
+    h.rd_0[n] = (-h.dl_a[n][0] + h.dl_b[n][0]) * h.kap[n][1] / h.kap[n][0];
+    for (int m = 1; m <= n; ++m) {
+      h.rd_a[n][m] = h.dl_a[n][m] * h.kap[n][m - 1] / h.kap[n][m];
+      h.rd_b[n][m] = (m + 1 <= n) ? h.dl_b[n][m] * h.kap[n][m + 1] / h.kap[n][m] : 0.0;
+    }
+  }
 }
 
 }  // namespace ts

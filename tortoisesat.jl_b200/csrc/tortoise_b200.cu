@@ -885,10 +885,11 @@ int ts_tvlqr_sim_batch(ts_ctx* c, int64_t n, const int64_t* N_i, const int64_t* 
 }
 
 // ---------------------------------------------------------------------------- fused Monte-Carlo
-// Algorithmic FLOP per unit (SURVEY.md section 8d / DESIGN.md): IGRF sample 2393 (2243 + rotations),
-// rk3 Jacobian 2600 + backward step 3500 per knot-iteration, 500 per line-search rollout knot,
-// TVLQR ~7700 per knot.
-static const double FL_FIELD = 2393.0, FL_ITER = 6100.0, FL_ROLL = 500.0, FL_TVLQR = 7700.0;
+// Algorithmic FLOP per unit: AL-iLQR figures COUNTED with an instrumented scalar on the kernels' own math
+// (tools/flopcount.cpp -> profiles/flop_counts_r2.json: JVP linearisation 8193 + cost gradients 51 + dense 7-state Riccati
+// step 3681 = 11925 per knot-iteration, 640 per line-search rollout knot; SURVEY 8d's estimate was 6100 / 500);
+// IGRF sample 2393 (2243 + rotations) and TVLQR ~7700 per knot are the SURVEY 8d estimates.
+static const double FL_FIELD = 2393.0, FL_ITER = 11925.0, FL_ROLL = 640.0, FL_TVLQR = 7700.0;
 
 int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts, const double* x0,
                        const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
@@ -1085,17 +1086,30 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     ka.X = d_X; ka.U = d_U; ka.K = nullptr; ka.out = d_out;
     std::vector<double> diff(NA);
     for (int64_t aa = 0; aa < na; ++aa) diff[aa] = slew_angle(x0 + 8 * act[aa], xf + 8 * act[aa]);
+    // everything stage 5 needs is reserved and uploaded BEFORE the solve is queued: a cudaMalloc between the two would
+    // wait for the solve and put its host latency on the device timeline
+    void *p_K = nullptr, *p_ab = nullptr, *p_xs = nullptr, *p_us = nullptr;
+    uint32_t* d_sid = nullptr;
+    int64_t* d_lin = nullptr;
+    std::vector<int64_t> lin(NA + 1, 0);
+    if (cfg->run_tvlqr) {
+      if ((rc = scratch_reserve(c, 9, (size_t)knots * 18 * 8, &p_K))) return rc;
+      std::vector<uint32_t> sid(NA);
+      for (int64_t a = 0; a < na; ++a) sid[a] = stream_id ? stream_id[act[a]] : (uint32_t)act[a];
+      if ((rc = upload(c, 14, sid.data(), NA, &d_sid))) return rc;
+      for (size_t a2 = 0; a2 < NA; ++a2) lin[a2 + 1] = lin[a2] + (hi[a2] - 1);
+      if ((rc = upload(c, 27, lin.data(), NA + 1, &d_lin))) return rc;
+      if ((rc = scratch_reserve(c, 26, (size_t)lin[NA] * 55 * 8 + 64, &p_ab))) return rc;
+      if (cfg->keep_trajectories) {
+        if ((rc = scratch_reserve(c, 20, (size_t)knots * 8 * 8 + 64, &p_xs))) return rc;
+        if ((rc = scratch_reserve(c, 21, (size_t)knots * 3 * 8 + 64, &p_us))) return rc;
+      }
+    }
     if ((rc = k3_launch(c, ka, hi.data(), diff.data()))) return rc;
     cudaEventRecord(e[4], c->stream);
     // ---- stage 5: TVLQR replay + slew-time rule
     double *d_Xs_keep = nullptr, *d_Us_keep = nullptr;
     if (cfg->run_tvlqr) {
-      void* p_K;
-      if ((rc = scratch_reserve(c, 9, (size_t)knots * 18 * 8, &p_K))) return rc;
-      uint32_t* d_sid = nullptr;
-      std::vector<uint32_t> sid(NA);
-      for (int64_t a = 0; a < na; ++a) sid[a] = stream_id ? stream_id[act[a]] : (uint32_t)act[a];
-      if ((rc = upload(c, 14, sid.data(), NA, &d_sid))) return rc;
       K4Args k4;
       k4.n_trials = na; k4.N_i = d_i; k4.offs = d_i + NA; k4.B_offs = d_i + 2 * NA; k4.B_rows = d_i + 3 * NA;
       k4.X_lqr = d_X; k4.U_lqr = d_U; k4.x0_lqr = d_f + 28 * NA; k4.Jmat = d_f + 16 * NA; k4.B_eci = d_Bf;
@@ -1107,24 +1121,13 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
       k4.opts.literal_postproc = 0;                          // needs X_sim storage; fused path uses the fixed rule (Q12)
       k4.noise = nullptr; k4.X_sim = nullptr; k4.U_sim = nullptr; k4.dX = nullptr; k4.K = (double*)p_K;
       if (cfg->keep_trajectories) {
-        void *p_xs, *p_us;
-        if ((rc = scratch_reserve(c, 20, (size_t)knots * 8 * 8 + 64, &p_xs))) return rc;
-        if ((rc = scratch_reserve(c, 21, (size_t)knots * 3 * 8 + 64, &p_us))) return rc;
         TS_CUDA(c, cudaMemsetAsync(p_xs, 0, (size_t)knots * 8 * 8, c->stream));
         TS_CUDA(c, cudaMemsetAsync(p_us, 0, (size_t)knots * 3 * 8, c->stream));
         k4.X_sim = (double*)p_xs; k4.U_sim = (double*)p_us;
         d_Xs_keep = k4.X_sim; d_Us_keep = k4.U_sim;
       }
       k4.N_sim = d_nsim; k4.slew_time = d_slew;
-      {
-        std::vector<int64_t> lin(NA + 1, 0);
-        for (size_t a2 = 0; a2 < NA; ++a2) lin[a2 + 1] = lin[a2] + (hi[a2] - 1);
-        int64_t* d_lin;
-        void* p_ab;
-        if ((rc = upload(c, 27, lin.data(), NA + 1, &d_lin))) return rc;
-        if ((rc = scratch_reserve(c, 26, (size_t)lin[NA] * 55 * 8 + 64, &p_ab))) return rc;
-        k4.AB = (double*)p_ab; k4.clk = k4.AB + (size_t)lin[NA] * 54; k4.lin_offs = d_lin; k4.lin_total = lin[NA];
-      }
+      k4.AB = (double*)p_ab; k4.clk = k4.AB + (size_t)lin[NA] * 54; k4.lin_offs = d_lin; k4.lin_total = lin[NA];
       k4_launch(c, k4);
     }
     cudaEventRecord(e[5], c->stream);
