@@ -330,6 +330,23 @@ int ts_dynamics_batch(ts_ctx* ctx, int mode, int64_t n, const double* x, const d
 int ts_rk3_step_batch(ts_ctx* ctx, int64_t n, const double* x, const double* u, const double* B, int64_t B_rows,
                       double index_scale, double clock_rate, const double* Jmat, double dt, double* xn);
 
+/* ---- comparison controller -------------------------------------------------- *
+ * The Psiaki-style PD magnetic controller closed loop of src/comparison/psiaki2005.jl:116-164 for n_trials trials:
+ * x[:,1] = x0; one explicit Euler step with zero moment (:124-125); then for i = 2:N-1
+ *   B_meas = qrot(q_inv(q_i), B_ECI[:,i]); w_bar = w_guess[:,i] - w_i; q_bar = qmult(q_i, q_guess[:,i]);
+ *   m = psiaki_controller(C_1, C_2, J, q_bar, w_bar, B_meas)      [src/comparison/psiaki_dynamics.jl:1-26]
+ *   x_{i+1} = rk4_psiaki(attitude_dynamics, x_i, dt, m, B_meas, J)  [:63-73; src/attitude_dynamics.jl:2-24], q normalised.
+ * HOST arrays: N_i, offs (knot offsets), x0 (n x 7), w_guess / q_guess (ragged N x 3 / N x 4: the eigen-axis reference of
+ * eigen_axis_slew), B_eci (ragged N x 3: the field at every step), Jmat (n x 9).  Outputs: X (ragged N x 7), M (ragged N x 3
+ * moments, nullable), q_err (ragged N x 4 error quaternions, nullable).                                              */
+int ts_psiaki_pd_batch(ts_ctx* ctx, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* x0,
+                       const double* w_guess, const double* q_guess, const double* B_eci, const double* Jmat, double dt,
+                       double C_1, double C_2, double* X, double* M, double* q_err);
+/* attitude_dynamics_linear(x,u,x_linear,B_B,J) [src/attitude_dynamics.jl:26-48]: x, x_linear n x 7, u n x 3, B_B n x 3,
+ * Jmat one 3x3 -> dx n x 7 (all HOST).                                                                              */
+int ts_attitude_dynamics_linear_batch(ts_ctx* ctx, int64_t n, const double* x, const double* u, const double* x_linear,
+                                      const double* B_B, const double* Jmat, double* dx);
+
 #ifdef __cplusplus
 }
 #endif

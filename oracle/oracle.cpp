@@ -27,6 +27,7 @@
 #include "orc_ilqr.hpp"
 #include "orc_tvlqr.hpp"
 #include "orc_philox.hpp"
+#include "orc_comparison.hpp"
 
 using namespace orc;
 
@@ -377,6 +378,17 @@ int orc_mc_run(const orc_mc_config* cfg, const double* kep6, const orc_field_opt
     if (cpu_seconds) cpu_seconds[t] = omp_get_wtime() - t_start;
   }
   return 0;
+}
+
+// ---------------------------------------------------------------- comparison controller
+void orc_psiaki_pd_simulation(int64_t N, const double* x0, const double* w_guess, const double* q_guess, const double* B, const double* J9,
+                              double dt, double C1, double C2, double* X, double* M, double* Qe) {
+  psiaki_pd_simulation(N, x0, w_guess, q_guess, B, J9, dt, C1, C2, X, M, Qe);
+}
+void orc_attitude_dynamics_linear(const double* x7, const double* u3, const double* xl7, const double* BB, const double* J9, double* dx7) {
+  double Jinv[9];
+  inv3(J9, Jinv);
+  attitude_dynamics_linear(x7, u3, xl7, BB, J9, Jinv, dx7);
 }
 
 // ---------------------------------------------------------------- Philox

@@ -118,6 +118,8 @@ def lib():
         L.orc_mc_slew_time.restype = C.c_double
         L.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
         L.orc_tvlqr_noise.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_psiaki_pd_simulation.argtypes = [C.c_int64] + [C.c_void_p] * 5 + [C.c_double] * 3 + [C.c_void_p] * 3
+        L.orc_attitude_dynamics_linear.argtypes = [C.c_void_p] * 6
         L.orc_mc_run.argtypes = [C.POINTER(McConfig)] + [C.c_void_p] * 9 + [C.c_int]
         L.orc_max_threads.restype = C.c_int
         _LIB = L

@@ -28,7 +28,7 @@ import sys
 
 import numpy as np
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 # ======================================================================================================
@@ -584,6 +584,51 @@ def mc_postprocess(sim_states_i, q_final, t_final_i, time_step_i, slew_limits, t
     return slew_time, (1 if slew_time == t_final_i else 0)
 
 
+def attitude_dynamics_linear(x, u, x_linear, B_B, J):
+    """src/attitude_dynamics.jl:26-48."""
+    omega = x[0:3]
+    q = x[3:7] / np.linalg.norm(x[3:7])
+    q_dot = 0.5 * qmult(q, np.concatenate([[0], x_linear[3:6]]))
+    tau_c = cross(u[0:3], B_B)
+    omega_dot = np.linalg.inv(J) @ (tau_c - cross(omega, J @ omega))
+    return np.concatenate([omega_dot, q_dot])
+
+
+def psiaki_controller(C_1, C_2, J, q, w_bar, B_meas, m_limit=None):
+    """src/comparison/psiaki_dynamics.jl:1-26 (the m_limit clamp is commented out in the reference)."""
+    T_req = -(C_1 * w_bar + C_2 * np.linalg.inv(J) @ q[1:4])
+    return cross(B_meas, T_req) / (np.linalg.norm(B_meas) ** 2)
+
+
+def rk4_psiaki(f, x, dt, u, B_B, J):
+    """src/comparison/psiaki_dynamics.jl:63-73."""
+    f1 = f(x, u, B_B, J)
+    f2 = f(x + .5 * f1 * dt, u, B_B, J)
+    f3 = f(x + .5 * f2 * dt, u, B_B, J)
+    f4 = f(x + f3 * dt, u, B_B, J)
+    return x + 1 / 6 * (f1 + 2 * f2 + 2 * f3 + f4) * dt
+
+
+def psiaki_pd_simulation(x0, w_guess, q_guess, B_ECI, J, dt, C_1, C_2):
+    """src/comparison/psiaki2005.jl:116-164.  w_guess 3 x N, q_guess 4 x N, B_ECI 3 x N (columns = steps)."""
+    N = w_guess.shape[1]
+    x = np.zeros((7, N))
+    x[:, 0] = x0
+    m_all = np.zeros((3, N))
+    qbar = np.zeros((4, N))
+    xd = attitude_dynamics(x[:, 0], np.zeros(3), B_ECI[:, 0], J)          # :124
+    x[:, 1] = x[:, 0] + dt * xd                                            # :125
+    for i in range(1, N - 1):                                              # for i = 2:length(t)-1
+        B_meas = qrot(q_inv(x[3:7, i]), B_ECI[:, i])                       # :141
+        w_bar = w_guess[:, i] - x[0:3, i]                                  # :145
+        qbar[:, i] = qmult(x[3:7, i], q_guess[:, i])                       # :152
+        m = psiaki_controller(C_1, C_2, J, qbar[:, i], w_bar, B_meas)      # :157
+        x[:, i + 1] = rk4_psiaki(attitude_dynamics, x[:, i], dt, m, B_meas, J)   # :161
+        x[3:7, i + 1] = x[3:7, i + 1] / np.linalg.norm(x[3:7, i + 1])      # :162
+        m_all[:, i] = m
+    return x, m_all, qbar
+
+
 # ======================================================================================================
 # Section B -- AL-iLQR, second implementation of SURVEY.md Appendix C (dense 8-state, numpy)
 # ======================================================================================================
@@ -985,7 +1030,46 @@ def main():
     out = os.path.join(HERE, "ref_fixtures.json")
     json.dump(fx, open(out, "w"))
     print("wrote", out, os.path.getsize(out), "bytes")
+    add_psiaki_section()
+
+
+def add_psiaki_section():
+    """Comparison-controller fixtures; `--only psiaki` regenerates just this section."""
+    out = os.path.join(HERE, "ref_fixtures.json")
+    fx = json.load(open(out))
+    rng = np.random.default_rng(77)
+    GM = 3.986004418E14 * (1 / 1000) ** 3
+    J1U = np.diag([0.00125] * 3)
+    J3U = np.diag([0.020833, 0.020833, 0.0041666])
+    cases = []
+    for name, Jm, tfin, C1, C2 in [("psiaki2005.jl:116-164 constants (1U, C_1 = 1e-6, C_2 = 1e-9)", J1U, 60.0, 1E-6, 1E-9),
+                                   ("3U, stronger gains", J3U, 40.0, 2E-4, 3E-6)]:
+        t = julia_range(0.0, 0.2, tfin)
+        N = len(t)
+        B, _, _ = magnetic_simulation([0, 6771.0, 96.6, 40.0, 0, 120.0], GM, 58155.0, 6371.0, 400.0, 0.0, tfin, N)
+        B_ECI = B[:N].T                                                   # psiaki2005.jl:73-74
+        q_0 = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])         # :99
+        x0g = np.concatenate([[0, 0, 0], q_0])
+        xfg = np.concatenate([[0, 0, 0], [1.0, 0, 0, 0]])
+        wg, qg = eigen_axis_slew(x0g, xfg, t)                              # :118
+        x0 = np.concatenate([wg[0], qg[0]])                                # x = [w_guess; q_guess] (:119), column 1
+        X, M, Qe = psiaki_pd_simulation(x0, wg.T, qg.T, B_ECI, Jm, 0.2, C1, C2)
+        cases.append(dict(name=name, J=L(Jm), dt=0.2, C_1=C1, C_2=C2, N=N, x0=L(x0), w_guess=L(wg), q_guess=L(qg), B_eci=L(B_ECI.T),
+                          X_rows={str(i): L(X[:, i]) for i in (0, 1, 2, N // 2, N - 1)},
+                          M_rows={str(i): L(M[:, i]) for i in (1, 2, N // 2, N - 2)},
+                          q_err_rows={str(i): L(Qe[:, i]) for i in (1, N // 2, N - 2)}))
+    x = np.concatenate([rng.normal(size=3) * 0.01, rng.normal(size=4)])
+    xl = rng.normal(size=7) * 0.02
+    u = rng.normal(size=3) * 0.1
+    Bb = rng.normal(size=3) * 3e-5
+    fx["psiaki"] = dict(cases=cases, linear=dict(x=L(x), u=L(u), x_linear=L(xl), B_B=L(Bb), J=L(J3U),
+                                                 dx=L(attitude_dynamics_linear(x, u, xl, Bb, J3U))))
+    json.dump(fx, open(out, "w"))
+    print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "psiaki":
+        add_psiaki_section()
+    else:
+        main()

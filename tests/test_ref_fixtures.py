@@ -219,3 +219,24 @@ def test_tvlqr_replay_and_postprocessing(orc, fx):
         s2 = L.orc_mc_slew_time(orc.P(X), X.shape[0], orc.P(qf), c["t_final"], c["time_step"], 0.05, 0.08727, 1, 7)
         assert abs(s1 - c["slew_time"]) < 1e-12 and abs(s2 - c["slew_time_literal_i7"]) < 1e-12
         assert (s1 == c["t_final"]) == bool(c["fail"])
+
+
+def test_comparison_controller(orc, fx):
+    """the oracle's Psiaki PD closed loop and attitude_dynamics_linear against the numpy transliteration of
+    comparison/psiaki2005.jl:116-164, psiaki_dynamics.jl:1-26,63-73 and attitude_dynamics.jl:26-48."""
+    L = orc.lib()
+    for c in fx["psiaki"]["cases"]:
+        N = c["N"]
+        X, M, Qe = np.zeros((N, 7)), np.zeros((N, 3)), np.zeros((N, 4))
+        L.orc_psiaki_pd_simulation(N, _p(c["x0"]), _p(c["w_guess"]), _p(c["q_guess"]), _p(c["B_eci"]), _p(c["J"]), c["dt"], c["C_1"], c["C_2"],
+                                   orc.P(X), orc.P(M), orc.P(Qe))
+        for k, row in c["X_rows"].items():
+            close(X[int(k)], row, 1e-11)
+        for k, row in c["M_rows"].items():
+            close(M[int(k)], row, 1e-9, 1e-16)
+        for k, row in c["q_err_rows"].items():
+            close(Qe[int(k)], row, 1e-11)
+    c = fx["psiaki"]["linear"]
+    dx = np.zeros(7)
+    L.orc_attitude_dynamics_linear(_p(c["x"]), _p(c["u"]), _p(c["x_linear"]), _p(c["B_B"]), _p(c["J"]), orc.P(dx))
+    close(dx, c["dx"], 1e-13)

@@ -9,6 +9,7 @@
 #include "k4_tvlqr.cuh"
 #include "k5_unitops.cuh"
 #include "k6_igrf12syn.cuh"
+#include "k7_comparison.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -1293,6 +1294,58 @@ int ts_rk3_step_batch(ts_ctx* c, int64_t n, const double* x, const double* u, co
   double* dd = io.out(xn, (size_t)n * 8);
   if (io.rc) return io.rc;
   k5_rk3_step<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dxs, du, dB, B_rows, index_scale, clock_rate, dJ, dt, dd);
+  return io.finish();
+}
+
+// ---------------------------------------------------------------------------- K7 comparison controller
+int ts_psiaki_pd_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const int64_t* offs, const double* x0, const double* w_guess,
+                       const double* q_guess, const double* B_eci, const double* Jmat, double dt, double C_1, double C_2, double* X,
+                       double* M, double* q_err) {
+  if (!c) return TS_ERR_ARG;
+  if (n_trials < 0 || (n_trials > 0 && (!N_i || !offs || !x0 || !w_guess || !q_guess || !B_eci || !Jmat || !X)))
+    return fail(c, TS_ERR_ARG, "ts_psiaki_pd_batch: null argument");
+  if (n_trials == 0) return TS_OK;
+  if (!(dt > 0)) return fail(c, TS_ERR_ARG, "ts_psiaki_pd_batch: dt must be > 0");
+  int64_t knots = 0;
+  for (int64_t t = 0; t < n_trials; ++t) {
+    if (N_i[t] < 1) return fail(c, TS_ERR_ARG, "trial %lld: N < 1", (long long)t);
+    knots = std::max(knots, offs[t] + N_i[t]);
+  }
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  K7Args a;
+  a.n_trials = n_trials;
+  a.N_i = io.in(N_i, (size_t)n_trials);
+  a.offs = io.in(offs, (size_t)n_trials);
+  a.x0 = io.in(x0, (size_t)n_trials * 7);
+  a.w_guess = io.in(w_guess, (size_t)knots * 3);
+  a.q_guess = io.in(q_guess, (size_t)knots * 4);
+  a.B_eci = io.in(B_eci, (size_t)knots * 3);
+  a.Jmat = io.in(Jmat, (size_t)n_trials * 9);
+  a.dt = dt; a.C1 = C_1; a.C2 = C_2;
+  a.X = io.out(X, (size_t)knots * 7);
+  a.M = io.out(M, (size_t)knots * 3);
+  a.Qe = io.out(q_err, (size_t)knots * 4);
+  if (io.rc) return io.rc;
+  k7_psiaki_pd_kernel<<<(unsigned)((n_trials + 63) / 64), 64, 0, c->stream>>>(a);
+  return io.finish();
+}
+
+int ts_attitude_dynamics_linear_batch(ts_ctx* c, int64_t n, const double* x, const double* u, const double* x_linear, const double* B_B,
+                                      const double* Jmat, double* dx) {
+  if (!c) return TS_ERR_ARG;
+  if (n < 0 || (n > 0 && (!x || !u || !x_linear || !B_B || !Jmat || !dx))) return fail(c, TS_ERR_ARG, "ts_attitude_dynamics_linear_batch: null argument");
+  if (n == 0) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  HostIO io(c);
+  const double* dxs = io.in(x, (size_t)n * 7);
+  const double* du = io.in(u, (size_t)n * 3);
+  const double* dl = io.in(x_linear, (size_t)n * 7);
+  const double* dB = io.in(B_B, (size_t)n * 3);
+  const double* dJ = io.in(Jmat, 9);
+  double* dd = io.out(dx, (size_t)n * 7);
+  if (io.rc) return io.rc;
+  k7_attitude_dynamics_linear<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dxs, du, dl, dB, dJ, dd);
   return io.finish();
 }
 

@@ -141,6 +141,8 @@ def load_library():
     L.ts_mc_trajectory_layout.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.ts_mc_fetch_trajectories.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.ts_igrf12syn_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int]
+    L.ts_psiaki_pd_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.c_void_p] * 3
+    L.ts_attitude_dynamics_linear_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
     L.ts_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
     L.ts_destroy_multi.argtypes = [C.c_void_p]
     L.ts_destroy_multi.restype = None
@@ -491,6 +493,31 @@ class Engine:
         self._check(self.lib.ts_igrf12syn_batch(self.h, int(isv), float(date), int(itype), n, _ptr(alt), _ptr(colat), _ptr(elong),
                                                 _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), _ptr(o[3]), 0))
         return tuple(o)
+
+
+    def psiaki_pd_batch(self, N_i, x0, w_guess, q_guess, B_eci, Jmat, dt, C_1, C_2):
+        """Batched Psiaki-style PD closed loop (comparison/psiaki2005.jl:116-164).  Ragged by offs = cumsum(N_i): w_guess
+        (sum N, 3), q_guess (sum N, 4), B_eci (sum N, 3); x0 (T, 7), Jmat (T, 9).  Returns X (sum N, 7), M (sum N, 3),
+        q_err (sum N, 4), offs."""
+        N_i = np.ascontiguousarray(N_i, dtype=np.int64)
+        T = N_i.shape[0]
+        offs = np.zeros(T + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(N_i)
+        tot = int(offs[-1])
+        x0, Jmat = _f64(np.asarray(x0).reshape(T, 7)), _f64(np.asarray(Jmat).reshape(T, 9))
+        wg, qg, B = _f64(np.asarray(w_guess).reshape(tot, 3)), _f64(np.asarray(q_guess).reshape(tot, 4)), _f64(np.asarray(B_eci).reshape(tot, 3))
+        X, M, Qe = np.zeros((tot, 7)), np.zeros((tot, 3)), np.zeros((tot, 4))
+        self._check(self.lib.ts_psiaki_pd_batch(self.h, T, _ptr(N_i), _ptr(offs), _ptr(x0), _ptr(wg), _ptr(qg), _ptr(B), _ptr(Jmat),
+                                                float(dt), float(C_1), float(C_2), _ptr(X), _ptr(M), _ptr(Qe)))
+        return X, M, Qe, offs
+
+    def attitude_dynamics_linear_batch(self, x, u, x_linear, B_B, Jmat):
+        x, u, xl, B = _f64(np.atleast_2d(x)), _f64(np.atleast_2d(u)), _f64(np.atleast_2d(x_linear)), _f64(np.atleast_2d(B_B))
+        n = x.shape[0]
+        dx = np.zeros((n, 7))
+        J = _f64(np.asarray(Jmat).reshape(9))
+        self._check(self.lib.ts_attitude_dynamics_linear_batch(self.h, n, _ptr(x), _ptr(u), _ptr(xl), _ptr(B), _ptr(J), _ptr(dx)))
+        return dx
 
 
 class MultiEngine:
@@ -915,3 +942,30 @@ def retry_failed(res, max_rounds=3, inclination=None, seed=1, **mc_kwargs):
                 if f in res and f in sub:
                     res[f][i] = sub[f][k]
     return np.nonzero(res["fails"] == 1.0)[0] + 1
+
+
+# ---------------------------------------------------------------------------
+# Comparison controller (src/comparison/psiaki_dynamics.jl, psiaki2005.jl, attitude_dynamics.jl:26-48)
+def attitude_dynamics_linear(x, u, x_linear, B_B, J):
+    """attitude_dynamics_linear(x,u,x_linear,B_B,J) -> xdot (7)  (attitude_dynamics.jl:26-48)."""
+    return default_engine().attitude_dynamics_linear_batch(np.asarray(x, dtype=float).reshape(1, 7), np.asarray(u, dtype=float).reshape(1, 3),
+                                                           np.asarray(x_linear, dtype=float).reshape(1, 7),
+                                                           np.asarray(B_B, dtype=float).reshape(1, 3), J)[0]
+
+
+def psiaki_controller(C_1, C_2, J, q, w_bar, B_meas, m_limit=None):
+    """psiaki_controller (comparison/psiaki_dynamics.jl:1-26; host helper -- the batched loop evaluates it on the GPU).  The
+    m_limit clamp is commented out in the reference and is not applied."""
+    q, w_bar, B_meas = np.asarray(q, dtype=float), np.asarray(w_bar, dtype=float), np.asarray(B_meas, dtype=float)
+    T_req = -(C_1 * w_bar + C_2 * np.linalg.inv(np.asarray(J, dtype=float)) @ q[1:4])
+    return np.cross(B_meas, T_req) / (np.linalg.norm(B_meas) ** 2)
+
+
+def psiaki_pd_simulation(x0, w_guess, q_guess, B_ECI, J, dt, C_1=1e-6, C_2=1e-9):
+    """The closed loop of comparison/psiaki2005.jl:116-164 for ONE slew (batch of 1): w_guess 3 x N, q_guess 4 x N, B_ECI
+    3 x N as in the script.  Returns x (7 x N), the moments (3 x N) and the error quaternions q_bar (4 x N)."""
+    w_guess, q_guess, B_ECI = np.asarray(w_guess, dtype=float), np.asarray(q_guess, dtype=float), np.asarray(B_ECI, dtype=float)
+    N = w_guess.shape[1]
+    X, M, Qe, _ = default_engine().psiaki_pd_batch([N], np.asarray(x0, dtype=float).reshape(1, 7), w_guess.T.copy(), q_guess.T.copy(),
+                                                   B_ECI.T.copy(), np.asarray(J, dtype=float).reshape(1, 9), dt, C_1, C_2)
+    return X.T.copy(), M.T.copy(), Qe.T.copy()
