@@ -161,6 +161,9 @@ typedef struct ts_ilqr_opts {
   int32_t k3_suspend_after;       /* 150 */
   int32_t k3_tail_share;          /* 1   */
   double k3_early_factor;         /* 2.0 */
+  int32_t k3_pair;                /* 1: the one-warp-per-trial launch gets a producer warp per trial that linearises the
+                                        next chunk while the solver warp runs the Riccati steps (k3_pair_kernel)      */
+  int32_t k3_pad_;
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);
 

@@ -25,9 +25,12 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "mc_fixed_orbit"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 args = sys.argv[3:]
 suspends = [150]
+pairs = [1]
 for i, a in enumerate(args):
     if a == "--suspend":
         suspends = [int(x) for x in args[i + 1].split(",")]
+    if a == "--pair":
+        pairs = [int(x) for x in args[i + 1].split(",")]
 eng = tb.Engine(0)
 tr = B.make_trials(workload, n, 0)
 fo = np.zeros(len(tr["fo"]), dtype=host.FIELD_OPTS_DTYPE)
@@ -55,11 +58,16 @@ def run(cfg, label):
 
 base_out = None
 for s in suspends:
-    cfg = B.mc_config(host, tr, n)
-    cfg.ilqr.k3_suspend_after = s
-    out, st = run(cfg, "suspend=%d" % s)
-    if base_out is None:
-        base_out = out.copy()
+    for pr in pairs:
+        cfg = B.mc_config(host, tr, n)
+        cfg.ilqr.k3_suspend_after = s
+        cfg.ilqr.k3_pair = pr
+        out, st = run(cfg, "suspend=%d pair=%d" % (s, pr))
+        if base_out is None:
+            base_out = out.copy()
+        else:
+            same = all(np.array_equal(out[f], base_out[f]) for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"))
+            print("   same iteration paths as the first run:", same, "| max |dJ|/|J| %.2e" % float(np.max(np.abs(out["J"] - base_out["J"]) / np.maximum(np.abs(base_out["J"]), 1e-300))), flush=True)
 
 if "--why" in args:
     cfg = B.mc_config(host, tr, n)

@@ -46,6 +46,7 @@ struct ts_ilqr_opts_dev {
   // K3 launch scheme (host side only)
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
+  int32_t k3_pair, k3_pad_;
 };
 // 64-byte per-trial record (C ABI: ts_trial_outcome).
 struct ts_trial_outcome_dev {
@@ -113,6 +114,18 @@ struct TrialWork {
   double* clk;   // [Nmax]         clock state
   double* bk;    // [Nmax][10]     field vectors of the three rk3 stages of each knot (9 used)
   long long Nmax;
+};
+
+// Teams that receive the Jacobian records of a chunk from a PRODUCER warp (k3_pair_kernel) declare
+// `static constexpr bool EXT_LIN = true` and provide lin_begin / rec_wait / rec_release / lin_abort; every other team
+// linearises its chunk itself.
+template <class Team, class = void>
+struct team_ext_lin {
+  static constexpr bool value = false;
+};
+template <class Team>
+struct team_ext_lin<Team, decltype((void)Team::EXT_LIN)> {
+  static constexpr bool value = Team::EXT_LIN;
 };
 
 // Work pointers always address global memory; when a TrialWork lives in shared memory (k3_wide_kernel) the compiler
@@ -267,7 +280,7 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
   for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
   for (int i = 0; i < 9; ++i) b[i] = bp[i];
   for (int i = 0; i < 6; ++i) lam[i] = lp_[i];
-  rk3_jac7_jvp(in.I, x, u, b, b + 3, b + 6, in.dt, rec);
+  if (!team_ext_lin<Team>::value) rk3_jac7_jvp(in.I, x, u, b, b + 3, b + 6, in.dt, rec);   // else: written by the producer warp
   for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
   double c6[6];
   bound_c(o, u, c6);
@@ -314,15 +327,19 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
     }
     bool not_pd = false;
     const int n_chunks = (N - 1 + W - 1) / W;
+    int pos = 0;   // position of the chunk in this sweep (0 = last chunk of the trajectory)
+    if constexpr (team_ext_lin<Team>::value) tm.lin_begin(xu_cur, gptr(w.bk), N);
     TS_NO_UNROLL
     for (int ch = n_chunks - 1; ch >= 0 && !not_pd; --ch) {
       const int base = ch * W;
       tm.sync();  // previous chunk's records fully consumed
       const long long tl0 = ts_clock();
-      if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, sm + L::REC0 + lane * REC);
+      double* recs = sm + L::REC0;
+      if constexpr (team_ext_lin<Team>::value) recs = tm.rec_wait(pos);   // Jacobians of this chunk from the producer warp
+      if (base + lane < N - 1) linearise_knot<Team>(in, o, w, xu_cur, base + lane, sc, mu, recs + lane * REC);
       tm.sync();
       cyc_lin += ts_clock() - tl0;
-      if (base >= W) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
+      if (!team_ext_lin<Team>::value && base >= W) {  // L2 prefetch of the next (lower) chunk's linearisation inputs: hidden behind the Riccati steps
         const int kn = base - W + lane;
         tm.prefetch_l2(xu_cur + (long long)kn * 10);
         tm.prefetch_l2(gptr(w.bk) + (long long)kn * 10);
@@ -332,7 +349,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       if (kk_hi > W - 1) kk_hi = W - 1;
       TS_NO_UNROLL
       for (int kk = kk_hi; kk >= 0; --kk) {
-        const double* rec = sm + L::REC0 + kk * REC;
+        const double* rec = recs + kk * REC;
         const int k = base + kk;
         if constexpr (W >= 32) {
           // ================= whole-warp team: the knot step spread over 30 lanes =================
@@ -539,6 +556,15 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           tm.sync();
         }
       }
+      if constexpr (team_ext_lin<Team>::value) {
+        if (!not_pd) {   // chunk consumed: hand its buffer back (the producer fills it for the chunk after next)
+          tm.rec_release(pos, pos + 2 < n_chunks);
+          ++pos;
+        }
+      }
+    }
+    if constexpr (team_ext_lin<Team>::value) {
+      if (not_pd) tm.lin_abort(pos, n_chunks);   // regularisation restart: drain the producer, then start the sweep again
     }
     if (!not_pd) break;
     reg_increase(o, reg);

@@ -619,4 +619,194 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
 }
 constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 
+// ---------------------------------------------------------------------------------------------
+// k3_pair_kernel: the one-warp-per-trial solver with a PRODUCER warp.  A straggler's latency is what ends the run, and
+// of the ~4.4 k cycles a whole warp spends per knot-iteration ~0.6 k is the linearisation of the next 32-knot chunk --
+// pure throughput work (one knot per lane, no dependence on the Riccati recursion) that sits on the critical path only
+// because the same warp does it.  Here a second warp of the block (on another SM sub-partition, with its own FP64
+// pipe) computes the Jacobian records [A|B] of chunk c-1 into the other half of a double buffer while the solver warp
+// runs the 32 sequential Riccati steps of chunk c.  Hand-over through named barriers (bar.arrive / bar.sync):
+//   CMD      solver: "new backward sweep over this trajectory" (or EXIT)         both warps sync
+//   FULL_b   producer arrives when buffer b holds a chunk, solver syncs before reading it
+//   EMPTY_b  solver arrives when it has consumed buffer b, producer syncs before refilling it (from the 3rd chunk on)
+// A regularisation restart (Quu not positive definite) at sweep position j drains position j+1 (always produced) and
+// tells the producer to stop before position j+2 (abort_pos; a position tag, not a flag, so that the producer's decision
+// does not depend on when it happens to look).
+// Same solver source, same arithmetic: results are those of k3_wide_kernel bit for bit.
+struct K3PairCmd {
+  const double* xu;    // trajectory to linearise
+  const double* bk;    // stage field vectors
+  int N;
+  int type;            // 1 = sweep, 0 = exit
+  volatile int abort_pos;  // -1, or the first sweep position the producer must NOT produce any more
+  int pad_;
+};
+enum { K3P_BAR_CMD = 1, K3P_BAR_FULL = 2, K3P_BAR_EMPTY = 4 };
+__device__ __forceinline__ void k3p_bar_sync(int id) { asm volatile("barrier.sync %0, 64;\n" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void k3p_bar_arrive(int id) { asm volatile("barrier.arrive %0, 64;\n" ::"r"(id) : "memory"); }
+
+struct GpuPairTeam : GpuWideTeam {
+  static constexpr bool EXT_LIN = true;
+  double* rec1;        // second record buffer (the first is SmL<32>::REC0)
+  K3PairCmd* cmd;
+  __device__ __forceinline__ void lin_begin(const double* xu, const double* bk, int N) const {
+    if (ln == 0) {
+      cmd->xu = xu;
+      cmd->bk = bk;
+      cmd->N = N;
+      cmd->type = 1;
+      cmd->abort_pos = -1;
+    }
+    __syncwarp();
+    __threadfence_block();
+    k3p_bar_sync(K3P_BAR_CMD);
+  }
+  __device__ __forceinline__ double* rec_wait(int pos) const {
+    k3p_bar_sync(K3P_BAR_FULL + (pos & 1));
+    double* p = (pos & 1) ? rec1 : sm + SmL<32>::REC0;
+    __builtin_assume(__isShared(p));
+    return p;
+  }
+  __device__ __forceinline__ void rec_release(int pos, bool more) const {
+    if (more) {
+      __threadfence_block();
+      k3p_bar_arrive(K3P_BAR_EMPTY + (pos & 1));
+    }
+  }
+  // abort at sweep position pos (whose FULL barrier has been passed): the producer has produced position pos+1 at most
+  __device__ __forceinline__ void lin_abort(int pos, int n_pos) const {
+    if (ln == 0) cmd->abort_pos = pos + 2;
+    __syncwarp();
+    __threadfence_block();
+    if (pos + 1 < n_pos) k3p_bar_sync(K3P_BAR_FULL + ((pos + 1) & 1));     // drain position pos+1 (always produced)
+    if (pos + 2 < n_pos) k3p_bar_arrive(K3P_BAR_EMPTY + (pos & 1));        // wake the producer at pos+2: it sees abort_pos and stops
+  }
+};
+constexpr int K3_PAIR_SMEM_DOUBLES = SmL<32>::TOTAL + 32 * REC + 8;
+constexpr int K3_PAIR_SMEM_BYTES = K3_PAIR_SMEM_DOUBLES * 8;
+
+__global__ void __launch_bounds__(64, 1) k3_pair_kernel(const K3Args a) {
+  extern __shared__ __align__(16) double k3_smem[];
+  __shared__ TrialWork w_sm;
+  const int lane32 = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* rec1 = k3_smem + SmL<32>::TOTAL;
+  K3PairCmd* cmd = reinterpret_cast<K3PairCmd*>(k3_smem + SmL<32>::TOTAL + 32 * REC);
+  if (warp == 1) {
+    // ------------------------------------------------------------------ producer warp
+    const TrialIn* inp = reinterpret_cast<const TrialIn*>(k3_smem + SmL<32>::TRIAL);
+    __builtin_assume(__isShared(inp));
+    for (;;) {
+      k3p_bar_sync(K3P_BAR_CMD);
+      if (cmd->type == 0) break;
+      const double* xu = gptr(cmd->xu);
+      const double* bkp = gptr(cmd->bk);
+      const int N = cmd->N;
+      const int n_pos = (N - 1 + 31) / 32;
+#pragma unroll 1
+      for (int pos = 0; pos < n_pos; ++pos) {
+        const int b = pos & 1;
+        if (pos >= 2) {
+          k3p_bar_sync(K3P_BAR_EMPTY + b);
+          const int ap = cmd->abort_pos;
+          if (ap >= 0 && pos >= ap) break;
+        }
+        const int k = (n_pos - 1 - pos) * 32 + lane32;
+        if (k < N - 1) {
+          double* rec = (b ? rec1 : k3_smem + SmL<32>::REC0) + lane32 * REC;
+          __builtin_assume(__isShared(rec));
+          const double* p = xu + (long long)k * 10;
+          const double* bp = bkp + (long long)k * 10;
+          double x[7], u[3], bb[9];
+          // (L2 loads: the solver warp wrote this trajectory with plain stores a moment ago)
+          for (int i = 0; i < 7; ++i) x[i] = __ldcg(p + i);
+          for (int i = 0; i < 3; ++i) u[i] = __ldcg(p + 7 + i);
+          for (int i = 0; i < 9; ++i) bb[i] = __ldcg(bp + i);
+          rk3_jac7_jvp(inp->I, x, u, bb, bb + 3, bb + 6, inp->dt, rec);
+        }
+        __syncwarp();
+        __threadfence_block();
+        k3p_bar_arrive(K3P_BAR_FULL + b);
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- solver warp (as k3_wide_kernel)
+  GpuPairTeam tm;
+  tm.ln = lane32;
+  tm.sm = k3_smem;
+  tm.rec1 = rec1;
+  tm.cmd = cmd;
+  TrialWork& w = w_sm;
+  if (lane32 == 0) {
+    w.Nmax = 0;
+    w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
+    w.slot_stride = 0;
+  }
+  __syncwarp();
+  long long region_cap = 0;
+  const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
+  const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
+  unsigned n_parked = *a.park_count;
+  if (n_parked > (unsigned)a.park_cap) n_parked = (unsigned)a.park_cap;
+  for (;;) {
+    unsigned long long qpos = 0;
+    if (lane32 == 0) qpos = atomicAdd(a.queue2, 1ull);
+    qpos = __shfl_sync(0xffffffffu, qpos, 0);
+    if (qpos >= n_parked) break;
+    const int64_t idx = a.park_order[qpos];
+    const int64_t t = a.park_trial[idx];
+    const TrialIn& in = k3_load_trial(tm, a, t);
+    const int N = in.N;
+    const long long Ne = N + (N & 1);
+    if (Ne > region_cap) {
+      unsigned long long off = 0;
+      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * dpk));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if ((long long)(off + Ne * dpk) > a.pool_cap) {
+        if (lane32 == 0) {
+          ts_trial_outcome_dev oc = {};
+          oc.status = ST_NAN;
+          oc.N = N;
+          a.out[t] = oc;
+        }
+        continue;
+      }
+      region_cap = Ne;
+      __syncwarp();
+      if (lane32 == 0) {
+        w.Nmax = Ne;
+        w.slot_stride = 9 * Ne * 10;
+        w.xu = w.xu_warp = a.pool + off;
+        w.kd = w.xu + (long long)nbuf * 10 * Ne;
+        w.lam = w.kd + 24 * Ne;
+        w.bk = w.lam + 6 * Ne;
+        w.clk = w.bk + 10 * Ne;
+      }
+      __syncwarp();
+    }
+    const double* pd = a.park_data + a.park_off[idx];
+    for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];
+    for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * Ne + i];
+    for (int i = lane32; i < N * 10; i += 32) w.bk[i] = pd[16 * Ne + i];
+    for (int i = lane32; i < N; i += 32) w.clk[i] = pd[26 * Ne + i];
+    TrialState st = a.park_state[idx];
+    st.cur = 0;
+    __syncwarp();
+    __threadfence_block();   // the producer reads the trajectory and field vectors this warp just wrote
+    while (st.phase != PH_DONE) {
+      if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
+      while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
+    }
+    ts_trial_outcome_dev oc;
+    solve_finish(in, st, oc);
+    k3_store_results(tm, a, t, w, N, st.cur, oc, st);
+    __syncwarp();
+  }
+  if (lane32 == 0) cmd->type = 0;
+  __syncwarp();
+  __threadfence_block();
+  k3p_bar_sync(K3P_BAR_CMD);
+}
+
 }  // namespace ts
