@@ -161,9 +161,12 @@ typedef struct ts_ilqr_opts {
   int32_t k3_suspend_after;       /* 150 */
   int32_t k3_tail_share;          /* 1   */
   double k3_early_factor;         /* 2.0 */
-  int32_t k3_pair;                /* 1: the one-warp-per-trial launch gets a producer warp per trial that linearises the
-                                        next chunk while the solver warp runs the Riccati steps (k3_pair_kernel)      */
-  int32_t k3_pad_;
+  int32_t k3_pair;                /* 0; 1: the one-warp-per-trial launch runs as k3_pair_kernel: 4 solver warps per SM, each
+                                        with a producer warp (same SM sub-partition) that linearises the next 32-knot chunk
+                                        while the solver runs the Riccati steps.  Same results; 5 % faster per iteration
+                                        when few trials are left, slower on a full ensemble (half the solver warps)  */
+  int32_t k3_wide_occ;            /* 0: as many one-warp blocks per SM as fit (8); n > 0: at most n.  Measured on the
+                                        4096-trial ensemble: 8 -> 5.72 s, 6 -> 5.98 s, 4 -> 6.64 s, 2 -> 10.5 s            */
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);
 

@@ -163,7 +163,7 @@ struct orc_ilqr_opts {
   // launch-scheme fields of the product's ts_ilqr_opts (same layout; meaningless on the CPU)
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
-  int32_t k3_pair, k3_pad_;
+  int32_t k3_pair, k3_wide_occ;
 };
 static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   IlqrOpts o;
@@ -198,7 +198,7 @@ void orc_ilqr_default_opts(orc_ilqr_opts* s) {
   s->a2_active_ge = o.a2_active_ge; s->a3_grad_over_N = o.a3_grad_over_N; s->a4_no_intermediate = o.a4_no_intermediate;
   s->a5_dual_active_only = o.a5_dual_active_only; s->a6_penalty_conditional = o.a6_penalty_conditional;
   s->a7_carry_cost = o.a7_carry_cost; s->constraint_decrease_ratio = o.constraint_decrease_ratio;
-  s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 1; s->k3_pad_ = 0;
+  s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 0; s->k3_wide_occ = 0;
 }
 
 // Batched solve.  Per trial t: N_i[t] knots, ragged arrays addressed through

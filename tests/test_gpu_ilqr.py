@@ -223,9 +223,11 @@ def test_straggler_handover_multi_wave(engine):
         assert np.max(np.abs(ref[0][o_all] - Xo[o_all])) < 1e-9
 
 
-def test_handover_matches_oracle(engine):
+@pytest.mark.parametrize("pair,occ", [(0, 0), (1, 0), (0, 3)])
+def test_handover_matches_oracle(engine, pair, occ):
     """Four trials per warp + straggler hand-over after 10 inner iterations against the oracle on a ragged batch with
-    gains (most trials finish in the one-warp-per-trial kernel)."""
+    gains (most trials finish in the one-warp-per-trial kernel); the second launch in its three forms: k3_wide_kernel,
+    k3_pair_kernel (producer warp per solver warp), and k3_wide_kernel capped at 3 blocks per SM."""
     rng = np.random.default_rng(5)
     slews = []
     for i in range(12):
@@ -235,6 +237,8 @@ def test_handover_matches_oracle(engine):
     import tortoisesat.jl_b200 as tb
     o = orc.default_ilqr_opts()
     o.k3_suspend_after = 10
+    o.k3_pair = pair
+    o.k3_wide_occ = occ
     same = _check(engine, slews, o, tb)
     assert engine.k3_last_split()[2] > 0
     assert same >= 10

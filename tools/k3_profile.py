@@ -1,6 +1,6 @@
 """ncu-sized K3 run on the BENCHMARK ensemble (BASELINE configs[2]: fixed orbit, N = 2044 knots, random attitudes).
 
-  python tools/k3_profile.py <n_trials> [max_outer] [suspend_after]
+  python tools/k3_profile.py <n_trials> [max_outer] [suspend_after] [k3_pair] [k3_wide_occ]
 
 Runs the first n_trials of bench.py's rank-0 ensemble through ts_monte_carlo_run (field -> weights -> K3, no
 replay) with the outer-iteration cap lowered so that an `ncu --set full` replay stays short; suspend_after = 3
@@ -31,6 +31,8 @@ cfg.run_tvlqr = 0
 cfg.ilqr.max_outer = max_outer
 if suspend >= 0:
     cfg.ilqr.k3_suspend_after = suspend
+cfg.ilqr.k3_pair = int(sys.argv[4]) if len(sys.argv) > 4 else cfg.ilqr.k3_pair
+cfg.ilqr.k3_wide_occ = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
 fo[0] = tr["fo"][0]
 out, st = eng.monte_carlo_run(cfg, tr["kep"], fo, sub["x0"], sub["xf"], sub["Jm"], q_noise0=sub["qn"],
@@ -41,3 +43,7 @@ print("trials", n, "N", int(out["N"][0]), "max_outer", max_outer, "suspend", sus
 print("knot_iterations %.6e rollout_knots %.6e inner mean/max %.1f %d status %s" % (
     kn, ro, out["inner_iters"].mean(), out["inner_iters"].max(), np.bincount(out["status"], minlength=6).tolist()))
 print("cycles per knot-iteration of the slowest trial at 1.965 GHz: %.0f" % (st.ms_solve * 1e-3 * 1.965e9 / (out["inner_iters"].max() * (out["N"][0] - 1))))
+cyc = eng.k3_last_cycles(n)   # SM cycles per trial: backward pass (incl. linearisation), forward passes, linearisation share
+ki = ((out["N"] - 1).astype(np.float64) * out["inner_iters"])
+print("SM cycles per knot-iteration, mean over trials: backward %.0f (of which linearisation %.0f) forward %.0f ; pair=%d occ=%d" % (
+    np.mean(cyc[:, 0] / ki), np.mean(cyc[:, 2] / ki), np.mean(cyc[:, 1] / ki), cfg.ilqr.k3_pair, cfg.ilqr.k3_wide_occ))

@@ -46,7 +46,7 @@ struct ts_ilqr_opts_dev {
   // K3 launch scheme (host side only)
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
-  int32_t k3_pair, k3_pad_;
+  int32_t k3_pair, k3_wide_occ;
 };
 // 64-byte per-trial record (C ABI: ts_trial_outcome).
 struct ts_trial_outcome_dev {

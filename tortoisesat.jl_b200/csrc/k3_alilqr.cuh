@@ -623,16 +623,21 @@ constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 // k3_pair_kernel: the one-warp-per-trial solver with a PRODUCER warp.  A straggler's latency is what ends the run, and
 // of the ~4.4 k cycles a whole warp spends per knot-iteration ~0.6 k is the linearisation of the next 32-knot chunk --
 // pure throughput work (one knot per lane, no dependence on the Riccati recursion) that sits on the critical path only
-// because the same warp does it.  Here a second warp of the block (on another SM sub-partition, with its own FP64
-// pipe) computes the Jacobian records [A|B] of chunk c-1 into the other half of a double buffer while the solver warp
-// runs the 32 sequential Riccati steps of chunk c.  Hand-over through named barriers (bar.arrive / bar.sync):
-//   CMD      solver: "new backward sweep over this trajectory" (or EXIT)         both warps sync
+// because the same warp does it.  Here a second warp computes the Jacobian records [A|B] of chunk c-1 into the other
+// half of a double buffer while the solver warp runs the 32 sequential Riccati steps of chunk c: the solver warp issues
+// one instruction every ~3 cycles (dependent FP64 chains), so the producer's instructions fill issue slots and FP64 pipe
+// cycles that would otherwise idle.
+// Geometry: ONE block of 8 warps per SM (192 KB of shared memory, 255 registers): warps 0..3 are solver warps, warp 4+i
+// is the producer of solver i; with the hardware's round-robin warp placement each SM sub-partition hosts exactly one
+// solver and one producer -- a solver never shares its sub-partition with another solver (at 8 solver warps per SM a
+// trial-iteration costs 7.7 ms, alone 4.6 ms).
+// Hand-over through named barriers, 4 per pair (bar.arrive / bar.sync on 64 threads):
+//   EMPTY_b  solver arrives when buffer b may be (re)filled: at the start of a sweep for both buffers, afterwards when
+//            it has consumed the chunk in it; producer syncs before producing
 //   FULL_b   producer arrives when buffer b holds a chunk, solver syncs before reading it
-//   EMPTY_b  solver arrives when it has consumed buffer b, producer syncs before refilling it (from the 3rd chunk on)
 // A regularisation restart (Quu not positive definite) at sweep position j drains position j+1 (always produced) and
 // tells the producer to stop before position j+2 (abort_pos; a position tag, not a flag, so that the producer's decision
-// does not depend on when it happens to look).
-// Same solver source, same arithmetic: results are those of k3_wide_kernel bit for bit.
+// does not depend on when it happens to look).  Same solver source, same arithmetic as k3_wide_kernel.
 struct K3PairCmd {
   const double* xu;    // trajectory to linearise
   const double* bk;    // stage field vectors
@@ -641,14 +646,14 @@ struct K3PairCmd {
   volatile int abort_pos;  // -1, or the first sweep position the producer must NOT produce any more
   int pad_;
 };
-enum { K3P_BAR_CMD = 1, K3P_BAR_FULL = 2, K3P_BAR_EMPTY = 4 };
 __device__ __forceinline__ void k3p_bar_sync(int id) { asm volatile("barrier.sync %0, 64;\n" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void k3p_bar_arrive(int id) { asm volatile("barrier.arrive %0, 64;\n" ::"r"(id) : "memory"); }
 
 struct GpuPairTeam : GpuWideTeam {
   static constexpr bool EXT_LIN = true;
-  double* rec1;        // second record buffer (the first is SmL<32>::REC0)
+  double* rec1;        // second record buffer (the first is SmL<32>::REC0 of the pair's region)
   K3PairCmd* cmd;
+  int bar0;            // first of the pair's four barrier ids: FULL_0, FULL_1, EMPTY_0, EMPTY_1
   __device__ __forceinline__ void lin_begin(const double* xu, const double* bk, int N) const {
     if (ln == 0) {
       cmd->xu = xu;
@@ -659,10 +664,11 @@ struct GpuPairTeam : GpuWideTeam {
     }
     __syncwarp();
     __threadfence_block();
-    k3p_bar_sync(K3P_BAR_CMD);
+    k3p_bar_arrive(bar0 + 2);                       // both buffers are free: the producer starts on positions 0 and 1
+    if (N - 1 > 32) k3p_bar_arrive(bar0 + 3);
   }
   __device__ __forceinline__ double* rec_wait(int pos) const {
-    k3p_bar_sync(K3P_BAR_FULL + (pos & 1));
+    k3p_bar_sync(bar0 + (pos & 1));
     double* p = (pos & 1) ? rec1 : sm + SmL<32>::REC0;
     __builtin_assume(__isShared(p));
     return p;
@@ -670,53 +676,62 @@ struct GpuPairTeam : GpuWideTeam {
   __device__ __forceinline__ void rec_release(int pos, bool more) const {
     if (more) {
       __threadfence_block();
-      k3p_bar_arrive(K3P_BAR_EMPTY + (pos & 1));
+      k3p_bar_arrive(bar0 + 2 + (pos & 1));
     }
   }
-  // abort at sweep position pos (whose FULL barrier has been passed): the producer has produced position pos+1 at most
+  // abort at sweep position pos (whose FULL barrier has been passed): the producer produces position pos+1 in any case
   __device__ __forceinline__ void lin_abort(int pos, int n_pos) const {
     if (ln == 0) cmd->abort_pos = pos + 2;
     __syncwarp();
     __threadfence_block();
-    if (pos + 1 < n_pos) k3p_bar_sync(K3P_BAR_FULL + ((pos + 1) & 1));     // drain position pos+1 (always produced)
-    if (pos + 2 < n_pos) k3p_bar_arrive(K3P_BAR_EMPTY + (pos & 1));        // wake the producer at pos+2: it sees abort_pos and stops
+    if (pos + 1 < n_pos) k3p_bar_sync(bar0 + ((pos + 1) & 1));     // drain position pos+1
+    if (pos + 2 < n_pos) k3p_bar_arrive(bar0 + 2 + (pos & 1));     // wake the producer at pos+2: it sees abort_pos and stops
   }
 };
-constexpr int K3_PAIR_SMEM_DOUBLES = SmL<32>::TOTAL + 32 * REC + 8;
-constexpr int K3_PAIR_SMEM_BYTES = K3_PAIR_SMEM_DOUBLES * 8;
+constexpr int K3_PAIRS_PER_BLOCK = 4;
+constexpr int K3_PAIR_REGION_DOUBLES = SmL<32>::TOTAL + 32 * REC + 8 + 8;   // solver layout | second record buffer | cmd | TrialWork
+static_assert(sizeof(K3PairCmd) <= 64 && sizeof(TrialWork) <= 64, "pair control blocks");
+constexpr int K3_PAIR_SMEM_BYTES = K3_PAIRS_PER_BLOCK * K3_PAIR_REGION_DOUBLES * 8;
 
-__global__ void __launch_bounds__(64, 1) k3_pair_kernel(const K3Args a) {
+__global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(const K3Args a) {
   extern __shared__ __align__(16) double k3_smem[];
-  __shared__ TrialWork w_sm;
   const int lane32 = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  double* rec1 = k3_smem + SmL<32>::TOTAL;
-  K3PairCmd* cmd = reinterpret_cast<K3PairCmd*>(k3_smem + SmL<32>::TOTAL + 32 * REC);
-  if (warp == 1) {
+  const int pair = warp & (K3_PAIRS_PER_BLOCK - 1);
+  const bool is_producer = warp >= K3_PAIRS_PER_BLOCK;
+  double* region = k3_smem + pair * K3_PAIR_REGION_DOUBLES;
+  double* rec1 = region + SmL<32>::TOTAL;
+  K3PairCmd* cmd = reinterpret_cast<K3PairCmd*>(region + SmL<32>::TOTAL + 32 * REC);
+  TrialWork& w = *reinterpret_cast<TrialWork*>(region + SmL<32>::TOTAL + 32 * REC + 8);
+  const int bar0 = pair * 4;
+  if (is_producer) {
     // ------------------------------------------------------------------ producer warp
-    const TrialIn* inp = reinterpret_cast<const TrialIn*>(k3_smem + SmL<32>::TRIAL);
+    const TrialIn* inp = reinterpret_cast<const TrialIn*>(region + SmL<32>::TRIAL);
     __builtin_assume(__isShared(inp));
     for (;;) {
-      k3p_bar_sync(K3P_BAR_CMD);
-      if (cmd->type == 0) break;
-      const double* xu = gptr(cmd->xu);
-      const double* bkp = gptr(cmd->bk);
-      const int N = cmd->N;
-      const int n_pos = (N - 1 + 31) / 32;
+      // a sweep starts when the solver frees buffer 0 (lin_begin); the command block is valid from then on
+      int pos = 0, n_pos = 1;
+      bool done = false;
 #pragma unroll 1
-      for (int pos = 0; pos < n_pos; ++pos) {
+      for (; pos < n_pos; ++pos) {
         const int b = pos & 1;
-        if (pos >= 2) {
-          k3p_bar_sync(K3P_BAR_EMPTY + b);
-          const int ap = cmd->abort_pos;
-          if (ap >= 0 && pos >= ap) break;
+        k3p_bar_sync(bar0 + 2 + b);
+        if (pos == 0) {
+          if (cmd->type == 0) {
+            done = true;
+            break;
+          }
+          n_pos = (cmd->N - 1 + 31) / 32;
         }
+        const int ap = cmd->abort_pos;
+        if (ap >= 0 && pos >= ap) break;
+        const int N = cmd->N;
         const int k = (n_pos - 1 - pos) * 32 + lane32;
         if (k < N - 1) {
-          double* rec = (b ? rec1 : k3_smem + SmL<32>::REC0) + lane32 * REC;
+          double* rec = (b ? rec1 : region + SmL<32>::REC0) + lane32 * REC;
           __builtin_assume(__isShared(rec));
-          const double* p = xu + (long long)k * 10;
-          const double* bp = bkp + (long long)k * 10;
+          const double* p = gptr(cmd->xu) + (long long)k * 10;
+          const double* bp = gptr(cmd->bk) + (long long)k * 10;
           double x[7], u[3], bb[9];
           // (L2 loads: the solver warp wrote this trajectory with plain stores a moment ago)
           for (int i = 0; i < 7; ++i) x[i] = __ldcg(p + i);
@@ -726,18 +741,19 @@ __global__ void __launch_bounds__(64, 1) k3_pair_kernel(const K3Args a) {
         }
         __syncwarp();
         __threadfence_block();
-        k3p_bar_arrive(K3P_BAR_FULL + b);
+        k3p_bar_arrive(bar0 + b);
       }
+      if (done) break;
     }
     return;
   }
   // -------------------------------------------------------------------- solver warp (as k3_wide_kernel)
   GpuPairTeam tm;
   tm.ln = lane32;
-  tm.sm = k3_smem;
+  tm.sm = region;
   tm.rec1 = rec1;
   tm.cmd = cmd;
-  TrialWork& w = w_sm;
+  tm.bar0 = bar0;
   if (lane32 == 0) {
     w.Nmax = 0;
     w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
@@ -806,7 +822,7 @@ __global__ void __launch_bounds__(64, 1) k3_pair_kernel(const K3Args a) {
   if (lane32 == 0) cmd->type = 0;
   __syncwarp();
   __threadfence_block();
-  k3p_bar_sync(K3P_BAR_CMD);
+  k3p_bar_arrive(bar0 + 2);   // wakes the producer at the start of a sweep: it sees type == 0 and exits
 }
 
 }  // namespace ts

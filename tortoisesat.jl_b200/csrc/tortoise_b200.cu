@@ -483,7 +483,7 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
   o->a2_active_ge = 0; o->a3_grad_over_N = 0; o->a4_no_intermediate = 0; o->a5_dual_active_only = 0;
   o->a6_penalty_conditional = 0; o->a7_carry_cost = 0; o->constraint_decrease_ratio = 0.25;
-  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 1; o->k3_pad_ = 0;
+  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 0; o->k3_wide_occ = 0;
 }
 
 // slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
@@ -517,12 +517,20 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
   int64_t wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w);
   const bool pair = a.opts.k3_pair != 0;
+  int wide_smem = K3_WIDE_SMEM_BYTES;
   if (pair) {
     int occ_p = 0;
     TS_CUDA(c, cudaFuncSetAttribute(k3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_PAIR_SMEM_BYTES));
-    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k3_pair_kernel, 64, K3_PAIR_SMEM_BYTES));
+    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k3_pair_kernel, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES));
     if (occ_p < 1) return fail(c, TS_ERR_CUDA, "k3 pair kernel does not fit on an SM");
-    wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_p);
+    wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_p * K3_PAIRS_PER_BLOCK);   // solver warps
+  } else if (a.opts.k3_wide_occ > 0 && a.opts.k3_wide_occ < occ_w) {
+    // fewer blocks per SM: pad the dynamic shared memory so that exactly k3_wide_occ one-warp blocks fit
+    wide_smem = std::max(K3_WIDE_SMEM_BYTES, (227 * 1024 / (a.opts.k3_wide_occ + 1) + 1024) & ~15);
+    TS_CUDA(c, cudaFuncSetAttribute(k3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
+    int occ2 = 0;
+    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k3_wide_kernel, 32, wide_smem));
+    wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * std::max(occ2, 1));
   }
   // Queue order.  (1) sort by horizon (descending): the four teams of a warp get similar trip counts.
   // (2) within a run of (nearly) equal horizons, sort by slew angle and DEAL the trials round-robin over the
@@ -670,9 +678,9 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     const int blocks_w = (int)std::max<int64_t>(1, std::min<int64_t>(a.park_cap, wide_warps));
     k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
     if (pair)
-      k3_pair_kernel<<<blocks_w, 64, K3_PAIR_SMEM_BYTES, c->stream>>>(a);
+      k3_pair_kernel<<<(blocks_w + K3_PAIRS_PER_BLOCK - 1) / K3_PAIRS_PER_BLOCK, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES, c->stream>>>(a);
     else
-      k3_wide_kernel<<<blocks_w, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
+      k3_wide_kernel<<<blocks_w, 32, wide_smem, c->stream>>>(a);
     c->launches += 2;
     TS_CUDA(c, cudaGetLastError());
     TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
