@@ -238,7 +238,7 @@ TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double s
   for (int i = 0; i < 6; ++i) {
     const bool act = (c[i] > act_thr) || (lam[i] > 0.0);
     Jc += lam[i] * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
-    cmax = fmax(cmax, fmax(0.0, c[i]));
+    cmax = fmax(cmax, c[i]);   // == max(cmax, max(0, c)): cmax starts at 0 and only grows
   }
 }
 TS_HD void add_terminal_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double mu, const double x[7], double e8,
@@ -628,6 +628,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
   constexpr int W = Team::W;
   double* sm = tm.smem() + L::FWD;
   const int n_chunks = (N - 1 + W - 1) / W;
+  const bool clk_bad = !(clk_absmax < o.max_state_value);   // the analytic clock state takes part in the max |x| test
   tm.sync();
   stage_chunk(tm, w, xu_cur, 0, N, sm);
   TS_NO_UNROLL
@@ -676,17 +677,14 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
         for (int i = 0; i < 3; ++i) q[7 + i] = ub[i];
         double xn[7];
         rk3_step7<0>(in.I, xb, ub, p + 40, p + 43, p + 46, in.dt, xn);
-        double mx = clk_absmax, mu_abs = 0.0;
+        // max |x|, max |u| (NaN counts as infinite) against the limits, as ten predicate tests: a NaN fails `<`
+        bool bad = clk_bad;
         for (int i = 0; i < 7; ++i) {
           xb[i] = xn[i];
-          mx = fmax(mx, fabs(xn[i]));
-          if (xn[i] != xn[i]) mx = INFINITY;
+          bad |= !(fabs(xn[i]) < o.max_state_value);
         }
-        for (int i = 0; i < 3; ++i) {
-          mu_abs = fmax(mu_abs, fabs(ub[i]));
-          if (ub[i] != ub[i]) mu_abs = INFINITY;
-        }
-        if (!(mx < o.max_state_value) || !(mu_abs < o.max_control_value)) {
+        for (int i = 0; i < 3; ++i) bad |= !(fabs(ub[i]) < o.max_control_value);
+        if (bad) {
           r.ok = false;
           break;
         }
