@@ -499,7 +499,7 @@ def main():
         fails = int(np.sum(r[5] == out["t_final"][ok]))
         return {"workload": workload_name("tvlqr16k", n_ok), "slews_per_s": world * n_ok / k_s, "ms": k_s * 1e3, "slews_per_gpu": int(n_ok),
                 "knots_mean": float(N_i.mean()), "slew_fail": int(sum_over_ranks(fails)),
-                "roofline": {"bound": "fp64", "kernel": "k4_tvlqr_kernel", "achieved": FL_TVLQR * knots / k_s / 1e12, "peak": peak_fp64,
+                "roofline": {"bound": "fp64", "kernel": "K4 replay: k4a_linearise (thread per knot) + k4b_riccati + k4n_records + k4c_replay (thread per slew)", "achieved": FL_TVLQR * knots / k_s / 1e12, "peak": peak_fp64,
                              "unit": "TFLOP/s", "frac": FL_TVLQR * knots / k_s / 1e12 / peak_fp64,
                              "flop_model": "%.0f FLOP per knot (rk4 Jacobian with the dt^2 quirk, G(q) projection, 6x6 Riccati, 4 noisy dynamics calls)" % FL_TVLQR,
                              "hbm_gbs_algorithmic": (11 + 9 + 18 * 2) * 8 * knots / k_s / 1e9},

@@ -238,7 +238,7 @@ TS_HD void add_stage_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double s
   for (int i = 0; i < 6; ++i) {
     const bool act = (c[i] > act_thr) || (lam[i] > 0.0);
     Jc += lam[i] * c[i] + (act ? 0.5 * mu * c[i] * c[i] : 0.0);
-    cmax = fmax(cmax, c[i]);   // == max(cmax, max(0, c)): cmax starts at 0 and only grows
+    cmax = (c[i] > cmax) ? c[i] : cmax;   // == fmax(cmax, fmax(0, c)): cmax starts at 0 and only grows; a NaN c is skipped either way
   }
 }
 TS_HD void add_terminal_cost(const TrialIn& in, const ts_ilqr_opts_dev& o, double mu, const double x[7], double e8,
