@@ -71,8 +71,27 @@ __global__ void __launch_bounds__(128) k4a_linearise_kernel(const K4Args a) {
   for (int i = 0; i < 54; ++i) o[i] = AB[i];
 }
 
+// ---- per-thread staging ring for the two sequential kernels.  One thread owns one slew and walks its knots in order; what
+// a knot needs (54 doubles of [A|B] for the Riccati step, 69 for a replay step) sits in arrays laid out per slew, so the
+// 32 threads of a warp touch 32 unrelated addresses per load and every knot used to wait out several DRAM round trips
+// (ncu on the round-2 first cut: long-scoreboard 81 % of the replay's warp-cycles, ~10 k cycles per knot).  Each thread
+// now copies the inputs of the knot K4_RING_D steps ahead into its own slice of shared memory with 8-byte cp.async and
+// waits only for the oldest copy: the DRAM latency is off the dependent chain.  (W odd: the lanes' slices start on
+// different banks.)
+constexpr int K4_RING_D = 4;
+constexpr int K4B_W = 55;   // 54 used
+constexpr int K4C_W = 71;   // 8 + 18 + 40 + 3 = 69 used
+constexpr int K4B_SMEM_BYTES = K4_RING_D * 32 * K4B_W * 8;
+constexpr int K4C_SMEM_BYTES = K4_RING_D * 32 * K4C_W * 8;
+__device__ __forceinline__ void k4_cp8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void k4_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void k4_wait_oldest() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K4_RING_D - 1) : "memory"); }
+
 // ---- K4b: the backward Riccati sweep (sequential in k), one thread per trial, over the stored linearisations
 __global__ void __launch_bounds__(32) k4b_riccati_kernel(const K4Args a) {
+  extern __shared__ __align__(16) double k4_smem[];
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_trials) return;
   const int N = (int)a.N_i[t];
@@ -81,8 +100,23 @@ __global__ void __launch_bounds__(32) k4b_riccati_kernel(const K4Args a) {
   for (int i = 0; i < 6; ++i) S[i * 6 + i] = a.opts.Qfd[i];
   const double* ab = a.AB + a.lin_offs[t] * 54;
   double* K = a.K + a.offs[t] * 18;
+  double* ring = k4_smem + threadIdx.x * K4B_W;
+  auto issue = [&](int k) {   // knot k -> slot (k mod D); an empty group when k is out of range keeps the group count uniform
+    if (k >= 0) {
+      double* dst = ring + (k % K4_RING_D) * 32 * K4B_W;
+      const double* src = ab + (long long)k * 54;
+#pragma unroll
+      for (int i = 0; i < 54; ++i) k4_cp8(dst + i, src + i);
+    }
+    k4_commit();
+  };
+  for (int d = 0; d < K4_RING_D; ++d) issue(N - 2 - d);
 #pragma unroll 1
-  for (int k = N - 2; k >= 0; --k) tvlqr_riccati_step(a.opts, ab + (long long)k * 54, S, K + (long long)k * 18);
+  for (int k = N - 2; k >= 0; --k) {
+    k4_wait_oldest();
+    tvlqr_riccati_step(a.opts, ring + (k % K4_RING_D) * 32 * K4B_W, S, K + (long long)k * 18);
+    issue(k - K4_RING_D);
+  }
   // the replay's clock state at every step (the reference accumulates it through rk4: sequential, exact replica), so
   // that K4n can look the stage field rows up in parallel
   double x8 = a.x0_lqr[t * 8 + 7];
@@ -130,7 +164,41 @@ __global__ void __launch_bounds__(128) k4n_records_kernel(const K4Args a) {
 }
 
 // ---- K4c: the closed-loop replay (sequential in k) + slew-time rule, one thread per trial
+struct K4cRingSrc {   // the replay's input policy (tvlqr_replay_src): step k from the staging ring, step k + D requested behind it
+  const double *X, *U, *K, *recs;
+  double* ring;
+  long long n_steps;   // steps 0 .. N-2 have inputs
+  __device__ __forceinline__ void issue(long long k) const {
+    if (k < n_steps) {
+      double* dst = ring + (int)(k % K4_RING_D) * 32 * K4C_W;
+      const double* x = X + k * 8;
+      const double* g = K + k * 18;
+      const double* r = recs + k * (4 * TV_REC);
+      const double* u = U + k * 3;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k4_cp8(dst + i, x + i);
+#pragma unroll
+      for (int i = 0; i < 18; ++i) k4_cp8(dst + 8 + i, g + i);
+#pragma unroll
+      for (int i = 0; i < 4 * TV_REC; ++i) k4_cp8(dst + 26 + i, r + i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) k4_cp8(dst + 26 + 4 * TV_REC + i, u + i);
+    }
+    k4_commit();
+  }
+  __device__ __forceinline__ void fetch(long long k, const double*& xr, const double*& Kk, const double*& ul, const double*& rk) const {
+    k4_wait_oldest();
+    const double* p = ring + (int)(k % K4_RING_D) * 32 * K4C_W;
+    xr = p;
+    Kk = p + 8;
+    rk = p + 26;
+    ul = p + 26 + 4 * TV_REC;
+  }
+  __device__ __forceinline__ void done(long long k) const { issue(k + K4_RING_D); }
+};
+static_assert(4 * TV_REC == 40 && 26 + 4 * TV_REC + 3 <= K4C_W, "replay staging slot layout");
 __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
+  extern __shared__ __align__(16) double k4_smem[];
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_trials) return;
   TvlqrIn in;
@@ -152,10 +220,18 @@ __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
   in.trial_index_1based = (long long)in.trial + 1;
   ts_tvlqr_opts_dev o = a.opts;
   o.tf = a.t_final[t];
-  const double* K = a.K + a.offs[t] * 18;
+  K4cRingSrc src;
+  src.X = in.X_lqr;
+  src.U = in.U_lqr;
+  src.K = a.K + a.offs[t] * 18;
+  src.recs = a.AB + a.lin_offs[t] * 54;
+  src.ring = k4_smem + threadIdx.x * K4C_W;
+  src.n_steps = in.N - 1;
+  for (int d = 0; d < K4_RING_D; ++d) src.issue(d);
   double slew = 0.0;
-  const long long ns = tvlqr_replay_t<true>(in, o, K, a.X_sim ? a.X_sim + a.offs[t] * 8 : nullptr, a.U_sim ? a.U_sim + a.offs[t] * 3 : nullptr,
-                                            a.dX ? a.dX + a.offs[t] * 6 : nullptr, &slew, a.AB + a.lin_offs[t] * 54);
+  const long long ns = tvlqr_replay_src<true>(in, o, src, a.X_sim ? a.X_sim + a.offs[t] * 8 : nullptr, a.U_sim ? a.U_sim + a.offs[t] * 3 : nullptr,
+                                              a.dX ? a.dX + a.offs[t] * 6 : nullptr, &slew);
+  asm volatile("cp.async.wait_all;\n" ::: "memory");   // copies requested past the last simulated step
   if (a.N_sim) a.N_sim[t] = ns;
   if (a.slew_time) a.slew_time[t] = slew;
 }
@@ -163,9 +239,15 @@ __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
 // host: the three launches of K4 (a.AB / a.lin_offs / a.lin_total must be set)
 inline void k4_launch(ts_ctx* c, const K4Args& a) {
   if (a.lin_total > 0) k4a_linearise_kernel<<<(unsigned)((a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
-  k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k4b_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4B_SMEM_BYTES);
+    cudaFuncSetAttribute(k4c_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4C_SMEM_BYTES);
+    attr_set = true;
+  }
+  k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4B_SMEM_BYTES, c->stream>>>(a);
   if (a.lin_total > 0) k4n_records_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
-  k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, 0, c->stream>>>(a);
+  k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4C_SMEM_BYTES, c->stream>>>(a);
   c->launches += 4;
 }
 

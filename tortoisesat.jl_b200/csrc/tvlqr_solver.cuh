@@ -359,9 +359,22 @@ TS_HD void tvlqr_step_records(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, lon
 // K4n) or null -> built on the fly.  The slew-time rule is evaluated without sqrt / acos: |w| < w_limit is w.w < w_limit^2
 // and 2 acos(min(q_e1,1)) < ang_limit is q_e1 > cos(ang_limit/2) (acos is decreasing; identical decisions except within one
 // rounding of the thresholds).
-template <bool PRE>
-TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
-                               double* dX, double* slew_time_out, const double* recs) {
+// Where the replay reads the per-step inputs from (reference state 8, gain 18, reference control 3, stage records 40):
+// straight from the arrays (host twin, unit entries), or from a per-thread staging ring filled ahead of the sequential
+// loop by asynchronous copies (K4c, k4_tvlqr.cuh).
+struct TvlqrDirectSrc {
+  const double *X, *U, *K, *recs;
+  TS_HD void fetch(long long k, const double*& xr, const double*& Kk, const double*& ul, const double*& rk) const {
+    xr = X + k * 8;
+    Kk = K + k * 18;
+    ul = U + k * 3;
+    rk = recs ? recs + k * (4 * TV_REC) : nullptr;
+  }
+  TS_HD void done(long long) const {}
+};
+template <bool PRE, class Src>
+TS_HD long long tvlqr_replay_src(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, Src& src, double* X_sim, double* U_sim,
+                                 double* dX, double* slew_time_out) {
   const int N = in.N;
   long long N_sim = range_len(o.t0, o.dt, o.tf);
   if (N_sim > N) N_sim = range_len(o.t0, o.dt, o.tf - o.dt);
@@ -389,7 +402,8 @@ TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, co
         for (int i = 0; i < 6; ++i) dX[k * 6 + i] = 0.0;
       break;
     }
-    const double* xr = in.X_lqr + k * 8;
+    const double *xr, *Kk, *ul, *rk_src;
+    src.fetch(k, xr, Kk, ul, rk_src);
     double d6[6], u[3];
     for (int i = 0; i < 3; ++i) d6[i] = x[i] - xr[i];
     {
@@ -400,11 +414,10 @@ TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, co
       d6[4] = qe[2];
       d6[5] = qe[3];
     }
-    const double* Kk = K + k * 18;
     for (int i = 0; i < 3; ++i) {
       double s = 0.0;
       for (int j = 0; j < 6; ++j) s += Kk[i * 6 + j] * d6[j];
-      u[i] = in.U_lqr[k * 3 + i] - s;
+      u[i] = ul[i] - s;
     }
     if (U_sim)
       for (int i = 0; i < 3; ++i) U_sim[k * 3 + i] = u[i];
@@ -414,7 +427,7 @@ TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, co
     double tcl[4], nxt;
     clock_rk4(x[7], in.clock_rate, o.dt, tcl, nxt);
     double rbuf[PRE ? 1 : 4 * TV_REC];
-    const double* rk = PRE ? recs + k * (4 * TV_REC) : rbuf;
+    const double* rk = PRE ? rk_src : rbuf;
     if (!PRE) tvlqr_step_records(in, o, k, x[7], rbuf);
     double k1[7], k2[7], k3[7], k4[7], xs[7];
     simulator7_rec(in.I, x, u, rk, k1);
@@ -430,6 +443,7 @@ TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, co
     for (int i = 0; i < 7; ++i) k4[i] = k4[i] * o.dt;
     for (int i = 0; i < 7; ++i) x[i] = x[i] + (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]) * TS_SIXTH;
     x[7] = nxt;
+    src.done(k);
   }
   if (o.literal_postproc && X_sim) {
     for (long long j = 1; j <= N_sim; ++j) {
@@ -445,6 +459,12 @@ TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, co
   }
   if (slew_time_out) *slew_time_out = slew;
   return N_sim;
+}
+template <bool PRE>
+TS_HD long long tvlqr_replay_t(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
+                               double* dX, double* slew_time_out, const double* recs) {
+  TvlqrDirectSrc src = {in.X_lqr, in.U_lqr, K, recs};
+  return tvlqr_replay_src<PRE>(in, o, src, X_sim, U_sim, dX, slew_time_out);
 }
 TS_HD long long tvlqr_replay(const TvlqrIn& in, const ts_tvlqr_opts_dev& o, const double* K, double* X_sim, double* U_sim,
                              double* dX, double* slew_time_out) {
