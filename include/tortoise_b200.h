@@ -167,6 +167,14 @@ typedef struct ts_ilqr_opts {
                                         when few trials are left, slower on a full ensemble (half the solver warps)  */
   int32_t k3_wide_occ;            /* 0: as many one-warp blocks per SM as fit (8); n > 0: at most n.  Measured on the
                                         4096-trial ensemble: 8 -> 5.72 s, 6 -> 5.98 s, 4 -> 6.64 s, 2 -> 10.5 s            */
+  int32_t quat_error;             /* 0; 1: the quaternion-aware variant the reference's Monte-Carlo script requests from its forked
+                                        solver (monte_carlo.jl:158 Model(..., quaternion_error, quaternion_expansion), :192
+                                        sat_att = true; hooks in quaternion_toolbox.jl:15-75): the feedback law uses
+                                        dx = [w - wbar; MRP(conj(qbar) (x) q)], the backward pass runs on the 6-dim error
+                                        state with A_e = E(x_k+1)' A E(x_k), B_e = E(x_k+1)' B, E = blkdiag(I3, G(q)).  Gains
+                                        come back in error coordinates (3 x 8 rows, entries 6 and 7 zero).  Needs equal
+                                        weights / goal mask on the four quaternion components.  One warp per trial.      */
+  int32_t pad_;
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);
 

@@ -164,6 +164,7 @@ struct orc_ilqr_opts {
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
   int32_t k3_pair, k3_wide_occ;
+  int32_t quat_error, pad_;
 };
 static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   IlqrOpts o;
@@ -181,6 +182,7 @@ static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   o.a2_active_ge = s->a2_active_ge; o.a3_grad_over_N = s->a3_grad_over_N; o.a4_no_intermediate = s->a4_no_intermediate;
   o.a5_dual_active_only = s->a5_dual_active_only; o.a6_penalty_conditional = s->a6_penalty_conditional;
   o.a7_carry_cost = s->a7_carry_cost; o.constraint_decrease_ratio = s->constraint_decrease_ratio;
+  o.quat_error = s->quat_error;
   return o;
 }
 void orc_ilqr_default_opts(orc_ilqr_opts* s) {
@@ -199,6 +201,7 @@ void orc_ilqr_default_opts(orc_ilqr_opts* s) {
   s->a5_dual_active_only = o.a5_dual_active_only; s->a6_penalty_conditional = o.a6_penalty_conditional;
   s->a7_carry_cost = o.a7_carry_cost; s->constraint_decrease_ratio = o.constraint_decrease_ratio;
   s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 0; s->k3_wide_occ = 0;
+  s->quat_error = o.quat_error; s->pad_ = 0;
 }
 
 // Batched solve.  Per trial t: N_i[t] knots, ragged arrays addressed through

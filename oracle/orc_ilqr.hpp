@@ -51,6 +51,21 @@ struct IlqrOpts {
   int a6_penalty_conditional = 0;  // A6: penalties scaled only if c_max > ratio * previous c_max (default: every outer iteration)
   int a7_carry_cost = 0;           // A7: J_prev of an inner solve = last cost under the OLD multipliers (default: re-evaluated)
   double constraint_decrease_ratio = 0.25;
+  // Quaternion-aware variant: what reference src/monte_carlo.jl:158,192 asks of its forked solver with
+  // Model(DerivFunction, n, m, quaternion_error, quaternion_expansion) and opts.sat_att = true.  The fork is not in
+  // /root/reference, so the way the two hooks enter the solver is FROZEN HERE (parity unpinned), from the hooks' own
+  // bodies (src/quaternion_toolbox.jl:15-75) and from the same authors' TVLQR, which projects the same way
+  // (src/attitude_controller.jl:59-81):
+  //   QA1 state difference in the feedback law: dx = quaternion_error(x, xbar) = [w - wbar; MRP(q_inv(qbar) (x) q); 0]
+  //       (7-vector: the clock state has no entry -- quaternion_toolbox.jl:63-75 fills 1:6 of zeros(7))
+  //   QA2 expansion in error coordinates with E(x) = perm_Gk = [I3 0; 0 G(q); 0 0] (8x7), G(q) = [-v'; s I + hat(v)]:
+  //       A_e = E(x_{k+1})' A E(x_k), B_e = E(x_{k+1})' B, l_x -> E(x_k)' l_x, l_xx -> E(x_k)' l_xx E(x_k)
+  //       (quaternion_toolbox.jl:15-38: perm_Gn * cost.Q * perm_Gk etc.; G from the raw, un-normalised quaternion)
+  //   QA3 terminal expansion likewise with E(x_N) (quaternion_toolbox.jl:40-52); constraint terms of the AL follow
+  //       their cost terms through the same projection
+  // Cost, constraints, multiplier updates and line search are those of the default solver.  Gains come out in error
+  // coordinates (3 x 7, stored 3 x 8 with a zero last column).
+  int quat_error = 0;
 };
 
 enum {
@@ -134,6 +149,27 @@ inline double al_cost(const IlqrProblem& p, const IlqrOpts& o, const Work& w, co
   return Jc;
 }
 
+// QA2: E(x) as an 8 x 8 array whose last column is zero (the error state has 7 entries; entry 7 is the always-zero
+// slot quaternion_error leaves at the end).
+inline void quat_E(const double* x, double E[n][n]) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) E[i][j] = 0.0;
+  for (int i = 0; i < 3; ++i) E[i][i] = 1.0;
+  const double s = x[3], v1 = x[4], v2 = x[5], v3 = x[6];
+  const double G[4][3] = {{-v1, -v2, -v3}, {s, -v3, v2}, {v3, s, -v1}, {-v2, v1, s}};
+  for (int r = 0; r < 4; ++r)
+    for (int j = 0; j < 3; ++j) E[3 + r][3 + j] = G[r][j];
+}
+// QA1: quaternion_error(X1, X2), quaternion_toolbox.jl:63-75, padded to 8 entries
+inline void quat_error(const double* X1, const double* X2, double dx[n]) {
+  for (int i = 0; i < n; ++i) dx[i] = 0.0;
+  for (int i = 0; i < 3; ++i) dx[i] = X1[i] - X2[i];
+  const double qi[4] = {X2[3], -X2[4], -X2[5], -X2[6]};
+  double qe[4];
+  qmult<double>(qi, X1 + 3, qe);
+  for (int i = 0; i < 3; ++i) dx[3 + i] = qe[1 + i] / (1.0 + qe[0]);
+}
+
 inline void jacobians(const IlqrProblem& p, Work& w) {
   using D = Dual<n + m>;
   for (int64_t k = 0; k < w.N - 1; ++k) {
@@ -213,14 +249,87 @@ restart:
         Sx[i] += w.lam_g[i] + w.mu_g[i] * e;
       }
     }
+    if (o.quat_error) {  // QA3: E_N' Sxx E_N, E_N' Sx
+      double E[n][n], T[n][n], Sp[n][n], sp[n];
+      quat_E(x, E);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double t = 0;
+          for (int l = 0; l < n; ++l) t += Sxx[i][l] * E[l][j];
+          T[i][j] = t;
+        }
+      for (int i = 0; i < n; ++i) {
+        double t = 0;
+        for (int l = 0; l < n; ++l) t += E[l][i] * Sx[l];
+        sp[i] = t;
+        for (int j = 0; j < n; ++j) {
+          double u = 0;
+          for (int l = 0; l < n; ++l) u += E[l][i] * T[l][j];
+          Sp[i][j] = u;
+        }
+      }
+      for (int i = 0; i < n; ++i) {
+        Sx[i] = sp[i];
+        for (int j = 0; j < n; ++j) Sxx[i][j] = Sp[i][j];
+      }
+    }
   }
   for (int64_t k = w.N - 2; k >= 0; --k) {
     const double* A = &w.A[k * n * n];
     const double* B = &w.B[k * n * m];
     const double* x = &w.X[k * n];
     const double* u = &w.U[k * m];
-    double lx[n], lu[m], luu[m];
+    double lx[n], lu[m], luu[m], lxx[n][n];
     for (int i = 0; i < n; ++i) lx[i] = sc * p.Qd[i] * (x[i] - p.xf[i]);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) lxx[i][j] = (i == j) ? sc * p.Qd[i] : 0.0;
+    double Ae[n * n], Be[n * m];
+    if (o.quat_error) {  // QA2: everything that multiplies a state difference moves to error coordinates
+      double E0[n][n], E1[n][n], T[n][n];
+      quat_E(x, E0);
+      quat_E(&w.X[(k + 1) * n], E1);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double t = 0;
+          for (int l = 0; l < n; ++l) t += A[i * n + l] * E0[l][j];
+          T[i][j] = t;
+        }
+      for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+          double t = 0;
+          for (int l = 0; l < n; ++l) t += E1[l][i] * T[l][j];
+          Ae[i * n + j] = t;
+        }
+        for (int j = 0; j < m; ++j) {
+          double t = 0;
+          for (int l = 0; l < n; ++l) t += E1[l][i] * B[l * m + j];
+          Be[i * m + j] = t;
+        }
+      }
+      double lxp[n], L1[n][n], L2[n][n];
+      for (int i = 0; i < n; ++i) {
+        double t = 0;
+        for (int l = 0; l < n; ++l) t += E0[l][i] * lx[l];
+        lxp[i] = t;
+        for (int j = 0; j < n; ++j) {
+          double v = 0;
+          for (int l = 0; l < n; ++l) v += lxx[i][l] * E0[l][j];
+          L1[i][j] = v;
+        }
+      }
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          double v = 0;
+          for (int l = 0; l < n; ++l) v += E0[l][i] * L1[l][j];
+          L2[i][j] = v;
+        }
+      for (int i = 0; i < n; ++i) {
+        lx[i] = lxp[i];
+        for (int j = 0; j < n; ++j) lxx[i][j] = L2[i][j];
+      }
+      A = Ae;
+      B = Be;
+    }
     double c[nb];
     bound_c(o, u, c);
     for (int i = 0; i < m; ++i) {
@@ -261,7 +370,7 @@ restart:
       for (int j = 0; j < n; ++j) {
         double s = 0;
         for (int l = 0; l < n; ++l) s += A[l * n + i] * SA[l][j];
-        Qxx[i][j] = s + ((i == j) ? sc * p.Qd[i] : 0.0);
+        Qxx[i][j] = s + lxx[i][j];
       }
     for (int i = 0; i < m; ++i) {
       for (int j = 0; j < m; ++j) {
@@ -343,7 +452,10 @@ inline bool rollout(const IlqrProblem& p, const IlqrOpts& o, Work& w, double alp
   for (int i = 0; i < n; ++i) w.Xb[i] = p.x0[i];
   for (int64_t k = 0; k < w.N - 1; ++k) {
     double dx[n];
-    for (int i = 0; i < n; ++i) dx[i] = w.Xb[k * n + i] - w.X[k * n + i];
+    if (o.quat_error)
+      quat_error(&w.Xb[k * n], &w.X[k * n], dx);
+    else
+      for (int i = 0; i < n; ++i) dx[i] = w.Xb[k * n + i] - w.X[k * n + i];
     for (int i = 0; i < m; ++i) {
       double s = w.U[k * m + i];
       for (int j = 0; j < n; ++j) s += w.K[k * m * n + i * n + j] * dx[j];

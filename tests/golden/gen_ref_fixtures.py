@@ -642,6 +642,25 @@ ALILQR_DEFAULTS = dict(max_outer=20, max_inner=50, max_linesearch=20, dJ_counter
                        a7_carry_cost=0, constraint_decrease_ratio=0.25)
 
 
+def quaternion_error(X1, X2):
+    """src/quaternion_toolbox.jl:63-75 (MRP of the error quaternion; 7 entries, the last one stays zero)."""
+    dx = np.zeros(7)
+    dx[0:3] = X1[0:3] - X2[0:3]
+    q_e = qmult(q_inv(X2[3:7]), X1[3:7])
+    dx[3:6] = q_e[1:4] / (1 + q_e[0])
+    return dx
+
+
+def perm_Gk(x):
+    """src/quaternion_toolbox.jl:22-35: perm_Gk (8 x 7) = [I3 0; 0 G(q); 0 0] with G(q) = [-v'; s I + hat(v)] of the raw
+    state quaternion; perm_Gn of the same state is its transpose."""
+    s_, v = x[3], x[4:7]
+    P = np.zeros((8, 7))
+    P[0:3, 0:3] = np.eye(3)
+    P[3:7, 3:6] = np.vstack([-v, s_ * np.eye(3) + hat(v)])
+    return P
+
+
 def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
     """AL-iLQR per SURVEY.md App. C on the problem of src/TortoiseSat.jl:145-146,169,178-199.  Returns X (N x 8),
     U ((N-1) x 3), K ((N-1) x 3 x 8), info dict."""
@@ -708,6 +727,7 @@ def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
 
     K = np.zeros((N - 1, m, n))
     d = np.zeros((N - 1, m))
+    qa = bool(o.get("quat_error", 0))   # quaternion-aware variant (monte_carlo.jl:158,192): 7-dim error state
     status, outer, inner_total, ls_total = 1, 0, 0, 0
     J, c_max, c_max_prev = 0.0, 0.0, np.inf
     J_carry = None
@@ -734,6 +754,10 @@ def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
                 e = X[N - 1] - xf
                 Sxx = Qf + np.diag(np.where(gm, mu_g, 0.0))
                 Sx = Qf @ e + np.where(gm, lam_g + mu_g * e, 0.0)
+                if qa:   # quaternion_expansion(cost, xN), quaternion_toolbox.jl:40-52
+                    EN = perm_Gk(X[N - 1])
+                    Sxx = EN.T @ Sxx @ EN
+                    Sx = EN.T @ Sx
                 dV1 = dV2 = 0.0
                 ok = True
                 for k in range(N - 2, -1, -1):
@@ -742,11 +766,16 @@ def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
                     act = active(c, lam_b[k])
                     Imu = np.where(act, mu_b[k], 0.0)
                     lx = sc * (Q @ (X[k] - xf))
+                    lxx = sc * Q
+                    if qa:   # quaternion_expansion(cost, x, u) and the dynamics in the same coordinates
+                        E0, E1 = perm_Gk(X[k]), perm_Gk(X[k + 1])
+                        A, B = E1.T @ A @ E0, E1.T @ B
+                        lx, lxx = E0.T @ lx, E0.T @ lxx @ E0
                     lu = sc * (R @ U[k]) + (lam_b[k, 0:3] + Imu[0:3] * c[0:3]) - (lam_b[k, 3:6] + Imu[3:6] * c[3:6])
                     luu = sc * R + np.diag(Imu[0:3] + Imu[3:6])
                     Qx = lx + A.T @ Sx
                     Qu = lu + B.T @ Sx
-                    Qxx = sc * Q + A.T @ Sxx @ A
+                    Qxx = lxx + A.T @ Sxx @ A
                     Quu = luu + B.T @ Sxx @ B
                     Qux = B.T @ Sxx @ A
                     Qr = 0.5 * (Quu + Quu.T) + rho * np.eye(m)
@@ -757,7 +786,7 @@ def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
                         break
                     Kk = -np.linalg.solve(L.T, np.linalg.solve(L, Qux))
                     dk = -np.linalg.solve(L.T, np.linalg.solve(L, Qu))
-                    K[k], d[k] = Kk, dk
+                    K[k, :, :Kk.shape[1]], d[k] = Kk, dk
                     Sx = Qx + Kk.T @ Quu @ dk + Kk.T @ Qu + Qux.T @ dk
                     Sxx = Qxx + Kk.T @ Quu @ Kk + Kk.T @ Qux + Qux.T @ Kk
                     Sxx = 0.5 * (Sxx + Sxx.T)
@@ -789,7 +818,8 @@ def alilqr_solve(g, x0, xf, Qd, Qfd, Rd, N, dt, opts=None, U0=None):
                 Xb[0] = x0
                 okr = True
                 for k in range(N - 1):
-                    Ub[k] = U[k] + K[k] @ (Xb[k] - X[k]) + alpha * d[k]
+                    dxk = quaternion_error(Xb[k], X[k]) if qa else Xb[k] - X[k]
+                    Ub[k] = U[k] + K[k][:, :len(dxk)] @ dxk + alpha * d[k]
                     Xb[k + 1] = step(Xb[k], Ub[k])
                     if not (np.max(np.abs(Xb[k + 1])) < o["max_state_value"]) or not (np.max(np.abs(Ub[k])) < o["max_control_value"]):
                         okr = False
@@ -1033,6 +1063,27 @@ def main():
     add_psiaki_section()
 
 
+def add_quat_section():
+    """Quaternion-aware AL-iLQR fixtures; `--only quat` regenerates just this section."""
+    path = os.path.join(HERE, "ref_fixtures.json")
+    fx = json.load(open(path))
+    GM = 3.986004418E14 * (1 / 1000) ** 3
+    out = []
+    for c in (fx["alilqr"][0], fx["alilqr"][2]):
+        tfin, Nn = c["t_final"], c["N"]
+        Bn, _, _ = magnetic_simulation(c["kep"], GM, 58155.0, 6371.0, 400.0, 0.0, tfin, Nn)
+        gg = Globals(Bn, Nn, np.array(c["J"]).reshape(3, 3), 5400.0, 0.0)
+        opts = dict(c["opts"], quat_error=1)
+        X, U, K, info = alilqr_solve(gg, np.array(c["x0"]), np.array(c["xf"]), np.array(c["Qd"]), np.array(c["Qfd"]), np.array(c["Rd"]),
+                                     Nn, 0.2, opts)
+        print("alilqr quat", c["name"], info, flush=True)
+        out.append(dict(c, name=c["name"] + " -- quaternion_error / quaternion_expansion", opts=opts, info=info,
+                        X_rows={str(i): L(X[i]) for i in (0, 1, Nn // 2, Nn - 1)}, U_rows={str(i): L(U[i]) for i in (0, 1, Nn // 2, Nn - 2)},
+                        K0=L(K[0]), U_absmax=float(np.max(np.abs(U)))))
+    fx["alilqr_quat"] = out
+    json.dump(fx, open(path, "w"))
+
+
 def add_psiaki_section():
     """Comparison-controller fixtures; `--only psiaki` regenerates just this section."""
     out = os.path.join(HERE, "ref_fixtures.json")
@@ -1069,6 +1120,9 @@ def add_psiaki_section():
 
 
 if __name__ == "__main__":
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "quat":
+        add_quat_section()
+        sys.exit(0)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "psiaki":
         add_psiaki_section()
     else:

@@ -88,7 +88,11 @@ struct CpuTeamT {
   }
 };
 
-template <int W_>
+struct CpuQuatTeam : CpuTeamT<32> {   // the quaternion-aware variant (ts_ilqr_opts.quat_error), whole-warp team
+  static constexpr bool QUAT = true;
+};
+
+template <int W_, class TeamT = CpuTeamT<W_>>
 static void solve_with_width(const TrialIn& in, const ts_ilqr_opts_dev* opts, int64_t N, double* X, double* U, double* K,
                              ts_trial_outcome_dev* out) {
   const size_t per_slot = (size_t)9 * N * 10;
@@ -108,7 +112,9 @@ static void solve_with_width(const TrialIn& in, const ts_ilqr_opts_dev* opts, in
   std::vector<std::thread> th;
   for (int l = 0; l < W_; ++l)
     th.emplace_back([&, l]() {
-      CpuTeamT<W_> tm{&sh, l};
+      TeamT tm;
+      tm.sh = &sh;
+      tm.ln = l;
       alilqr_solve_team(tm, in, *opts, w, oc[l], cur[l]);
     });
   for (auto& t : th) t.join();
@@ -183,7 +189,9 @@ void hs_alilqr_solve_w(int width, int64_t N, const double* x0, const double* xf,
   in.index_scale = index_scale;
   in.clock_rate = clock_rate;
   in.U0 = U0;
-  if (width == 32)
+  if (opts->quat_error)
+    solve_with_width<32, CpuQuatTeam>(in, opts, N, X, U, K, out);
+  else if (width == 32)
     solve_with_width<32>(in, opts, N, X, U, K, out);
   else
     solve_with_width<8>(in, opts, N, X, U, K, out);

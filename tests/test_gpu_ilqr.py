@@ -270,3 +270,34 @@ def test_cycle_diagnostics_are_separate_from_outcomes(engine):
     assert np.all(out["t_final"] == 0) and np.all(out["slew_time"] == 0) and np.all(out["flops"] == 0)
     cyc = engine.k3_last_cycles(2)
     assert cyc.shape == (2, 3) and np.all(cyc[:, 0] > 0) and np.all(cyc[:, 1] > 0) and np.all(cyc[:, 2] <= cyc[:, 0])
+
+
+def test_quaternion_aware_variant_matches_oracle(engine):
+    """SURVEY 8(f2), ts_ilqr_opts.quat_error (monte_carlo.jl:158,192 + quaternion_toolbox.jl:15-75): k3_quat_kernel -- one
+    warp per trial from the initial rollout, error-state backward pass, MRP feedback -- against the oracle's dense
+    version of the same variant on a ragged batch (more trials than a warp has lanes are not needed: one trial per
+    warp); gains come back in error coordinates."""
+    import tortoisesat.jl_b200 as tb
+    rng = np.random.default_rng(11)
+    slews = []
+    for i in range(10):
+        J = S.J_3U if i % 3 == 2 else S.J_1P
+        s = S.build_slew([0, 6578, 96, 0, 0, 90], J, S.quat_axis_angle(rng.normal(size=3), rng.uniform(3, 25)),
+                         np.array([1.0, 0, 0, 0]), t_final=float(rng.integers(20, 50)))
+        slews.append(s)
+    o = orc.default_ilqr_opts()
+    o.quat_error = 1
+    same = _check(engine, slews, o, tb)
+    assert same >= 8
+    assert engine.k3_last_split()[2] == 0                       # no hand-over: a single launch
+    X, U, K, out, offs = engine.alilqr_solve_batch(**_pack(slews), opts=_gpu_opts(tb, o))
+    assert np.all(K.reshape(-1, 3, 8)[:, :, 6:] == 0.0)
+    o0 = orc.default_ilqr_opts()
+    X0, U0, K0, out0, _ = engine.alilqr_solve_batch(**_pack(slews), opts=_gpu_opts(tb, o0))
+    assert np.any(out0["inner_iters"] != out["inner_iters"])    # a different algorithm, not a relabelled default
+    # unequal quaternion weights are refused (E'QE would not be diagonal)
+    bad = _pack(slews[:1])
+    bad["Qd"] = np.array(bad["Qd"], dtype=float).copy()
+    bad["Qd"][0, 4] *= 2.0
+    with pytest.raises(tb.TortoiseError):
+        engine.alilqr_solve_batch(**bad, opts=_gpu_opts(tb, o))

@@ -226,6 +226,50 @@ def test_bench_ensemble_sample_matches_oracle(engine):
         assert abs(g["c_max"] - r["c_max"]) <= 1e-6 * max(1.0, r["c_max"])
 
 
+def test_fused_monte_carlo_quaternion_aware(engine):
+    """The fused Monte-Carlo call with ts_ilqr_opts.quat_error = 1 (the solver configuration monte_carlo.jl:158,192
+    actually requests): field pass -> weights -> k3_quat_kernel -> TVLQR replay, every trial against the oracle pipeline
+    run with the same option."""
+    from tortoisesat.jl_b200 import host
+    rng = np.random.default_rng(77)
+    n = 5
+    cfg = host.default_mc_config(n, shared_orbit=True, run_tvlqr=True, tf=2400.0, cutoff=30.0, alpha=0.1)
+    cfg.tvlqr.noise_mode, cfg.tvlqr.seed = 2, 99
+    cfg.ilqr.quat_error = 1
+    kep = np.array([[0, 6771.0, 96.6, 0.0, 0.0, 90.0]])
+    fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
+    fo[0] = (GM, 58155.0, 2019.0, 6771000.0, 0, 0, 0)
+    qf = np.array([math.sqrt(2) / 2, math.sqrt(2) / 2, 0, 0])
+    x0 = np.zeros((n, 8))
+    xf = np.tile(np.concatenate([[0, 0, 0], qf, [1.0]]), (n, 1))
+    for t in range(n):
+        dq = S.quat_axis_angle(rng.normal(size=3), rng.uniform(5, 40))
+        q = np.zeros(4)
+        orc.lib().orc_qmult(orc.P(orc.f64(qf)), orc.P(dq), orc.P(q))
+        x0[t, 3:7] = q
+    Jm = np.tile(S.J_1U.reshape(-1), (n, 1))
+    qn = rng.normal(size=(n, 3)) * (math.pi / 180) ** 2
+    out, st = engine.monte_carlo_run(cfg, kep, fo, x0, xf, Jm, q_noise0=qn, stream_id=np.arange(n))
+    oq = orc.default_ilqr_opts()
+    oq.quat_error = 1
+    for t in range(n):
+        s = S.build_slew(kep[0], S.J_1U, x0[t, 3:7], xf[t, 3:7], mjd=58155.0, igrf_date=2019.0, field_radius_m=6771000.0,
+                         t0=cfg.t0, tf=cfg.tf, N_scope=int(cfg.N_scope), cutoff=cfg.cutoff, dt=cfg.dt, alpha=cfg.alpha, beta=cfg.beta)
+        Xs, Us, Ks, ref = S.oracle_solve([s], oq)
+        o, g_ = S.tvlqr_opts_pair(noise_mode=2, seed=99, R=float(cfg.tvlqr.Rd[0]))
+        x0l = s.x0.copy()
+        x0l[3:7] = _perturb(s.x0[3:7], qn[t])
+        x0l[7] = 0
+        a = S.oracle_tvlqr(s, Xs[0], Us[0], x0l, o, trial=t)
+        g = out[t]
+        assert g["N"] == s.N
+        assert g["status"] == ref[0]["status"] and g["outer_iters"] == ref[0]["outer_iters"], (t, g, ref[0])
+        assert abs(g["J"] - ref[0]["J"]) <= 1e-6 * abs(ref[0]["J"])
+        assert abs(g["c_max"] - ref[0]["c_max"]) <= 1e-6 * max(1.0, ref[0]["c_max"])
+        if g["inner_iters"] == ref[0]["inner_iters"]:
+            assert g["slew_time"] == a[5], (t, g["slew_time"], a[5])
+
+
 def test_monte_carlo_trajectories_match_oracle(engine):
     """keep_trajectories = 1: the arrays monte_carlo.jl leaves in globals (states, control_inputs, sim_states,
     sim_control_inputs, B_ECI_total; monte_carlo.jl:52-66,149,200-201,232-233) come back through

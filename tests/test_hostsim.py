@@ -123,3 +123,26 @@ def test_stage_cost_dt_and_3u_inertia():
         assert oc[f] == out[0][f], f
     assert abs(oc["J"] - out[0]["J"]) <= 1e-6 * abs(out[0]["J"])
     assert np.max(np.abs(K - Ks[0])) <= 1e-8 * np.max(np.abs(Ks[0]))
+
+
+@pytest.mark.parametrize("angle,tfin,Jm", [(5.0, 60.0, "1P"), (20.0, 30.0, "1P"), (3.0, 50.0, "3U")])
+def test_quaternion_aware_team_matches_oracle(angle, tfin, Jm):
+    """SURVEY 8(f2), ts_ilqr_opts.quat_error: the kernel source's QUAT team (7-state, analytic Jacobians projected in
+    place, diagonal c|q|^2 cost block, 30-lane Riccati step) against the oracle's literal dense version of the same
+    variant: same iteration path, gains in error coordinates (last two columns zero)."""
+    s = S.build_slew([0, 6578, 96, 0, 0, 90], S.J_1P if Jm == "1P" else S.J_3U, S.quat_axis_angle([1, 0, 1], angle),
+                     np.array([1.0, 0, 0, 0]), t_final=tfin)
+    o = orc.default_ilqr_opts()
+    o.quat_error = 1
+    Xs, Us, Ks, out = S.oracle_solve([s], o)
+    o0 = orc.default_ilqr_opts()
+    _, _, _, out0 = S.oracle_solve([s], o0)
+    X, U, K, oc = S.hostsim_solve(s, o, width=32)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "N"):
+        assert oc[f] == out[0][f], f
+    assert abs(oc["J"] - out[0]["J"]) <= 1e-6 * abs(out[0]["J"])
+    assert np.max(np.abs(X - Xs[0])) < 1e-9 and np.max(np.abs(U - Us[0])) < 1e-9
+    assert np.max(np.abs(K - Ks[0])) <= 1e-8 * np.max(np.abs(Ks[0]))
+    assert np.all(K[:, :, 6:] == 0.0)
+    # and it IS a different algorithm: the iteration path differs from the default solver's
+    assert (out[0]["inner_iters"], out[0]["ls_rollouts"]) != (out0[0]["inner_iters"], out0[0]["ls_rollouts"])

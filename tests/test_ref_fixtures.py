@@ -179,6 +179,33 @@ def test_alilqr_second_implementation(orc, fx):
             close(Ks[0][0], c["K0"], 1e-6, 1e-9)
 
 
+def test_quaternion_aware_variant_second_implementation(orc, fx):
+    """the oracle's quat_error mode (8 x 8 arrays padded with a zero error-state slot) against the numpy
+    transliteration of the reference's own hooks -- quaternion_error and quaternion_expansion of quaternion_toolbox.jl, a
+    true 7 x 7 error-state Riccati recursion: identical iteration paths, J to 1e-8, trajectories to 1e-7."""
+    import slew_setup as S
+    assert len(fx["alilqr_quat"]) >= 2
+    for c in fx["alilqr_quat"]:
+        s = _slew_from_fixture(S, c)
+        o = orc.default_ilqr_opts()
+        for k, v in c["opts"].items():
+            setattr(o, k, v)
+        assert o.quat_error == 1
+        Xs, Us, Ks, out = S.oracle_solve([s], opts=o)
+        r, info = out[0], c["info"]
+        assert (r["status"], r["outer_iters"], r["inner_iters"], r["ls_rollouts"]) == \
+               (info["status"], info["outer_iters"], info["inner_iters"], info["ls_rollouts"]), (c["name"], r, info)
+        assert abs(r["J"] - info["J"]) <= 1e-8 * abs(info["J"])
+        assert abs(r["c_max"] - info["c_max"]) <= 1e-8
+        for k, row in c["X_rows"].items():
+            close(Xs[0][int(k)], row, 1e-7)
+        for k, row in c["U_rows"].items():
+            close(Us[0][int(k)], row, 1e-6, 1e-9)
+        K0 = np.array(c["K0"])
+        close(Ks[0][0], K0, 1e-6, 1e-9)
+        assert np.all(K0[:, 6:] == 0.0) and np.all(Ks[0][0][:, 6:] == 0.0)     # gains live in the 6-dim error state
+
+
 def test_tvlqr_replay_and_postprocessing(orc, fx):
     import slew_setup as S
     L = orc.lib()

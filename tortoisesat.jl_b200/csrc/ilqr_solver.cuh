@@ -47,6 +47,7 @@ struct ts_ilqr_opts_dev {
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
   int32_t k3_pair, k3_wide_occ;
+  int32_t quat_error, pad_;
 };
 // 64-byte per-trial record (C ABI: ts_trial_outcome).
 struct ts_trial_outcome_dev {
@@ -127,6 +128,30 @@ template <class Team>
 struct team_ext_lin<Team, decltype((void)Team::EXT_LIN)> {
   static constexpr bool value = Team::EXT_LIN;
 };
+
+// Teams that run the QUATERNION-AWARE variant (ts_ilqr_opts.quat_error; SURVEY 8(f2), reference monte_carlo.jl:158,192 +
+// quaternion_toolbox.jl:15-75) declare `static constexpr bool QUAT = true`: the backward pass then works on the error
+// state [dw(3); dphi(3); 0] with A_e = E(x_k+1)' A E(x_k), B_e = E(x_k+1)' B, E = blkdiag(I3, G(q)) (7 x 7 here, last
+// column zero), cost gradients / Hessians projected the same way, and the rollout feeds back
+// dx = [w - wbar; MRP(conj(qbar) (x) q); 0].  A compile-time switch so that the default kernels do not change by a
+// single instruction.  Requires equal LQR weights and an all-or-nothing goal mask on the four quaternion components
+// (the reference's Bryson weights are): E' (c I4) E = c |q|^2 I3 is then diagonal and fits the diagonal-Q Riccati step.
+template <class Team, class = void>
+struct team_quat {
+  static constexpr bool value = false;
+};
+template <class Team>
+struct team_quat<Team, decltype((void)Team::QUAT)> {
+  static constexpr bool value = Team::QUAT;
+};
+// G(q) = [-v'; s I + hat(v)] (4 x 3) of the raw quaternion q = (s, v)  (quaternion_toolbox.jl:22-27)
+TS_HD void quat_G(const double q[4], double G[4][3]) {
+  const double s_ = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+  G[0][0] = -v1; G[0][1] = -v2; G[0][2] = -v3;
+  G[1][0] = s_;  G[1][1] = -v3; G[1][2] = v2;
+  G[2][0] = v3;  G[2][1] = s_;  G[2][2] = -v1;
+  G[3][0] = -v2; G[3][1] = v1;  G[3][2] = s_;
+}
 
 // Work pointers always address global memory; when a TrialWork lives in shared memory (k3_wide_kernel) the compiler
 // can no longer infer that from the kernel parameters, and would fall back to generic LD/ST.
@@ -296,6 +321,29 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
     rec[77 + i] = lu;
     rec[80 + i] = luu;
   }
+  if constexpr (team_quat<Team>::value) {
+    // error coordinates (in place, in the knot's shared-memory record): columns 3..6 of [A] times G(q_k), then rows
+    // 3..6 of [A|B] times G(q_k+1)'; the 7th row / column of the error state is identically zero
+    double G0[4][3], G1[4][3];
+    quat_G(x + 3, G0);
+    quat_G(p + 10 + 3, G1);   // the next knot of the nominal trajectory (k <= N-2)
+    for (int i = 0; i < 7; ++i) {
+      const double a0 = rec[3 * 7 + i], a1 = rec[4 * 7 + i], a2 = rec[5 * 7 + i], a3 = rec[6 * 7 + i];
+      for (int j = 0; j < 3; ++j) rec[(3 + j) * 7 + i] = a0 * G0[0][j] + a1 * G0[1][j] + a2 * G0[2][j] + a3 * G0[3][j];
+      rec[6 * 7 + i] = 0.0;
+    }
+    for (int c = 0; c < 10; ++c) {
+      const double r0 = rec[c * 7 + 3], r1 = rec[c * 7 + 4], r2 = rec[c * 7 + 5], r3 = rec[c * 7 + 6];
+      for (int j = 0; j < 3; ++j) rec[c * 7 + 3 + j] = G1[0][j] * r0 + G1[1][j] * r1 + G1[2][j] * r2 + G1[3][j] * r3;
+      rec[c * 7 + 6] = 0.0;
+    }
+    {
+      const double l0 = rec[73], l1 = rec[74], l2 = rec[75], l3 = rec[76];
+      for (int j = 0; j < 3; ++j) rec[73 + j] = G0[0][j] * l0 + G0[1][j] * l1 + G0[2][j] * l2 + G0[3][j] * l3;
+      rec[76] = 0.0;
+    }
+    rec[83] = sc * in.Qd[3] * (x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);   // E' (c I4) E = c |q|^2 I3
+  }
 }
 
 // Backward Riccati sweep over the current trajectory.  Returns false if the regularisation ran away.
@@ -321,6 +369,21 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
       if (o.goal_mask & (1 << lane)) {
         sxx += mu;
         sx += lam_g[lane] + mu * e;
+      }
+      if constexpr (team_quat<Team>::value) {
+        if (lane >= 3) {   // E_N' (.) E_N: attitude error coordinates 3..5, nothing in 6
+          double G[4][3], v[4];
+          quat_G(xN + 3, G);
+          for (int r = 0; r < 4; ++r) {
+            const double er = xN[3 + r] - in.xf[3 + r];
+            v[r] = in.Qfd[3 + r] * er;
+            if (o.goal_mask & (1 << (3 + r))) v[r] += lam_g[3 + r] + mu * er;
+          }
+          const int a_ = (lane < 6) ? lane - 3 : 0;
+          const double w3 = in.Qfd[3] + ((o.goal_mask & 8) ? mu : 0.0);
+          sxx = (lane < 6) ? w3 * (xN[3] * xN[3] + xN[4] * xN[4] + xN[5] * xN[5] + xN[6] * xN[6]) : 0.0;
+          sx = (lane < 6) ? G[0][a_] * v[0] + G[1][a_] * v[1] + G[2][a_] * v[2] + G[3][a_] * v[3] : 0.0;
+        }
       }
       for (int i = 0; i < 7; ++i) sm[L::SCOL + lane * 8 + i] = (i == lane) ? sxx : 0.0;
       sm[L::SVEC + lane] = sx;
@@ -390,10 +453,12 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             for (int l = 0; l < 7; ++l) arow[l] = rec[li * 7 + l];
             double t = 0.0;
             for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j0 * 8 + l];
-            Qxx0 = t + ((li == j0) ? sc * in.Qd[li] : 0.0);
+            double qd_li = sc * in.Qd[li];   // l_xx(li, li)
+            if constexpr (team_quat<Team>::value) qd_li = (li < 3) ? qd_li : ((li < 6) ? rec[83] : 0.0);
+            Qxx0 = t + ((li == j0) ? qd_li : 0.0);
             t = 0.0;
             for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j1 * 8 + l];
-            Qxx1 = t + ((li == j1) ? sc * in.Qd[li] : 0.0);
+            Qxx1 = t + ((li == j1) ? qd_li : 0.0);
             const bool isux = lane < 21;
             const int u = isux ? lane : (lane < 30 ? lane - 21 : 0);
             const int rr = u % 3, cc = isux ? u / 3 : 7 + u / 3;
@@ -456,6 +521,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           }
           tm.sync();
         } else {
+          static_assert(!team_quat<Team>::value, "the quaternion-aware variant runs on the whole-warp team only");
           // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
           double S[28], s[7];
           for (int i = 0; i < 7; ++i)
@@ -652,7 +718,17 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
         const double* kd = p + 10;
         double ub[3];
         double dx[7];
-        for (int i = 0; i < 7; ++i) dx[i] = xb[i] - p[i];
+        if constexpr (team_quat<Team>::value) {   // quaternion_error(x, xbar), quaternion_toolbox.jl:63-75
+          for (int i = 0; i < 3; ++i) dx[i] = xb[i] - p[i];
+          const double qi[4] = {p[3], -p[4], -p[5], -p[6]};
+          double qe[4];
+          qmult(qi, xb + 3, qe);
+          const double inv = 1.0 / (1.0 + qe[0]);
+          for (int i = 0; i < 3; ++i) dx[3 + i] = qe[1 + i] * inv;
+          dx[6] = 0.0;
+        } else {
+          for (int i = 0; i < 7; ++i) dx[i] = xb[i] - p[i];
+        }
         for (int i = 0; i < 3; ++i) {
           double t = p[7 + i];
           for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j];

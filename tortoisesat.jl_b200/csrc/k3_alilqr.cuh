@@ -620,6 +620,79 @@ __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
 constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 
 // ---------------------------------------------------------------------------------------------
+// k3_quat_kernel: the QUATERNION-AWARE variant (ts_ilqr_opts.quat_error; solver switches in
+// ilqr_solver.cuh under team_quat): every trial is solved from its initial rollout by one whole warp -- the 32-lane team
+// of k3_wide_kernel with QUAT = true -- pulled from the horizon-sorted queue; a warp keeps the pool region of its first
+// (longest) trial.  No four-per-warp phase: the error-state Riccati step exists for the 30-lane layout only.
+struct GpuWideQuatTeam : GpuWideTeam {
+  static constexpr bool QUAT = true;
+};
+__global__ void __launch_bounds__(32, 1) k3_quat_kernel(const K3Args a) {
+  extern __shared__ __align__(16) double k3_smem[];
+  const int lane32 = threadIdx.x & 31;
+  GpuWideQuatTeam tm;
+  tm.ln = lane32;
+  tm.sm = k3_smem;
+  __shared__ TrialWork w_sm;
+  TrialWork& w = w_sm;
+  if (lane32 == 0) {
+    w.Nmax = 0;
+    w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
+    w.slot_stride = 0;
+  }
+  __syncwarp();
+  long long region_cap = 0;
+  const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
+  const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
+  for (;;) {
+    unsigned long long qpos = 0;
+    if (lane32 == 0) qpos = atomicAdd(a.queue2, 1ull);
+    qpos = __shfl_sync(0xffffffffu, qpos, 0);
+    if (qpos >= (unsigned long long)a.n_trials) break;
+    const int64_t t = a.order[qpos];
+    const TrialIn& in = k3_load_trial(tm, a, t);
+    const int N = in.N;
+    const long long Ne = N + (N & 1);
+    if (Ne > region_cap) {
+      unsigned long long off = 0;
+      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * dpk));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if ((long long)(off + Ne * dpk) > a.pool_cap) {   // cannot happen (pool sized for the longest horizons): fail loudly
+        if (lane32 == 0) {
+          ts_trial_outcome_dev oc = {};
+          oc.status = ST_NAN;
+          oc.N = N;
+          a.out[t] = oc;
+        }
+        continue;
+      }
+      region_cap = Ne;
+      __syncwarp();
+      if (lane32 == 0) {
+        w.Nmax = Ne;
+        w.slot_stride = 9 * Ne * 10;
+        w.xu = w.xu_warp = a.pool + off;
+        w.kd = w.xu + (long long)nbuf * 10 * Ne;
+        w.lam = w.kd + 24 * Ne;
+        w.bk = w.lam + 6 * Ne;
+        w.clk = w.bk + 10 * Ne;
+      }
+      __syncwarp();
+    }
+    TrialState st;
+    solve_init(tm, in, a.opts, w, st);
+    while (st.phase != PH_DONE) {
+      if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
+      while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
+    }
+    ts_trial_outcome_dev oc;
+    solve_finish(in, st, oc);
+    k3_store_results(tm, a, t, w, N, st.cur, oc, st);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k3_pair_kernel: the one-warp-per-trial solver with a PRODUCER warp.  A straggler's latency is what ends the run, and
 // of the ~4.4 k cycles a whole warp spends per knot-iteration ~0.6 k is the linearisation of the next 32-knot chunk --
 // pure throughput work (one knot per lane, no dependence on the Riccati recursion) that sits on the critical path only

@@ -483,7 +483,7 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
   o->a2_active_ge = 0; o->a3_grad_over_N = 0; o->a4_no_intermediate = 0; o->a5_dual_active_only = 0;
   o->a6_penalty_conditional = 0; o->a7_carry_cost = 0; o->constraint_decrease_ratio = 0.25;
-  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 0; o->k3_wide_occ = 0;
+  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 0; o->k3_wide_occ = 0; o->quat_error = 0; o->pad_ = 0;
 }
 
 // slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
@@ -498,7 +498,73 @@ static double slew_angle(const double* x0, const double* xf) {
 // pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel (stragglers handed over to one warp each).
 // The launch scheme is controlled by ts_ilqr_opts.k3_* (suspend_after, early_factor, tail_share).  Work is queued on
 // the context's stream; nothing here synchronises.
+// The quaternion-aware variant (opts.quat_error): one launch of k3_quat_kernel, one warp per trial from the initial rollout.
+static int k3_launch_quat(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
+  const int64_t n_trials = a.n_trials;
+  const int qm = (a.opts.goal_mask >> 3) & 0xF;
+  if (qm != 0 && qm != 0xF)
+    return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
+  int occ_w = 0;
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_quat_kernel, 32, K3_WIDE_SMEM_BYTES));
+  if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 quaternion kernel does not fit on an SM");
+  const int64_t warps = std::max<int64_t>(1, std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w));
+  std::vector<int64_t> order((size_t)n_trials);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return N_i_host[x] > N_i_host[y]; });
+  int rc;
+  int64_t* d_order = nullptr;
+  if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
+  // a warp keeps the region of its first trial, and the queue is sorted by horizon: the `warps` longest horizons
+  const double dpk = (double)k3_wide_doubles_per_knot(a.opts.max_linesearch);
+  double pool_need = 0.0;
+  int64_t Nmax = 0;
+  for (int64_t i = 0; i < warps; ++i) pool_need += dpk * (double)(N_i_host[order[(size_t)i]] + 1);
+  for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
+  void *p_q, *p_diag, *p_pool;
+  if ((rc = scratch_reserve(c, 25, (size_t)pool_need * sizeof(double) + 256, &p_pool))) return rc;
+  if ((rc = scratch_reserve(c, 4, 128, &p_q))) return rc;
+  if ((rc = scratch_reserve(c, 19, (size_t)n_trials * 3 * sizeof(double) + 64, &p_diag))) return rc;
+  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 128, c->stream));
+  TS_CUDA(c, cudaMemsetAsync(p_diag, 0, (size_t)n_trials * 3 * sizeof(double), c->stream));
+  a.order = d_order;
+  a.Nmax = Nmax + (Nmax & 1);
+  a.w_base = nullptr;
+  a.warp_off = nullptr;
+  a.warp_cap = nullptr;
+  a.n_warps = warps;
+  a.pool = (double*)p_pool;
+  a.pool_used = (unsigned long long*)p_q + 10;
+  a.pool_cap = (long long)pool_need;
+  a.queue = (unsigned long long*)p_q;
+  a.queue2 = (unsigned long long*)p_q + 2;
+  a.diag = (double*)p_diag;
+  c->k3_diag_n = n_trials;
+  a.tail_share = 0;
+  a.park_budget = 0;
+  a.park_budget_early = 0;
+  a.park_cap = 0;
+  a.park_count = (unsigned*)p_q + 8;
+  a.park_used = (unsigned long long*)p_q + 5;
+  a.park_state = nullptr;
+  a.park_trial = nullptr;
+  a.park_off = nullptr;
+  a.park_data = nullptr;
+  a.park_data_cap = 0;
+  a.park_order = nullptr;
+  c->k3_timed = true;
+  c->d_k3_parked = a.park_count;
+  c->k3_park_cap = 0;
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
+  k3_quat_kernel<<<(unsigned)warps, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
+  c->launches++;
+  TS_CUDA(c, cudaGetLastError());
+  TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
+  return TS_OK;
+}
+
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
+  if (a.opts.quat_error) return k3_launch_quat(c, a, N_i_host);
   const int64_t n_trials = a.n_trials;
   int64_t Nmax = 0;
   for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
@@ -702,6 +768,11 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   ts_ilqr_opts o;
   if (opts) o = *opts; else ts_ilqr_default_opts(&o);
   if (o.max_linesearch < 0 || o.max_linesearch > 63) return fail(c, TS_ERR_ARG, "max_linesearch must be in [0,63]");
+  if (o.quat_error)
+    for (int64_t t = 0; t < n_trials; ++t)
+      for (int i = 4; i < 7; ++i)
+        if (Qd[t * 8 + i] != Qd[t * 8 + 3] || Qfd[t * 8 + i] != Qfd[t * 8 + 3])
+          return fail(c, TS_ERR_ARG, "quat_error: the four quaternion weights of Q and Qf must be equal (E'QE is then diagonal)");
   int64_t total_knots = 0, total_rows = 0;
   for (int64_t t = 0; t < n_trials; ++t) {
     if (N_i[t] < 2) return fail(c, TS_ERR_ARG, "trial %lld: N < 2", (long long)t);

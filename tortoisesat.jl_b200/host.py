@@ -41,7 +41,8 @@ class IlqrOpts(C.Structure):
                [(k, C.c_int32) for k in ("a2_active_ge", "a3_grad_over_N", "a4_no_intermediate", "a5_dual_active_only",
                                          "a6_penalty_conditional", "a7_carry_cost")] + \
                [("constraint_decrease_ratio", C.c_double), ("k3_suspend_after", C.c_int32), ("k3_tail_share", C.c_int32),
-                ("k3_early_factor", C.c_double), ("k3_pair", C.c_int32), ("k3_wide_occ", C.c_int32)]
+                ("k3_early_factor", C.c_double), ("k3_pair", C.c_int32), ("k3_wide_occ", C.c_int32),
+                ("quat_error", C.c_int32), ("pad_", C.c_int32)]
 
 
 class TvlqrOpts(C.Structure):
@@ -821,7 +822,8 @@ def attitude_simulation(f, f_gains, integration, X_lqr, U_lqr, dt_lqr, x0_lqr, t
 
 def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=58155.0, igrf_date=2019.0, t0=0.0, tf=60 * 40.0,
                 cutoff=30.0, N=5000, J=None, q_0=None, q_final=(np.sqrt(2) / 2, np.sqrt(2) / 2, 0.0, 0.0), alpha=1.0e-1, beta=1.0e3,
-                seed=0, run_tvlqr=True, ilqr=None, rng=None, random_attitudes=False, trajectories=True, eigen_axis_fix=False):
+                seed=0, run_tvlqr=True, ilqr=None, rng=None, random_attitudes=False, trajectories=True, eigen_axis_fix=False,
+                sat_att=False):
     """The loop of monte_carlo.jl:118-262 (solver block of TortoiseSat.jl:178-199) for number_sims trials in ONE
     library call.  Returns the arrays the script leaves in globals (monte_carlo.jl:52-66,237-240): A (number_sims x 6),
     t_final, slew_time, fails, and -- with trajectories=True -- the per-trial lists `states` (8 x N_i), `control_inputs`
@@ -829,7 +831,9 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
     the outcome records and the statistics block.  Randomisation as in monte_carlo.jl:122-127,207 (RAAN and anomaly
     uniform in [0,360); q_0 = [1,0,0,0] for every trial as at monte_carlo.jl:108-111 unless random_attitudes=True, which
     draws q_0 uniformly on S^3 -- the BASELINE configs[2] ensemble; initial attitude noise randn(3)*(pi/180)^2), from
-    numpy's generator instead of Julia's global RNG."""
+    numpy's generator instead of Julia's global RNG.  sat_att=True selects the quaternion-aware solver the script asks of
+    its forked TrajectoryOptimization (monte_carlo.jl:158 Model(DerivFunction, n, m, quaternion_error,
+    quaternion_expansion), :192 solver.opts.sat_att = true): ts_ilqr_opts.quat_error."""
     rng = np.random.default_rng(seed) if rng is None else rng
     n = int(number_sims)
     J = np.diag([0.00125, 0.00125, 0.00125]) if J is None else np.asarray(J, dtype=float)
@@ -852,6 +856,8 @@ def monte_carlo(number_sims=100, alt=400.0, R_E=6371.0, inclination=96.6, MJD_0=
                             alpha=alpha, beta=beta)
     if ilqr is not None:
         cfg.ilqr = ilqr
+    if sat_att:
+        cfg.ilqr.quat_error = 1
     cfg.tvlqr.noise_mode, cfg.tvlqr.seed = 2, int(seed)
     for i in range(6):                                   # monte_carlo.jl:69-71,216-226
         cfg.tvlqr.Qd[i], cfg.tvlqr.Qfd[i] = 10.0, 1000.0
