@@ -572,6 +572,25 @@ def main():
                 line["tvlqr16k"] = tvlqr_block(2048 if n >= 4096 else n // 2, 3)
             except Exception as ex:  # pragma: no cover
                 line.setdefault("sweep", {"error": str(ex)})
+        # the quaternion-aware solver variant the reference's Monte-Carlo script requests (monte_carlo.jl:158,192),
+        # one pass over the same ensemble (k3_quat_kernel: one warp per trial from the initial rollout)
+        if a.workload == "mc_fixed_orbit":
+            try:
+                tr, cfg, fo, sid = main_r["tr"], main_r["cfg"], main_r["fo"], main_r["sid"]
+                cfg.ilqr.quat_error = 1
+                barrier()
+                out, st = eng.monte_carlo_run(cfg, tr["kep"], fo, tr["x0"], tr["xf"], tr["Jm"], q_noise0=tr["qn"], stream_id=sid)
+                cfg.ilqr.quat_error = 0
+                dev_s = max_over_ranks((st.ms_field + st.ms_prep + st.ms_solve + st.ms_tvlqr) * 1e-3)
+                hist = np.bincount(out["status"], minlength=6)[:6]
+                act = out["status"] != 5
+                line["quaternion_variant"] = {"workload": workload_name(a.workload, n) + " with ts_ilqr_opts.quat_error = 1",
+                                              "trials_per_s": world * n / dev_s, "ms_solve": st.ms_solve, "steps": 1, "warmup": 0,
+                                              "status_rank0": {STATUS[k]: int(hist[k]) for k in range(6)},
+                                              "inner_iters_mean_rank0": float(out["inner_iters"][act].mean()),
+                                              "slew_fail_rank0": int(st.n_fail_slew)}
+            except Exception as ex:  # pragma: no cover
+                line["quaternion_variant"] = {"error": str(ex)}
         try:
             line["igrf12"] = igrf_block(100_000_000 if n >= 1024 else 1_000_000, 3)
         except Exception as ex:  # pragma: no cover

@@ -239,12 +239,9 @@ __global__ void __launch_bounds__(32) k4c_replay_kernel(const K4Args a) {
 // host: the three launches of K4 (a.AB / a.lin_offs / a.lin_total must be set)
 inline void k4_launch(ts_ctx* c, const K4Args& a) {
   if (a.lin_total > 0) k4a_linearise_kernel<<<(unsigned)((a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k4b_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4B_SMEM_BYTES);
-    cudaFuncSetAttribute(k4c_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4C_SMEM_BYTES);
-    attr_set = true;
-  }
+  // (a per-device attribute: set on every launch -- ts_create_multi drives several devices from one process)
+  cudaFuncSetAttribute(k4b_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4B_SMEM_BYTES);
+  cudaFuncSetAttribute(k4c_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4C_SMEM_BYTES);
   k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4B_SMEM_BYTES, c->stream>>>(a);
   if (a.lin_total > 0) k4n_records_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
   k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4C_SMEM_BYTES, c->stream>>>(a);
