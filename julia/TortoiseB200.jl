@@ -42,6 +42,12 @@ struct IlqrOpts             # ts_ilqr_opts
     penalty_initial::Float64; penalty_scaling::Float64; penalty_max::Float64; dual_max::Float64
     ls_lower::Float64; ls_upper::Float64; bp_reg_increase::Float64; bp_reg_max::Float64; bp_reg_min::Float64; bp_reg_fp::Float64
     max_cost_value::Float64; max_state_value::Float64; max_control_value::Float64; u_max::Float64; u_min::Float64
+    # SURVEY App. C assumption registry (0 = frozen default, 1 = the named alternative)
+    a2_active_ge::Int32; a3_grad_over_N::Int32; a4_no_intermediate::Int32; a5_dual_active_only::Int32
+    a6_penalty_conditional::Int32; a7_carry_cost::Int32; constraint_decrease_ratio::Float64
+    # launch scheme of K3
+    k3_suspend_after::Int32; k3_tail_share::Int32; k3_early_factor::Float64; k3_pair::Int32; k3_wide_occ::Int32
+    quat_error::Int32; pad_::Int32     # 1: quaternion_error / quaternion_expansion variant (monte_carlo.jl:158,192)
 end
 struct TrialOutcome         # ts_trial_outcome (64 bytes)
     status::Int32; outer_iters::Int32; inner_iters::Int32; ls_rollouts::Int32; N::Int64
@@ -55,13 +61,15 @@ struct TvlqrOpts            # ts_tvlqr_opts
 end
 struct McConfig             # ts_mc_config
     n_trials::Int64; shared_orbit::Int32; run_tvlqr::Int32; t0::Float64; tf::Float64; N_scope::Int64
-    cutoff::Float64; dt::Float64; alpha::Float64; beta::Float64; ilqr::IlqrOpts; tvlqr::TvlqrOpts
+    cutoff::Float64; dt::Float64; alpha::Float64; beta::Float64; eigen_axis_fix::Int32; keep_trajectories::Int32
+    ilqr::IlqrOpts; tvlqr::TvlqrOpts
 end
 struct McStats              # ts_mc_stats
     n_trials::Int64; n_converged::Int64; n_no_cutoff::Int64; n_fail_slew::Int64
     sum_slew_time::Float64; sum_slew_time_sq::Float64; sum_t_final::Float64; sum_inner_iters::Float64
     sum_ls_rollouts::Float64; sum_knots::Float64; flops::Float64
     ms_field::Float64; ms_prep::Float64; ms_solve::Float64; ms_tvlqr::Float64
+    n_status::NTuple{6,Int64}          # trials per TS_ST_* code
 end
 function default_ilqr_opts()
     r = Ref{IlqrOpts}()
@@ -185,10 +193,10 @@ function eigen_axis_slew(x0, xf, t; e::Engine = engine())
     nt = length(t); dt = t[2] - t[1]
     Qd = zeros(8); Qfd = zeros(8); Rd = zeros(3); wg = zeros(3, nt); qg = zeros(4, nt)
     rc = ccall((:ts_slew_weights_batch, LIB), Cint,
-               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cint,
                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
-               e.h, 1, [x0[1:7]; 0.0], [xf[1:7]; 0.0], vec(Matrix(1.0I, 3, 3)), Float64[t[end]], t[1], dt, 1.0, 1.0,
-               Qd, Qfd, Rd, Int64[0], wg, qg)
+               e.h, 1, [x0[1:7]; 0.0], [xf[1:7]; 0.0], vec(Matrix(1.0I, 3, 3)), Float64[t[end]], t[1], dt, 1.0, 1.0, 0,
+               Qd, Qfd, Rd, Int64[0], wg, qg)      # 0: the literal qmult(q_f, q_0) of eigen_axis_slew.jl:16
     check(e, rc)
     Matrix(wg'), Matrix(qg')
 end
@@ -196,9 +204,9 @@ end
 function bryson_weights(x0, xf, J, t_final; t0 = 0.0, dt = 0.2, α = 1.e1, β = 1.e3, e::Engine = engine())
     Qd = zeros(8); Qfd = zeros(8); Rd = zeros(3)
     rc = ccall((:ts_slew_weights_batch, LIB), Cint,
-               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble,
+               (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cint,
                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
-               e.h, 1, collect(Float64, x0), collect(Float64, xf), vec(Matrix{Float64}(J')), Float64[t_final], t0, dt, α, β,
+               e.h, 1, collect(Float64, x0), collect(Float64, xf), vec(Matrix{Float64}(J')), Float64[t_final], t0, dt, α, β, 0,
                Qd, Qfd, Rd, C_NULL, C_NULL, C_NULL)
     check(e, rc)
     Matrix(Diagonal(Qd)), Matrix(Diagonal(Rd)), Matrix(Diagonal(Qfd))
@@ -258,8 +266,12 @@ end
 # (src/monte_carlo.jl:52-66,237-240): A, t_final, slew_time, fails + the per-trial outcome records.
 function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination = 96.6, MJD_0 = 58155.0, igrf_date = 2019.0,
                      t0 = 0.0, tf = 60 * 40, cutoff = 30, N = 5000, J = [0.00125 0 0; 0 0.00125 0; 0 0 0.00125],
-                     q_0 = nothing, q_final = [sqrt(2) / 2; sqrt(2) / 2; 0; 0], α = 1.e-1, β = 1.e3, seed = 0, run_tvlqr = true,
-                     ilqr::IlqrOpts = default_ilqr_opts(), e::Engine = engine())
+                     q_0 = [1.0; 0; 0; 0], q_final = [sqrt(2) / 2; sqrt(2) / 2; 0; 0], α = 1.e-1, β = 1.e3, seed = 0, run_tvlqr = true,
+                     ilqr::IlqrOpts = default_ilqr_opts(), sat_att = false, trajectories = true, e::Engine = engine())
+    # sat_att = true: the solver configuration of monte_carlo.jl:158,192 (quaternion_error / quaternion_expansion hooks)
+    if sat_att
+        ilqr = IlqrOpts((f == :quat_error ? Int32(1) : getfield(ilqr, f) for f in fieldnames(IlqrOpts))...)
+    end
     GM = 3.986004418E14 * (1 / 1000)^3
     A = zeros(6, number_sims)                       # column i = A[i,:] of the reference
     fo = Vector{FieldOpts}(undef, number_sims)
@@ -267,7 +279,7 @@ function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination =
     for i in 1:number_sims
         A[:, i] = [0, alt + R_E, inclination, rand() * 360, 0, rand() * 360]      # monte_carlo.jl:122-127
         fo[i] = FieldOpts(GM, MJD_0, igrf_date, (alt + R_E) * 1000.0, 0.0, 0.0, 0)
-        x0[4:7, i] = q_0 === nothing ? normalize(randn(4)) : q_0
+        x0[4:7, i] = q_0 === nothing ? normalize(randn(4)) : q_0          # monte_carlo.jl:108-111 uses [1,0,0,0]
         xf[4:7, i] = q_final; xf[8, i] = 1
         Jm[:, i] = vec(Matrix{Float64}(J'))
         qn[:, i] = randn(3) * (1 * pi / 180)^2                                    # monte_carlo.jl:207
@@ -275,7 +287,7 @@ function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination =
     tv = default_tvlqr_opts()
     tv = TvlqrOpts(0.2, t0, 0.0, ntuple(_ -> 10.0, 6), ntuple(_ -> 1000.0, 6), ntuple(_ -> 0.5e3, 3), tv.dt_squared, 2, seed,
                    0.05, 0.08727, 0, 0)                                            # monte_carlo.jl:69-71,216-226
-    cfg = McConfig(number_sims, 0, run_tvlqr ? 1 : 0, t0, tf, N, cutoff, 0.2, α, β, ilqr, tv)
+    cfg = McConfig(number_sims, 0, run_tvlqr ? 1 : 0, t0, tf, N, cutoff, 0.2, α, β, 0, trajectories ? 1 : 0, ilqr, tv)
     out = Vector{TrialOutcome}(undef, number_sims); st = Ref{McStats}()
     rc = ccall((:ts_monte_carlo_run, LIB), Cint,
                (Ptr{Cvoid}, Ref{McConfig}, Ptr{Float64}, Ptr{FieldOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
@@ -284,7 +296,49 @@ function monte_carlo(; number_sims = 100, alt = 400, R_E = 6371.0, inclination =
     check(e, rc)
     t_final = [o.t_final for o in out]; slew_time = [o.slew_time for o in out]
     fails = [o.slew_time == o.t_final ? 1.0 : 0.0 for o in out]                  # monte_carlo.jl:257-261
-    (A = Matrix(A'), t_final = t_final, slew_time = slew_time, fails = fails, outcomes = out, stats = st[])
+    res = (A = Matrix(A'), t_final = t_final, slew_time = slew_time, fails = fails, outcomes = out, stats = st[])
+    trajectories || return res
+    # the per-trial arrays the script keeps (monte_carlo.jl:52-66,149,200-201,232-233), fetched from HBM
+    ko = zeros(Int64, number_sims + 1); ro = zeros(Int64, number_sims + 1)
+    check(e, ccall((:ts_mc_trajectory_layout, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}), e.h, number_sims, ko, ro))
+    X = zeros(8, ko[end]); U = zeros(3, ko[end]); Xs = zeros(8, ko[end]); Us = zeros(3, ko[end]); B = zeros(3, ro[end])
+    check(e, ccall((:ts_mc_fetch_trajectories, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.h, X, U, run_tvlqr ? Xs : C_NULL, run_tvlqr ? Us : C_NULL, B))
+    rng(t) = (ko[t] + 1):ko[t + 1]
+    merge(res, (states = [X[:, rng(t)] for t in 1:number_sims], control_inputs = [U[:, rng(t)[1:end-1]] for t in 1:number_sims],
+                sim_states = [Xs[:, rng(t)] for t in 1:number_sims], sim_control_inputs = [Us[:, rng(t)] for t in 1:number_sims],
+                B_ECI_total = [Matrix(B[:, (ro[t] + 1):(ro[t] + 2 * length(rng(t)))]') for t in 1:number_sims]))
+end
+
+# igrf12syn(isv,date,itype,alt,colat,elong) -> (x,y,z,f)      reference src/igrf.jl:335-534 (scalar call = batch of one)
+function igrf12syn(isv::Integer, date::Number, itype::Integer, alt::Number, colat::Number, elong::Number; e::Engine = engine())
+    x = zeros(1); y = zeros(1); z = zeros(1); f = zeros(1)
+    check(e, ccall((:ts_igrf12syn_batch, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Cdouble, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Float64}, Cint), e.h, isv, date, itype, 1, Float64[alt], Float64[colat], Float64[elong], x, y, z, f, 0))
+    x[1], y[1], z[1], f[1]
+end
+
+# attitude_dynamics_linear(x,u,x_linear,B_B,J)                  reference src/attitude_dynamics.jl:26-48
+function attitude_dynamics_linear(x, u, x_linear, B_B, J; e::Engine = engine())
+    dx = zeros(7)
+    check(e, ccall((:ts_attitude_dynamics_linear_batch, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.h, 1, collect(Float64, x), collect(Float64, u), collect(Float64, x_linear), collect(Float64, B_B),
+                   vec(Matrix{Float64}(J')), dx))
+    dx
+end
+
+# The PD magnetic controller loop of comparison/psiaki2005.jl:116-164 (one trial; B_ECI is 3 x N as in the script)
+function psiaki_pd_simulation(x0, w_guess, q_guess, B_ECI, J, dt; C_1 = 1e-6, C_2 = 1e-9, e::Engine = engine())
+    N = size(B_ECI, 2)
+    X = zeros(7, N); M = zeros(3, N); Qe = zeros(4, N)
+    check(e, ccall((:ts_psiaki_pd_batch, LIB), Cint,
+                   (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble,
+                    Cdouble, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.h, 1, Int64[N], Int64[0], collect(Float64, x0), Matrix{Float64}(w_guess), Matrix{Float64}(q_guess),
+                   Matrix{Float64}(B_ECI), vec(Matrix{Float64}(J')), dt, C_1, C_2, X, M, Qe))
+    X, M, Qe
 end
 
 # ----------------------------------------------------------------------------- element-wise building blocks
@@ -346,6 +400,7 @@ hat(x) = [0 -x[3] x[2]; x[3] 0 -x[1]; -x[2] x[1] 0]                             
 
 export Engine, params, input_parameters, igrf12, igrf12_batch, igrf_data, magnetic_simulation, magnetic_gramian, kep_ECI, OrbitPlotter,
        legendre, dlegendre, DerivFunction, gain_simulator, attitude_dynamics,
-       condition_based_time, eigen_axis_slew, bryson_weights, solve_slew, attitude_simulation, monte_carlo, qmult, qrot, q_inv, hat
+       condition_based_time, eigen_axis_slew, bryson_weights, solve_slew, attitude_simulation, monte_carlo, qmult, qrot, q_inv, hat,
+       igrf12syn, attitude_dynamics_linear, psiaki_pd_simulation
 
 end # module

@@ -62,3 +62,28 @@ def test_struct_layouts_match_the_header(tmp_path):
             host.OUTCOME_DTYPE.itemsize]
     assert sizes == mine, (sizes, mine)
     assert host.FIELD_OPTS_DTYPE.itemsize == sizes[2]
+    # the Julia structs (julia/TortoiseB200.jl; no Julia in the image): field types parsed from the source, C layout rules
+    import re
+    jl = open(os.path.join(ROOT, "julia", "TortoiseB200.jl")).read()
+    prim = {"Int32": 4, "UInt32": 4, "Int64": 8, "UInt64": 8, "Float64": 8}
+
+    def jl_size(name, seen={}):
+        if name in seen:
+            return seen[name]
+        body = re.search(r"^struct %s\b.*?\n(.*?)^end" % name, jl, re.S | re.M).group(1)
+        off, align = 0, 1
+        for ftype in re.findall(r"::\s*([A-Za-z0-9_{},]+)", re.sub(r"#.*", "", body)):
+            m = re.match(r"NTuple\{(\d+),(\w+)\}", ftype)
+            if m:
+                sz, al = int(m.group(1)) * prim[m.group(2)], prim[m.group(2)]
+            elif ftype in prim:
+                sz = al = prim[ftype]
+            else:
+                sz, al = jl_size(ftype)
+            off = (off + al - 1) // al * al + sz
+            align = max(align, al)
+        seen[name] = ((off + align - 1) // align * align, align)
+        return seen[name]
+
+    jl_sizes = [jl_size(n)[0] for n in ("IlqrOpts", "TvlqrOpts", "FieldOpts", "McConfig", "McStats", "TrialOutcome")]
+    assert jl_sizes == sizes, (jl_sizes, sizes)
