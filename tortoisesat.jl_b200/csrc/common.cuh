@@ -31,6 +31,7 @@ struct ts_ctx {
   double* d_tabH = nullptr;  // 91 x 25
   double* d_tabGH = nullptr; // 3450 (igrf12syn)
   int* d_flag = nullptr;     // generic device error/flag word
+  void* d_gh_stage = nullptr; // K1: the call's interpolated coefficient table (2 x 104 double2)
   // trajectories of the last ts_monte_carlo_run with keep_trajectories (device pointers into the scratch arenas)
   struct McLast {
     bool valid = false;

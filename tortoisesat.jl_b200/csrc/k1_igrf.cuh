@@ -16,20 +16,31 @@ namespace ts {
 constexpr int K1_THREADS = 128;
 constexpr int K1_MIN_BLOCKS = 4;  // <= 128 registers: 16 warps per SM keep the FP64 pipe busier than 168 regs / 12 warps
 
+// The date-interpolated, rescaled Gauss coefficients of one call (2 x 104 (g,h) pairs, igrf_stage_coeffs), computed ONCE
+// per call by this one-block kernel; every block of K1 then copies the 3.3 KB table from L2 into its shared memory.
+// (Round 1 re-did the interpolation -- table look-ups, two FP64 divisions, the (n,m) search -- in every block of 128
+// points: ~17 % of a warp's lifetime spent before its first FP64 instruction.)
+__global__ void __launch_bounds__(128) k1_stage_kernel(const double* __restrict__ tabG, const double* __restrict__ tabH, double date,
+                                                       double2* __restrict__ gh) {
+  igrf_stage_coeffs(gh, tabG, tabH, date);
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
-k1_igrf12_batch(const double* __restrict__ tabG, const double* __restrict__ tabH, double date, int64_t n,
+k1_igrf12_batch(const double2* __restrict__ gh, int64_t n,
                 const double* __restrict__ r_m, const double* __restrict__ lat, const double* __restrict__ lon,
                 double* __restrict__ Bn, double* __restrict__ Be, double* __restrict__ Bd, int* __restrict__ bad_flag) {
   __shared__ double2 s_gh[2 * IGRF_NCOEF];
-  igrf_stage_coeffs(s_gh, tabG, tabH, date);
+  // the point's own inputs are requested first: their DRAM latency overlaps the table copy and the barrier
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const double la = live ? lat[i] : 0.0, lo = live ? lon[i] : 0.0, rr = live ? r_m[i] : 6371200.0;
+  for (int k = threadIdx.x; k < 2 * IGRF_NCOEF; k += K1_THREADS) s_gh[k] = gh[k];
   __syncthreads();
   const double PI = 3.141592653589793;
   // one point per thread: a grid-stride loop lets the compiler hoist the c[][] recursion
   // constants into registers (255 regs + spills); without it the body needs 168, no spills.
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double la = lat[i], lo = lon[i], rr = r_m[i];
+  if (!live) return;
   double bn, be, bd;
   // reference validation, igrf.jl:84-88 (NaN inputs fail it too)
   if (!(la >= -PI / 2 && la <= PI / 2 && lo >= -PI && lo <= PI)) {

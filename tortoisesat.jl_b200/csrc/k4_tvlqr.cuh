@@ -130,6 +130,150 @@ __global__ void __launch_bounds__(32) k4b_riccati_kernel(const K4Args a) {
   }
 }
 
+// ---- K4b as a TEAM kernel: 16 lanes per slew (two slews per warp).  The Riccati step is a chain of small dense products
+// whose columns are independent: lane c < 6 owns column c of A (S A, B'S A, its gain column, its closed-loop column,
+// S Acl, its column of the new S), lanes 6..8 own the columns of B (S B, B'S B); three exchanges through the team's
+// shared memory per step (B'SB | K, Acl | new S).  Every dot product keeps the summation order of tvlqr_riccati_step, so
+// the gains are bit-identical to the one-thread version (which the host emulator and the oracle tests run); one thread
+// per slew needed ~1200 dependent-issue FMAs per knot (2.6 k cycles), a lane of the team ~220.  [A|B] records are staged
+// K4_RING_D steps ahead by the team's lanes with 16-byte cp.async (27 pieces per record).
+constexpr int K4B_TEAM = 16;
+constexpr int K4B_TEAMS_PER_BLOCK = 4;
+constexpr int K4B_XB = K4_RING_D * 54;                 // exchange area behind the ring: BSB 9 (+pad) | K 18 (+pad) | Acl 36 | Sn 36
+constexpr int K4B_TEAM_DOUBLES = K4B_XB + 12 + 20 + 36 + 36;
+static_assert(K4B_TEAM_DOUBLES % 2 == 0 && (K4B_XB % 2) == 0, "16-byte alignment of the team regions");
+__global__ void __launch_bounds__(K4B_TEAM * K4B_TEAMS_PER_BLOCK) k4b_riccati_team_kernel(const K4Args a) {
+  __shared__ __align__(16) double sm_all[K4B_TEAMS_PER_BLOCK * K4B_TEAM_DOUBLES];
+  const int team = threadIdx.x / K4B_TEAM, c = threadIdx.x % K4B_TEAM;
+  const int64_t t = (int64_t)blockIdx.x * K4B_TEAMS_PER_BLOCK + team;
+  if (t >= a.n_trials) return;   // the whole team leaves together
+  const unsigned mask = 0xFFFFu << (16 * ((threadIdx.x / K4B_TEAM) & 1));
+  double* ring = sm_all + team * K4B_TEAM_DOUBLES;
+  double* xBSB = ring + K4B_XB;
+  double* xK = xBSB + 12;
+  double* xAcl = xK + 20;
+  double* xSn = xAcl + 36;
+  const int N = (int)a.N_i[t];
+  double S[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) S[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) S[i * 6 + i] = a.opts.Qfd[i];
+  const double* ab = a.AB + a.lin_offs[t] * 54;
+  double* K = a.K + a.offs[t] * 18;
+  auto issue = [&](int k) {   // record k -> slot (k mod D): 27 pieces of 16 bytes, lanes 0..13 take two each
+    if (k >= 0) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (k % K4_RING_D) * 54);
+      const double* src = ab + (long long)k * 54;
+      for (int pc = c; pc < 27; pc += 14)
+        if (c < 14) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * pc), "l"(src + 2 * pc) : "memory");
+    }
+    k4_commit();
+  };
+  for (int d = 0; d < K4_RING_D; ++d) issue(N - 2 - d);
+  const bool isA = c < 6, isB = c >= 6 && c < 9;
+  const int cc = isA ? c : (isB ? c - 6 : 0);
+#pragma unroll 1
+  for (int k = N - 2; k >= 0; --k) {
+    k4_wait_oldest();
+    __syncwarp(mask);
+    const double* A = ring + (k % K4_RING_D) * 54;
+    const double* B = A + 36;
+    // ---- stage 1: SX = S col, BX = B' SX  (col = column cc of A, or of B on lanes 6..8)
+    double col[6], SX[6], BX[3];
+#pragma unroll
+    for (int l = 0; l < 6; ++l) col[l] = isB ? B[l * 3 + cc] : A[l * 6 + cc];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * col[l];
+      SX[i] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) s += B[l * 3 + r] * SX[l];
+      BX[r] = s;
+    }
+    if (isB)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) xBSB[r * 3 + cc] = BX[r] + ((r == cc) ? a.opts.Rd[r] : 0.0);
+    __syncwarp(mask);
+    // ---- stage 2: gain column, closed-loop column, S Acl column
+    double BSB[9], Minv[9], Kc[3], Ac[6], SAc[6];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) BSB[i] = xBSB[i];
+    inv3_adj(BSB, Minv);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) s += Minv[r * 3 + l] * BX[l];
+      Kc[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) s += B[i * 3 + l] * Kc[l];
+      Ac[i] = col[i] - s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < 6; ++l) s += S[i * 6 + l] * Ac[l];
+      SAc[i] = s;
+    }
+    if (isA) {
+      double* Kout = K + (long long)k * 18;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        xK[r * 6 + cc] = Kc[r];
+        Kout[r * 6 + cc] = Kc[r];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xAcl[i * 6 + cc] = Ac[i];
+    }
+    __syncwarp(mask);
+    // ---- stage 3: column cc of the new S
+    if (isA) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double s = (i == cc) ? a.opts.Qd[i] : 0.0;
+        double kr = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) kr += xK[l * 6 + i] * a.opts.Rd[l] * Kc[l];
+        s += kr;
+        double tt = 0.0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) tt += xAcl[l * 6 + i] * SAc[l];
+        xSn[i * 6 + cc] = s + tt;
+      }
+    }
+    __syncwarp(mask);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) S[i] = xSn[i];
+    __syncwarp(mask);   // everybody has read the record and the exchange area: the slot may be refilled
+    issue(k - K4_RING_D);
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  if (c == 0) {
+    // the replay's clock state at every step (the reference accumulates it through rk4: sequential, exact replica)
+    double x8 = a.x0_lqr[t * 8 + 7];
+    double* clk = a.clk + a.lin_offs[t];
+#pragma unroll 1
+    for (int k = 0; k < N - 1; ++k) {
+      clk[k] = x8;
+      double tcl[4], nxt;
+      clock_rk4(x8, a.clock_rate[t], a.opts.dt, tcl, nxt);
+      x8 = nxt;
+    }
+  }
+}
+
 // ---- K4n: the stage records of the replay (tvlqr_solver.cuh): for every rk4 stage of every step the disturbance draws of
 // simulator.jl:5,10,22 (Philox4x32-10 + Box-Muller, counter-based on (seed, trial, step, stage)), the perturbation
 // quaternion (sincos) and the perturbed field row of the stage's clock value -- one thread per (trial, step, stage).  In
@@ -242,7 +386,11 @@ inline void k4_launch(ts_ctx* c, const K4Args& a) {
   // (a per-device attribute: set on every launch -- ts_create_multi drives several devices from one process)
   cudaFuncSetAttribute(k4b_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4B_SMEM_BYTES);
   cudaFuncSetAttribute(k4c_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K4C_SMEM_BYTES);
-  k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4B_SMEM_BYTES, c->stream>>>(a);
+  if (a.lin_total > 0)
+    k4b_riccati_team_kernel<<<(unsigned)((a.n_trials + K4B_TEAMS_PER_BLOCK - 1) / K4B_TEAMS_PER_BLOCK), K4B_TEAM * K4B_TEAMS_PER_BLOCK, 0,
+                              c->stream>>>(a);
+  else
+    k4b_riccati_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4B_SMEM_BYTES, c->stream>>>(a);
   if (a.lin_total > 0) k4n_records_kernel<<<(unsigned)((4 * a.lin_total + 127) / 128), 128, 0, c->stream>>>(a);
   k4c_replay_kernel<<<(unsigned)((a.n_trials + 31) / 32), 32, K4C_SMEM_BYTES, c->stream>>>(a);
   c->launches += 4;

@@ -82,7 +82,8 @@ int ts_create(ts_ctx** out, int device_id) {
       cudaEventCreate(&c->ev_k3[0]) != cudaSuccess || cudaEventCreate(&c->ev_k3[1]) != cudaSuccess ||
       cudaEventCreate(&c->ev_k3[2]) != cudaSuccess ||
       cudaMalloc(&c->d_tabG, sizeof(TS_IGRF12_G)) != cudaSuccess || cudaMalloc(&c->d_tabH, sizeof(TS_IGRF12_H)) != cudaSuccess ||
-      cudaMalloc(&c->d_tabGH, sizeof(TS_IGRF12_GH)) != cudaSuccess || cudaMalloc(&c->d_flag, 64) != cudaSuccess) {
+      cudaMalloc(&c->d_tabGH, sizeof(TS_IGRF12_GH)) != cudaSuccess || cudaMalloc(&c->d_flag, 64) != cudaSuccess ||
+      cudaMalloc(&c->d_gh_stage, 2 * IGRF_NCOEF * sizeof(double2)) != cudaSuccess) {
     ts_destroy(c);
     return TS_ERR_CUDA;
   }
@@ -109,6 +110,7 @@ void ts_destroy(ts_ctx* c) {
   if (c->d_tabH) cudaFree(c->d_tabH);
   if (c->d_tabGH) cudaFree(c->d_tabGH);
   if (c->d_flag) cudaFree(c->d_flag);
+  if (c->d_gh_stage) cudaFree(c->d_gh_stage);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int i = 0; i < 3; ++i)
@@ -201,13 +203,19 @@ int ts_fp64_latency_probe(ts_ctx* c, double* cycles4) {
   return TS_OK;
 }
 
+// the call's coefficient table (c->d_gh_stage), queued on the context's stream ahead of the K1 launches that read it
+static void k1_stage(ts_ctx* c, double date) {
+  k1_stage_kernel<<<1, 128, 0, c->stream>>>(c->d_tabG, c->d_tabH, date, (double2*)c->d_gh_stage);
+  c->launches++;
+}
 static void k1_launch(ts_ctx* c, cudaStream_t st, double date, int64_t n, const double* r, const double* la, const double* lo,
                       double* bn, double* be, double* bd) {
   const unsigned blocks = (unsigned)((n + K1_THREADS - 1) / K1_THREADS);
+  const double2* gh = (const double2*)c->d_gh_stage;
   if (igrf_nmax_for_date(date) == 13)
-    k1_igrf12_batch<13><<<blocks, K1_THREADS, 0, st>>>(c->d_tabG, c->d_tabH, date, n, r, la, lo, bn, be, bd, c->d_flag);
+    k1_igrf12_batch<13><<<blocks, K1_THREADS, 0, st>>>(gh, n, r, la, lo, bn, be, bd, c->d_flag);
   else
-    k1_igrf12_batch<10><<<blocks, K1_THREADS, 0, st>>>(c->d_tabG, c->d_tabH, date, n, r, la, lo, bn, be, bd, c->d_flag);
+    k1_igrf12_batch<10><<<blocks, K1_THREADS, 0, st>>>(gh, n, r, la, lo, bn, be, bd, c->d_flag);
   c->launches++;
 }
 
@@ -230,6 +238,7 @@ static int igrf12_host_pipeline(ts_ctx* c, double date, int64_t n, const double*
     stage[i] = (double*)p;
   }
   TS_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  k1_stage(c, date);   // both pipeline streams wait for pipe_ev
   TS_CUDA(c, cudaEventRecord(c->pipe_ev, c->stream));
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   std::vector<cudaEvent_t> ev((size_t)n_chunks * 2, nullptr);
@@ -283,6 +292,7 @@ int ts_igrf12_batch(ts_ctx* c, double date, int64_t n, const double* r_m, const 
   if (!pointers_are_device) return igrf12_host_pipeline(c, date, n, r_m, lat, lon, Bn, Be, Bd);
   TS_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
   KernelTimer t(c);
+  k1_stage(c, date);
   k1_launch(c, c->stream, date, n, r_m, lat, lon, Bn, Be, Bd);
   t.stop();
   TS_CUDA(c, cudaGetLastError());
