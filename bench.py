@@ -573,7 +573,7 @@ def main():
             except Exception as ex:  # pragma: no cover
                 line.setdefault("sweep", {"error": str(ex)})
         # the quaternion-aware solver variant the reference's Monte-Carlo script requests (monte_carlo.jl:158,192),
-        # one pass over the same ensemble (k3_quat_kernel: one warp per trial from the initial rollout)
+        # one pass over the same ensemble (the QUAT instantiations of both K3 kernels)
         if a.workload == "mc_fixed_orbit":
             try:
                 tr, cfg, fo, sid = main_r["tr"], main_r["cfg"], main_r["fo"], main_r["sid"]

@@ -173,7 +173,7 @@ typedef struct ts_ilqr_opts {
                                         dx = [w - wbar; MRP(conj(qbar) (x) q)], the backward pass runs on the 6-dim error
                                         state with A_e = E(x_k+1)' A E(x_k), B_e = E(x_k+1)' B, E = blkdiag(I3, G(q)).  Gains
                                         come back in error coordinates (3 x 8 rows, entries 6 and 7 zero).  Needs equal
-                                        weights / goal mask on the four quaternion components.  One warp per trial.      */
+                                        weights / goal mask on the four quaternion components.                           */
   int32_t pad_;
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);

@@ -88,7 +88,8 @@ struct CpuTeamT {
   }
 };
 
-struct CpuQuatTeam : CpuTeamT<32> {   // the quaternion-aware variant (ts_ilqr_opts.quat_error), whole-warp team
+template <int W_>
+struct CpuQuatTeamT : CpuTeamT<W_> {   // the quaternion-aware variant (ts_ilqr_opts.quat_error)
   static constexpr bool QUAT = true;
 };
 
@@ -189,8 +190,10 @@ void hs_alilqr_solve_w(int width, int64_t N, const double* x0, const double* xf,
   in.index_scale = index_scale;
   in.clock_rate = clock_rate;
   in.U0 = U0;
-  if (opts->quat_error)
-    solve_with_width<32, CpuQuatTeam>(in, opts, N, X, U, K, out);
+  if (opts->quat_error && width == 32)
+    solve_with_width<32, CpuQuatTeamT<32>>(in, opts, N, X, U, K, out);
+  else if (opts->quat_error)
+    solve_with_width<8, CpuQuatTeamT<8>>(in, opts, N, X, U, K, out);
   else if (width == 32)
     solve_with_width<32>(in, opts, N, X, U, K, out);
   else

@@ -228,7 +228,7 @@ def test_bench_ensemble_sample_matches_oracle(engine):
 
 def test_fused_monte_carlo_quaternion_aware(engine):
     """The fused Monte-Carlo call with ts_ilqr_opts.quat_error = 1 (the solver configuration monte_carlo.jl:158,192
-    actually requests): field pass -> weights -> k3_quat_kernel -> TVLQR replay, every trial against the oracle pipeline
+    actually requests): field pass -> weights -> QUAT K3 kernels -> TVLQR replay, every trial against the oracle pipeline
     run with the same option."""
     from tortoisesat.jl_b200 import host
     rng = np.random.default_rng(77)

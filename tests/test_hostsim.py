@@ -144,5 +144,10 @@ def test_quaternion_aware_team_matches_oracle(angle, tfin, Jm):
     assert np.max(np.abs(X - Xs[0])) < 1e-9 and np.max(np.abs(U - Us[0])) < 1e-9
     assert np.max(np.abs(K - Ks[0])) <= 1e-8 * np.max(np.abs(Ks[0]))
     assert np.all(K[:, :, 6:] == 0.0)
+    # the 8-lane team (four trials per warp on the GPU) runs the same variant bit for bit: a trial may be handed over
+    X8, U8, K8, o8 = S.hostsim_solve(s, o, width=8)
+    for f in ("status", "outer_iters", "inner_iters", "ls_rollouts", "J", "c_max"):
+        assert o8[f] == oc[f], f
+    assert np.array_equal(X8, X) and np.array_equal(U8, U) and np.array_equal(K8, K)
     # and it IS a different algorithm: the iteration path differs from the default solver's
     assert (out[0]["inner_iters"], out[0]["ls_rollouts"]) != (out0[0]["inner_iters"], out0[0]["ls_rollouts"])

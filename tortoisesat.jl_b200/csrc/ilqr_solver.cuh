@@ -453,12 +453,20 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             for (int l = 0; l < 7; ++l) arow[l] = rec[li * 7 + l];
             double t = 0.0;
             for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j0 * 8 + l];
-            double qd_li = sc * in.Qd[li];   // l_xx(li, li)
-            if constexpr (team_quat<Team>::value) qd_li = (li < 3) ? qd_li : ((li < 6) ? rec[83] : 0.0);
-            Qxx0 = t + ((li == j0) ? qd_li : 0.0);
+            if constexpr (team_quat<Team>::value) {   // l_xx(li, li) in error coordinates
+              const double qd_li = (li < 3) ? sc * in.Qd[li] : ((li < 6) ? rec[83] : 0.0);
+              Qxx0 = t + ((li == j0) ? qd_li : 0.0);
+            } else {
+              Qxx0 = t + ((li == j0) ? sc * in.Qd[li] : 0.0);
+            }
             t = 0.0;
             for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j1 * 8 + l];
-            Qxx1 = t + ((li == j1) ? qd_li : 0.0);
+            if constexpr (team_quat<Team>::value) {
+              const double qd_li = (li < 3) ? sc * in.Qd[li] : ((li < 6) ? rec[83] : 0.0);
+              Qxx1 = t + ((li == j1) ? qd_li : 0.0);
+            } else {
+              Qxx1 = t + ((li == j1) ? sc * in.Qd[li] : 0.0);
+            }
             const bool isux = lane < 21;
             const int u = isux ? lane : (lane < 30 ? lane - 21 : 0);
             const int rr = u % 3, cc = isux ? u / 3 : 7 + u / 3;
@@ -521,7 +529,6 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           }
           tm.sync();
         } else {
-          static_assert(!team_quat<Team>::value, "the quaternion-aware variant runs on the whole-warp team only");
           // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
           double S[28], s[7];
           for (int i = 0; i < 7; ++i)
@@ -540,7 +547,12 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             for (int i = 0; i < 7; ++i) {
               double t = 0.0;
               for (int l = 0; l < 7; ++l) t += rec[i * 7 + l] * m[l];
-              Qxxc[i] = t + ((i == lane) ? sc * in.Qd[i] : 0.0);
+              if constexpr (team_quat<Team>::value) {   // l_xx(i, i) in error coordinates: c |q|^2 on 3..5, nothing on 6
+                const double qd_i = (i < 3) ? sc * in.Qd[i] : ((i < 6) ? rec[83] : 0.0);
+                Qxxc[i] = t + ((i == lane) ? qd_i : 0.0);
+              } else {
+                Qxxc[i] = t + ((i == lane) ? sc * in.Qd[i] : 0.0);
+              }
             }
             for (int c = 0; c < 3; ++c) {
               double t = 0.0;

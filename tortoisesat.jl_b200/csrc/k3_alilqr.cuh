@@ -259,244 +259,19 @@ __device__ __forceinline__ double k3_shfl_d(double v, int src) { return __shfl_s
 __device__ __forceinline__ int k3_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ long long k3_shfl_ll(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+struct GpuTeamQuat : GpuTeam {   // the quaternion-aware variant (ts_ilqr_opts.quat_error; team_quat in ilqr_solver.cuh)
+  static constexpr bool QUAT = true;
+};
+#define K3_BODY_TEAM GpuTeam
 __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(const K3Args a) {
-  extern __shared__ __align__(16) double k3_smem[];
-  const int warp_in_block = threadIdx.x >> 5;
-  const int lane32 = threadIdx.x & 31;
-  const int team = lane32 >> 3;
-  const int64_t gwarp = (int64_t)blockIdx.x * K3_WARPS_PER_BLOCK + warp_in_block;
-  const int64_t slot = gwarp * 4 + team;
-  double* warp_smem = k3_smem + (warp_in_block * 4) * TEAM_SMEM_DOUBLES;
-  GpuTeam tm;
-  tm.ln = lane32 & 7;
-  tm.shift = team * 8;
-  tm.mask = 0xffu << tm.shift;
-  tm.sm = warp_smem + team * TEAM_SMEM_DOUBLES;
-  (void)slot;
-  TrialWork w;
-  const long long cap = a.warp_cap[gwarp];          // knots every slot of this warp can hold
-  const long long per_slot = cap * K3_SLOT_DOUBLES_PER_KNOT;
-  double* const warp_base = a.w_base + a.warp_off[gwarp];
-  w.Nmax = cap;
-  w.xu = warp_base + team * per_slot;
-  w.xu_warp = warp_base;
-  w.slot_stride = per_slot;
-  w.kd = w.xu + 90 * cap;
-  w.lam = w.kd + 24 * cap;
-  w.bk = w.lam + 6 * cap;
-  w.clk = w.bk + 10 * cap;
-  bool first_pull = true;
-  for (;;) {
-    unsigned long long base = 0;
-    if (first_pull) {
-      base = (unsigned long long)gwarp * 4ull;        // static first group: the one this warp's slots were sized for
-      first_pull = false;
-    } else {
-      if (lane32 == 0) base = atomicAdd(a.queue, 4ull);   // a.queue starts at 4 * n_warps
-      base = __shfl_sync(0xffffffffu, base, 0);
-    }
-    if ((int64_t)base >= a.n_trials) break;
-    const int64_t qi = (int64_t)base + team;
-    const bool have = qi < a.n_trials;
-    const int64_t t = have ? (a.order ? a.order[qi] : qi) : 0;
-    TrialState st;
-    st.phase = PH_DONE;
-    const TrialIn* inp = reinterpret_cast<const TrialIn*>(tm.smem() + SM_TRIAL);
-    if (have) {
-      k3_load_trial(tm, a, t);
-      solve_init(tm, *inp, a.opts, w, st);
-      st.cur = team * 9;   // trajectory buffers are addressed in the warp's 36-buffer space from here on
-    }
-    bool stored = !have;
-    bool may_park = a.park_budget > 0;
-    // ---- iterate: one iLQR iteration per pass for every unfinished team; the warp re-converges here
-    for (;;) {
-      if (!stored && st.phase == PH_DONE) {  // finished: write results now, so the slot's buffers can be lent out
-        ts_trial_outcome_dev oc;
-        solve_finish(*inp, st, oc);
-        k3_store_results(tm, a, t, w, inp->N, st.cur, oc, st);
-        stored = true;
-      }
-      // straggler hand-over: nothing left in the queue and this trial is past its iteration allowance -> park it
-      // (between two iterations, so its whole state is TrialState + the four live arrays) for k3_wide_kernel
-      if (may_park && !stored && st.phase == PH_BACKWARD && (long long)st.inner_total * inp->N >= a.park_budget) {  // team-uniform
-        // lane 0 decides for the team (the queue may move between two lanes' reads)
-        unsigned place = 0xffffffffu;
-        long long off = 0;
-        const int N = inp->N;
-        const long long Ne = N + (N & 1);
-        if (tm.ln == 0 && (*(volatile unsigned long long*)a.queue >= (unsigned long long)a.n_trials ||
-                           (long long)st.inner_total * N >= a.park_budget_early)) {
-          place = 0xfffffffeu;
-          off = (long long)atomicAdd(a.park_used, (unsigned long long)(27 * Ne));
-          if (off + 27 * Ne <= a.park_data_cap) {
-            place = atomicAdd(a.park_count, 1u);
-            if (place >= (unsigned)a.park_cap) place = 0xfffffffeu;
-          }
-        }
-        place = __shfl_sync(tm.mask, place, 0, TEAM);
-        off = __shfl_sync(tm.mask, off, 0, TEAM);
-        if (place == 0xffffffffu) {
-          // queue not drained yet: fresh trials keep every lane busy, stay
-        } else if (place < (unsigned)a.park_cap) {
-          double* pd = a.park_data + off;
-          const double* xc = xu_buf<TEAM>(w, st.cur);
-          for (int i = tm.ln; i < N * 10; i += TEAM) pd[i] = xc[i];
-          for (int i = tm.ln; i < N * 6; i += TEAM) pd[10 * Ne + i] = w.lam[i];
-          for (int i = tm.ln; i < N * 10; i += TEAM) pd[16 * Ne + i] = w.bk[i];
-          for (int i = tm.ln; i < N; i += TEAM) pd[26 * Ne + i] = w.clk[i];
-          if (tm.ln == 0) {
-            a.park_state[place] = st;
-            a.park_trial[place] = t;
-            a.park_off[place] = off;
-          }
-          st.phase = PH_DONE;
-          stored = true;
-        } else {
-          may_park = false;  // no room left: finish here
-        }
-      }
-      const unsigned act = __ballot_sync(0xffffffffu, st.phase != PH_DONE);
-      if (!act) break;
-      const unsigned teams_act = ((act & 0x000000ffu) ? 1u : 0u) | ((act & 0x0000ff00u) ? 2u : 0u) | ((act & 0x00ff0000u) ? 4u : 0u) |
-                                 ((act & 0xff000000u) ? 8u : 0u);
-      // "tail sharing": when a single trial of the group is left, its three finished siblings lend their lanes
-      // and trajectory buffers to its line search (candidates 8..31 in the same batch) -- with ONE call site of
-      // forward_batch for both modes, so the kernel does not grow.
-      // assignment of the finished teams to the unfinished ones: idle team j helps active team j mod k as
-      // "part" 1 + j/k; a trial's candidates are c = b0 + 8*part + lane, so one batch covers 8 * (#parts) steps
-      int wt = team, part = 0, nparts = 1;
-      int sp1 = team, sp2 = team, sp3 = team;   // owner's view: the teams that compute parts 1..3 of MY trial
-      if (a.tail_share && teams_act != 0xfu) {
-        const unsigned A = teams_act, I = ~teams_act & 0xfu;
-        const int k = __popc(A), ni = __popc(I);
-        if (A & (1u << team)) {
-          const int r = __popc(A & ((1u << team) - 1u));           // my rank among the active teams
-          nparts = 1 + ((ni > r) ? (ni - r + k - 1) / k : 0);
-          if (nparts > 1) sp1 = k3_nth_bit(I, r);
-          if (nparts > 2) sp2 = k3_nth_bit(I, r + k);
-          if (nparts > 3) sp3 = k3_nth_bit(I, r + 2 * k);
-        } else {
-          const int j = __popc(I & ((1u << team) - 1u));           // my rank among the idle teams
-          const int r = j % k;
-          wt = k3_nth_bit(A, r);
-          part = 1 + j / k;
-          nparts = 1 + (ni - r + k - 1) / k;
-        }
-      }
-      if (st.phase == PH_BACKWARD) solve_backward(tm, *inp, a.opts, w, st);
-      for (;;) {  // forward batches until every trial of the group has taken (or given up on) its step
-        const unsigned fw = __ballot_sync(0xffffffffu, st.phase == PH_FORWARD);
-        if (!fw) break;
-        const int src = wt * 8;
-        const int cur_w = k3_shfl_i(st.cur, src);
-        const int b0_w = k3_shfl_i(st.b0, src);
-        const double mu_w = k3_shfl_d(st.mu, src), Jp_w = k3_shfl_d(st.J_prev, src), dV1_w = k3_shfl_d(st.dV1, src),
-                     dV2_w = k3_shfl_d(st.dV2, src), cam_w = k3_shfl_d(st.clk_absmax, src);
-        const bool fwd_w = k3_shfl_i(st.phase, src) == PH_FORWARD;
-        double lg_w[8];
-        for (int i = 0; i < 8; ++i) lg_w[i] = k3_shfl_d(st.lam_g[i], src);
-        const TrialIn* in_w = reinterpret_cast<const TrialIn*>(warp_smem + wt * TEAM_SMEM_DOUBLES + SM_TRIAL);
-        __builtin_assume(__isShared(in_w));
-        TrialWork ww = w;   // gains / multipliers / field vectors of the trial being rolled out
-        ww.xu = warp_base + wt * per_slot;
-        ww.kd = ww.xu + 90 * cap;
-        ww.lam = ww.kd + 24 * cap;
-        ww.bk = ww.lam + 6 * cap;
-        ww.clk = ww.bk + 10 * cap;
-        const int n_cand = a.opts.max_linesearch + 1;
-        const int c = b0_w + 8 * part + tm.ln;
-        const bool live = fwd_w && (c < n_cand);
-        // candidate buffer: one of this team's own 9 buffers, never the one holding the current trajectory
-        const int lc = cur_w - team * 9;
-        const int bufi = team * 9 + ((lc >= 0 && lc < 9 && tm.ln >= lc) ? tm.ln + 1 : tm.ln);
-        double alpha = 1.0;
-        for (int i = 0; i < c; ++i) alpha /= 2.0;
-        const double sc = a.opts.stage_cost_dt ? a.dt : 1.0;
-        const long long tf0 = ts_clock();
-        RollOut r;
-        r.ok = false;
-        r.J = r.cmax = r.grad = 0.0;
-        if (fwd_w)  // team-uniform: teams whose trial is not in its forward phase just wait at the ballot below
-          r = forward_batch(tm, *in_w, a.opts, ww, xu_buf<TEAM>(w, cur_w), xu_buf<TEAM>(w, bufi), live, alpha, sc, mu_w, lg_w, cam_w);
-        bool acc = false;
-        if (live && r.ok) {
-          const double expected = -alpha * (dV1_w + alpha * dV2_w);
-          const double z = (expected > 0.0) ? (Jp_w - r.J) / expected : -1.0;
-          acc = !((z <= a.opts.ls_lower || z > a.opts.ls_upper) && (r.J >= Jp_w));
-        }
-        const unsigned bits32 = __ballot_sync(0xffffffffu, acc);
-        // the owner assembles its trial's acceptance bits in candidate order from the teams that computed each part
-        unsigned bits = 0;
-        if (wt == team) {
-          bits = (bits32 >> (8 * team)) & 0xffu;
-          if (nparts > 1) bits |= ((bits32 >> (8 * sp1)) & 0xffu) << 8;
-          if (nparts > 2) bits |= ((bits32 >> (8 * sp2)) & 0xffu) << 16;
-          if (nparts > 3) bits |= ((bits32 >> (8 * sp3)) & 0xffu) << 24;
-        }
-        const int step = 8 * nparts;
-        double Jn = 0.0, grad = 0.0, cmx = 0.0;
-        int cur_new = cur_w, a_idx = -1;
-        if (bits) a_idx = __ffs(bits) - 1;
-        {  // the accepted candidate's results travel to the owner's lanes
-          const int pa = a_idx >> 3;
-          const int st_team = (pa == 0) ? team : ((pa == 1) ? sp1 : ((pa == 2) ? sp2 : sp3));
-          const int sl = (a_idx < 0) ? lane32 : (8 * st_team + (a_idx & 7));
-          Jn = k3_shfl_d(r.J, sl);
-          cmx = k3_shfl_d(r.cmax, sl);
-          grad = k3_shfl_d(r.grad, sl);
-          cur_new = k3_shfl_i(bufi, sl);
-        }
-        __syncwarp();
-        if (st.phase == PH_FORWARD) {  // bookkeeping by the team that owns the trial
-          st.cyc_fwd += ts_clock() - tf0;
-          if (a_idx >= 0) {
-            st.ls_total += st.b0 + a_idx + 1;
-            st.c_max = cmx;
-            if (cur_new / 9 != team) {
-              // the winning candidate was rolled out by a helper into ITS slot: bring it home, so that a trial's
-              // current trajectory always lives in its own slot (a helper may serve another trial next time)
-              const int home = team * 9 + ((st.cur - team * 9) + 1) % 9;
-              const double* srcb = xu_buf<TEAM>(w, cur_new);
-              double* dstb = xu_buf<TEAM>(w, home);
-              const long long nd = (long long)inp->N * 10;
-              for (long long i = tm.ln; i < nd; i += TEAM) dstb[i] = srcb[i];
-              tm.sync();
-              cur_new = home;
-            }
-            st.cur = cur_new;
-            solve_after_forward(tm, *inp, a.opts, w, st, Jn, grad);
-          } else {
-            st.b0 += step;
-            if (st.b0 >= n_cand) {  // line search exhausted (App. C step 4)
-              st.ls_total += n_cand;
-              Reg reg;
-              reg.rho = st.rho;
-              reg.drho = st.drho;
-              reg_increase(a.opts, reg);
-              reg.rho += a.opts.bp_reg_fp;
-              st.rho = reg.rho;
-              st.drho = reg.drho;
-              const double* xc = xu_buf<TEAM>(w, st.cur);
-              double g = 0.0;
-              for (int k = tm.ln; k < inp->N - 1; k += TEAM) {
-                const double* p = xc + (long long)k * 10;
-                const double* kd = w.kd + (long long)k * 24;
-                double mxg = 0.0;
-                for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
-                g += mxg;
-              }
-              const double gr = tm.sum(g) / (double)(a.opts.a3_grad_over_N ? inp->N : inp->N - 1);
-              solve_after_forward(tm, *inp, a.opts, w, st, (st.it == 1) ? st.J_true : st.J_prev, gr);   // see solve_forward
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
+#include "k3_alilqr_body.inc"
 }
-
+#undef K3_BODY_TEAM
+#define K3_BODY_TEAM GpuTeamQuat
+__global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_quat_kernel(const K3Args a) {
+#include "k3_alilqr_body.inc"
+}
+#undef K3_BODY_TEAM
 // ---------------------------------------------------------------------------------------------
 // Second launch: every parked straggler is finished by ONE WHOLE WARP (32-lane team): 32 knots linearised per
 // chunk, all 21 line-search candidates in one batch, one warp per SM sub-partition when few trials are left.
@@ -538,159 +313,20 @@ __global__ void __launch_bounds__(1024, 1) k3_park_order_kernel(const K3Args a) 
   for (unsigned i = tid; i < n; i += 1024) a.park_order[atomicAdd(&start[bin_of(i)], 1)] = (int)i;
 }
 
-__global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
-  extern __shared__ __align__(16) double k3_smem[];
-  const int lane32 = threadIdx.x & 31;
-  const int64_t gwarp = blockIdx.x;
-  GpuWideTeam tm;
-  tm.ln = lane32;
-  tm.sm = k3_smem;
-  (void)gwarp;
-  // the warp's work pointers change with every region it takes from the pool, so they cannot be re-derived from kernel
-  // parameters the way the first launch does; they live in shared memory (one LDS per use) instead of eight 64-bit
-  // registers held across the whole solve in a kernel that already sits at the 255-register limit
-  __shared__ TrialWork w_sm;
-  TrialWork& w = w_sm;
-  if (lane32 == 0) {
-    w.Nmax = 0;
-    w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
-    w.slot_stride = 0;
-  }
-  __syncwarp();
-  long long region_cap = 0;   // knots the warp's current region can hold
-  const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
-  const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
-  unsigned n_parked = *a.park_count;
-  if (n_parked > (unsigned)a.park_cap) n_parked = (unsigned)a.park_cap;
-  for (;;) {
-    unsigned long long qpos = 0;
-    if (lane32 == 0) qpos = atomicAdd(a.queue2, 1ull);
-    qpos = __shfl_sync(0xffffffffu, qpos, 0);
-    if (qpos >= n_parked) break;
-    const int64_t idx = a.park_order[qpos];
-    const int64_t t = a.park_trial[idx];
-    const TrialIn& in = k3_load_trial(tm, a, t);
-    const int N = in.N;
-    const long long Ne = N + (N & 1);
-    if (Ne > region_cap) {  // first trial of this warp, or one longer than its region: take a new region from the pool
-      unsigned long long off = 0;
-      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * dpk));
-      off = __shfl_sync(0xffffffffu, off, 0);
-      if ((long long)(off + Ne * dpk) > a.pool_cap) {
-        // cannot happen: the host sizes the pool for the park_cap longest horizons; fail loudly rather than corrupt
-        if (lane32 == 0) {
-          ts_trial_outcome_dev oc = {};
-          oc.status = ST_NAN;
-          oc.N = N;
-          a.out[t] = oc;
-        }
-        continue;
-      }
-      region_cap = Ne;
-      __syncwarp();
-      if (lane32 == 0) {
-        w.Nmax = Ne;                                   // buffer i of the warp = xu_warp + i * Ne * 10 (see xu_buf)
-        w.slot_stride = 9 * Ne * 10;
-        w.xu = w.xu_warp = a.pool + off;
-        w.kd = w.xu + (long long)nbuf * 10 * Ne;
-        w.lam = w.kd + 24 * Ne;
-        w.bk = w.lam + 6 * Ne;
-        w.clk = w.bk + 10 * Ne;
-      }
-      __syncwarp();
-    }
-    const double* pd = a.park_data + a.park_off[idx];
-    for (int i = lane32; i < N * 10; i += 32) w.xu[i] = pd[i];
-    for (int i = lane32; i < N * 6; i += 32) w.lam[i] = pd[10 * Ne + i];
-    for (int i = lane32; i < N * 10; i += 32) w.bk[i] = pd[16 * Ne + i];
-    for (int i = lane32; i < N; i += 32) w.clk[i] = pd[26 * Ne + i];
-    TrialState st = a.park_state[idx];
-    st.cur = 0;
-    __syncwarp();
-    while (st.phase != PH_DONE) {
-      if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
-      while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
-    }
-    ts_trial_outcome_dev oc;
-    solve_finish(in, st, oc);
-    k3_store_results(tm, a, t, w, N, st.cur, oc, st);
-    __syncwarp();
-  }
-}
-constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
-
-// ---------------------------------------------------------------------------------------------
-// k3_quat_kernel: the QUATERNION-AWARE variant (ts_ilqr_opts.quat_error; solver switches in
-// ilqr_solver.cuh under team_quat): every trial is solved from its initial rollout by one whole warp -- the 32-lane team
-// of k3_wide_kernel with QUAT = true -- pulled from the horizon-sorted queue; a warp keeps the pool region of its first
-// (longest) trial.  No four-per-warp phase: the error-state Riccati step exists for the 30-lane layout only.
 struct GpuWideQuatTeam : GpuWideTeam {
   static constexpr bool QUAT = true;
 };
-__global__ void __launch_bounds__(32, 1) k3_quat_kernel(const K3Args a) {
-  extern __shared__ __align__(16) double k3_smem[];
-  const int lane32 = threadIdx.x & 31;
-  GpuWideQuatTeam tm;
-  tm.ln = lane32;
-  tm.sm = k3_smem;
-  __shared__ TrialWork w_sm;
-  TrialWork& w = w_sm;
-  if (lane32 == 0) {
-    w.Nmax = 0;
-    w.xu = w.xu_warp = w.kd = w.lam = w.bk = w.clk = nullptr;
-    w.slot_stride = 0;
-  }
-  __syncwarp();
-  long long region_cap = 0;
-  const int nbuf = k3_wide_buffers(a.opts.max_linesearch);
-  const long long dpk = k3_wide_doubles_per_knot(a.opts.max_linesearch);
-  for (;;) {
-    unsigned long long qpos = 0;
-    if (lane32 == 0) qpos = atomicAdd(a.queue2, 1ull);
-    qpos = __shfl_sync(0xffffffffu, qpos, 0);
-    if (qpos >= (unsigned long long)a.n_trials) break;
-    const int64_t t = a.order[qpos];
-    const TrialIn& in = k3_load_trial(tm, a, t);
-    const int N = in.N;
-    const long long Ne = N + (N & 1);
-    if (Ne > region_cap) {
-      unsigned long long off = 0;
-      if (lane32 == 0) off = atomicAdd(a.pool_used, (unsigned long long)(Ne * dpk));
-      off = __shfl_sync(0xffffffffu, off, 0);
-      if ((long long)(off + Ne * dpk) > a.pool_cap) {   // cannot happen (pool sized for the longest horizons): fail loudly
-        if (lane32 == 0) {
-          ts_trial_outcome_dev oc = {};
-          oc.status = ST_NAN;
-          oc.N = N;
-          a.out[t] = oc;
-        }
-        continue;
-      }
-      region_cap = Ne;
-      __syncwarp();
-      if (lane32 == 0) {
-        w.Nmax = Ne;
-        w.slot_stride = 9 * Ne * 10;
-        w.xu = w.xu_warp = a.pool + off;
-        w.kd = w.xu + (long long)nbuf * 10 * Ne;
-        w.lam = w.kd + 24 * Ne;
-        w.bk = w.lam + 6 * Ne;
-        w.clk = w.bk + 10 * Ne;
-      }
-      __syncwarp();
-    }
-    TrialState st;
-    solve_init(tm, in, a.opts, w, st);
-    while (st.phase != PH_DONE) {
-      if (st.phase == PH_BACKWARD) solve_backward(tm, in, a.opts, w, st);
-      while (st.phase == PH_FORWARD) solve_forward(tm, in, a.opts, w, st);
-    }
-    ts_trial_outcome_dev oc;
-    solve_finish(in, st, oc);
-    k3_store_results(tm, a, t, w, N, st.cur, oc, st);
-    __syncwarp();
-  }
+#define K3_BODY_TEAM GpuWideTeam
+__global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
+#include "k3_wide_body.inc"
 }
+#undef K3_BODY_TEAM
+#define K3_BODY_TEAM GpuWideQuatTeam
+__global__ void __launch_bounds__(32, 1) k3_wide_quat_kernel(const K3Args a) {
+#include "k3_wide_body.inc"
+}
+#undef K3_BODY_TEAM
+constexpr int K3_WIDE_SMEM_BYTES = SmL<32>::TOTAL * 8;
 
 // ---------------------------------------------------------------------------------------------
 // k3_pair_kernel: the one-warp-per-trial solver with a PRODUCER warp.  A straggler's latency is what ends the run, and

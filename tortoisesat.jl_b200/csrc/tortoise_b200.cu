@@ -508,78 +508,21 @@ static double slew_angle(const double* x0, const double* xf) {
 // pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel (stragglers handed over to one warp each).
 // The launch scheme is controlled by ts_ilqr_opts.k3_* (suspend_after, early_factor, tail_share).  Work is queued on
 // the context's stream; nothing here synchronises.
-// The quaternion-aware variant (opts.quat_error): one launch of k3_quat_kernel, one warp per trial from the initial rollout.
-static int k3_launch_quat(ts_ctx* c, K3Args& a, const int64_t* N_i_host) {
-  const int64_t n_trials = a.n_trials;
-  const int qm = (a.opts.goal_mask >> 3) & 0xF;
-  if (qm != 0 && qm != 0xF)
-    return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
-  int occ_w = 0;
-  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_quat_kernel, 32, K3_WIDE_SMEM_BYTES));
-  if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 quaternion kernel does not fit on an SM");
-  const int64_t warps = std::max<int64_t>(1, std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w));
-  std::vector<int64_t> order((size_t)n_trials);
-  std::iota(order.begin(), order.end(), (int64_t)0);
-  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return N_i_host[x] > N_i_host[y]; });
-  int rc;
-  int64_t* d_order = nullptr;
-  if ((rc = upload(c, 5, order.data(), (size_t)n_trials, &d_order))) return rc;
-  // a warp keeps the region of its first trial, and the queue is sorted by horizon: the `warps` longest horizons
-  const double dpk = (double)k3_wide_doubles_per_knot(a.opts.max_linesearch);
-  double pool_need = 0.0;
-  int64_t Nmax = 0;
-  for (int64_t i = 0; i < warps; ++i) pool_need += dpk * (double)(N_i_host[order[(size_t)i]] + 1);
-  for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
-  void *p_q, *p_diag, *p_pool;
-  if ((rc = scratch_reserve(c, 25, (size_t)pool_need * sizeof(double) + 256, &p_pool))) return rc;
-  if ((rc = scratch_reserve(c, 4, 128, &p_q))) return rc;
-  if ((rc = scratch_reserve(c, 19, (size_t)n_trials * 3 * sizeof(double) + 64, &p_diag))) return rc;
-  TS_CUDA(c, cudaMemsetAsync(p_q, 0, 128, c->stream));
-  TS_CUDA(c, cudaMemsetAsync(p_diag, 0, (size_t)n_trials * 3 * sizeof(double), c->stream));
-  a.order = d_order;
-  a.Nmax = Nmax + (Nmax & 1);
-  a.w_base = nullptr;
-  a.warp_off = nullptr;
-  a.warp_cap = nullptr;
-  a.n_warps = warps;
-  a.pool = (double*)p_pool;
-  a.pool_used = (unsigned long long*)p_q + 10;
-  a.pool_cap = (long long)pool_need;
-  a.queue = (unsigned long long*)p_q;
-  a.queue2 = (unsigned long long*)p_q + 2;
-  a.diag = (double*)p_diag;
-  c->k3_diag_n = n_trials;
-  a.tail_share = 0;
-  a.park_budget = 0;
-  a.park_budget_early = 0;
-  a.park_cap = 0;
-  a.park_count = (unsigned*)p_q + 8;
-  a.park_used = (unsigned long long*)p_q + 5;
-  a.park_state = nullptr;
-  a.park_trial = nullptr;
-  a.park_off = nullptr;
-  a.park_data = nullptr;
-  a.park_data_cap = 0;
-  a.park_order = nullptr;
-  c->k3_timed = true;
-  c->d_k3_parked = a.park_count;
-  c->k3_park_cap = 0;
-  TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
-  TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
-  k3_quat_kernel<<<(unsigned)warps, 32, K3_WIDE_SMEM_BYTES, c->stream>>>(a);
-  c->launches++;
-  TS_CUDA(c, cudaGetLastError());
-  TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
-  return TS_OK;
-}
-
 static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
-  if (a.opts.quat_error) return k3_launch_quat(c, a, N_i_host);
   const int64_t n_trials = a.n_trials;
+  // the quaternion-aware variant (opts.quat_error) runs the same two-launch scheme on the QUAT instantiations
+  const bool quat = a.opts.quat_error != 0;
+  if (quat) {
+    const int qm = (a.opts.goal_mask >> 3) & 0xF;
+    if (qm != 0 && qm != 0xF)
+      return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
+  }
+  void (*const narrow_kernel)(const K3Args) = quat ? k3_alilqr_quat_kernel : k3_alilqr_kernel;
+  void (*const wide_kernel)(const K3Args) = quat ? k3_wide_quat_kernel : k3_wide_kernel;
   int64_t Nmax = 0;
   for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
   int occ = 0;
-  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_alilqr_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, narrow_kernel, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES));
   if (occ < 1) return fail(c, TS_ERR_CUDA, "k3 kernel does not fit on an SM");
   const int64_t groups = (n_trials + 3) / 4;
   const int64_t max_warps = (int64_t)c->sm_count * occ * K3_WARPS_PER_BLOCK;
@@ -589,10 +532,10 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   // the one-warp-per-trial launch uses four slots (36 trajectory buffers) per warp: up to a full wave of warps,
   // never more than there can be parked trials
   int occ_w = 0;
-  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, k3_wide_kernel, 32, K3_WIDE_SMEM_BYTES));
+  TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, wide_kernel, 32, K3_WIDE_SMEM_BYTES));
   if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
   int64_t wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w);
-  const bool pair = a.opts.k3_pair != 0;
+  const bool pair = a.opts.k3_pair != 0 && !quat;   // (the producer-warp kernel exists for the default solver only)
   int wide_smem = K3_WIDE_SMEM_BYTES;
   if (pair) {
     int occ_p = 0;
@@ -603,9 +546,9 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   } else if (a.opts.k3_wide_occ > 0 && a.opts.k3_wide_occ < occ_w) {
     // fewer blocks per SM: pad the dynamic shared memory so that exactly k3_wide_occ one-warp blocks fit
     wide_smem = std::max(K3_WIDE_SMEM_BYTES, (227 * 1024 / (a.opts.k3_wide_occ + 1) + 1024) & ~15);
-    TS_CUDA(c, cudaFuncSetAttribute(k3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
+    TS_CUDA(c, cudaFuncSetAttribute(wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem));
     int occ2 = 0;
-    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k3_wide_kernel, 32, wide_smem));
+    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, wide_kernel, 32, wide_smem));
     wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * std::max(occ2, 1));
   }
   // Queue order.  (1) sort by horizon (descending): the four teams of a warp get similar trip counts.
@@ -744,7 +687,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   c->d_k3_parked = a.park_count;
   c->k3_park_cap = a.park_cap;
   TS_CUDA(c, cudaEventRecord(c->ev_k3[0], c->stream));
-  k3_alilqr_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
+  narrow_kernel<<<blocks, K3_WARPS_PER_BLOCK * 32, K3_SMEM_BYTES, c->stream>>>(a);
   c->launches++;
   TS_CUDA(c, cudaGetLastError());
   TS_CUDA(c, cudaEventRecord(c->ev_k3[1], c->stream));
@@ -756,7 +699,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     if (pair)
       k3_pair_kernel<<<(blocks_w + K3_PAIRS_PER_BLOCK - 1) / K3_PAIRS_PER_BLOCK, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES, c->stream>>>(a);
     else
-      k3_wide_kernel<<<blocks_w, 32, wide_smem, c->stream>>>(a);
+      wide_kernel<<<blocks_w, 32, wide_smem, c->stream>>>(a);
     c->launches += 2;
     TS_CUDA(c, cudaGetLastError());
     TS_CUDA(c, cudaEventRecord(c->ev_k3[2], c->stream));
