@@ -190,10 +190,12 @@ def test_fused_monte_carlo_sweep_and_no_cutoff(engine):
     assert np.all(out2["status"] == 5) and st2.n_no_cutoff == n
 
 
-def test_bench_ensemble_sample_matches_oracle(engine):
+@pytest.mark.parametrize("quat", [0, 1])
+def test_bench_ensemble_sample_matches_oracle(engine, quat):
     """The first 16 trials of bench.py's configs[2] ensemble at FULL size (N = 2044 knots, random attitudes on S^3,
     20 x 50 AL-iLQR iterations; several of them go through the straggler hand-over): identical status and
-    outer / inner / line-search counters, converged cost and constraint violation to 1e-6 (north_star's bar)."""
+    outer / inner / line-search counters, converged cost and constraint violation to 1e-6 (north_star's bar).
+    quat = 1: the same with the quaternion-aware solver variant (ts_ilqr_opts.quat_error)."""
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
     import bench as B
@@ -205,6 +207,7 @@ def test_bench_ensemble_sample_matches_oracle(engine):
         sub[k] = tr[k][:n]
     cfg = B.mc_config(host, sub, n)
     cfg.run_tvlqr = 0
+    cfg.ilqr.quat_error = quat
     fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
     fo[0] = tr["fo"][0]
     out, st = engine.monte_carlo_run(cfg, tr["kep"], fo, sub["x0"], sub["xf"], sub["Jm"], q_noise0=sub["qn"])
@@ -216,7 +219,9 @@ def test_bench_ensemble_sample_matches_oracle(engine):
                          cutoff=tr["cutoff"], alpha=0.1, **({} if base is None else dict(t_final=base.t_final)))
         base = base or s
         slews.append(s)
-    Xs, Us, Ks, ref = S.oracle_solve(slews, nthreads=orc.lib().orc_max_threads(), want_K=False)
+    oo = orc.default_ilqr_opts()
+    oo.quat_error = quat
+    Xs, Us, Ks, ref = S.oracle_solve(slews, oo, nthreads=orc.lib().orc_max_threads(), want_K=False)
     for t in range(n):
         g, r = out[t], ref[t]
         assert g["N"] == slews[t].N == 2044

@@ -1,4 +1,7 @@
-"""GPU probe: the first n trials of the benchmark ensemble (configs[2], N = 2044) through ts_monte_carlo_run vs the CPU oracle."""
+"""GPU probe: the first n trials of the benchmark ensemble (configs[2], N = 2044) through ts_monte_carlo_run vs the CPU oracle.
+
+  python tools/parity_sample.py [n] [--quat]      --quat: the quaternion-aware solver variant (ts_ilqr_opts.quat_error = 1)
+"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -8,7 +11,8 @@ import slew_setup as S
 import tortoisesat.jl_b200 as tb
 from tortoisesat.jl_b200 import host
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 32
+quat = "--quat" in sys.argv
 eng = tb.Engine(0)
 tr = B.make_trials("mc_fixed_orbit", 4096, 0)
 sub = dict(tr)
@@ -16,6 +20,7 @@ for k in ("x0", "xf", "Jm", "qn"):
     sub[k] = tr[k][:n]
 cfg = B.mc_config(host, sub, n)
 cfg.run_tvlqr = 0
+cfg.ilqr.quat_error = 1 if quat else 0
 fo = np.zeros(1, dtype=host.FIELD_OPTS_DTYPE)
 fo[0] = tr["fo"][0]
 out, st = eng.monte_carlo_run(cfg, tr["kep"], fo, sub["x0"], sub["xf"], sub["Jm"], q_noise0=sub["qn"], stream_id=np.arange(n).astype(np.uint32))
@@ -29,7 +34,9 @@ for t in range(n):
                      alpha=0.1, **({} if base is None else dict(t_final=base.t_final)))
     base = base or s
     slews.append(s)
-Xs, Us, Ks, ref = S.oracle_solve(slews, nthreads=S.orc.lib().orc_max_threads(), want_K=False)
+oo = S.orc.default_ilqr_opts()
+oo.quat_error = 1 if quat else 0
+Xs, Us, Ks, ref = S.oracle_solve(slews, oo, nthreads=S.orc.lib().orc_max_threads(), want_K=False)
 print("oracle s", time.time() - t0)
 nbad = 0
 for t in range(n):
