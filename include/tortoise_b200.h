@@ -161,10 +161,13 @@ typedef struct ts_ilqr_opts {
   int32_t k3_suspend_after;       /* 150 */
   int32_t k3_tail_share;          /* 1   */
   double k3_early_factor;         /* 2.0 */
-  int32_t k3_pair;                /* 0; 1: the one-warp-per-trial launch runs as k3_pair_kernel: 4 solver warps per SM, each
+  int32_t k3_pair;                /* 2; 1: the one-warp-per-trial launch runs as k3_pair_kernel: 4 solver warps per SM, each
                                         with a producer warp (same SM sub-partition) that linearises the next 32-knot chunk
-                                        while the solver runs the Riccati steps.  Same results; 5 % faster per iteration
-                                        when few trials are left, slower on a full ensemble (half the solver warps)  */
+                                        while the solver runs the Riccati steps; 0: never; 2: when the ensemble's horizons
+                                        are ragged (longest >= 2 x mean).  Same algorithm (last-bit differences from FMA
+                                        contraction, like between the two default kernels).  Measured: slower on an
+                                        equal-horizon ensemble (half the solver warps: 6.32 s vs 5.72 s), faster on the
+                                        sweep, whose second launch is the chain of a few very long slews (13.4 s vs 16.2 s) */
   int32_t k3_wide_occ;            /* 0: as many one-warp blocks per SM as fit (8); n > 0: at most n.  Measured on the
                                         4096-trial ensemble: 8 -> 5.72 s, 6 -> 5.98 s, 4 -> 6.64 s, 2 -> 10.5 s            */
   int32_t quat_error;             /* 0; 1: the quaternion-aware variant the reference's Monte-Carlo script requests from its forked

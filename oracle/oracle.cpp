@@ -200,7 +200,7 @@ void orc_ilqr_default_opts(orc_ilqr_opts* s) {
   s->a2_active_ge = o.a2_active_ge; s->a3_grad_over_N = o.a3_grad_over_N; s->a4_no_intermediate = o.a4_no_intermediate;
   s->a5_dual_active_only = o.a5_dual_active_only; s->a6_penalty_conditional = o.a6_penalty_conditional;
   s->a7_carry_cost = o.a7_carry_cost; s->constraint_decrease_ratio = o.constraint_decrease_ratio;
-  s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 0; s->k3_wide_occ = 0;
+  s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 2; s->k3_wide_occ = 0;
   s->quat_error = o.quat_error; s->pad_ = 0;
 }
 

@@ -493,7 +493,7 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
   o->a2_active_ge = 0; o->a3_grad_over_N = 0; o->a4_no_intermediate = 0; o->a5_dual_active_only = 0;
   o->a6_penalty_conditional = 0; o->a7_carry_cost = 0; o->constraint_decrease_ratio = 0.25;
-  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 0; o->k3_wide_occ = 0; o->quat_error = 0; o->pad_ = 0;
+  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 2; o->k3_wide_occ = 0; o->quat_error = 0; o->pad_ = 0;
 }
 
 // slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
@@ -535,7 +535,15 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, wide_kernel, 32, K3_WIDE_SMEM_BYTES));
   if (occ_w < 1) return fail(c, TS_ERR_CUDA, "k3 wide kernel does not fit on an SM");
   int64_t wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_w);
-  const bool pair = a.opts.k3_pair != 0 && !quat;   // (the producer-warp kernel exists for the default solver only)
+  // second launch with a producer warp per solver warp (k3_pair_kernel): 1 = always, 0 = never, 2 = when the horizons are
+  // ragged (longest >= 2 x mean).  Measured: on the fixed-orbit ensemble (all horizons equal, 2243 stragglers on 1184
+  // warps) halving the solver warps costs more than the hidden linearisation gains (6.32 s vs 5.72 s); on the sweep the
+  // second launch is the sequential chain of a few very long slews and the producer shortens exactly that chain
+  // (13.4 s vs 16.2 s).  (The producer-warp kernel exists for the default solver only.)
+  double N_mean = 0.0;
+  for (int64_t t = 0; t < n_trials; ++t) N_mean += (double)N_i_host[t];
+  N_mean /= (double)std::max<int64_t>(n_trials, 1);
+  const bool pair = !quat && (a.opts.k3_pair == 1 || (a.opts.k3_pair == 2 && (double)Nmax >= 2.0 * N_mean));
   int wide_smem = K3_WIDE_SMEM_BYTES;
   if (pair) {
     int occ_p = 0;
