@@ -30,18 +30,20 @@ def up_to_date():
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: a variant build (-DNAME=VALUE ...) into another file, for A/B runs through TS_B200_LIB."""
+    if not force and not defines and out is None and up_to_date():
         return LIB
+    out = out or LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++", "-o", LIB,
-                                                                           os.path.join(CSRC, "tortoise_b200.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + [
+        "-ccbin", "/usr/bin/g++", "-o", out, os.path.join(CSRC, "tortoise_b200.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

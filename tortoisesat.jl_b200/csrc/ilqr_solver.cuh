@@ -70,27 +70,53 @@ TS_HD long long ts_clock() {
 enum { ST_CONVERGED = 0, ST_MAX_OUTER = 1, ST_COST_BLOWUP = 2, ST_REG_MAX = 3, ST_NAN = 4, ST_NO_CUTOFF = 5 };
 
 constexpr int TEAM = 8;                       // lanes of a (narrow) team
-constexpr int REC = 84;                       // doubles per knot record in shared memory
+// Shared-memory strides (compile-time, overridable for A/B builds; the round-1 layout is TS_SMEM_SKEW=0).  Measured on the
+// 4096-trial benchmark ensemble, K3 time with the cofactor Quu solve: round-1 layout (84 / 8 / regions 128-byte
+// multiples apart) 7.35 s -> 85 / 9 / skewed 7.04 s -> 84 / 10 / skewed 6.95 s -> 86 / 9 / skewed 6.92 s.
+#ifndef TS_SMEM_SKEW
+#define TS_SMEM_SKEW 1
+#endif
+#ifndef TS_REC
+#define TS_REC (TS_SMEM_SKEW ? 86 : 84)
+#endif
+#ifndef TS_SS
+#define TS_SS (TS_SMEM_SKEW ? 9 : 8)
+#endif
+// doubles per knot record in shared memory (84 used).  The lanes of a chunk write their records side by side: with a
+// stride of 84 doubles (672 B = 32 mod 128) 32 lanes share four 8-byte bank slots, with 86 (48 mod 128) eight, and the
+// records stay 16-byte aligned for the vectorised reads of the Riccati step (85 would be conflict-free but costs them).
+constexpr int REC = TS_REC;
 constexpr int FWD_REC = 50;                   // [x7 u3 | K 21 d 3 | lam 6 | B 9 +pad] doubles per staged knot
 // Shared-memory layout of a team of W lanes (W = 8: one of four teams of a warp; W = 32: the whole warp
 // working on ONE trial -- "wide" mode, used for the straggler of a warp once its three siblings are done).
 template <int W>
 struct SmL {
   static constexpr int REC0 = 0;                   // [W][REC]   Jacobians + cost gradients of the chunk
-  static constexpr int SCOL = REC0 + W * REC;      // [7][8]     new S columns
-  static constexpr int SVEC = SCOL + 56;           // [8]        new s
-  static constexpr int KQ = SVEC + 8;              // [7][6]     K(:,j), Qux(:,j)
+  // row stride of S and of M = S*[A|B]: the whole-warp step reads them by row AND by column from 28-30 lanes at once,
+  // and a narrow team's lanes store one column each; with a stride of 8 doubles 7-10 rows fall on two 8-byte bank
+  // slots (4- and 5-way conflicts), with 9 every row starts on its own slot (whole-warp step: 141 -> 78 shared-memory
+  // wavefronts in stages A + B of a knot)
+  static constexpr int SS = TS_SS;
+  static constexpr int SCOL = REC0 + W * REC;      // [7][SS]    new S columns
+  static constexpr int SVEC = SCOL + 7 * SS;       // [7]        new s
+  static constexpr int KQ = SVEC + ((TS_SS & 1) ? 7 : 8);   // [7][6]     K(:,j), Qux(:,j)
   static constexpr int QUU = KQ + 42;              // [9] Quu, [3] Qu
-  static constexpr int MM = QUU + 12;              // whole-warp team only: [10][8] M = S*[A|B], [10] q = [A|B]'*s
-  static constexpr int QV = MM + 80;
-  static constexpr int BWD_END = QUU + 12 + (W >= 32 ? 92 : 0);
+  static constexpr int MM = QUU + 12;              // whole-warp team only: [10][SS] M = S*[A|B], [10] q = [A|B]'*s
+  static constexpr int QV = MM + 10 * SS;
+  static constexpr int BWD_END = QUU + 12 + (W >= 32 ? 10 * SS + 12 : 0);
   static constexpr int FWD = 0;                    // [2][W][FWD_REC] staged chunks of the forward pass (overlay)
   static constexpr int FWD_END = 2 * W * FWD_REC;
   static constexpr int WORK = (BWD_END > FWD_END ? BWD_END : FWD_END) + ((BWD_END > FWD_END ? BWD_END : FWD_END) & 1);
   static constexpr int TRIAL = WORK;               // the trial's TrialIn block (read-only during the solve)
   static constexpr int TOTAL = WORK + 64;
 };
-constexpr int TEAM_SMEM_DOUBLES = SmL<TEAM>::TOTAL;   // 864 doubles = 6912 B per narrow team
+// 876 doubles = 7008 B per narrow team.  876 = 12 (mod 16): the four teams of a warp run the same code on their own
+// regions, and most of their shared-memory reads are team-wide broadcasts (one address per team); with regions a
+// multiple of 128 B apart the four addresses of such a read share their banks (4 wavefronts), +-32 B of skew per team
+// puts them on four different 8-byte slots (1 wavefront), and an 8-lane row (64 B per team) takes the minimum of 2.
+constexpr int TEAM_SMEM_DOUBLES = SmL<TEAM>::TOTAL;
+static_assert(!TS_SMEM_SKEW || TEAM_SMEM_DOUBLES % 16 == 4 || TEAM_SMEM_DOUBLES % 16 == 12, "narrow team regions must be skewed by 32 B (mod 128 B)");
+static_assert(8 * (4 * TEAM_SMEM_DOUBLES * 8 + 1024) <= 233472, "eight four-team warps per SM must fit the 228 KB of shared memory");
 static_assert(SmL<32>::TOTAL <= 4 * SmL<TEAM>::TOTAL, "the wide layout must fit the four narrow regions of a warp");
 constexpr int SM_TRIAL = SmL<TEAM>::TRIAL;
 
@@ -229,6 +255,48 @@ TS_HD void chol3_solve(const double L[9], const double b[3], double x[3]) {
   x[2] = y[2] * L[8];
   x[1] = (y[1] - L[7] * x[2]) * L[4];
   x[0] = (y[0] - L[3] * x[1] - L[6] * x[2]) * L[0];
+}
+
+// The 3x3 system of the backward pass as it sits on the critical path of every knot.  Default (TS_QUU_SOLVER = 1): the
+// symmetric cofactor matrix and ONE reciprocal of the determinant -- cofactors (2 dependent FP64 operations), determinant
+// (3), reciprocal, and a solve is three independent 3-term dot products scaled by 1/det, which do not wait for the
+// reciprocal: ~15 dependent operations for "factor + solve" instead of ~50 with three chained rsqrt in the Cholesky
+// factor and the two triangular sweeps.  The PD test is Sylvester's criterion on the same matrix (leading minors
+// a00, a00 a11 - a01^2, det > 0), which is the Cholesky pivot test (s0 = a00, s1 = m2 / a00, s2 = det / m2) in exact
+// arithmetic.  TS_QUU_SOLVER = 0 compiles the reciprocal-Cholesky version back in (A/B and flop counting).
+#ifndef TS_QUU_SOLVER
+#define TS_QUU_SOLVER 1
+#endif
+TS_HD bool quu_factor(const double A[9], double F[9]) {
+#if TS_QUU_SOLVER == 0
+  return chol3(A, F);
+#else
+  const double a00 = A[0], a01 = A[3], a02 = A[6], a11 = A[4], a12 = A[7], a22 = A[8];   // lower triangle, as chol3 reads it
+  const double c00 = a11 * a22 - a12 * a12;
+  const double c01 = a02 * a12 - a01 * a22;
+  const double c02 = a01 * a12 - a02 * a11;
+  const double c11 = a00 * a22 - a02 * a02;
+  const double c12 = a01 * a02 - a00 * a12;
+  const double c22 = a00 * a11 - a01 * a01;
+  const double det = a00 * c00 + a01 * c01 + a02 * c02;
+  F[0] = c00; F[1] = c01; F[2] = c02; F[3] = c11; F[4] = c12; F[5] = c22;
+#ifdef __CUDA_ARCH__
+  F[6] = __drcp_rn(det);
+#else
+  F[6] = 1.0 / det;
+#endif
+  F[7] = F[8] = 0.0;
+  return (a00 > 0.0) & (c22 > 0.0) & (det > 0.0);
+#endif
+}
+TS_HD void quu_solve(const double F[9], const double b[3], double x[3]) {
+#if TS_QUU_SOLVER == 0
+  chol3_solve(F, b, x);
+#else
+  x[0] = (F[0] * b[0] + F[1] * b[1] + F[2] * b[2]) * F[6];
+  x[1] = (F[1] * b[0] + F[3] * b[1] + F[4] * b[2]) * F[6];
+  x[2] = (F[2] * b[0] + F[4] * b[1] + F[5] * b[2]) * F[6];
+#endif
 }
 
 struct StageAL {  // stage cost pieces at (x,u)
@@ -385,7 +453,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           sx = (lane < 6) ? G[0][a_] * v[0] + G[1][a_] * v[1] + G[2][a_] * v[2] + G[3][a_] * v[3] : 0.0;
         }
       }
-      for (int i = 0; i < 7; ++i) sm[L::SCOL + lane * 8 + i] = (i == lane) ? sxx : 0.0;
+      for (int i = 0; i < 7; ++i) sm[L::SCOL + lane * L::SS + i] = (i == lane) ? sxx : 0.0;
       sm[L::SVEC + lane] = sx;
     }
     bool not_pd = false;
@@ -434,7 +502,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           {  // ---- stage A: lanes 0..27 one row of S against up to three columns; lanes 28..31 the vector s
             double X[7];
             for (int l = 0; l < 7; ++l) {
-              const double srow = 0.5 * (sm[L::SCOL + l * 8 + li] + sm[L::SCOL + li * 8 + l]);
+              const double srow = 0.5 * (sm[L::SCOL + l * L::SS + li] + sm[L::SCOL + li * L::SS + l]);
               X[l] = rowlane ? srow : sm[L::SVEC + l];
             }
             const int c0 = rowlane ? lg : lane - 28;
@@ -443,7 +511,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               const int cc = c < 10 ? c : 9;
               double t = 0.0;
               for (int l = 0; l < 7; ++l) t += X[l] * rec[cc * 7 + l];
-              if (c < 10) sm[rowlane ? (L::MM + c * 8 + li) : (L::QV + c)] = t;
+              if (c < 10) sm[rowlane ? (L::MM + c * L::SS + li) : (L::QV + c)] = t;
             }
           }
           tm.sync();
@@ -452,7 +520,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             double arow[7];
             for (int l = 0; l < 7; ++l) arow[l] = rec[li * 7 + l];
             double t = 0.0;
-            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j0 * 8 + l];
+            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j0 * L::SS + l];
             if constexpr (team_quat<Team>::value) {   // l_xx(li, li) in error coordinates
               const double qd_li = (li < 3) ? sc * in.Qd[li] : ((li < 6) ? rec[83] : 0.0);
               Qxx0 = t + ((li == j0) ? qd_li : 0.0);
@@ -460,7 +528,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               Qxx0 = t + ((li == j0) ? sc * in.Qd[li] : 0.0);
             }
             t = 0.0;
-            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j1 * 8 + l];
+            for (int l = 0; l < 7; ++l) t += arow[l] * sm[L::MM + j1 * L::SS + l];
             if constexpr (team_quat<Team>::value) {
               const double qd_li = (li < 3) ? sc * in.Qd[li] : ((li < 6) ? rec[83] : 0.0);
               Qxx1 = t + ((li == j1) ? qd_li : 0.0);
@@ -471,7 +539,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             const int u = isux ? lane : (lane < 30 ? lane - 21 : 0);
             const int rr = u % 3, cc = isux ? u / 3 : 7 + u / 3;
             t = 0.0;
-            for (int l = 0; l < 7; ++l) t += rec[(7 + rr) * 7 + l] * sm[L::MM + cc * 8 + l];
+            for (int l = 0; l < 7; ++l) t += rec[(7 + rr) * 7 + l] * sm[L::MM + cc * L::SS + l];
             const double tq = t + ((rr == cc - 7) ? rec[80 + rr] : 0.0);
             if (lane < 30) sm[isux ? (L::KQ + cc * 3 + rr) : (L::QUU + rr * 3 + (cc - 7))] = isux ? t : tq;   // Qux(rr,cc) | Quu(rr,cc-7)
           }
@@ -481,14 +549,14 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           for (int i = 0; i < 3; ++i) Qu[i] = rec[77 + i] + sm[L::QV + 7 + i];
           for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
-          if (!chol3(Qr, Lc)) {
+          if (!quu_factor(Qr, Lc)) {
             not_pd = true;  // identical decision in every lane
             break;
           }
           double d[3], Quud[3];
           {
             const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
-            chol3_solve(Lc, nb, d);
+            quu_solve(Lc, nb, d);
             for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
           }
           for (int l = 0; l < 3; ++l) {
@@ -501,7 +569,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
             for (int c = 0; c < 3; ++c) Quxi[c] = sm[L::KQ + li * 3 + c];
             {
               const double nb[3] = {-Quxi[0], -Quxi[1], -Quxi[2]};
-              chol3_solve(Lc, nb, Ki);
+              quu_solve(Lc, nb, Ki);
             }
             if (lane < 7)
               for (int c = 0; c < 3; ++c) kdk[li * 3 + c] = Ki[c];
@@ -513,7 +581,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               double Quxj[3], Kj[3], QuuK[3];
               for (int c = 0; c < 3; ++c) Quxj[c] = sm[L::KQ + j * 3 + c];
               const double nb[3] = {-Quxj[0], -Quxj[1], -Quxj[2]};
-              chol3_solve(Lc, nb, Kj);
+              quu_solve(Lc, nb, Kj);
               for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kj[0] + Quu[i * 3 + 1] * Kj[1] + Quu[i * 3 + 2] * Kj[2];
               double t = q ? Qxx1 : Qxx0;
               for (int l = 0; l < 3; ++l) t += Ki[l] * QuuK[l];
@@ -523,7 +591,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               for (int l = 0; l < 3; ++l) ts += Kj[l] * Quud[l];
               for (int l = 0; l < 3; ++l) ts += Kj[l] * Qu[l];
               for (int l = 0; l < 3; ++l) ts += Quxj[l] * d[l];
-              if (valid) sm[L::SCOL + j * 8 + li] = t;
+              if (valid) sm[L::SCOL + j * L::SS + li] = t;
               if (valid && li == j) sm[L::SVEC + j] = ts;
             }
           }
@@ -532,7 +600,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           // ---- P0: value function of knot k+1 from shared memory, symmetrised (App. C: Sxx = (Sxx+Sxx')/2)
           double S[28], s[7];
           for (int i = 0; i < 7; ++i)
-            for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[L::SCOL + j * 8 + i] + sm[L::SCOL + i * 8 + j]);
+            for (int j = i; j < 7; ++j) S[sym_idx(i, j)] = 0.5 * (sm[L::SCOL + j * L::SS + i] + sm[L::SCOL + i * L::SS + j]);
           for (int i = 0; i < 7; ++i) s[i] = sm[L::SVEC + i];
           // ---- P1: column products
           double Qxxc[7], Quxc[3], Qx = 0.0;
@@ -587,20 +655,20 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
           for (int i = 0; i < 3; ++i) Qu[i] = sm[L::QUU + 9 + i];
           for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = 0.5 * (Quu[i * 3 + j] + Quu[j * 3 + i]) + ((i == j) ? reg.rho : 0.0);
-          if (!chol3(Qr, L)) {
+          if (!quu_factor(Qr, L)) {
             not_pd = true;  // identical decision in every lane of the team
             break;
           }
           double Kc[3] = {0.0, 0.0, 0.0}, d[3], Quud[3], QuuK[3] = {0.0, 0.0, 0.0};
           {
             const double nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
-            chol3_solve(L, nb, d);
+            quu_solve(L, nb, d);
             for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3 + 0] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
           }
           double* kdk = gptr(w.kd) + (long long)k * 24;
           if (lane < 7) {
             const double nb[3] = {-Quxc[0], -Quxc[1], -Quxc[2]};
-            chol3_solve(L, nb, Kc);
+            quu_solve(L, nb, Kc);
             for (int i = 0; i < 3; ++i) QuuK[i] = Quu[i * 3 + 0] * Kc[0] + Quu[i * 3 + 1] * Kc[1] + Quu[i * 3 + 2] * Kc[2];
             for (int c = 0; c < 3; ++c) {
               sm[L::KQ + lane * 6 + c] = Kc[c];
@@ -623,7 +691,7 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               for (int l = 0; l < 3; ++l) t += kq[l] * QuuK[l];
               for (int l = 0; l < 3; ++l) t += kq[l] * Quxc[l];
               for (int l = 0; l < 3; ++l) t += kq[3 + l] * Kc[l];
-              sm[L::SCOL + lane * 8 + i] = t;
+              sm[L::SCOL + lane * L::SS + i] = t;
             }
             double t = Qx;
             for (int l = 0; l < 3; ++l) t += Kc[l] * Quud[l];

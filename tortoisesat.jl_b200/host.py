@@ -107,7 +107,8 @@ class TortoiseError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libtortoise_b200.so")
+    """The in-tree library; TS_B200_LIB selects another build of the same sources (A/B runs of compile-time variants)."""
+    return os.environ.get("TS_B200_LIB") or os.path.join(_HERE, "libtortoise_b200.so")
 
 
 def load_library():
