@@ -46,6 +46,24 @@ TS_HD void cross3(const double a[3], const double b[3], double o[3]) {
   o[1] = a[2] * b[0] - a[0] * b[2];
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
+// J*w and Jinv*r.  DJ = true: the inertia matrix is diagonal (principal axes: every preset of input_parameters.jl:4-66) and
+// the products with its exact zeros are left out: the same values (x + 0*y == x), 3 instead of 9 operations per product.
+template <bool DJ>
+TS_HD void mul_J(const Inertia& I, const double w[3], double o[3]) {
+  if (DJ) {
+    o[0] = I.J[0] * w[0]; o[1] = I.J[4] * w[1]; o[2] = I.J[8] * w[2];
+  } else {
+    for (int i = 0; i < 3; ++i) o[i] = I.J[i * 3 + 0] * w[0] + I.J[i * 3 + 1] * w[1] + I.J[i * 3 + 2] * w[2];
+  }
+}
+template <bool DJ>
+TS_HD void mul_Jinv(const Inertia& I, const double r[3], double o[3]) {
+  if (DJ) {
+    o[0] = I.Jinv[0] * r[0]; o[1] = I.Jinv[4] * r[1]; o[2] = I.Jinv[8] * r[2];
+  } else {
+    for (int i = 0; i < 3; ++i) o[i] = I.Jinv[i * 3 + 0] * r[0] + I.Jinv[i * 3 + 1] * r[1] + I.Jinv[i * 3 + 2] * r[2];
+  }
+}
 // Hamilton product, scalar first (qmult.jl:1-3)
 TS_HD void qmult(const double a[4], const double b[4], double o[4]) {
   o[0] = a[0] * b[0] - (a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
@@ -68,7 +86,7 @@ TS_HD void qrot(const double q[4], const double r[3], double o[3]) {
 
 // xdot = f(x,u) for x = [omega(3); q(4)], field row Bn (ECI, Tesla).
 // u_scale_mode 0: u*1e-2 (DerivFunction.jl:37); 1: u/100 (simulator/gain_simulator) -- quirk Q8.
-template <int UMODE>
+template <int UMODE, bool DJ = false>
 TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7]) {
   const double inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
   const double q[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
@@ -85,10 +103,10 @@ TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const d
   }
   double tau[3], Jw[3], wJw[3];
   cross3(us, BB, tau);
-  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * x[0] + I.J[i * 3 + 1] * x[1] + I.J[i * 3 + 2] * x[2];
+  mul_J<DJ>(I, x, Jw);
   cross3(x, Jw, wJw);
-  const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
-  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
+  const double r[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
+  mul_Jinv<DJ>(I, r, dx);
   for (int i = 0; i < 4; ++i) dx[3 + i] = 0.5 * qd[i];
 }
 
@@ -198,17 +216,17 @@ TS_HD void dyn_f_jac(const Inertia& I, const double x[7], const double u[3], con
 }
 
 // rk3 ZOH step (attitude_controller.jl:178-187 == TrajOpt rk3); Bs = field rows of the 3 stages.
-template <int UMODE>
+template <int UMODE, bool DJ = false>
 TS_HD void rk3_step7(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
                      double dt, double xn[7]) {
   double k1[7], k2[7], k3[7], xs[7];
-  dyn_f<UMODE>(I, x, u, B1, k1);
+  dyn_f<UMODE, DJ>(I, x, u, B1, k1);
   for (int i = 0; i < 7; ++i) k1[i] = k1[i] * dt;
   for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * k1[i];
-  dyn_f<UMODE>(I, xs, u, B2, k2);
+  dyn_f<UMODE, DJ>(I, xs, u, B2, k2);
   for (int i = 0; i < 7; ++i) k2[i] = k2[i] * dt;
   for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] + 2.0 * k2[i];
-  dyn_f<UMODE>(I, xs, u, B3, k3);
+  dyn_f<UMODE, DJ>(I, xs, u, B3, k3);
   for (int i = 0; i < 7; ++i) k3[i] = k3[i] * dt;
   for (int i = 0; i < 7; ++i) xn[i] = x[i] + (k1[i] + 4.0 * k2[i] + k3[i]) * TS_SIXTH;
 }
@@ -267,6 +285,7 @@ struct StagePt {           // 11 doubles per stage: small enough for three of th
   double inq, s, v[3], w[3], Bn[3];
 };
 // f(x,u) at a stage point + the intermediates its JVP needs
+template <bool DJ = false>
 TS_HD void stage_eval(const Inertia& I, const double x[7], const double us[3], const double* Bn, StagePt& sp, double dx[7]) {
   sp.inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
   sp.s = x[3] * sp.inq;
@@ -281,16 +300,17 @@ TS_HD void stage_eval(const Inertia& I, const double x[7], const double us[3], c
   cross3(sp.v, t1, c2);
   for (int i = 0; i < 3; ++i) BB[i] = sp.Bn[i] + 2.0 * c2[i];
   cross3(us, BB, tau);
-  for (int i = 0; i < 3; ++i) Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
+  mul_J<DJ>(I, sp.w, Jw);
   cross3(sp.w, Jw, wJw);
-  const double r0 = tau[0] - wJw[0], r1 = tau[1] - wJw[1], r2 = tau[2] - wJw[2];
-  for (int i = 0; i < 3; ++i) dx[i] = I.Jinv[i * 3 + 0] * r0 + I.Jinv[i * 3 + 1] * r1 + I.Jinv[i * 3 + 2] * r2;
+  const double r[3] = {tau[0] - wJw[0], tau[1] - wJw[1], tau[2] - wJw[2]};
+  mul_Jinv<DJ>(I, r, dx);
   dx[3] = 0.5 * (-(sp.v[0] * sp.w[0] + sp.v[1] * sp.w[1] + sp.v[2] * sp.w[2]));
   dx[4] = 0.5 * (sp.s * sp.w[0] + (sp.v[1] * sp.w[2] - sp.v[2] * sp.w[1]));
   dx[5] = 0.5 * (sp.s * sp.w[1] + (sp.v[2] * sp.w[0] - sp.v[0] * sp.w[2]));
   dx[6] = 0.5 * (sp.s * sp.w[2] + (sp.v[0] * sp.w[1] - sp.v[1] * sp.w[0]));
 }
 // out = fx*vx + fu*vu at the stage point (t1, BB and J*w are recomputed: 36 FLOP instead of 12 live doubles)
+template <bool DJ = false>
 TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double us[3], const double vx[7], const double vu[3], double out[7]) {
   const double dot = sp.s * vx[3] + sp.v[0] * vx[4] + sp.v[1] * vx[5] + sp.v[2] * vx[6];
   const double ds = (vx[3] - sp.s * dot) * sp.inq;
@@ -316,26 +336,25 @@ TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double us[3], co
   double ta[3], tb[3], g1[3], g2[3], Jw[3], Jdw[3];
   cross3(dus, BB, ta);
   cross3(us, dBB, tb);
-  for (int i = 0; i < 3; ++i) {
-    Jw[i] = I.J[i * 3 + 0] * sp.w[0] + I.J[i * 3 + 1] * sp.w[1] + I.J[i * 3 + 2] * sp.w[2];
-    Jdw[i] = I.J[i * 3 + 0] * dw[0] + I.J[i * 3 + 1] * dw[1] + I.J[i * 3 + 2] * dw[2];
-  }
+  mul_J<DJ>(I, sp.w, Jw);
+  mul_J<DJ>(I, dw, Jdw);
   cross3(dw, Jw, g1);
   cross3(sp.w, Jdw, g2);
   const double r[3] = {ta[0] + tb[0] - g1[0] - g2[0], ta[1] + tb[1] - g1[1] - g2[1], ta[2] + tb[2] - g1[2] - g2[2]};
-  for (int i = 0; i < 3; ++i) out[i] = I.Jinv[i * 3 + 0] * r[0] + I.Jinv[i * 3 + 1] * r[1] + I.Jinv[i * 3 + 2] * r[2];
+  mul_Jinv<DJ>(I, r, out);
 }
 // Jacobian of the rk3 step by JVPs; column c of [A|B] is written to colmajor[c*7 .. c*7+6].
+template <bool DJ = false>
 TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
                         double dt, double* colmajor) {
   StagePt s1, s2, s3;
   double k1[7], k2[7], k3[7], xs[7];
   const double us[3] = {u[0] * 1.e-2, u[1] * 1.e-2, u[2] * 1.e-2};
-  stage_eval(I, x, us, B1, s1, k1);
+  stage_eval<DJ>(I, x, us, B1, s1, k1);
   for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k1[i] * dt);
-  stage_eval(I, xs, us, B2, s2, k2);
+  stage_eval<DJ>(I, xs, us, B2, s2, k2);
   for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] * dt + 2.0 * (k2[i] * dt);
-  stage_eval(I, xs, us, B3, s3, k3);
+  stage_eval<DJ>(I, xs, us, B3, s3, k3);
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
@@ -343,17 +362,17 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
     double vx[7], vu[3], t1[7], t2[7], t3[7], y[7];
     for (int i = 0; i < 7; ++i) vx[i] = (i == c) ? 1.0 : 0.0;
     for (int i = 0; i < 3; ++i) vu[i] = (7 + i == c) ? 1.0 : 0.0;
-    stage_jvp(I, s1, us, vx, vu, t1);
+    stage_jvp<DJ>(I, s1, us, vx, vu, t1);
     for (int i = 0; i < 7; ++i) {
       t1[i] *= dt;
       y[i] = vx[i] + 0.5 * t1[i];
     }
-    stage_jvp(I, s2, us, y, vu, t2);
+    stage_jvp<DJ>(I, s2, us, y, vu, t2);
     for (int i = 0; i < 7; ++i) {
       t2[i] *= dt;
       y[i] = vx[i] - t1[i] + 2.0 * t2[i];
     }
-    stage_jvp(I, s3, us, y, vu, t3);
+    stage_jvp<DJ>(I, s3, us, y, vu, t3);
     for (int i = 0; i < 7; ++i) colmajor[c * 7 + i] = vx[i] + (t1[i] + 4.0 * t2[i] + t3[i] * dt) * TS_SIXTH;
   }
 }

@@ -170,6 +170,16 @@ template <class Team>
 struct team_quat<Team, decltype((void)Team::QUAT)> {
   static constexpr bool value = Team::QUAT;
 };
+// Teams of the DIAGONAL-INERTIA kernels declare `static constexpr bool DIAGJ = true`: the host launches them when every
+// trial's inertia matrix is diagonal (mul_J / mul_Jinv in ilqr_math.cuh: same values, a third of the operations).
+template <class Team, class = void>
+struct team_diagj {
+  static constexpr bool value = false;
+};
+template <class Team>
+struct team_diagj<Team, decltype((void)Team::DIAGJ)> {
+  static constexpr bool value = Team::DIAGJ;
+};
 // G(q) = [-v'; s I + hat(v)] (4 x 3) of the raw quaternion q = (s, v)  (quaternion_toolbox.jl:22-27)
 TS_HD void quat_G(const double q[4], double G[4][3]) {
   const double s_ = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
@@ -373,7 +383,7 @@ TS_FN_NOINLINE void linearise_knot(const TrialIn& in, const ts_ilqr_opts_dev& o,
   for (int i = 0; i < 3; ++i) u[i] = p[7 + i];
   for (int i = 0; i < 9; ++i) b[i] = bp[i];
   for (int i = 0; i < 6; ++i) lam[i] = lp_[i];
-  if (!team_ext_lin<Team>::value) rk3_jac7_jvp(in.I, x, u, b, b + 3, b + 6, in.dt, rec);   // else: written by the producer warp
+  if (!team_ext_lin<Team>::value) rk3_jac7_jvp<team_diagj<Team>::value>(in.I, x, u, b, b + 3, b + 6, in.dt, rec);   // else: written by the producer warp
   for (int i = 0; i < 7; ++i) rec[70 + i] = sc * in.Qd[i] * (x[i] - in.xf[i]);
   double c6[6];
   bound_c(o, u, c6);
@@ -745,9 +755,38 @@ TS_FN double trajectory_cost(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev
 // staged through shared memory in double-buffered 8-knot chunks (asynchronous copies issued one
 // chunk ahead, so the ~1 us HBM/L2 latency is off the sequential critical path).
 struct RollOut {
-  double J, cmax, grad;
+  double J, cmax;
   bool ok;
 };
+// The gradient measure of the convergence test, mean_k max_i |d_k,i| / (|u_k,i| + 1), of a STORED trajectory (the
+// accepted line-search candidate, or the kept one when the line search is exhausted).  It used to be accumulated inside
+// every speculative rollout (three |.|, a cross-multiplied maximum and a division per knot and candidate: 7 % of the
+// rollout loop's instructions, needed for one candidate in 21).  Lane l evaluates knot base + l; the terms are then
+// added up on the first TEAM lanes in ascending knot order per (k mod TEAM) class, whatever the team width, so the sum
+// does not depend on where a trial runs.
+template <class Team>
+TS_FN double trajectory_grad(Team& tm, const ts_ilqr_opts_dev& o, const TrialWork& w, const double* xu, int N) {
+  constexpr int W = Team::W;
+  const int lane = tm.lane();
+  double g = 0.0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 4   // the loads of four steps in flight (the candidate was written a moment ago: L2 latency)
+#endif
+  for (int base = 0; base < N - 1; base += W) {
+    const int k = base + lane;
+    double m = 0.0;
+    if (k < N - 1) {
+      const double* p = xu + (long long)k * 10;
+      const double* kd = gptr(w.kd) + (long long)k * 24;
+      for (int i = 0; i < 3; ++i) m = fmax(m, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
+    }
+    for (int j = 0; j < W / TEAM; ++j) {
+      const double mj = (W > TEAM) ? tm.bcast(m, (lane % TEAM) + TEAM * j) : m;
+      if (lane < TEAM) g += mj;
+    }
+  }
+  return tm.sum(g) / (double)(o.a3_grad_over_N ? N : N - 1);
+}
 template <class Team>
 TS_FN void stage_chunk(Team& tm, const TrialWork& w, const double* xu_cur, int base, int N, double* buf) {
   const int k = base + tm.lane();
@@ -766,7 +805,7 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
                                      double clk_absmax) {
   RollOut r;
   r.ok = live;
-  double Jc = 0.0, cmax = 0.0, gsum = 0.0;
+  double Jc = 0.0, cmax = 0.0;
   double xb[7];
   for (int i = 0; i < 7; ++i) xb[i] = in.x0[i];
   const int N = in.N;
@@ -817,22 +856,11 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
         }
         const double e8 = (in.Qd[7] != 0.0) ? (gptr(w.clk)[k] - in.xf[7]) : 0.0;
         add_stage_cost(in, o, sc, mu, xb, e8, ub, p + 34, Jc, cmax);
-        {  // max_i |d_i| / (|u_i| + 1) with one division: pick the maximiser by cross-multiplication
-          double na = fabs(kd[21]), da = fabs(ub[0]) + 1.0;
-          for (int i = 1; i < 3; ++i) {
-            const double nb = fabs(kd[21 + i]), db = fabs(ub[i]) + 1.0;
-            if (nb * da > na * db) {
-              na = nb;
-              da = db;
-            }
-          }
-          gsum += na / da;
-        }
         double* q = xu_cand + (long long)k * 10;
         for (int i = 0; i < 7; ++i) q[i] = xb[i];
         for (int i = 0; i < 3; ++i) q[7 + i] = ub[i];
         double xn[7];
-        rk3_step7<0>(in.I, xb, ub, p + 40, p + 43, p + 46, in.dt, xn);
+        rk3_step7<0, team_diagj<Team>::value>(in.I, xb, ub, p + 40, p + 43, p + 46, in.dt, xn);
         // max |x|, max |u| (NaN counts as infinite) against the limits, as ten predicate tests: a NaN fails `<`
         bool bad = clk_bad;
         for (int i = 0; i < 7; ++i) {
@@ -856,7 +884,6 @@ TS_FN_NOINLINE RollOut forward_batch(Team& tm, const TrialIn& in, const ts_ilqr_
   }
   r.J = Jc;
   r.cmax = cmax;
-  r.grad = gsum / (double)(o.a3_grad_over_N ? N : N - 1);
   return r;
 }
 
@@ -910,7 +937,7 @@ TS_FN void solve_init(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o, co
       for (int i = 0; i < 3; ++i) q[7 + i] = u[i];
       const double* b = gptr(w.bk) + (long long)k * 10;
       double xn[7];
-      rk3_step7<0>(in.I, xb, u, b, b + 3, b + 6, in.dt, xn);
+      rk3_step7<0, team_diagj<Team>::value>(in.I, xb, u, b, b + 3, b + 6, in.dt, xn);
       for (int i = 0; i < 7; ++i) xb[i] = xn[i];
     }
     double* q = xu + (long long)(N - 1) * 10;
@@ -1068,9 +1095,9 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
     st.ls_total += st.b0 + a + 1;
     const double Jn = tm.bcast(r.J, a);
     st.c_max = tm.bcast(r.cmax, a);
-    const double grad = tm.bcast(r.grad, a);
     st.cur = (a < st.cur) ? a : a + 1;
-    tm.sync();
+    tm.sync();   // the accepted lane's trajectory is visible to the team
+    const double grad = trajectory_grad(tm, o, w, xu_buf<Team::W>(w, st.cur), N);
     st.cyc_fwd += ts_clock() - t0;
     solve_after_forward(tm, in, o, w, st, Jn, grad);
     return;
@@ -1090,16 +1117,7 @@ TS_FN void solve_forward(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
   reg.rho += o.bp_reg_fp;
   st.rho = reg.rho;
   st.drho = reg.drho;
-  double g = 0.0;
-  if (lane < TEAM)  // width-independent summation order, see trajectory_cost
-    for (int k = lane; k < N - 1; k += TEAM) {
-      const double* p = xu_cur + (long long)k * 10;
-      const double* kd = gptr(w.kd) + (long long)k * 24;
-      double mxg = 0.0;
-      for (int i = 0; i < 3; ++i) mxg = fmax(mxg, fabs(kd[21 + i]) / (fabs(p[7 + i]) + 1.0));
-      g += mxg;
-    }
-  const double grad = tm.sum(g) / (double)(o.a3_grad_over_N ? N : N - 1);
+  const double grad = trajectory_grad(tm, o, w, xu_cur, N);
   st.cyc_fwd += ts_clock() - t0;
   // the kept trajectory's cost under the current multipliers (the oracle re-evaluates al_cost of the unchanged
   // trajectory): J_prev, except in the first iteration of an inner solve under A7, where J_prev is the carried-over value

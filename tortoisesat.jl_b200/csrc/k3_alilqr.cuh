@@ -262,8 +262,16 @@ __device__ __forceinline__ long long k3_shfl_ll(long long v, int src) { return _
 struct GpuTeamQuat : GpuTeam {   // the quaternion-aware variant (ts_ilqr_opts.quat_error; team_quat in ilqr_solver.cuh)
   static constexpr bool QUAT = true;
 };
+struct GpuTeamDiag : GpuTeam {   // every trial's inertia matrix is diagonal (team_diagj in ilqr_solver.cuh)
+  static constexpr bool DIAGJ = true;
+};
 #define K3_BODY_TEAM GpuTeam
 __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_kernel(const K3Args a) {
+#include "k3_alilqr_body.inc"
+}
+#undef K3_BODY_TEAM
+#define K3_BODY_TEAM GpuTeamDiag
+__global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_diag_kernel(const K3Args a) {
 #include "k3_alilqr_body.inc"
 }
 #undef K3_BODY_TEAM
@@ -316,8 +324,16 @@ __global__ void __launch_bounds__(1024, 1) k3_park_order_kernel(const K3Args a) 
 struct GpuWideQuatTeam : GpuWideTeam {
   static constexpr bool QUAT = true;
 };
+struct GpuWideDiagTeam : GpuWideTeam {
+  static constexpr bool DIAGJ = true;
+};
 #define K3_BODY_TEAM GpuWideTeam
 __global__ void __launch_bounds__(32, 1) k3_wide_kernel(const K3Args a) {
+#include "k3_wide_body.inc"
+}
+#undef K3_BODY_TEAM
+#define K3_BODY_TEAM GpuWideDiagTeam
+__global__ void __launch_bounds__(32, 1) k3_wide_diag_kernel(const K3Args a) {
 #include "k3_wide_body.inc"
 }
 #undef K3_BODY_TEAM
@@ -402,7 +418,8 @@ constexpr int K3_PAIR_REGION_DOUBLES = SmL<32>::TOTAL + 32 * REC + 8 + 8;   // s
 static_assert(sizeof(K3PairCmd) <= 64 && sizeof(TrialWork) <= 64, "pair control blocks");
 constexpr int K3_PAIR_SMEM_BYTES = K3_PAIRS_PER_BLOCK * K3_PAIR_REGION_DOUBLES * 8;
 
-__global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(const K3Args a) {
+template <class PairTeam>
+__device__ __forceinline__ void k3_pair_body(const K3Args& a) {
   extern __shared__ __align__(16) double k3_smem[];
   const int lane32 = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -446,7 +463,7 @@ __global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(con
           for (int i = 0; i < 7; ++i) x[i] = __ldcg(p + i);
           for (int i = 0; i < 3; ++i) u[i] = __ldcg(p + 7 + i);
           for (int i = 0; i < 9; ++i) bb[i] = __ldcg(bp + i);
-          rk3_jac7_jvp(inp->I, x, u, bb, bb + 3, bb + 6, inp->dt, rec);
+          rk3_jac7_jvp<team_diagj<PairTeam>::value>(inp->I, x, u, bb, bb + 3, bb + 6, inp->dt, rec);
         }
         __syncwarp();
         __threadfence_block();
@@ -457,7 +474,7 @@ __global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(con
     return;
   }
   // -------------------------------------------------------------------- solver warp (as k3_wide_kernel)
-  GpuPairTeam tm;
+  PairTeam tm;
   tm.ln = lane32;
   tm.sm = region;
   tm.rec1 = rec1;
@@ -533,5 +550,10 @@ __global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(con
   __threadfence_block();
   k3p_bar_arrive(bar0 + 2);   // wakes the producer at the start of a sweep: it sees type == 0 and exits
 }
+struct GpuPairDiagTeam : GpuPairTeam {
+  static constexpr bool DIAGJ = true;
+};
+__global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_kernel(const K3Args a) { k3_pair_body<GpuPairTeam>(a); }
+__global__ void __launch_bounds__(64 * K3_PAIRS_PER_BLOCK, 1) k3_pair_diag_kernel(const K3Args a) { k3_pair_body<GpuPairDiagTeam>(a); }
 
 }  // namespace ts

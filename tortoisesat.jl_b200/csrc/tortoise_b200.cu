@@ -508,7 +508,15 @@ static double slew_angle(const double* x0, const double* xf) {
 // pull groups of 4 trials, one per 8-lane team) followed by k3_wide_kernel (stragglers handed over to one warp each).
 // The launch scheme is controlled by ts_ilqr_opts.k3_* (suspend_after, early_factor, tail_share).  Work is queued on
 // the context's stream; nothing here synchronises.
-static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr) {
+// true when every 3x3 inertia matrix of the (host) array is diagonal: K3 then runs the *_diag_kernel instantiations
+static bool all_inertia_diagonal(const double* Jmat, int64_t n) {
+  for (int64_t t = 0; t < n; ++t)
+    for (int i = 0; i < 9; ++i)
+      if (i % 4 != 0 && Jmat[9 * t + i] != 0.0) return false;
+  return true;
+}
+
+static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double* difficulty_host = nullptr, bool diag_inertia = false) {
   const int64_t n_trials = a.n_trials;
   // the quaternion-aware variant (opts.quat_error) runs the same two-launch scheme on the QUAT instantiations
   const bool quat = a.opts.quat_error != 0;
@@ -517,8 +525,11 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     if (qm != 0 && qm != 0xF)
       return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
   }
-  void (*const narrow_kernel)(const K3Args) = quat ? k3_alilqr_quat_kernel : k3_alilqr_kernel;
-  void (*const wide_kernel)(const K3Args) = quat ? k3_wide_quat_kernel : k3_wide_kernel;
+  // diagonal inertia matrices (every preset of the reference): instantiations without the products by their zeros
+  const bool dj = diag_inertia && !quat;
+  void (*const narrow_kernel)(const K3Args) = quat ? k3_alilqr_quat_kernel : (dj ? k3_alilqr_diag_kernel : k3_alilqr_kernel);
+  void (*const wide_kernel)(const K3Args) = quat ? k3_wide_quat_kernel : (dj ? k3_wide_diag_kernel : k3_wide_kernel);
+  void (*const pair_kernel)(const K3Args) = dj ? k3_pair_diag_kernel : k3_pair_kernel;
   int64_t Nmax = 0;
   for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
   int occ = 0;
@@ -547,8 +558,8 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
   int wide_smem = K3_WIDE_SMEM_BYTES;
   if (pair) {
     int occ_p = 0;
-    TS_CUDA(c, cudaFuncSetAttribute(k3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_PAIR_SMEM_BYTES));
-    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, k3_pair_kernel, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES));
+    TS_CUDA(c, cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_PAIR_SMEM_BYTES));
+    TS_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, pair_kernel, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES));
     if (occ_p < 1) return fail(c, TS_ERR_CUDA, "k3 pair kernel does not fit on an SM");
     wide_warps = std::min<int64_t>(n_trials, (int64_t)c->sm_count * occ_p * K3_PAIRS_PER_BLOCK);   // solver warps
   } else if (a.opts.k3_wide_occ > 0 && a.opts.k3_wide_occ < occ_w) {
@@ -705,7 +716,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
     const int blocks_w = (int)std::max<int64_t>(1, std::min<int64_t>(a.park_cap, wide_warps));
     k3_park_order_kernel<<<1, 1024, 0, c->stream>>>(a);
     if (pair)
-      k3_pair_kernel<<<(blocks_w + K3_PAIRS_PER_BLOCK - 1) / K3_PAIRS_PER_BLOCK, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES, c->stream>>>(a);
+      pair_kernel<<<(blocks_w + K3_PAIRS_PER_BLOCK - 1) / K3_PAIRS_PER_BLOCK, 64 * K3_PAIRS_PER_BLOCK, K3_PAIR_SMEM_BYTES, c->stream>>>(a);
     else
       wide_kernel<<<blocks_w, 32, wide_smem, c->stream>>>(a);
     c->launches += 2;
@@ -782,7 +793,7 @@ int ts_alilqr_solve_batch(ts_ctx* c, int64_t n_trials, const int64_t* N_i, const
   std::vector<double> diff(T);
   for (size_t t = 0; t < T; ++t) diff[t] = slew_angle(x0 + 8 * t, xf + 8 * t);
   KernelTimer tm(c);
-  if ((rc = k3_launch(c, a, N_i, diff.data()))) return rc;
+  if ((rc = k3_launch(c, a, N_i, diff.data(), all_inertia_diagonal(Jmat, n_trials)))) return rc;
   tm.stop();
   if ((rc = dev_back(c, dX, X, (size_t)total_knots * 8 * sizeof(double)))) return rc;
   if ((rc = dev_back(c, dU, U, (size_t)total_knots * 3 * sizeof(double)))) return rc;
@@ -1157,7 +1168,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
         if ((rc = scratch_reserve(c, 21, (size_t)knots * 3 * 8 + 64, &p_us))) return rc;
       }
     }
-    if ((rc = k3_launch(c, ka, hi.data(), diff.data()))) return rc;
+    if ((rc = k3_launch(c, ka, hi.data(), diff.data(), all_inertia_diagonal(Jmat, n)))) return rc;
     cudaEventRecord(e[4], c->stream);
     // ---- stage 5: TVLQR replay + slew-time rule
     double *d_Xs_keep = nullptr, *d_Us_keep = nullptr;
