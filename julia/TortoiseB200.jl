@@ -47,7 +47,7 @@ struct IlqrOpts             # ts_ilqr_opts
     a6_penalty_conditional::Int32; a7_carry_cost::Int32; constraint_decrease_ratio::Float64
     # launch scheme of K3
     k3_suspend_after::Int32; k3_tail_share::Int32; k3_early_factor::Float64; k3_pair::Int32; k3_wide_occ::Int32
-    quat_error::Int32; pad_::Int32     # 1: quaternion_error / quaternion_expansion variant (monte_carlo.jl:158,192)
+    quat_error::Int32; k3_generic_inertia::Int32     # 1: quaternion_error / quaternion_expansion variant (monte_carlo.jl:158,192)
 end
 struct TrialOutcome         # ts_trial_outcome (64 bytes)
     status::Int32; outer_iters::Int32; inner_iters::Int32; ls_rollouts::Int32; N::Int64

@@ -164,7 +164,7 @@ struct orc_ilqr_opts {
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
   int32_t k3_pair, k3_wide_occ;
-  int32_t quat_error, pad_;
+  int32_t quat_error, k3_generic_inertia;
 };
 static IlqrOpts make_opts(const orc_ilqr_opts* s) {
   IlqrOpts o;
@@ -201,7 +201,7 @@ void orc_ilqr_default_opts(orc_ilqr_opts* s) {
   s->a5_dual_active_only = o.a5_dual_active_only; s->a6_penalty_conditional = o.a6_penalty_conditional;
   s->a7_carry_cost = o.a7_carry_cost; s->constraint_decrease_ratio = o.constraint_decrease_ratio;
   s->k3_suspend_after = 150; s->k3_tail_share = 1; s->k3_early_factor = 2.0; s->k3_pair = 2; s->k3_wide_occ = 0;
-  s->quat_error = o.quat_error; s->pad_ = 0;
+  s->quat_error = o.quat_error; s->k3_generic_inertia = 0;
 }
 
 // Batched solve.  Per trial t: N_i[t] knots, ragged arrays addressed through

@@ -46,7 +46,7 @@ class IlqrOpts(C.Structure):
                                          "a6_penalty_conditional", "a7_carry_cost")] + \
                [("constraint_decrease_ratio", C.c_double), ("k3_suspend_after", C.c_int32), ("k3_tail_share", C.c_int32),
                 ("k3_early_factor", C.c_double), ("k3_pair", C.c_int32), ("k3_wide_occ", C.c_int32),
-                ("quat_error", C.c_int32), ("pad_", C.c_int32)]
+                ("quat_error", C.c_int32), ("k3_generic_inertia", C.c_int32)]
 
 
 class Outcome(C.Structure):

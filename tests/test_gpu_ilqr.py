@@ -261,6 +261,40 @@ def test_assumption_flips_on_gpu(engine, flag):
     assert _check(engine, slews, o, tb) >= 2
 
 
+def test_general_and_diagonal_inertia_kernels(engine):
+    """K3 picks diagonal-inertia kernel instantiations when every J is diagonal (all reference presets).  (1) they give
+    the same iteration paths and results as the general kernels (ts_ilqr_opts.k3_generic_inertia = 1) on a ragged batch that
+    goes through both launches; (2) a batch with products of inertia (off-diagonal J) runs the general kernels and matches the
+    oracle; (3) the producer-warp kernel in both instantiations."""
+    import tortoisesat.jl_b200 as tb
+    rng = np.random.default_rng(5)
+    qf = np.array([1.0, 0, 0, 0])
+    slews = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_3U if i % 2 else S.J_1P, S.quat_axis_angle(rng.normal(size=3), rng.uniform(3, 25)),
+                          qf, t_final=float(rng.integers(20, 45))) for i in range(9)]
+    for pair in (0, 1):
+        o = orc.default_ilqr_opts()
+        o.k3_suspend_after = 10
+        o.k3_pair = pair
+        res = []
+        for generic in (0, 1):
+            g = _gpu_opts(tb, o)
+            g.k3_generic_inertia = generic
+            res.append(engine.alilqr_solve_batch(**_pack(slews), opts=g))
+            assert engine.k3_last_split()[2] > 0
+        # (different instantiations: the compiler's FMA contraction choices differ in the last bit, as between the
+        #  four-per-warp and the one-per-warp kernel)
+        for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
+            assert np.array_equal(res[0][3][f], res[1][3][f]), f
+        assert np.max(np.abs(res[0][3]["J"] - res[1][3]["J"]) / np.abs(res[1][3]["J"])) < 1e-9
+        assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-9 and np.max(np.abs(res[0][1] - res[1][1])) < 1e-8
+    Jfull = np.array([[0.020833, 0.0011, -0.0007], [0.0011, 0.018, 0.0009], [-0.0007, 0.0009, 0.0041666]])
+    slews2 = [S.build_slew([0, 6578, 96, 0, 0, 90], Jfull, S.quat_axis_angle(rng.normal(size=3), rng.uniform(3, 20)), qf,
+                           t_final=float(rng.integers(25, 45))) for i in range(5)]
+    o = orc.default_ilqr_opts()
+    o.k3_suspend_after = 10
+    assert _check(engine, slews2, o, tb) >= 4
+
+
 def test_cycle_diagnostics_are_separate_from_outcomes(engine):
     """ts_alilqr_solve_batch returns outcome records whose t_final / slew_time / flops are 0 (they belong to the fused
     Monte-Carlo path); the SM-cycle counters come through ts_k3_last_cycles."""

@@ -31,10 +31,17 @@ struct Inertia {
   double Jinv[9];
 };
 
-// 1/sqrt(s): one MUFU + Newton steps on the GPU instead of sqrt followed by four divisions
+// 1/sqrt(s) instead of sqrt followed by four divisions.  On the GPU: the hardware seed (MUFU.RSQ64H, ~2^-22) and ONE
+// third-order step y0 + y0 e (1/2 + 3/8 e), e = 1 - s y0^2 -- the arithmetic of the library's rsqrt() fast path (5 FP64
+// operations) without its range checks and slow-path call (12 more instructions, three times per rollout knot).  The
+// argument is the squared norm of an attitude quaternion (or a Cholesky pivot > 0); zero, denormal, infinite or NaN
+// arguments give inf / NaN here, which the rollout's |x| < max_state_value test rejects like any diverged candidate.
 TS_HD double rnorm(double s) {
 #ifdef __CUDA_ARCH__
-  return rsqrt(s);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+  const double e = fma(-s, y0 * y0, 1.0);
+  return fma(fma(e, 0.375, 0.5), e * y0, y0);
 #else
   return 1.0 / sqrt(s);
 #endif
@@ -71,6 +78,14 @@ TS_HD void qmult(const double a[4], const double b[4], double o[4]) {
   o[2] = a[0] * b[2] + b[0] * a[2] + (a[3] * b[1] - a[1] * b[3]);
   o[3] = a[0] * b[3] + b[0] * a[3] + (a[1] * b[2] - a[2] * b[1]);
 }
+// a (x) (0, v): the Hamilton product with a pure-vector right factor, i.e. qmult without its products by the zero scalar
+// part (the same values for finite operands; 12 instead of 19 operations, three times per rollout knot)
+TS_HD void qmult_pure(const double a[4], const double v[3], double o[4]) {
+  o[0] = -(a[1] * v[0] + a[2] * v[1] + a[3] * v[2]);
+  o[1] = a[0] * v[0] + (a[2] * v[2] - a[3] * v[1]);
+  o[2] = a[0] * v[1] + (a[3] * v[0] - a[1] * v[2]);
+  o[3] = a[0] * v[2] + (a[1] * v[1] - a[2] * v[0]);
+}
 // qrot.jl:1-3
 TS_HD void qrot(const double q[4], const double r[3], double o[3]) {
   double c1[3], w[3], c2[3];
@@ -90,9 +105,8 @@ template <int UMODE, bool DJ = false>
 TS_HD void dyn_f(const Inertia& I, const double x[7], const double u[3], const double Bn[3], double dx[7]) {
   const double inq = rnorm(x[3] * x[3] + x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
   const double q[4] = {x[3] * inq, x[4] * inq, x[5] * inq, x[6] * inq};
-  const double w4[4] = {0.0, x[0], x[1], x[2]};
   double qd[4];
-  qmult(q, w4, qd);
+  qmult_pure(q, x, qd);   // qmult(q, [0; omega]), DerivFunction.jl:33
   double BB[3];
   qrot(q, Bn, BB);
   double us[3];

@@ -47,7 +47,7 @@ struct ts_ilqr_opts_dev {
   int32_t k3_suspend_after, k3_tail_share;
   double k3_early_factor;
   int32_t k3_pair, k3_wide_occ;
-  int32_t quat_error, pad_;
+  int32_t quat_error, k3_generic_inertia;
 };
 // 64-byte per-trial record (C ABI: ts_trial_outcome).
 struct ts_trial_outcome_dev {
@@ -597,13 +597,14 @@ TS_FN bool backward_pass(Team& tm, const TrialIn& in, const ts_ilqr_opts_dev& o,
               for (int l = 0; l < 3; ++l) t += Ki[l] * QuuK[l];
               for (int l = 0; l < 3; ++l) t += Ki[l] * Quxj[l];
               for (int l = 0; l < 3; ++l) t += Quxi[l] * Kj[l];
-              double ts = rec[70 + j] + sm[L::QV + j];   // new s(j): stored by the lane that holds column j's gain (li == j)
-              for (int l = 0; l < 3; ++l) ts += Kj[l] * Quud[l];
-              for (int l = 0; l < 3; ++l) ts += Kj[l] * Qu[l];
-              for (int l = 0; l < 3; ++l) ts += Quxj[l] * d[l];
               if (valid) sm[L::SCOL + j * L::SS + li] = t;
-              if (valid && li == j) sm[L::SVEC + j] = ts;
             }
+            // new s(li) from this lane's own gain column (K(:,li), Qux(:,li)); lanes 0..6 store the seven entries
+            double ts = rec[70 + li] + sm[L::QV + li];
+            for (int l = 0; l < 3; ++l) ts += Ki[l] * Quud[l];
+            for (int l = 0; l < 3; ++l) ts += Ki[l] * Qu[l];
+            for (int l = 0; l < 3; ++l) ts += Quxi[l] * d[l];
+            if (lane < 7) sm[L::SVEC + li] = ts;
           }
           tm.sync();
         } else {

@@ -493,7 +493,7 @@ void ts_ilqr_default_opts(ts_ilqr_opts* o) {
   o->u_max = 1.0; o->u_min = -1.0;
   o->a2_active_ge = 0; o->a3_grad_over_N = 0; o->a4_no_intermediate = 0; o->a5_dual_active_only = 0;
   o->a6_penalty_conditional = 0; o->a7_carry_cost = 0; o->constraint_decrease_ratio = 0.25;
-  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 2; o->k3_wide_occ = 0; o->quat_error = 0; o->pad_ = 0;
+  o->k3_suspend_after = 150; o->k3_tail_share = 1; o->k3_early_factor = 2.0; o->k3_pair = 2; o->k3_wide_occ = 0; o->quat_error = 0; o->k3_generic_inertia = 0;
 }
 
 // slew angle between the initial and the goal attitude (host): the difficulty proxy of the K3 queue order
@@ -526,7 +526,7 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
       return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
   }
   // diagonal inertia matrices (every preset of the reference): instantiations without the products by their zeros
-  const bool dj = diag_inertia && !quat;
+  const bool dj = diag_inertia && !quat && !a.opts.k3_generic_inertia;
   void (*const narrow_kernel)(const K3Args) = quat ? k3_alilqr_quat_kernel : (dj ? k3_alilqr_diag_kernel : k3_alilqr_kernel);
   void (*const wide_kernel)(const K3Args) = quat ? k3_wide_quat_kernel : (dj ? k3_wide_diag_kernel : k3_wide_kernel);
   void (*const pair_kernel)(const K3Args) = dj ? k3_pair_diag_kernel : k3_pair_kernel;
