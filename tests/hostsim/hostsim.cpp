@@ -158,6 +158,15 @@ void hs_rk3_jac7_jvp(const double* J9, const double* x7, const double* u3, const
   inv3_gj(I.J, I.Jinv);
   rk3_jac7_jvp(I, x7, u3, B1, B2, B3, dt, colmajor70);
 }
+// the diagonal-inertia instantiation (mul_J<true> / mul_Jinv<true>: K3's *_diag_kernel), and its rollout step
+void hs_rk3_jac7_jvp_diag(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
+                          double dt, double* colmajor70, double* xn7) {
+  Inertia I;
+  memcpy(I.J, J9, 72);
+  inv3_gj(I.J, I.Jinv);
+  rk3_jac7_jvp<true>(I, x7, u3, B1, B2, B3, dt, colmajor70);
+  rk3_step7<0, true>(I, x7, u3, B1, B2, B3, dt, xn7);
+}
 void hs_rk4_jac7(const double* J9, const double* x7, const double* u3, const double* B1, const double* B2, const double* B3,
                  const double* B4, double dt, double* xn7, double* AB70) {
   Inertia I;

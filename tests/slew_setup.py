@@ -43,6 +43,7 @@ def hostsim():
                                                                                      C.c_void_p, C.c_void_p]
         _HS.hs_rk3_jac7.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_rk3_jac7_jvp.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p]
+        _HS.hs_rk3_jac7_jvp_diag.argtypes = [C.c_void_p] * 6 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_rk4_jac7.argtypes = [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_void_p]
         _HS.hs_dyn_f.argtypes = [C.c_void_p] * 5
         _HS.hs_philox4x32_10.argtypes = [C.c_void_p] * 3

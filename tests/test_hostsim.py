@@ -39,6 +39,12 @@ def test_analytic_rk3_jacobian_vs_forward_mode_duals(J):
                            orc.P(r[2]), dt, orc.P(cm))
         assert np.max(np.abs(cm.T[:, :7] - A[:7, :7])) < 1e-14
         assert np.max(np.abs(cm.T[:, 7:] - B[:7])) < 1e-12 * max(1.0, np.max(np.abs(B)))
+        if np.count_nonzero(J - np.diag(np.diagonal(J))) == 0:
+            # the diagonal-inertia instantiation (K3's *_diag_kernel): the same values with the zero products left out
+            cd, xd = np.zeros((10, 7)), np.zeros(7)
+            hs.hs_rk3_jac7_jvp_diag(orc.P(np.ascontiguousarray(J)), orc.P(np.ascontiguousarray(x[:7])), orc.P(u), orc.P(r[0]),
+                                    orc.P(r[1]), orc.P(r[2]), dt, orc.P(cd), orc.P(xd))
+            assert np.max(np.abs(cd - cm)) < 1e-15 and np.max(np.abs(xd - xn)) < 1e-16
 
 
 CASES = [  # (slew angle deg, horizon s, goal mask, expected status)

@@ -357,7 +357,74 @@ TS_HD void stage_jvp(const Inertia& I, const StagePt& sp, const double us[3], co
   const double r[3] = {ta[0] + tb[0] - g1[0] - g2[0], ta[1] + tb[1] - g1[1] - g2[1], ta[2] + tb[2] - g1[2] - g2[2]};
   mul_Jinv<DJ>(I, r, out);
 }
-// Jacobian of the rk3 step by JVPs; column c of [A|B] is written to colmajor[c*7 .. c*7+6].
+// Stage-1 JVPs of the rk3 step for the ten UNIT directions.  In the first stage the direction is e_c itself, so nine
+// tenths of the generic stage_jvp are products with exact zeros; written out per direction type they cost ~25 (omega),
+// ~70 (quaternion) and ~12 (control) operations instead of ~165, and the stage point's BB, t1 and J*w are formed once for
+// all ten.  Same values as stage_jvp on e_c (sums with exact zeros dropped).  out = (fx e_c or fu e_c) * dt.
+struct Stage1Pt {
+  double t1[3], BB[3], Jw[3];
+};
+template <bool DJ>
+TS_HD void stage1_prepare(const Inertia& I, const StagePt& sp, Stage1Pt& p1) {
+  double vxB[3], cc[3];
+  cross3(sp.v, sp.Bn, vxB);
+  for (int i = 0; i < 3; ++i) p1.t1[i] = vxB[i] + sp.s * sp.Bn[i];
+  cross3(sp.v, p1.t1, cc);
+  for (int i = 0; i < 3; ++i) p1.BB[i] = sp.Bn[i] + 2.0 * cc[i];
+  mul_J<DJ>(I, sp.w, p1.Jw);
+}
+template <bool DJ, int C>   // C = 0..2: direction e_C in omega
+TS_HD void stage1_jvp_w(const Inertia& I, const StagePt& sp, const Stage1Pt& p1, double dt, double* out) {
+  constexpr int C1 = (C + 1) % 3, C2 = (C + 2) % 3;
+  // b = v x e_C, g1 = e_C x (J w), g2 = w x (J e_C)
+  double b[3], g1[3], g2[3], Jc[3], r[3], o3[3];
+  b[C] = 0.0; b[C1] = sp.v[C2]; b[C2] = -sp.v[C1];
+  g1[C] = 0.0; g1[C1] = -p1.Jw[C2]; g1[C2] = p1.Jw[C1];
+  if (DJ) {
+    Jc[C] = I.J[C * 4]; Jc[C1] = 0.0; Jc[C2] = 0.0;
+    g2[C] = 0.0; g2[C1] = sp.w[C2] * Jc[C]; g2[C2] = -(sp.w[C1] * Jc[C]);
+  } else {
+    for (int i = 0; i < 3; ++i) Jc[i] = I.J[i * 3 + C];
+    cross3(sp.w, Jc, g2);
+  }
+  for (int i = 0; i < 3; ++i) r[i] = -g1[i] - g2[i];
+  mul_Jinv<DJ>(I, r, o3);
+  for (int i = 0; i < 3; ++i) out[i] = o3[i] * dt;
+  out[3] = (0.5 * (-sp.v[C])) * dt;
+  for (int i = 0; i < 3; ++i) out[4 + i] = (0.5 * (((i == C) ? sp.s : 0.0) + b[i])) * dt;
+}
+template <bool DJ, int C>   // C = 0..3: direction e_C in the raw quaternion (s, v0, v1, v2)
+TS_HD void stage1_jvp_q(const Inertia& I, const StagePt& sp, const Stage1Pt& p1, const double us[3], double dt, double* out) {
+  const double dot = (C == 0) ? sp.s : sp.v[C > 0 ? C - 1 : 0];   // q_hat[C]
+  const double ds = (((C == 0) ? 1.0 : 0.0) - sp.s * dot) * sp.inq;
+  double dv[3];
+  for (int i = 0; i < 3; ++i) dv[i] = (((C == i + 1) ? 1.0 : 0.0) - sp.v[i] * dot) * sp.inq;
+  double a[3];
+  cross3(dv, sp.w, a);
+  out[3] = (0.5 * (-(dv[0] * sp.w[0] + dv[1] * sp.w[1] + dv[2] * sp.w[2]))) * dt;
+  for (int i = 0; i < 3; ++i) out[4 + i] = (0.5 * (ds * sp.w[i] + a[i])) * dt;
+  double dt1[3], c1[3], c2[3];
+  cross3(dv, sp.Bn, dt1);
+  for (int i = 0; i < 3; ++i) dt1[i] += ds * sp.Bn[i];
+  cross3(dv, p1.t1, c1);
+  cross3(sp.v, dt1, c2);
+  const double dBB[3] = {2.0 * (c1[0] + c2[0]), 2.0 * (c1[1] + c2[1]), 2.0 * (c1[2] + c2[2])};
+  double tb[3], o3[3];
+  cross3(us, dBB, tb);
+  mul_Jinv<DJ>(I, tb, o3);
+  for (int i = 0; i < 3; ++i) out[i] = o3[i] * dt;
+}
+template <bool DJ, int C>   // C = 0..2: direction e_C in the control
+TS_HD void stage1_jvp_u(const Inertia& I, const Stage1Pt& p1, double dt, double* out) {
+  constexpr int C1 = (C + 1) % 3, C2 = (C + 2) % 3;
+  double ta[3], o3[3];   // (1e-2 e_C) x BB
+  ta[C] = 0.0; ta[C1] = -(1.e-2 * p1.BB[C2]); ta[C2] = 1.e-2 * p1.BB[C1];
+  mul_Jinv<DJ>(I, ta, o3);
+  for (int i = 0; i < 3; ++i) out[i] = o3[i] * dt;
+  for (int i = 3; i < 7; ++i) out[i] = 0.0;
+}
+// Jacobian of the rk3 step by JVPs; column c of [A|B] is written to colmajor[c*7 .. c*7+6] (the lane's knot record in
+// shared memory, which also holds the ten stage-1 products between the two passes).
 template <bool DJ = false>
 TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], const double* B1, const double* B2, const double* B3,
                         double dt, double* colmajor) {
@@ -365,6 +432,20 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
   double k1[7], k2[7], k3[7], xs[7];
   const double us[3] = {u[0] * 1.e-2, u[1] * 1.e-2, u[2] * 1.e-2};
   stage_eval<DJ>(I, x, us, B1, s1, k1);
+  {  // pass 1: t1_c = (stage-1 JVP of e_c) * dt, unrolled over the ten directions
+    Stage1Pt p1;
+    stage1_prepare<DJ>(I, s1, p1);
+    stage1_jvp_w<DJ, 0>(I, s1, p1, dt, colmajor + 0);
+    stage1_jvp_w<DJ, 1>(I, s1, p1, dt, colmajor + 7);
+    stage1_jvp_w<DJ, 2>(I, s1, p1, dt, colmajor + 14);
+    stage1_jvp_q<DJ, 0>(I, s1, p1, us, dt, colmajor + 21);
+    stage1_jvp_q<DJ, 1>(I, s1, p1, us, dt, colmajor + 28);
+    stage1_jvp_q<DJ, 2>(I, s1, p1, us, dt, colmajor + 35);
+    stage1_jvp_q<DJ, 3>(I, s1, p1, us, dt, colmajor + 42);
+    stage1_jvp_u<DJ, 0>(I, p1, dt, colmajor + 49);
+    stage1_jvp_u<DJ, 1>(I, p1, dt, colmajor + 56);
+    stage1_jvp_u<DJ, 2>(I, p1, dt, colmajor + 63);
+  }
   for (int i = 0; i < 7; ++i) xs[i] = x[i] + 0.5 * (k1[i] * dt);
   stage_eval<DJ>(I, xs, us, B2, s2, k2);
   for (int i = 0; i < 7; ++i) xs[i] = x[i] - k1[i] * dt + 2.0 * (k2[i] * dt);
@@ -372,13 +453,12 @@ TS_HD void rk3_jac7_jvp(const Inertia& I, const double x[7], const double u[3], 
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-  for (int c = 0; c < 10; ++c) {
+  for (int c = 0; c < 10; ++c) {   // pass 2: stages 2 and 3 (generic JVPs)
     double vx[7], vu[3], t1[7], t2[7], t3[7], y[7];
     for (int i = 0; i < 7; ++i) vx[i] = (i == c) ? 1.0 : 0.0;
     for (int i = 0; i < 3; ++i) vu[i] = (7 + i == c) ? 1.0 : 0.0;
-    stage_jvp<DJ>(I, s1, us, vx, vu, t1);
     for (int i = 0; i < 7; ++i) {
-      t1[i] *= dt;
+      t1[i] = colmajor[c * 7 + i];
       y[i] = vx[i] + 0.5 * t1[i];
     }
     stage_jvp<DJ>(I, s2, us, y, vu, t2);
