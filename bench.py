@@ -47,12 +47,16 @@ FL_ITER, FL_ROLL, FL_TVLQR, FL_IGRF = 6100.0, 500.0, 7700.0, 2243.0
 FL_MODELS = {"survey_estimate": (6100.0, 500.0)}
 try:
     _fc = json.load(open(os.path.join(ROOT, "profiles", "flop_counts_r2.json")))
-    FL_ITER, FL_ROLL = float(_fc["per_knot_iteration"]), float(_fc["per_rollout_knot"])
+    # the benchmark ensembles use the 1U inertia (diagonal): K3 runs its diagonal-inertia instantiations
+    FL_ITER, FL_ROLL = float(_fc["per_knot_iteration_diag"]), float(_fc["per_rollout_knot_diag"])
     FL_TVLQR = float(_fc.get("tvlqr_per_knot", FL_TVLQR))
     FL_MODELS["reference_algorithm_counted"] = (float(_fc["oracle_per_knot_iteration"]), float(_fc["oracle_per_rollout_knot"]))
-    FLOP_SOURCE = "counted kernel math, %.0f FLOP per knot-iteration (JVP linearisation %d + cost gradients %d + Riccati step %d) + %.0f per " \
-                  "line-search rollout knot: tools/flopcount.cpp -> profiles/flop_counts_r2.json" % (
-                      FL_ITER, _fc["linearise"], _fc["cost_gradients"], _fc["riccati"], FL_ROLL)
+    FL_MODELS["general_inertia_kernels_counted"] = (float(_fc["per_knot_iteration"]), float(_fc["per_rollout_knot"]))
+    FL_MODELS["first_round2_count"] = (float(_fc["first_round2_count"]["per_knot_iteration"]), float(_fc["first_round2_count"]["per_rollout_knot"]))
+    FLOP_SOURCE = "counted kernel math (diagonal-inertia instantiation), %.0f FLOP per knot-iteration (JVP linearisation %d + cost gradients " \
+                  "%d + Riccati step %d + gradient measure %d) + %.0f per line-search rollout knot: tools/flopcount.cpp -> " \
+                  "profiles/flop_counts_r2.json" % (FL_ITER, _fc["linearise_diag"], _fc["cost_gradients"], _fc["riccati"],
+                                                   _fc["gradient_measure"], FL_ROLL)
 except Exception:
     FLOP_SOURCE = "SURVEY 8d estimate: 6100 per knot-iteration (rk3 Jacobian 2600 + Riccati step 3500) + 500 per rollout knot"
 # HBM traffic of K3 per knot-iteration: ncu dram__bytes_read+write of THIS configuration (N = 2044, 4096 trials)

@@ -164,13 +164,13 @@ int main() {
     for (int j = 0; j < 3; ++j) { CD t(0.0); for (int l = 0; l < 7; ++l) t += AB[(7 + j) * 7 + l] * s7[l]; Qu[j] = rec[77 + j] + t; }
     CD Qr[9], L[9], d[3], Quud[3], nb[3] = {-Qu[0], -Qu[1], -Qu[2]};
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Qr[i * 3 + j] = CD(0.5) * (Quu[i * 3 + j] + Quu[j * 3 + i]) + CD(i == j ? 1e-3 : 0.0);
-    ts::chol3(Qr, L);
-    ts::chol3_solve(L, nb, d);
+    ts::quu_factor(Qr, L);
+    ts::quu_solve(L, nb, d);
     for (int i = 0; i < 3; ++i) Quud[i] = Quu[i * 3] * d[0] + Quu[i * 3 + 1] * d[1] + Quu[i * 3 + 2] * d[2];
     CD Kc[21], QuuK[21], dV1(0.0), dV2(0.0);
     for (int j = 0; j < 7; ++j) {
       CD b3[3] = {-Qux[j * 3], -Qux[j * 3 + 1], -Qux[j * 3 + 2]};
-      ts::chol3_solve(L, b3, Kc + j * 3);
+      ts::quu_solve(L, b3, Kc + j * 3);
       for (int i = 0; i < 3; ++i) QuuK[j * 3 + i] = Quu[i * 3] * Kc[j * 3] + Quu[i * 3 + 1] * Kc[j * 3 + 1] + Quu[i * 3 + 2] * Kc[j * 3 + 2];
     }
     for (int l = 0; l < 3; ++l) { dV1 += d[l] * Qu[l]; dV2 += CD(0.5) * d[l] * Quud[l]; }
@@ -180,26 +180,43 @@ int main() {
     }
     for (int i = 0; i < 7; ++i) for (int j = i; j < 7; ++j) S[i * 7 + j] = CD(0.5) * (S[i * 7 + j] + S[j * 7 + i]);
   }
-  Counters k_ric = diff(g_cnt, c0); show("Riccati knot step (dense 7-state, 3x3 Cholesky once)", k_ric, 1);
+  Counters k_ric = diff(g_cnt, c0); show("Riccati knot step (dense 7-state, 3x3 cofactor solve once)", k_ric, 1);
   c0 = g_cnt;
-  {  // one line-search rollout knot: feedback, AL stage cost, gradient term, rk3 step, divergence check
-    CD xb[7], ub[3], kd[24], dx[7], Jc(0.0), cmax(0.0), gsum(0.0), xn[7];
+  {  // one line-search rollout knot: feedback, AL stage cost, rk3 step (the divergence check is comparisons only)
+    CD xb[7], ub[3], kd[24], dx[7], Jc(0.0), cmax(0.0), xn[7];
     for (int i = 0; i < 7; ++i) xb[i] = x[i] + CD(1e-3);
     for (int i = 0; i < 24; ++i) kd[i] = CD(0.01 * i);
     for (int i = 0; i < 7; ++i) dx[i] = xb[i] - x[i];
     for (int i = 0; i < 3; ++i) { CD t = u[i]; for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j]; t += CD(0.25) * kd[21 + i]; ub[i] = t; }
     ts::add_stage_cost(in, ko, CD(1.0), CD(10.0), xb, CD(0.0), ub, lam, Jc, cmax);
-    CD na = fabs(kd[21]), da = fabs(ub[0]) + CD(1.0);
-    for (int i = 1; i < 3; ++i) { CD nb2 = fabs(kd[21 + i]), db = fabs(ub[i]) + CD(1.0); if (nb2 * da > na * db) { na = nb2; da = db; } }
-    gsum += na / da;
     ts::rk3_step7<0>(in.I, xb, ub, bk, bk + 3, bk + 6, in.dt, xn);
   }
   Counters k_roll = diff(g_cnt, c0); show("line-search rollout knot (feedback + AL cost + rk3)", k_roll, 1);
-  const double k_iter = (double)(k_lin.flops() + k_grad.flops() + k_ric.flops()), k_rollf = (double)k_roll.flops();
-  printf("\nsummary per knot-iteration / per rollout knot:  oracle (literal) %.0f / %.0f    kernel math (lean) %.0f / %.0f\n", orc_iter, orc_roll,
-         k_iter, k_rollf);
-  printf("JSON {\"per_knot_iteration\": %.0f, \"per_rollout_knot\": %.0f, \"linearise\": %lld, \"cost_gradients\": %lld, \"riccati\": %lld, "
+  // the same two units in the diagonal-inertia instantiation (every preset of input_parameters.jl; what the benchmark runs)
+  c0 = g_cnt;
+  ts::rk3_jac7_jvp<true>(in.I, x, u, bk, bk + 3, bk + 6, in.dt, rec);
+  Counters k_lin_d = diff(g_cnt, c0); show("linearisation, diagonal inertia", k_lin_d, 1);
+  c0 = g_cnt;
+  {
+    CD xb[7], ub[3], kd[24], dx[7], Jc(0.0), cmax(0.0), xn[7];
+    for (int i = 0; i < 7; ++i) xb[i] = x[i] + CD(1e-3);
+    for (int i = 0; i < 24; ++i) kd[i] = CD(0.01 * i);
+    for (int i = 0; i < 7; ++i) dx[i] = xb[i] - x[i];
+    for (int i = 0; i < 3; ++i) { CD t = u[i]; for (int j = 0; j < 7; ++j) t += kd[j * 3 + i] * dx[j]; t += CD(0.25) * kd[21 + i]; ub[i] = t; }
+    ts::add_stage_cost(in, ko, CD(1.0), CD(10.0), xb, CD(0.0), ub, lam, Jc, cmax);
+    ts::rk3_step7<0, true>(in.I, xb, ub, bk, bk + 3, bk + 6, in.dt, xn);
+  }
+  Counters k_roll_d = diff(g_cnt, c0); show("line-search rollout knot, diagonal inertia", k_roll_d, 1);
+  // gradient measure of the convergence test: once per knot of the accepted trajectory (3 divisions, 3 additions)
+  const long long k_gradm = 6;
+  const double k_iter = (double)(k_lin.flops() + k_grad.flops() + k_ric.flops() + k_gradm), k_rollf = (double)k_roll.flops();
+  const double k_iter_d = (double)(k_lin_d.flops() + k_grad.flops() + k_ric.flops() + k_gradm), k_rollf_d = (double)k_roll_d.flops();
+  printf("\nsummary per knot-iteration / per rollout knot:  oracle (literal) %.0f / %.0f    kernel math %.0f / %.0f    diagonal inertia %.0f / %.0f\n",
+         orc_iter, orc_roll, k_iter, k_rollf, k_iter_d, k_rollf_d);
+  printf("JSON {\"per_knot_iteration\": %.0f, \"per_rollout_knot\": %.0f, \"per_knot_iteration_diag\": %.0f, \"per_rollout_knot_diag\": %.0f, "
+         "\"linearise\": %lld, \"linearise_diag\": %lld, \"cost_gradients\": %lld, \"riccati\": %lld, \"gradient_measure\": %lld, "
          "\"oracle_per_knot_iteration\": %.0f, \"oracle_per_rollout_knot\": %.0f, \"oracle_jacobians\": %.0f, \"oracle_backward\": %.0f}\n",
-         k_iter, k_rollf, k_lin.flops(), k_grad.flops(), k_ric.flops(), orc_iter, orc_roll, c_jac.flops() / K, c_bwd.flops() / K);
+         k_iter, k_rollf, k_iter_d, k_rollf_d, k_lin.flops(), k_lin_d.flops(), k_grad.flops(), k_ric.flops(), k_gradm, orc_iter, orc_roll,
+         c_jac.flops() / K, c_bwd.flops() / K);
   return 0;
 }

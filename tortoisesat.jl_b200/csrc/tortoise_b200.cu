@@ -949,10 +949,11 @@ int ts_tvlqr_sim_batch(ts_ctx* c, int64_t n, const int64_t* N_i, const int64_t* 
 
 // ---------------------------------------------------------------------------- fused Monte-Carlo
 // Algorithmic FLOP per unit: AL-iLQR figures COUNTED with an instrumented scalar on the kernels' own math
-// (tools/flopcount.cpp -> profiles/flop_counts_r2.json: JVP linearisation 8193 + cost gradients 51 + dense 7-state Riccati
-// step 3681 = 11925 per knot-iteration, 640 per line-search rollout knot; SURVEY 8d's estimate was 6100 / 500);
+// (tools/flopcount.cpp -> profiles/flop_counts_r2.json: JVP linearisation 6485 + cost gradients 51 + dense 7-state Riccati
+// step 3688 + gradient measure 6 = 10230 per knot-iteration, 607 per line-search rollout knot; 9285 / 535 in the
+// diagonal-inertia instantiation; SURVEY 8d's estimate was 6100 / 500);
 // IGRF sample 2393 (2243 + rotations) and TVLQR ~7700 per knot are the SURVEY 8d estimates.
-static const double FL_FIELD = 2393.0, FL_ITER = 11925.0, FL_ROLL = 640.0, FL_TVLQR = 7700.0;
+static const double FL_FIELD = 2393.0, FL_ITER = 10230.0, FL_ROLL = 607.0, FL_ITER_DIAG = 9285.0, FL_ROLL_DIAG = 535.0, FL_TVLQR = 7700.0;
 
 int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, const ts_field_opts* fopts, const double* x0,
                        const double* xf, const double* Jmat, const double* q_noise0, const uint32_t* stream_id,
@@ -1206,13 +1207,15 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     cudaEventElapsedTime(&ms, e[2], e[3]); ms_prep = ms;
     cudaEventElapsedTime(&ms, e[3], e[4]); ms_solve = ms;
     cudaEventElapsedTime(&ms, e[4], e[5]); ms_tvlqr = ms;
+    const bool dj_ = all_inertia_diagonal(Jmat, n) && !cfg->ilqr.quat_error && !cfg->ilqr.k3_generic_inertia;
+    const double fl_iter = dj_ ? FL_ITER_DIAG : FL_ITER, fl_roll = dj_ ? FL_ROLL_DIAG : FL_ROLL;
     for (int64_t a = 0; a < na; ++a) {
       const int64_t t = act[a], f = cfg->shared_orbit ? 0 : t;
       out[t] = oa[a];
       out[t].t_final = tfin[f];
       out[t].slew_time = cfg->run_tvlqr ? slew[a] : 0.0;
       const double kn = (double)(Nf[f] - 1);
-      out[t].flops = kn * ((double)oa[a].inner_iters * FL_ITER + (double)oa[a].ls_rollouts * FL_ROLL) + (cfg->run_tvlqr ? kn * FL_TVLQR : 0.0);
+      out[t].flops = kn * ((double)oa[a].inner_iters * fl_iter + (double)oa[a].ls_rollouts * fl_roll) + (cfg->run_tvlqr ? kn * FL_TVLQR : 0.0);
     }
     if (cfg->keep_trajectories) {
       ts_ctx::McLast& L = c->mc_last;
