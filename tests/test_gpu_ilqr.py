@@ -265,16 +265,17 @@ def test_general_and_diagonal_inertia_kernels(engine):
     """K3 picks diagonal-inertia kernel instantiations when every J is diagonal (all reference presets).  (1) they give
     the same iteration paths and results as the general kernels (ts_ilqr_opts.k3_generic_inertia = 1) on a ragged batch that
     goes through both launches; (2) a batch with products of inertia (off-diagonal J) runs the general kernels and matches the
-    oracle; (3) the producer-warp kernel in both instantiations."""
+    oracle; (3) the producer-warp kernel and the quaternion-aware kernels in both instantiations."""
     import tortoisesat.jl_b200 as tb
     rng = np.random.default_rng(5)
     qf = np.array([1.0, 0, 0, 0])
     slews = [S.build_slew([0, 6578, 96, 0, 0, 90], S.J_3U if i % 2 else S.J_1P, S.quat_axis_angle(rng.normal(size=3), rng.uniform(3, 25)),
                           qf, t_final=float(rng.integers(20, 45))) for i in range(9)]
-    for pair in (0, 1):
+    for pair, quat in ((0, 0), (1, 0), (0, 1)):       # (1, 0): the producer-warp kernel; (0, 1): the quaternion-aware kernels
         o = orc.default_ilqr_opts()
         o.k3_suspend_after = 10
         o.k3_pair = pair
+        o.quat_error = quat
         res = []
         for generic in (0, 1):
             g = _gpu_opts(tb, o)

@@ -280,6 +280,14 @@ __global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_quat_ker
 #include "k3_alilqr_body.inc"
 }
 #undef K3_BODY_TEAM
+struct GpuTeamQuatDiag : GpuTeamQuat {
+  static constexpr bool DIAGJ = true;
+};
+#define K3_BODY_TEAM GpuTeamQuatDiag
+__global__ void __launch_bounds__(K3_WARPS_PER_BLOCK * 32, 1) k3_alilqr_quat_diag_kernel(const K3Args a) {
+#include "k3_alilqr_body.inc"
+}
+#undef K3_BODY_TEAM
 // ---------------------------------------------------------------------------------------------
 // Second launch: every parked straggler is finished by ONE WHOLE WARP (32-lane team): 32 knots linearised per
 // chunk, all 21 line-search candidates in one batch, one warp per SM sub-partition when few trials are left.
@@ -339,6 +347,14 @@ __global__ void __launch_bounds__(32, 1) k3_wide_diag_kernel(const K3Args a) {
 #undef K3_BODY_TEAM
 #define K3_BODY_TEAM GpuWideQuatTeam
 __global__ void __launch_bounds__(32, 1) k3_wide_quat_kernel(const K3Args a) {
+#include "k3_wide_body.inc"
+}
+#undef K3_BODY_TEAM
+struct GpuWideQuatDiagTeam : GpuWideQuatTeam {
+  static constexpr bool DIAGJ = true;
+};
+#define K3_BODY_TEAM GpuWideQuatDiagTeam
+__global__ void __launch_bounds__(32, 1) k3_wide_quat_diag_kernel(const K3Args a) {
 #include "k3_wide_body.inc"
 }
 #undef K3_BODY_TEAM

@@ -526,9 +526,11 @@ static int k3_launch(ts_ctx* c, K3Args& a, const int64_t* N_i_host, const double
       return fail(c, TS_ERR_ARG, "quat_error: the goal mask must hold all four quaternion components or none");
   }
   // diagonal inertia matrices (every preset of the reference): instantiations without the products by their zeros
-  const bool dj = diag_inertia && !quat && !a.opts.k3_generic_inertia;
-  void (*const narrow_kernel)(const K3Args) = quat ? k3_alilqr_quat_kernel : (dj ? k3_alilqr_diag_kernel : k3_alilqr_kernel);
-  void (*const wide_kernel)(const K3Args) = quat ? k3_wide_quat_kernel : (dj ? k3_wide_diag_kernel : k3_wide_kernel);
+  const bool dj = diag_inertia && !a.opts.k3_generic_inertia;
+  void (*const narrow_kernel)(const K3Args) = quat ? (dj ? k3_alilqr_quat_diag_kernel : k3_alilqr_quat_kernel)
+                                                   : (dj ? k3_alilqr_diag_kernel : k3_alilqr_kernel);
+  void (*const wide_kernel)(const K3Args) = quat ? (dj ? k3_wide_quat_diag_kernel : k3_wide_quat_kernel)
+                                                 : (dj ? k3_wide_diag_kernel : k3_wide_kernel);
   void (*const pair_kernel)(const K3Args) = dj ? k3_pair_diag_kernel : k3_pair_kernel;
   int64_t Nmax = 0;
   for (int64_t t = 0; t < n_trials; ++t) Nmax = std::max(Nmax, N_i_host[t]);
@@ -1207,7 +1209,7 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
     cudaEventElapsedTime(&ms, e[2], e[3]); ms_prep = ms;
     cudaEventElapsedTime(&ms, e[3], e[4]); ms_solve = ms;
     cudaEventElapsedTime(&ms, e[4], e[5]); ms_tvlqr = ms;
-    const bool dj_ = all_inertia_diagonal(Jmat, n) && !cfg->ilqr.quat_error && !cfg->ilqr.k3_generic_inertia;
+    const bool dj_ = all_inertia_diagonal(Jmat, n) && !cfg->ilqr.k3_generic_inertia;
     const double fl_iter = dj_ ? FL_ITER_DIAG : FL_ITER, fl_roll = dj_ ? FL_ROLL_DIAG : FL_ROLL;
     for (int64_t a = 0; a < na; ++a) {
       const int64_t t = act[a], f = cfg->shared_orbit ? 0 : t;
