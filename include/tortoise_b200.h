@@ -63,6 +63,10 @@ int ts_k3_last_split(ts_ctx* ctx, double* persistent_ms, double* straggler_ms, i
  * order of the trials that reached the solver in ts_monte_carlo_run): cycles3 = n_trials x 3 HOST doubles
  * [backward pass, forward pass (line search), linearisation share of the backward pass].                        */
 int ts_k3_last_cycles(ts_ctx* ctx, int64_t n_trials, double* cycles3);
+/* the trials the most recent AL-iLQR solve on ctx handed from the first to the second launch (profiling aid for the
+ * hand-over order): for each, its index in that call's trial order and the outer / total inner iteration counters
+ * it had when it was parked.  HOST arrays of `cap` entries; *n_out = entries written.                           */
+int ts_k3_last_parked(ts_ctx* ctx, int64_t cap, int64_t* trial, int32_t* outer_at_park, int32_t* inner_at_park, int64_t* n_out);
 
 /* Measures the FP64 FMA peak of the bound GPU with a register-resident DFMA
  * micro-benchmark (the roofline denominator; MEASURED_PEAKS.json has no FP64 row). */

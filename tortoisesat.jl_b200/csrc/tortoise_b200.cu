@@ -145,6 +145,31 @@ int ts_k3_last_split(ts_ctx* c, double* persistent_ms, double* straggler_ms, int
   return TS_OK;
 }
 
+int ts_k3_last_parked(ts_ctx* c, int64_t cap, int64_t* trial, int32_t* outer_at_park, int32_t* inner_at_park, int64_t* n_out) {
+  if (!c || !n_out || cap < 0 || (cap > 0 && (!trial || !outer_at_park || !inner_at_park))) return TS_ERR_ARG;
+  *n_out = 0;
+  if (!c->k3_timed || !c->d_k3_parked || c->k3_park_cap <= 0 || !c->scratch[15]) return TS_OK;
+  TS_CUDA(c, cudaSetDevice(c->device));
+  TS_CUDA(c, cudaStreamSynchronize(c->stream));
+  unsigned np = 0;
+  TS_CUDA(c, cudaMemcpy(&np, c->d_k3_parked, sizeof(np), cudaMemcpyDeviceToHost));
+  if (np > (unsigned)c->k3_park_cap) np = (unsigned)c->k3_park_cap;
+  const size_t n = std::min<size_t>((size_t)np, (size_t)cap), pc = (size_t)c->k3_park_cap;
+  std::vector<TrialState> st(n);
+  std::vector<int64_t> tr(n);
+  if (n) {
+    TS_CUDA(c, cudaMemcpy(st.data(), c->scratch[15], n * sizeof(TrialState), cudaMemcpyDeviceToHost));
+    TS_CUDA(c, cudaMemcpy(tr.data(), (const char*)c->scratch[15] + pc * sizeof(TrialState), n * 8, cudaMemcpyDeviceToHost));
+  }
+  for (size_t i = 0; i < n; ++i) {
+    trial[i] = tr[i];
+    outer_at_park[i] = st[i].outer;
+    inner_at_park[i] = st[i].inner_total;
+  }
+  *n_out = (int64_t)n;
+  return TS_OK;
+}
+
 int ts_k3_last_cycles(ts_ctx* c, int64_t n_trials, double* cycles3) {
   if (!c || !cycles3 || n_trials < 0) return TS_ERR_ARG;
   if (n_trials > c->k3_diag_n || !c->scratch[19]) return fail(c, TS_ERR_ARG, "ts_k3_last_cycles: the last solve covered %lld trials", (long long)c->k3_diag_n);

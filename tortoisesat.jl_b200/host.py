@@ -137,6 +137,8 @@ def load_library():
     L.ts_last_kernel_ms.restype = C.c_double
     L.ts_k3_last_split.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.ts_k3_last_split.restype = C.c_int
+    L.ts_k3_last_parked.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    L.ts_k3_last_parked.restype = C.c_int
     L.ts_k3_last_cycles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.ts_fp64_peak_probe.argtypes = [C.c_void_p, c_double_p]
     L.ts_fp64_latency_probe.argtypes = [C.c_void_p, c_double_p]
@@ -470,6 +472,14 @@ class Engine:
         cyc = np.zeros((int(n_trials), 3))
         self._check(self.lib.ts_k3_last_cycles(self.h, int(n_trials), _ptr(cyc)))
         return cyc
+
+    def k3_last_parked(self, cap):
+        """Trials the last AL-iLQR solve handed to its second launch: (trial index, outer count, inner count at parking)."""
+        cap = int(cap)
+        tr, ou, inn = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        n = C.c_int64(0)
+        self._check(self.lib.ts_k3_last_parked(self.h, cap, _ptr(tr), _ptr(ou), _ptr(inn), C.byref(n)))
+        return tr[:n.value], ou[:n.value], inn[:n.value]
 
     def mc_trajectories(self, n_trials, want=("X", "U", "X_sim", "U_sim", "B_eci")):
         """Trajectories of the last monte_carlo_run with cfg.keep_trajectories = 1: dict with knot_offs, row_offs and the
