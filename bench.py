@@ -60,9 +60,9 @@ try:
 except Exception:
     FLOP_SOURCE = "SURVEY 8d estimate: 6100 per knot-iteration (rk3 Jacobian 2600 + Riccati step 3500) + 500 per rollout knot"
 # HBM traffic of K3 per knot-iteration: ncu dram__bytes_read+write of THIS configuration (N = 2044, 4096 trials)
-K3_TRAFFIC = {"bytes_per_knot_iter": 1650.0, "source": "profiles/k3_traffic_r2a.csv"}
+K3_TRAFFIC = {"bytes_per_knot_iter": 1650.0, "source": "profiles/k3_traffic_r3.csv"}
 try:
-    K3_TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic_r2.json")))
+    K3_TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic_r3.json")))
 except Exception:
     pass
 STATUS = ["converged", "max_outer", "cost_blowup", "reg_max", "nan", "no_cutoff"]
@@ -455,7 +455,7 @@ def main():
                      "outer_iters_quantiles_50_90_100": np.percentile(allout["outer_iters"][act], [50, 90, 100]).tolist() if act.any() else [],
                      "ls_rollouts_mean": float(allout["ls_rollouts"][act].mean()) if act.any() else 0.0,
                      "slew_fail": int(vec[3]), "mean_slew_time_s": float(vec[4] / max(1.0, vec[0] - vec[2]))},
-            roofline={"bound": "fp64", "kernel": "K3 AL-iLQR solve: k3_alilqr_kernel (4 trials per warp) + k3_wide_kernel (one warp per straggler)",
+            roofline={"bound": "fp64", "kernel": "K3 AL-iLQR solve: k3_alilqr_diag_kernel (4 trials per warp) + k3_wide_diag_kernel (one warp per straggler): the diagonal-inertia instantiations of k3_alilqr_kernel / k3_wide_kernel",
                       "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s", "frac": ach / peak_fp64,
                       "traffic": K3_TRAFFIC["bytes_per_knot_iter"] * knot_iters, "traffic_source": "%s: %.0f B per knot-iteration (ncu "
                       "dram__bytes_read+write of this configuration) x this run's knot-iterations" % (K3_TRAFFIC["source"], K3_TRAFFIC["bytes_per_knot_iter"]),
