@@ -6,16 +6,19 @@
 //   magnetic_gramian(B_N,dt)                   src/magnetic_toolbox.jl:1-12
 //   condition_based_time(B_gram,cutoff)        src/magnetic_toolbox.jl:14-31
 //
-// Three kernels:
-//   k2a_orbit_euler   one thread per trial, strictly sequential explicit Euler
-//                     (2N steps), positions/velocities streamed to HBM;
+// Kernels:
+//   k2a_orbit_euler   one thread per trial, strictly sequential explicit Euler (2N steps, ~45 instructions each:
+//                     orbit_rhs_fast), positions/velocities streamed to HBM;
 //   k2b_field_rows    one thread per (trial, sample): GMST -> ECEF -> lat/long ->
 //                     IGRF-12 (igrf_device.cuh, coefficients of the trial's date
 //                     staged in shared memory per block) -> NED->ENU->ECEF->ECI;
-//   k2c_gramian_cutoff one thread per trial: running gramian + 3x3 symmetric
-//                     Jacobi eigenvalues, first sample with cond < cutoff.
-// Roofline: k2b is FP64-pipe bound (IGRF, ~2.4 kFLOP/sample, 48 B/sample);
-// k2a/k2c are latency-bound sequential scans of negligible cost (<1% of a trial).
+//   k2c_cutoff_scan   one block per trial: block-wide prefix scan of the gramian terms, cond() of every prefix in
+//                     parallel, first sample below the cutoff by ballot (the fused Monte-Carlo path: two sample ranges,
+//                     the second one only for the orbits that did not reach the cutoff in the first);
+//   k2c_gramian_cutoff one thread per trial: running gramian in the reference's summation order + 3x3 symmetric Jacobi
+//                     eigenvalues (the stand-alone magnetic_gramian / condition_based_time entry points).
+// Roofline: k2b is FP64-pipe bound (IGRF, ~2.4 kFLOP/sample, 48 B/sample); k2a is a latency-bound sequential chain.
+// Measured on the 8192-orbit sweep (round 2): field stage 80 ms -> 15.7 ms (10.1 ms for 4096 orbits).
 #pragma once
 #include "common.cuh"
 #include "igrf_device.cuh"
@@ -100,6 +103,30 @@ __device__ __forceinline__ void orbit_rhs_dev(const double x[6], double dx[6]) {
   dx[5] = (g * -x[2] / nr) + J2 * x[2] / nr7 * c2;
 }
 
+// The same right-hand side for the sequential Euler integration of k2a (up to 47 000 dependent steps per orbit): one
+// reciprocal square root (hardware seed + one third-order step) and products instead of a square root and seven
+// divisions -- ~45 instead of ~235 instructions per step.  Each quotient of the literal form above is reproduced to
+// <= 1 ulp; positions after 10^4 steps agree with the oracle to < 1e-13 relative (tests: 1e-12).
+__device__ __forceinline__ void orbit_rhs_fast(const double x[6], double dx[6]) {
+  const double GM = 3.986004418E14 * ((1.0 / 1000) * (1.0 / 1000) * (1.0 / 1000));
+  const double J2 = 0.0010826359;
+  const double s = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+  const double e = fma(-s, y0 * y0, 1.0);
+  const double inv = fma(fma(e, 0.375, 0.5), e * y0, y0);   // 1 / |r|
+  const double inv2 = inv * inv, inv3 = inv2 * inv, inv7 = inv3 * inv2 * inv2;
+  const double rxy = x[0] * x[0] + x[1] * x[1];
+  const double c01 = 6 * x[2] - 1.5 * rxy, c2 = 3 * x[2] - 4.5 * rxy;
+  const double a = -(GM * inv3), j = J2 * inv7;
+  dx[0] = x[3];
+  dx[1] = x[4];
+  dx[2] = x[5];
+  dx[3] = a * x[0] + (j * x[0]) * c01;
+  dx[4] = a * x[1] + (j * x[1]) * c01;
+  dx[5] = a * x[2] + (j * x[2]) * c2;
+}
+
 // pos/vel: per trial (2N+1) x 3 rows starting at row B_offs[t] + t.  vel may be null.
 __global__ void __launch_bounds__(128)
 k2a_orbit_euler(int64_t n_trials, const double* __restrict__ kep6, const ts_field_opts_dev* __restrict__ opts,
@@ -125,7 +152,7 @@ k2a_orbit_euler(int64_t n_trials, const double* __restrict__ kep6, const ts_fiel
       v[i * 3 + 2] = u[5];
     }
     double du[6];
-    orbit_rhs_dev(u, du);
+    orbit_rhs_fast(u, du);
 #pragma unroll
     for (int c = 0; c < 6; ++c) u[c] = u[c] + dt * du[c];
   }
@@ -139,15 +166,16 @@ template <int NMAX>
 __global__ void __launch_bounds__(K2B_THREADS)
 k2b_field_rows(const double* __restrict__ tabG, const double* __restrict__ tabH, const ts_field_opts_dev* __restrict__ opts,
                const int64_t* __restrict__ B_offs, const int64_t* __restrict__ rows_limit, const double* __restrict__ pos,
-               double* __restrict__ B_eci, int nmax_select) {
+               double* __restrict__ B_eci, int nmax_select, int64_t i_lo = 0, const int64_t* __restrict__ skip_found = nullptr) {
   __shared__ double2 s_gh[2 * IGRF_NCOEF];
   const int64_t t = blockIdx.x;
+  if (skip_found && skip_found[t] != 0) return;   // scoping pass, later sample ranges: this orbit already has its cutoff
   const ts_field_opts_dev o = opts[t];
   if (igrf_nmax_for_date(o.igrf_date) != nmax_select) return;  // handled by the other instantiation
   const int64_t rows = 2 * o.N;
   int64_t live = rows - 1;
   if (rows_limit && rows_limit[t] > 0 && rows_limit[t] < live) live = rows_limit[t];
-  const int64_t i0 = (int64_t)blockIdx.y * K2B_THREADS;
+  const int64_t i0 = i_lo + (int64_t)blockIdx.y * K2B_THREADS;
   if (i0 >= rows) return;
   igrf_stage_coeffs(s_gh, tabG, tabH, o.igrf_date);
   __syncthreads();
@@ -279,6 +307,87 @@ k2c_gramian_cutoff(int64_t n_trials, const double* __restrict__ B_eci, const int
     }
   }
   if (tf_index) tf_index[t] = found;
+}
+
+// The cutoff search of the fused Monte-Carlo path, one BLOCK per orbit (k2c_gramian_cutoff above walks the samples with
+// one thread per orbit: up to 10^4 dependent Jacobi eigen-solves, 34 ms for an 8192-orbit sweep).  Samples [i_lo, i_hi)
+// in chunks of one per thread: h_i*dt -> block-wide inclusive scan of the six gramian entries (+ the carry of the
+// previous chunks / of an earlier call, `carry` 6 doubles per orbit) -> cond() of every prefix in parallel -> the first
+// sample below the cutoff by ballot.  The prefix sums are formed pairwise instead of left to right, i.e. they differ from
+// the sequential gramian in the last bits (relative 1e-16) -- far below the ~1e-4 by which cond() moves per sample, so
+// the index is the same (tests compare it with the oracle's on every trial).  tf_index[t] != 0 on entry: nothing to do.
+constexpr int K2C_THREADS = 128;
+__global__ void __launch_bounds__(K2C_THREADS)
+k2c_cutoff_scan(const double* __restrict__ B_eci, const int64_t* __restrict__ B_offs, const int64_t* __restrict__ rows,
+                const double* __restrict__ dts, const double* __restrict__ cutoffs, int64_t i_lo, int64_t i_hi,
+                double* __restrict__ carry, int64_t* __restrict__ tf_index) {
+  __shared__ double s_tot[K2C_THREADS / 32][6];
+  __shared__ int s_first[K2C_THREADS / 32];
+  const int64_t t = blockIdx.x;
+  if (tf_index[t] != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double* B = B_eci + B_offs[t] * 3;
+  int64_t R = rows[t];
+  if (R > i_hi) R = i_hi;
+  const double dt = dts[t], cutoff = cutoffs[t];
+  double car[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) car[k] = (i_lo > 0) ? carry[t * 6 + k] : 0.0;
+  for (int64_t base = i_lo; base < R; base += K2C_THREADS) {
+    const int64_t i = base + tid;
+    double v[6];
+    if (i < R) {
+      hat_hatT_dev(B + i * 3, v);
+      if (i != 0) {   // the first term has no dt (quirk Q9)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = v[k] * dt;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {   // inclusive scan inside the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v[k], o);
+        if (lane >= o) v[k] += u;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_tot[wid][k] = v[k];
+    }
+    __syncthreads();
+    double acc[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double pre = car[k];
+      for (int w = 0; w < wid; ++w) pre += s_tot[w][k];
+      acc[k] = pre + v[k];
+    }
+    const bool hit = (i < R) && (cond_sym3_dev(acc) < cutoff);
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_first[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : K2C_THREADS;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {   // carry for the next chunk: everything up to the block's last sample
+      double tot = car[k];
+      for (int w = 0; w < K2C_THREADS / 32; ++w) tot += s_tot[w][k];
+      car[k] = tot;
+    }
+    __syncthreads();
+    int first = K2C_THREADS;
+    for (int w = 0; w < K2C_THREADS / 32; ++w) first = min(first, s_first[w]);
+    if (first < K2C_THREADS) {
+      if (tid == 0) tf_index[t] = base + first + 1;
+      return;
+    }
+    __syncthreads();   // s_tot / s_first are rewritten by the next chunk
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) carry[t * 6 + k] = car[k];
+  }
 }
 
 // condition_based_time on caller-supplied gramians (rows x 9 per trial).

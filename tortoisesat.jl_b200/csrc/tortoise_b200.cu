@@ -1020,26 +1020,36 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
   void *p_pos, *p_Bs, *p_sm;
   if ((rc = scratch_reserve(c, 0, (size_t)(offs_s[nf] + nf) * 3 * 8, &p_pos))) return rc;
   if ((rc = scratch_reserve(c, 7, (size_t)offs_s[nf] * 3 * 8, &p_Bs))) return rc;
-  if ((rc = scratch_reserve(c, 10, NF * 32, &p_sm))) return rc;
+  if ((rc = scratch_reserve(c, 10, NF * 80, &p_sm))) return rc;
   std::vector<int64_t> rows_s(NF, 2 * cfg->N_scope);
   std::vector<double> dts(NF, (cfg->tf - cfg->t0) / (double)cfg->N_scope), cuts(NF, cfg->cutoff);
   int64_t* d_rows_s = (int64_t*)p_sm;
   double* d_dts = (double*)((char*)p_sm + NF * 8);
   double* d_cuts = (double*)((char*)p_sm + NF * 16);
   int64_t* d_idx = (int64_t*)((char*)p_sm + NF * 24);
+  double* d_carry = (double*)((char*)p_sm + NF * 32);   // running gramian of an orbit between two sample ranges
   TS_CUDA(c, cudaMemcpyAsync(d_rows_s, rows_s.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
   TS_CUDA(c, cudaMemcpyAsync(d_dts, dts.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
   TS_CUDA(c, cudaMemcpyAsync(d_cuts, cuts.data(), NF * 8, cudaMemcpyHostToDevice, c->stream));
   cudaEventRecord(e[0], c->stream);
   k2a_orbit_euler<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, d_kep, d_fo, d_offs_s, nullptr, (double*)p_pos, nullptr);
   c->launches++;
+  // field rows and cutoff search in two sample ranges: most orbits reach the cutoff within the first few thousand
+  // samples, and the second range skips those (no host round trip: the kernels look at d_idx themselves)
+  TS_CUDA(c, cudaMemsetAsync(d_idx, 0, NF * 8, c->stream));
   {
-    dim3 grid((unsigned)nf, (unsigned)((2 * cfg->N_scope + K2B_THREADS - 1) / K2B_THREADS));
-    if (any13) { k2b_field_rows<13><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 13); c->launches++; }
-    if (any10) { k2b_field_rows<10><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 10); c->launches++; }
+    const int64_t S2 = 2 * cfg->N_scope, SA = std::min<int64_t>(S2, 4096);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int64_t lo = pass ? SA : 0, hi = pass ? S2 : SA;
+      if (hi <= lo) break;
+      const int64_t* skip = pass ? d_idx : nullptr;
+      dim3 grid((unsigned)nf, (unsigned)((hi - lo + K2B_THREADS - 1) / K2B_THREADS));
+      if (any13) { k2b_field_rows<13><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 13, lo, skip); c->launches++; }
+      if (any10) { k2b_field_rows<10><<<grid, K2B_THREADS, 0, c->stream>>>(c->d_tabG, c->d_tabH, d_fo, d_offs_s, nullptr, (double*)p_pos, (double*)p_Bs, 10, lo, skip); c->launches++; }
+      k2c_cutoff_scan<<<(unsigned)nf, K2C_THREADS, 0, c->stream>>>((double*)p_Bs, d_offs_s, d_rows_s, d_dts, d_cuts, lo, hi, d_carry, d_idx);
+      c->launches++;
+    }
   }
-  k2c_gramian_cutoff<<<(unsigned)((nf + 127) / 128), 128, 0, c->stream>>>(nf, (double*)p_Bs, d_offs_s, d_rows_s, d_dts, d_cuts, nullptr, d_idx);
-  c->launches++;
   cudaEventRecord(e[6], c->stream);   // end of the scoping stage on the device (the host sync below is not device time)
   TS_CUDA(c, cudaGetLastError());
   std::vector<int64_t> idx(NF);
@@ -1054,7 +1064,10 @@ int ts_monte_carlo_run(ts_ctx* c, const ts_mc_config* cfg, const double* kep6, c
   double field_samples = 0.0;
   for (int64_t f = 0; f < nf; ++f) {
     fo2[f] = fo[f];
-    field_samples += 2.0 * (double)cfg->N_scope - 1.0;
+    {  // scoping samples evaluated for this orbit: the first range, and the second one only if the cutoff was not in it
+      const int64_t S2 = 2 * cfg->N_scope, SA = std::min<int64_t>(S2, 4096);
+      field_samples += (idx[f] > 0 && idx[f] <= SA) ? (double)SA : (double)S2 - 1.0;
+    }
     if (idx[f] > 0) {
       tfin[f] = (double)idx[f] * (cfg->tf - cfg->t0) / (double)cfg->N_scope;
       Nf[f] = (int64_t)floor((tfin[f] - cfg->t0) / cfg->dt);
