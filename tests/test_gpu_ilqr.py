@@ -282,12 +282,26 @@ def test_general_and_diagonal_inertia_kernels(engine):
             g.k3_generic_inertia = generic
             res.append(engine.alilqr_solve_batch(**_pack(slews), opts=g))
             assert engine.k3_last_split()[2] > 0
-        # (different instantiations: the compiler's FMA contraction choices differ in the last bit, as between the
-        #  four-per-warp and the one-per-warp kernel)
-        for f in ("status", "outer_iters", "inner_iters", "ls_rollouts"):
-            assert np.array_equal(res[0][3][f], res[1][3][f]), f
-        assert np.max(np.abs(res[0][3]["J"] - res[1][3]["J"]) / np.abs(res[1][3]["J"])) < 1e-9
-        assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-9 and np.max(np.abs(res[0][1] - res[1][1])) < 1e-8
+        # Different instantiations: the compiler's FMA contraction choices differ in the last bit, as between the
+        # four-per-warp and the one-per-warp kernel.  Status and outer count must agree on every slew; the inner path of
+        # a slew that runs ~1000 iterations without converging is rounding-sensitive (seen on a B200: one line search
+        # out of ~700 took 7128 instead of 7127 rollouts), so the counters must agree exactly on all but at most two
+        # slews and to 2 % on those, and trajectories are compared tightly where the paths are identical.
+        a, b = res[0][3], res[1][3]
+        for f in ("status", "outer_iters"):
+            assert np.array_equal(a[f], b[f]), (pair, quat, f, a[f], b[f])
+        same = (a["inner_iters"] == b["inner_iters"]) & (a["ls_rollouts"] == b["ls_rollouts"])
+        assert same.sum() >= len(slews) - 2, (pair, quat, a["inner_iters"], b["inner_iters"], a["ls_rollouts"], b["ls_rollouts"])
+        for f in ("inner_iters", "ls_rollouts"):
+            assert np.all(np.abs(a[f].astype(np.int64) - b[f]) <= 0.02 * b[f] + 1), (pair, quat, f, a[f], b[f])
+        conv = a["status"] == 0                                          # TS_ST_CONVERGED
+        assert np.all(same[conv]), (pair, quat, same, a["status"])      # converged slews: identical paths
+        assert np.max(np.abs(a["J"] - b["J"]) / np.abs(b["J"])) < 1e-6
+        offs = res[0][4]
+        for t in np.nonzero(same)[0]:
+            assert abs(a["J"][t] - b["J"][t]) <= 1e-9 * abs(b["J"][t])
+            assert np.max(np.abs(res[0][0][offs[t]:offs[t + 1]] - res[1][0][offs[t]:offs[t + 1]])) < 1e-9
+            assert np.max(np.abs(res[0][1][offs[t]:offs[t + 1]] - res[1][1][offs[t]:offs[t + 1]])) < 1e-8
     Jfull = np.array([[0.020833, 0.0011, -0.0007], [0.0011, 0.018, 0.0009], [-0.0007, 0.0009, 0.0041666]])
     slews2 = [S.build_slew([0, 6578, 96, 0, 0, 90], Jfull, S.quat_axis_angle(rng.normal(size=3), rng.uniform(3, 20)), qf,
                            t_final=float(rng.integers(25, 45))) for i in range(5)]
