@@ -1,6 +1,6 @@
 """GPU probe on the BENCHMARK ensembles (bench.make_trials): where the solves end up, and why.
 
-  python tools/mc_probe.py <mc_fixed_orbit|mc_sweep> <n_trials> [--suspend a,b,...] [--pair 0,1] [--occ 0,4,6] [--flips] [--why]
+  python tools/mc_probe.py <mc_fixed_orbit|mc_sweep> <n_trials> [--suspend a,b,...] [--pair 0,1] [--occ 0,4,6] [--early 1.0,2.0] [--flips] [--why]
 
 Per run: K3 time and its split between the two kernels, per-status histogram, inner-iteration quantiles.
 --why     keeps the trajectories and decomposes c_max of the non-converged trials: which constraint (control bound
@@ -27,11 +27,14 @@ args = sys.argv[3:]
 suspends = [150]
 pairs = [1]
 occs = [0]
+earlies = [None]
 for i, a in enumerate(args):
     if a == "--occ":
         occs = [int(x) for x in args[i + 1].split(",")]
     if a == "--suspend":
         suspends = [int(x) for x in args[i + 1].split(",")]
+    if a == "--early":
+        earlies = [float(x) for x in args[i + 1].split(",")]
     if a == "--pair":
         pairs = [int(x) for x in args[i + 1].split(",")]
 eng = tb.Engine(0)
@@ -61,12 +64,14 @@ def run(cfg, label):
 
 base_out = None
 for s in suspends:
-    for pr, oc in [(p_, o_) for p_ in pairs for o_ in (occs if p_ == 0 else [0])]:
+    for pr, oc, ea in [(p_, o_, e_) for p_ in pairs for o_ in (occs if p_ == 0 else [0]) for e_ in earlies]:
         cfg = B.mc_config(host, tr, n)
         cfg.ilqr.k3_suspend_after = s
         cfg.ilqr.k3_pair = pr
         cfg.ilqr.k3_wide_occ = oc
-        out, st = run(cfg, "suspend=%d pair=%d occ=%d" % (s, pr, oc))
+        if ea is not None:
+            cfg.ilqr.k3_early_factor = ea
+        out, st = run(cfg, "suspend=%d pair=%d occ=%d early=%s" % (s, pr, oc, ea))
         if base_out is None:
             base_out = out.copy()
         else:
